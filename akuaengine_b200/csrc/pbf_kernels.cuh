@@ -1,0 +1,537 @@
+// pbf_kernels.cuh — hand-written sm_100a kernels for the PBF step (device-resident SoA float4 state).
+//
+// Each kernel cites the reference kernel(s) it replaces (paths relative to the reference repository root). The
+// reference's 13 kernels run one thread per particle over a 108-byte AoS with a per-particle neighbour list that
+// round-trips through host memory; here the state is SoA float4 (x,y,z,mass) / (vx,vy,vz,density), the neighbour list is a
+// column-major (ELL) device array so that the k-th neighbours of 32 consecutive particles are one 128-byte line, and
+// the per-iteration kernels are fused so that each neighbour's position is gathered once per sweep:
+//   pass A = K5+K6  (density, both lambda loops)            pass B = K7+K8 (+K9+K10 on the last iteration)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace akua {
+
+enum : int { KEY_HASH = 0, KEY_LINEAR = 1 };
+
+struct SphParams {
+    float h, h2;
+    float poly6Coef;    // 315/(64*3.14*h^9)   (SmoothingKernelsCUDA.h:20; pi is 3.14f in the reference)
+    float spikyCoef;    // -45/(3.14*h^6)      (SmoothingKernelsCUDA.h:27)
+    float selfW;        // poly6(0)
+    float invRestDensity;
+    float relaxation;
+    float corrK, corrN, invPoly6Dq;  // artificial pressure: -k * (W(d2)/W(dq^2))^n
+    int corrNIsFour;
+};
+
+struct GridParams {
+    float cellSize;     // K2 cell size (the reference passes smoothRadius, NeighbourSearchCUDA.cu:163)
+    float lookupCellSize;  // K4 cell size (spatialHashCellSize, :177); equal to cellSize by contract
+    uint32_t tableSize; // REFERENCE_HASH
+    int3 gridMin;       // LINEAR_CELL: cell coordinate of grid corner
+    int3 gridDim;
+};
+
+struct BoxParams {
+    float3 bmin, bmax;
+    float collisionMinDist, collisionStiffness;   // 0.025, 0.5 (ConstraintSolverCUDA.cu:137-138)
+    float dampingMinDist, restitution, oneMinusFriction;  // 0.025 (IntegrationCUDA.cu:88), 0, 1-0.95 (PBFSolver.cpp:64)
+};
+
+// ------------------------------------------------------------------------------------------------ device math
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    // exactly the reference's contraction (kernel_find_neighbours SASS): fma(dz,dz, fma(dx,dx, dy*dy))
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+__device__ __forceinline__ float poly6(float d2, const SphParams& P) {  // SmoothingKernelsCUDA.h:16-21
+    float t = P.h2 - d2;
+    return d2 > P.h2 ? 0.0f : P.poly6Coef * (t * t * t);
+}
+// Spiky gradient, SmoothingKernelsCUDA.h:23-28. Returns the scalar s such that grad = s * r_vector
+// (s = coef*(h-r)^2 / r, 0 outside (1e-5, h]).
+template <bool FAST>
+__device__ __forceinline__ float spiky_scale(float d2, const SphParams& P) {
+    float r, invr;
+    if (FAST) { invr = rsqrtf(d2); r = d2 * invr; }
+    else      { r = sqrtf(d2); invr = 1.0f / r; }
+    float t = P.h - r;
+    float s = P.spikyCoef * (t * t) * invr;
+    return (r > P.h || r < 1e-5f) ? 0.0f : s;
+}
+__device__ __forceinline__ int3 cell_of(float x, float y, float z, float cellSize) {
+    // NeighbourSearchCUDA.cu:15-21: floorf of a true IEEE division
+    return make_int3((int)floorf(__fdiv_rn(x, cellSize)), (int)floorf(__fdiv_rn(y, cellSize)),
+                     (int)floorf(__fdiv_rn(z, cellSize)));
+}
+__device__ __forceinline__ uint32_t ref_hash(int cx, int cy, int cz, uint32_t tableSize) {
+    // NeighbourSearchCUDA.cu:23-27
+    return (((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u) ^ ((uint32_t)cz * 83492791u)) % tableSize;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams& G) {
+    int x = clampi(c.x - G.gridMin.x, 0, G.gridDim.x - 1);
+    int y = clampi(c.y - G.gridMin.y, 0, G.gridDim.y - 1);
+    int z = clampi(c.z - G.gridMin.z, 0, G.gridDim.z - 1);
+    return (uint32_t)((x * G.gridDim.y + y) * G.gridDim.z + z);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 + K2
+// kernel_predict_position (IntegrationCUDA.cu:27-36) fused with kernel_compute_hashes (NeighbourSearchCUDA.cu:36-44).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                                     float4* __restrict__ xs, uint32_t* __restrict__ keys, uint32_t n,
+                                                     float dt, float3 g, GridParams G, int doPredict) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x;
+    if (doPredict) {
+        float4 p = pos[i], v = vel[i];
+        float vx = __fmaf_rn(g.x, dt, v.x), vy = __fmaf_rn(g.y, dt, v.y), vz = __fmaf_rn(g.z, dt, v.z);
+        x = make_float4(__fmaf_rn(vx, dt, p.x), __fmaf_rn(vy, dt, p.y), __fmaf_rn(vz, dt, p.z), p.w);
+        xs[i] = x;
+    } else {
+        x = xs[i];
+    }
+    if (keys) {
+        int3 c = cell_of(x.x, x.y, x.z, G.cellSize);
+        keys[i] = MODE == KEY_HASH ? ref_hash(c.x, c.y, c.z, G.tableSize) : linear_key(c, G);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reorder + K3
+// Gathers the state into key-sorted order (the reference physically sorts the structs, NeighbourSearchCUDA.cu:167-170)
+// and records bucket / cell ranges (kernel_build_hash_table, :52-65).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_reorder_ranges(const uint32_t* __restrict__ keysSorted,
+                                                        const uint32_t* __restrict__ perm, uint32_t n,
+                                                        const float4* __restrict__ posIn, const float4* __restrict__ velIn,
+                                                        const float4* __restrict__ xsIn, const uint32_t* __restrict__ idIn,
+                                                        float4* __restrict__ posOut, float4* __restrict__ velOut,
+                                                        float4* __restrict__ xsOut, uint32_t* __restrict__ idOut,
+                                                        uint32_t* __restrict__ bucketStart, uint2* __restrict__ cellRange) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = perm[i];
+    posOut[i] = posIn[src];
+    velOut[i] = velIn[src];
+    xsOut[i] = xsIn[src];
+    idOut[i] = idIn[src];
+    uint32_t k = keysSorted[i];
+    bool first = (i == 0) || (keysSorted[i - 1] != k);
+    if (MODE == KEY_HASH) {
+        if (first) bucketStart[k] = i;
+    } else {
+        bool last = (i == n - 1) || (keysSorted[i + 1] != k);
+        if (first) cellRange[k].x = i;
+        if (last) cellRange[k].y = i + 1;
+    }
+}
+// Undo last step's bucket-start writes instead of refilling the 128*N-entry table (the reference allocates and fills
+// it with UINT32_MAX every step: NeighbourSearchCUDA.cu:157 — 512 B per particle per step).
+__global__ void __launch_bounds__(256) k_clear_buckets(const uint32_t* __restrict__ keysSorted, uint32_t n,
+                                                       uint32_t* __restrict__ bucketStart) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = keysSorted[i];
+    if (i == 0 || keysSorted[i - 1] != k) bucketStart[k] = 0xffffffffu;
+}
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ p, uint64_t count, uint32_t v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// kernel_find_neighbours (NeighbourSearchCUDA.cu:72-130): 27-cell scan in the reference's order (dx outer, dz inner,
+// bucket order = sorted order), strict d2 < h*h, self skipped, capped at maxNeighbours. The list is written
+// column-major: entry k of particle i lives at list[k*stride + i].
+template <int MODE>
+__global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restrict__ xs,
+                                                          const uint32_t* __restrict__ keysSorted,
+                                                          const uint32_t* __restrict__ bucketStart,
+                                                          const uint2* __restrict__ cellRange, uint32_t n,
+                                                          uint32_t stride, uint32_t maxN, uint32_t* __restrict__ list,
+                                                          uint32_t* __restrict__ cnt, GridParams G, float h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xs[i];
+    const float h2 = __fmul_rn(h, h);
+    const int3 c = cell_of(xi.x, xi.y, xi.z, G.lookupCellSize);
+    uint32_t count = 0;
+    if (MODE == KEY_HASH) {
+        for (int dx = -1; dx <= 1; dx++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dz = -1; dz <= 1; dz++) {
+                    uint32_t hash = ref_hash(c.x + dx, c.y + dy, c.z + dz, G.tableSize);
+                    uint32_t cand = bucketStart[hash];
+                    if (cand == 0xffffffffu) continue;
+                    while (cand < n && count < maxN) {
+                        if (cand == i) { cand++; continue; }
+                        if (keysSorted[cand] != hash) break;
+                        float4 xj = __ldg(&xs[cand]);
+                        float d2 = dist2(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+                        if (d2 < h2) { list[(size_t)count * stride + i] = cand; count++; }
+                        cand++;
+                    }
+                }
+    } else {
+        const int cx = clampi(c.x - G.gridMin.x, 0, G.gridDim.x - 1);
+        const int cy = clampi(c.y - G.gridMin.y, 0, G.gridDim.y - 1);
+        const int cz = clampi(c.z - G.gridMin.z, 0, G.gridDim.z - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G.gridDim.z - 1);
+        for (int dx = -1; dx <= 1; dx++) {
+            int X = cx + dx;
+            if (X < 0 || X >= G.gridDim.x) continue;
+            for (int dy = -1; dy <= 1; dy++) {
+                int Y = cy + dy;
+                if (Y < 0 || Y >= G.gridDim.y) continue;
+                // the (up to) three z-adjacent cells are contiguous in sorted order: one row range
+                const uint2* row = cellRange + ((size_t)X * G.gridDim.y + Y) * G.gridDim.z;
+                uint32_t s = 0xffffffffu, e = 0;
+                for (int z = z0; z <= z1; z++) {
+                    uint2 r = __ldg(&row[z]);
+                    if (r.y > r.x) { s = min(s, r.x); e = max(e, r.y); }
+                }
+                for (uint32_t cand = s; cand < e && count < maxN; cand++) {
+                    if (cand == i) continue;
+                    float4 xj = __ldg(&xs[cand]);
+                    float d2 = dist2(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
+                    if (d2 < h2) { list[(size_t)count * stride + i] = cand; count++; }
+                }
+            }
+        }
+    }
+    cnt[i] = count;
+}
+
+// ------------------------------------------------------------------------------------------------ pass A = K5 + K6
+// kernel_calculate_densities (ConstraintSolverCUDA.cu:16-42) + kernel_calculate_lambdas (:51-97), one neighbour loop.
+// Each accumulator sees its terms in the reference's order, so fusing the loops does not change the sums.
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
+                                                        const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
+                                                        float* __restrict__ density, float* __restrict__ lambda,
+                                                        SphParams P) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xs[i];
+    const uint32_t c = cnt[i];
+    float rho = xi.w * P.selfW;
+    float gx = 0.f, gy = 0.f, gz = 0.f, sum = 0.f;
+    const uint32_t* lp = list + i;
+#pragma unroll 4
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t j = lp[(size_t)k * stride];
+        float4 xj = __ldg(&xs[j]);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float d2 = dist2(dx, dy, dz);
+        rho = fmaf(xj.w, poly6(d2, P), rho);
+        float s = spiky_scale<FAST>(d2, P);
+        float ax = s * dx, ay = s * dy, az = s * dz;        // grad W_spiky
+        gx = fmaf(xj.w, ax, gx); gy = fmaf(xj.w, ay, gy); gz = fmaf(xj.w, az, gz);
+        float q = -P.invRestDensity * xj.w;                  // grad_pj C_i = q * gradW
+        float bx = q * ax, by = q * ay, bz = q * az;
+        sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
+    }
+    gx *= P.invRestDensity; gy *= P.invRestDensity; gz *= P.invRestDensity;
+    float C = rho * P.invRestDensity - 1.0f;
+    float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
+    density[i] = rho;
+    lambda[i] = lam;
+}
+
+// ------------------------------------------------------------------------------------------------ K8 / K9 / K10 pieces
+__device__ __forceinline__ float collide_axis(float x, float lo, float hi, const BoxParams& B) {
+    // handle_particle_collision, ConstraintSolverCUDA.cu:136-157 (both tests see the uncorrected coordinate)
+    float c = 0.0f;
+    float a = lo + B.collisionMinDist, b = hi - B.collisionMinDist;
+    if (x < a) c += B.collisionStiffness * (a - x);
+    if (x > b) c += B.collisionStiffness * (b - x);
+    return x + c;
+}
+// resolve_collision (IntegrationCUDA.cu:51-73) specialised to an axis-aligned plane with normal sign*e_axis:
+// va is the velocity component along the axis, vb/vc the tangential ones.
+__device__ __forceinline__ void damp_plane(float dist, float sign, float& va, float& vb, float& vc, const BoxParams& B) {
+    float approaching = sign * va;
+    if (dist < B.dampingMinDist) {
+        if (approaching < 0.0f) {
+            va = -B.restitution * va;
+            vb = B.oneMinusFriction * vb;
+            vc = B.oneMinusFriction * vc;
+        } else if (fabsf(approaching) < 1e-5f) {
+            va = 0.0f;
+            vb = B.oneMinusFriction * vb;
+            vc = B.oneMinusFriction * vc;
+        }
+    }
+}
+// kernel_apply_boundary_velocity_damping, IntegrationCUDA.cu:75-102: planes in order xmin,xmax,ymin,ymax,zmin,zmax
+__device__ __forceinline__ void damp_velocity(float px, float py, float pz, float& vx, float& vy, float& vz,
+                                              const BoxParams& B) {
+    damp_plane(px - B.bmin.x, 1.0f, vx, vy, vz, B);
+    damp_plane(B.bmax.x - px, -1.0f, vx, vy, vz, B);
+    damp_plane(py - B.bmin.y, 1.0f, vy, vx, vz, B);
+    damp_plane(B.bmax.y - py, -1.0f, vy, vx, vz, B);
+    damp_plane(pz - B.bmin.z, 1.0f, vz, vx, vy, B);
+    damp_plane(B.bmax.z - pz, -1.0f, vz, vx, vy, B);
+}
+
+// ------------------------------------------------------------------------------------------------ pass B = K7 + K8 (+K9+K10)
+// kernel_calculate_position_delta (ConstraintSolverCUDA.cu:99-130) + kernel_correct_position (:159-169); Jacobi, so the
+// corrected x* goes to the other half of a double buffer. FINAL additionally commits: kernel_update_position_and_velocity
+// (IntegrationCUDA.cu:38-49) and kernel_apply_boundary_velocity_damping (:75-102), both per-particle.
+template <bool FAST, bool FINAL>
+__global__ void __launch_bounds__(256) k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
+                                                     const float* __restrict__ lambda, const uint32_t* __restrict__ list,
+                                                     const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
+                                                     SphParams P, BoxParams B, float4* __restrict__ dposOut,
+                                                     float4* __restrict__ pos, float4* __restrict__ vel,
+                                                     const float* __restrict__ density, float dt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xsIn[i];
+    const float li = lambda[i];
+    const uint32_t c = cnt[i];
+    float px = 0.f, py = 0.f, pz = 0.f;
+    const uint32_t* lp = list + i;
+#pragma unroll 4
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t j = lp[(size_t)k * stride];
+        float4 xj = __ldg(&xsIn[j]);
+        float lj = __ldg(&lambda[j]);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float d2 = dist2(dx, dy, dz);
+        float ratio = poly6(d2, P) * P.invPoly6Dq;
+        float pw;
+        if (P.corrNIsFour) { float r2 = ratio * ratio; pw = r2 * r2; }
+        else pw = powf(ratio, P.corrN);
+        float corr = -P.corrK * pw;
+        float coef = (li + lj + corr) * xj.w * spiky_scale<FAST>(d2, P);
+        px = fmaf(coef, dx, px); py = fmaf(coef, dy, py); pz = fmaf(coef, dz, pz);
+    }
+    px *= P.invRestDensity; py *= P.invRestDensity; pz *= P.invRestDensity;
+    if (dposOut) dposOut[i] = make_float4(px, py, pz, 0.f);
+    float x = collide_axis(xi.x + px, B.bmin.x, B.bmax.x, B);
+    float y = collide_axis(xi.y + py, B.bmin.y, B.bmax.y, B);
+    float z = collide_axis(xi.z + pz, B.bmin.z, B.bmax.z, B);
+    xsOut[i] = make_float4(x, y, z, xi.w);
+    if (FINAL) {
+        float4 p = pos[i];
+        float vx = (x - p.x) / dt, vy = (y - p.y) / dt, vz = (z - p.z) / dt;
+        damp_velocity(x, y, z, vx, vy, vz, B);
+        pos[i] = make_float4(x, y, z, xi.w);
+        vel[i] = make_float4(vx, vy, vz, density[i]);
+    }
+}
+
+// Stand-alone K9 / K10 for the phase-level API (and solverIterations == 0).
+__global__ void __launch_bounds__(256) k_update(const float4* __restrict__ xs, float4* __restrict__ pos,
+                                                float4* __restrict__ vel, const float* __restrict__ density, uint32_t n,
+                                                float dt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x = xs[i], p = pos[i];
+    pos[i] = x;
+    vel[i] = make_float4((x.x - p.x) / dt, (x.y - p.y) / dt, (x.z - p.z) / dt, density[i]);
+}
+__global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos, float4* __restrict__ vel, uint32_t n,
+                                                 BoxParams B) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i], v = vel[i];
+    damp_velocity(p.x, p.y, p.z, v.x, v.y, v.z, B);
+    vel[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ K11
+// kernel_compute_vorticities, IntegrationCUDA.cu:104-128. Also stores |omega| so K12 gathers 4 B per neighbour, not 12.
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
+                                                   const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
+                                                   uint32_t stride, uint32_t n, float4* __restrict__ omega,
+                                                   float* __restrict__ omegaLen, SphParams P) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xs[i], vi = vel[i];
+    const uint32_t c = cnt[i];
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    const uint32_t* lp = list + i;
+#pragma unroll 4
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t j = lp[(size_t)k * stride];
+        float4 xj = __ldg(&xs[j]);
+        float4 vj = __ldg(&vel[j]);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float s = spiky_scale<FAST>(dist2(dx, dy, dz), P);
+        float gx = s * dx, gy = s * dy, gz = s * dz;
+        float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+        float cx = uy * gz - uz * gy, cy = uz * gx - ux * gz, cz = ux * gy - uy * gx;  // MathUtilsCUDA.h:12-18
+        wx = fmaf(-xj.w, cx, wx); wy = fmaf(-xj.w, cy, wy); wz = fmaf(-xj.w, cz, wz);
+    }
+    float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
+    omega[i] = make_float4(wx, wy, wz, len);
+    omegaLen[i] = len;
+}
+
+// ------------------------------------------------------------------------------------------------ K12
+// kernel_apply_vorticity_confinement, IntegrationCUDA.cu:130-165. Reads neighbours' |omega|, writes only its own
+// velocity: race-free in place.
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
+                                                     const float* __restrict__ omegaLen, const float* __restrict__ density,
+                                                     const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
+                                                     uint32_t stride, uint32_t n, float4* __restrict__ vel, SphParams P,
+                                                     float dt, float eps) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xs[i], oi = omega[i];
+    const uint32_t c = cnt[i];
+    const float invDensity = 1.0f / density[i];
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+    const uint32_t* lp = list + i;
+#pragma unroll 4
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t j = lp[(size_t)k * stride];
+        float4 xj = __ldg(&xs[j]);
+        float lj = __ldg(&omegaLen[j]);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float coef = xj.w * (oi.w - lj) * spiky_scale<FAST>(dist2(dx, dy, dz), P);
+        ex = fmaf(coef, dx, ex); ey = fmaf(coef, dy, ey); ez = fmaf(coef, dz, ez);
+    }
+    ex *= invDensity; ey *= invDensity; ez *= invDensity;
+    float len = sqrtf(fmaf(ez, ez, fmaf(ex, ex, ey * ey)));
+    if (len < 1e-5f) return;
+    float nx = ex / len, ny = ey / len, nz = ez / len;
+    float fx = eps * (ny * oi.z - nz * oi.y), fy = eps * (nz * oi.x - nx * oi.z), fz = eps * (nx * oi.y - ny * oi.x);
+    float4 v = vel[i];
+    v.x = fmaf(dt, fx, v.x); v.y = fmaf(dt, fy, v.y); v.z = fmaf(dt, fz, v.z);
+    vel[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ K13
+// kernel_apply_xsph_viscosity, IntegrationCUDA.cu:167-195 — as a Jacobi sweep (velIn -> velOut). The reference updates
+// velocity in place while neighbours read it (a data race, :187,:194); Jacobi is one of its legal outcomes and is
+// deterministic.
+__global__ void __launch_bounds__(256) k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
+                                              const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
+                                              uint32_t stride, uint32_t n, float4* __restrict__ velOut, SphParams P,
+                                              float cvisc) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 xi = xs[i], vi = velIn[i];
+    const uint32_t c = cnt[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    const uint32_t* lp = list + i;
+#pragma unroll 4
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t j = lp[(size_t)k * stride];
+        float4 xj = __ldg(&xs[j]);
+        float4 vj = __ldg(&velIn[j]);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float w = poly6(dist2(dx, dy, dz), P);
+        float mr = xj.w / vj.w;  // m_j / rho_j
+        ax = fmaf(mr * (vj.x - vi.x), w, ax); ay = fmaf(mr * (vj.y - vi.y), w, ay); az = fmaf(mr * (vj.z - vi.z), w, az);
+    }
+    velOut[i] = make_float4(fmaf(cvisc, ax, vi.x), fmaf(cvisc, ay, vi.y), fmaf(cvisc, az, vi.z), vi.w);
+}
+
+// ------------------------------------------------------------------------------------------------ AoS-108 interchange
+// Particle layout: include/AkuaEngine/Simulation/Particle.h:8-31 (27 words). A CTA stages 256 structs through shared
+// memory so that global accesses are coalesced; the 27-word stride is odd, so the per-thread reads are conflict-free.
+constexpr int kAosWords = 27;
+__global__ void __launch_bounds__(256) k_unpack_aos(const uint32_t* __restrict__ aos, uint32_t n, float4* __restrict__ pos,
+                                                    float4* __restrict__ vel, float4* __restrict__ xs,
+                                                    float4* __restrict__ omega, float* __restrict__ omegaLen,
+                                                    float4* __restrict__ dpos, float* __restrict__ density,
+                                                    float* __restrict__ lambda, uint32_t* __restrict__ keys,
+                                                    float4* __restrict__ color, float* __restrict__ size,
+                                                    uint32_t* __restrict__ id) {
+    __shared__ uint32_t sm[256 * kAosWords];
+    const uint32_t base = blockIdx.x * 256u;
+    const uint32_t count = min(256u, n - base);
+    const uint32_t* src = aos + (size_t)base * kAosWords;
+    for (uint32_t w = threadIdx.x; w < count * kAosWords; w += 256) sm[w] = src[w];
+    __syncthreads();
+    if (threadIdx.x >= count) return;
+    const uint32_t i = base + threadIdx.x;
+    const float* f = reinterpret_cast<const float*>(sm + threadIdx.x * kAosWords);
+    float mass = f[18], rho = f[19];
+    pos[i] = make_float4(f[0], f[1], f[2], mass);
+    vel[i] = make_float4(f[3], f[4], f[5], rho);
+    xs[i] = make_float4(f[6], f[7], f[8], mass);
+    dpos[i] = make_float4(f[12], f[13], f[14], 0.f);
+    float len = sqrtf(fmaf(f[17], f[17], fmaf(f[15], f[15], f[16] * f[16])));
+    omega[i] = make_float4(f[15], f[16], f[17], len);
+    omegaLen[i] = len;
+    density[i] = rho;
+    lambda[i] = f[20];
+    keys[i] = sm[threadIdx.x * kAosWords + 21];
+    color[i] = make_float4(f[22], f[23], f[24], f[25]);
+    size[i] = f[26];
+    id[i] = i;
+}
+__global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, uint32_t n, const float4* __restrict__ pos,
+                                                  const float4* __restrict__ vel, const float4* __restrict__ xs,
+                                                  const float4* __restrict__ omega, const float4* __restrict__ dpos,
+                                                  const float* __restrict__ density, const float* __restrict__ lambda,
+                                                  const uint32_t* __restrict__ keys, const float4* __restrict__ color,
+                                                  const float* __restrict__ size, const uint32_t* __restrict__ id) {
+    __shared__ uint32_t sm[256 * kAosWords];
+    const uint32_t base = blockIdx.x * 256u;
+    const uint32_t count = min(256u, n - base);
+    if (threadIdx.x < count) {
+        const uint32_t i = base + threadIdx.x;
+        float* f = reinterpret_cast<float*>(sm + threadIdx.x * kAosWords);
+        float4 p = pos[i], v = vel[i], x = xs[i], o = omega[i], d = dpos[i];
+        uint32_t pid = id[i];
+        float4 c = color[pid];
+        f[0] = p.x; f[1] = p.y; f[2] = p.z;
+        f[3] = v.x; f[4] = v.y; f[5] = v.z;
+        f[6] = x.x; f[7] = x.y; f[8] = x.z;
+        f[9] = v.x; f[10] = v.y; f[11] = v.z;   // new_velocity := velocity (see akua_pbf.h)
+        f[12] = d.x; f[13] = d.y; f[14] = d.z;
+        f[15] = o.x; f[16] = o.y; f[17] = o.z;
+        f[18] = p.w; f[19] = density[i]; f[20] = lambda[i];
+        sm[threadIdx.x * kAosWords + 21] = keys[i];
+        f[22] = c.x; f[23] = c.y; f[24] = c.z; f[25] = c.w;
+        f[26] = size[pid];
+    }
+    __syncthreads();
+    uint32_t* dst = aos + (size_t)base * kAosWords;
+    for (uint32_t w = threadIdx.x; w < count * kAosWords; w += 256) dst[w] = sm[w];
+}
+
+// neighbour list: column-major device layout -> the reference's row-major n x maxNeighbours (debug tap only)
+__global__ void __launch_bounds__(256) k_list_to_rowmajor(const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
+                                                          uint32_t stride, uint32_t n, uint32_t maxN,
+                                                          uint32_t* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * maxN) return;
+    uint32_t i = (uint32_t)(t / maxN), k = (uint32_t)(t % maxN);
+    out[t] = k < cnt[i] ? list[(size_t)k * stride + i] : 0u;
+}
+
+// |rho/rho0 - 1| partial sums / maxima per CTA
+__global__ void __launch_bounds__(256) k_density_error(const float* __restrict__ density, uint32_t n, float invRho0,
+                                                       float* __restrict__ partSum, float* __restrict__ partMax) {
+    __shared__ float ssum[8], smax[8];
+    float s = 0.f, m = 0.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float e = fabsf(density[i] * invRho0 - 1.0f);
+        s += e; m = fmaxf(m, e);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ssum[warp] = s; smax[warp] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { s += ssum[w]; m = fmaxf(m, smax[w]); }
+        partSum[blockIdx.x] = s; partMax[blockIdx.x] = m;
+    }
+}
+
+}  // namespace akua

@@ -1,0 +1,668 @@
+// pbf_solver.cu — host side of the B200-native PBF step: owns the device-resident SoA state, sequences the kernels of
+// pbf_kernels.cuh / radix_sort.cuh on one stream, and exports the C ABI declared in include/akua_pbf.h.
+//
+// Mirrors AkuaEngine::PBFSolver (include/AkuaEngine/Simulation/PBFSolver.h, src/Simulation/PBFSolver.cpp). Where the
+// reference maps a GL buffer, allocates thrust::device_vectors, copies the neighbour list to the host and back and calls
+// cudaDeviceSynchronize after every kernel (25 per step), this solver allocates everything once in create(), keeps all
+// state on the device, and issues the whole step asynchronously on one stream.
+#include "../../include/akua_pbf.h"
+#include "pbf_kernels.cuh"
+#include "radix_sort.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace akua;
+
+namespace {
+
+constexpr int kBlock = 256;
+inline uint32_t gridFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
+
+enum Phase { PH_PREDICT = 0, PH_SORT, PH_REORDER, PH_LISTS, PH_SOLVE, PH_POST, PH_END, PH_COUNT };
+
+}  // namespace
+
+struct akua_pbf_solver {
+    int64_t n = 0;         // live particles
+    int64_t capacity = 0;  // array capacity
+    akua_pbf_config cfg{};
+    akua_corr_params corr{};
+    akua_pbf_options opt{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // SoA state in the solver's current (key-sorted) order
+    float4 *pos = nullptr, *posAlt = nullptr;  // x,y,z,mass
+    float4 *vel = nullptr, *velAlt = nullptr;  // vx,vy,vz,density
+    float4 *xs = nullptr, *xsAlt = nullptr;    // predicted position x*, w = mass (double buffer)
+    uint32_t *id = nullptr, *idAlt = nullptr;  // upload index of each particle
+    float *density = nullptr, *lambda = nullptr, *omegaLen = nullptr;
+    float4 *omega = nullptr, *dpos = nullptr;
+    // payload in upload order (the solver never reads it: Particle::color / ::size)
+    float4* color = nullptr;
+    float* size = nullptr;
+    // neighbour search
+    uint32_t *keysUnsorted = nullptr, *keyA = nullptr, *keyB = nullptr, *valA = nullptr, *valB = nullptr;
+    uint32_t *keysSorted = nullptr, *perm = nullptr;  // alias keyA/B, valA/B after a sort
+    uint32_t* bucketStart = nullptr;                  // REFERENCE_HASH: tableSize entries
+    bool bucketsDirty = false;
+    uint2* cellRange = nullptr;                       // LINEAR_CELL: numCells entries
+    int64_t cellCapacity = 0;
+    GridParams grid{};
+    int keyBits = 1;
+    uint32_t *nbrList = nullptr, *nbrCount = nullptr;
+    uint32_t nbrStride = 0;
+    rsort::Workspace sortWs;
+    // interchange staging
+    void* aosStage = nullptr;
+    float *partSum = nullptr, *partMax = nullptr;
+    // bookkeeping
+    akua_pbf_counters ctr{};
+    bool haveBox = false;
+    float lastBoxMin[3] = {0, 0, 0}, lastBoxMax[3] = {0, 0, 0};
+    bool timing = false;
+    cudaEvent_t ev[PH_COUNT] = {};
+    float lastMs[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool timingValid = false;
+};
+
+namespace {
+
+#define AK_CUDA(s, call)                                                                               \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            (s)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return AKUA_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+#define AK_LAUNCH_CHECK(s, name)                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                                           \
+        if (e_ != cudaSuccess) {                                                                       \
+            (s)->err = std::string("launch ") + name + ": " + cudaGetErrorString(e_);                  \
+            return AKUA_ERR_CUDA;                                                                      \
+        }                                                                                              \
+        (s)->ctr.kernel_launches++;                                                                    \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+SphParams makeSph(const akua_pbf_solver* s) {
+    SphParams P{};
+    const float h = s->cfg.smoothRadius;
+    P.h = h;
+    P.h2 = h * h;
+    // Same float expressions as include/AkuaEngine/CUDA/SmoothingKernelsCUDA.h:20,27, evaluated once on the host.
+    P.poly6Coef = 315.0f / (64.0f * 3.14f * powf(h, 9.0f));
+    P.spikyCoef = -45.0f / (3.14f * powf(h, 6.0f));
+    float t0 = P.h2 - 0.0f;
+    P.selfW = P.poly6Coef * (t0 * t0 * t0);
+    P.invRestDensity = 1.0f / s->cfg.restDensity;  // ConstraintSolverCUDA.cu:201
+    P.relaxation = s->cfg.relaxation;
+    P.corrK = s->corr.k;
+    P.corrN = s->corr.n;
+    float dq2 = s->corr.delta_q * s->corr.delta_q;
+    float tq = P.h2 - dq2;
+    float wdq = dq2 > P.h2 ? 0.0f : P.poly6Coef * (tq * tq * tq);
+    P.invPoly6Dq = 1.0f / wdq;
+    P.corrNIsFour = (s->corr.n == 4.0f) ? 1 : 0;
+    return P;
+}
+
+BoxParams makeBox(const float* bmin, const float* bmax) {
+    BoxParams B{};
+    B.bmin = make_float3(bmin[0], bmin[1], bmin[2]);
+    B.bmax = make_float3(bmax[0], bmax[1], bmax[2]);
+    B.collisionMinDist = 0.025f;   // ConstraintSolverCUDA.cu:137
+    B.collisionStiffness = 0.5f;   // ConstraintSolverCUDA.cu:138
+    B.dampingMinDist = 0.025f;     // IntegrationCUDA.cu:88
+    B.restitution = 0.0f;          // PBFSolver.cpp:64
+    B.oneMinusFriction = 1.0f - 0.95f;
+    return B;
+}
+
+int bitsFor(uint64_t maxKey) {
+    int b = 1;
+    while (b < 32 && (maxKey >> b) != 0) b++;
+    return b;
+}
+
+void rememberBox(akua_pbf_solver* s, const float* bmin, const float* bmax) {
+    for (int a = 0; a < 3; a++) { s->lastBoxMin[a] = bmin[a]; s->lastBoxMax[a] = bmax[a]; }
+    s->haveBox = true;
+}
+
+// LINEAR_CELL grid: covers the box plus a two-cell margin (the collision response is a soft clamp, so particles can sit
+// slightly outside the box). Particles beyond the margin are clamped into the border cells — still correct (the distance
+// test decides), only slower.
+int layoutGrid(akua_pbf_solver* s, const float* bmin, const float* bmax) {
+    if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) return AKUA_OK;
+    const float cs = s->cfg.smoothRadius;
+    int lo[3], dim[3];
+    int64_t cells = 1;
+    for (int a = 0; a < 3; a++) {
+        if (!(bmax[a] > bmin[a])) { s->err = "box max must exceed box min"; return AKUA_ERR_INVALID; }
+        lo[a] = (int)std::floor(bmin[a] / cs) - 2;
+        int hi = (int)std::floor(bmax[a] / cs) + 2;
+        dim[a] = hi - lo[a] + 1;
+        cells *= dim[a];
+    }
+    if (cells >= (int64_t)1 << 31) { s->err = "LINEAR_CELL grid too large (>= 2^31 cells)"; return AKUA_ERR_INVALID; }
+    if (cells > s->cellCapacity) {  // only when the box grows beyond anything seen so far
+        if (s->cellRange) { AK_CUDA(s, cudaStreamSynchronize(s->stream)); AK_CUDA(s, cudaFree(s->cellRange)); }
+        s->cellRange = nullptr;
+        AK_CUDA(s, dalloc(&s->cellRange, (size_t)cells));
+        s->cellCapacity = cells;
+    }
+    s->grid.gridMin = make_int3(lo[0], lo[1], lo[2]);
+    s->grid.gridDim = make_int3(dim[0], dim[1], dim[2]);
+    s->keyBits = bitsFor((uint64_t)cells - 1);
+    s->ctr.num_cells = cells;
+    return AKUA_OK;
+}
+
+int ensureStage(akua_pbf_solver* s) {
+    if (!s->aosStage) AK_CUDA(s, cudaMalloc(&s->aosStage, (size_t)s->capacity * 108));
+    return AKUA_OK;
+}
+
+void mark(akua_pbf_solver* s, Phase p) {
+    if (s->timing) cudaEventRecord(s->ev[p], s->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------- phases
+int phasePredictKey(akua_pbf_solver* s, float dt, bool doPredict, bool doKeys) {
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) return AKUA_OK;
+    float3 g = make_float3(s->cfg.gravity[0], s->cfg.gravity[1], s->cfg.gravity[2]);
+    uint32_t* keys = doKeys ? s->keysUnsorted : nullptr;
+    if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH)
+        k_predict_key<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+    else
+        k_predict_key<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+    AK_LAUNCH_CHECK(s, "k_predict_key");
+    return AKUA_OK;
+}
+
+int phaseSortReorderLists(akua_pbf_solver* s) {
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) return AKUA_OK;
+    const bool hash = s->opt.key_mode == AKUA_KEY_REFERENCE_HASH;
+    if (hash) {
+        if (s->bucketsDirty) {
+            k_clear_buckets<<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, n, s->bucketStart);
+            AK_LAUNCH_CHECK(s, "k_clear_buckets");
+        }
+    } else {
+        AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
+    }
+    int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, n, s->keyBits, s->sortWs,
+                                     s->stream, &s->keysSorted, &s->perm);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
+    }
+    s->ctr.kernel_launches += launches;
+    s->ctr.sort_passes_last = launches / 3;
+    mark(s, PH_REORDER);
+    if (hash)
+        k_reorder_ranges<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
+            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
+    else
+        k_reorder_ranges<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
+            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
+    AK_LAUNCH_CHECK(s, "k_reorder_ranges");
+    std::swap(s->pos, s->posAlt);
+    std::swap(s->vel, s->velAlt);
+    std::swap(s->xs, s->xsAlt);
+    std::swap(s->id, s->idAlt);
+    s->bucketsDirty = hash;
+    mark(s, PH_LISTS);
+    if (hash)
+        k_build_neighbours<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
+            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
+    else
+        k_build_neighbours<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
+            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
+    AK_LAUNCH_CHECK(s, "k_build_neighbours");
+    return AKUA_OK;
+}
+
+// `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
+int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const float* bmax, bool commit, float dt,
+               bool* committed) {
+    const uint32_t n = (uint32_t)s->n;
+    *committed = false;
+    if (n == 0) return AKUA_OK;
+    const SphParams P = makeSph(s);
+    const BoxParams B = makeBox(bmin, bmax);
+    const bool fast = s->opt.fast_math != 0;
+    for (int it = 0; it < iterations; it++) {
+        if (fast) k_density_lambda<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+        else      k_density_lambda<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+        AK_LAUNCH_CHECK(s, "k_density_lambda");
+        const bool fin = commit && it == iterations - 1;
+#define AK_DELTA(F, L) k_delta_apply<F, L><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
+            s->nbrCount, s->nbrStride, n, P, B, s->dpos, s->pos, s->vel, s->density, dt)
+        if (fast) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
+        else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
+#undef AK_DELTA
+        AK_LAUNCH_CHECK(s, "k_delta_apply");
+        std::swap(s->xs, s->xsAlt);
+        if (fin) *committed = true;
+    }
+    return AKUA_OK;
+}
+
+int phaseUpdate(akua_pbf_solver* s, float dt) {
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) return AKUA_OK;
+    k_update<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->pos, s->vel, s->density, n, dt);
+    AK_LAUNCH_CHECK(s, "k_update");
+    return AKUA_OK;
+}
+int phaseDamping(akua_pbf_solver* s, const float* bmin, const float* bmax) {
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) return AKUA_OK;
+    k_damping<<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, n, makeBox(bmin, bmax));
+    AK_LAUNCH_CHECK(s, "k_damping");
+    return AKUA_OK;
+}
+int phasePost(akua_pbf_solver* s, float dt) {
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) return AKUA_OK;
+    const SphParams P = makeSph(s);
+    const bool fast = s->opt.fast_math != 0;
+    if (fast) k_vorticity<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
+    else      k_vorticity<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
+    AK_LAUNCH_CHECK(s, "k_vorticity");
+    if (fast) k_confinement<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    else      k_confinement<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    AK_LAUNCH_CHECK(s, "k_confinement");
+    k_xsph<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->velAlt, P, s->cfg.viscosity);
+    AK_LAUNCH_CHECK(s, "k_xsph");
+    std::swap(s->vel, s->velAlt);
+    return AKUA_OK;
+}
+
+int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
+    if (!s || !bmin || !bmax) return AKUA_ERR_INVALID;
+    if (iterations < 0) { s->err = "solverIterations must be >= 0"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    rememberBox(s, bmin, bmax);
+    int rc = layoutGrid(s, bmin, bmax);
+    if (rc) return rc;
+    mark(s, PH_PREDICT);
+    if ((rc = phasePredictKey(s, dt, true, true))) return rc;            // PBFSolver.cpp:30 (+ K2)
+    mark(s, PH_SORT);
+    if ((rc = phaseSortReorderLists(s))) return rc;                       // PBFSolver.cpp:33
+    mark(s, PH_SOLVE);
+    bool committed = false;
+    if ((rc = phaseSolve(s, iterations, bmin, bmax, true, dt, &committed))) return rc;  // PBFSolver.cpp:45
+    if (!committed) {                                                     // solverIterations == 0
+        if ((rc = phaseUpdate(s, dt))) return rc;                         // PBFSolver.cpp:61
+        if ((rc = phaseDamping(s, bmin, bmax))) return rc;                // PBFSolver.cpp:64
+    }
+    mark(s, PH_POST);
+    if ((rc = phasePost(s, dt))) return rc;                               // PBFSolver.cpp:67
+    mark(s, PH_END);
+    s->timingValid = s->timing;
+    s->ctr.steps++;
+    return AKUA_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================== C ABI
+extern "C" {
+
+int akua_pbf_abi_version(void) { return AKUA_PBF_ABI_VERSION; }
+
+void akua_pbf_default_config(akua_pbf_config* c) {  // PBFConfig.h:18-29
+    if (!c) return;
+    c->restDensity = 7600.0f; c->particle_spacing = 0.05f; c->smoothRadius = 0.1f; c->spatialHashCellSize = 0.1f;
+    c->relaxation = 600.0f; c->vorticityEpsilon = 0.00001f; c->viscosity = 0.01f; c->maxNeighbours = 128;
+    c->solverIterations = 4; c->gravity[0] = 0.0f; c->gravity[1] = -9.8f; c->gravity[2] = 0.0f;
+}
+void akua_pbf_default_corr(akua_corr_params* c) {  // PBFConfig.h:10-15
+    if (!c) return;
+    c->enabled = 1; c->k = 0.0001f; c->n = 4.0f; c->delta_q = 0.03f;
+}
+void akua_pbf_default_options(akua_pbf_options* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->key_mode = AKUA_KEY_LINEAR_CELL; o->device = 0; o->use_graph = 1; o->fast_math = 0; o->capacity_factor = 1.0f;
+}
+
+int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_config* cfg, const akua_corr_params* corr,
+                    const akua_pbf_options* opt) {
+    if (!out) return AKUA_ERR_INVALID;
+    *out = nullptr;
+    if (!cfg || !corr || numParticles < 0 || numParticles >= ((int64_t)1 << 31)) return AKUA_ERR_INVALID;
+    if (!(cfg->smoothRadius > 0.0f) || cfg->maxNeighbours <= 0 || cfg->solverIterations < 0) return AKUA_ERR_INVALID;
+    if (cfg->spatialHashCellSize != cfg->smoothRadius) return AKUA_ERR_INVALID;  // see akua_pbf.h
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return AKUA_ERR_NO_DEVICE;
+    akua_pbf_solver* s = new (std::nothrow) akua_pbf_solver();
+    if (!s) return AKUA_ERR_ALLOC;
+    s->cfg = *cfg;
+    s->corr = *corr;
+    if (opt) s->opt = *opt; else akua_pbf_default_options(&s->opt);
+    if (s->opt.capacity_factor < 1.0f) s->opt.capacity_factor = 1.0f;
+    s->device = s->opt.device;
+    s->n = numParticles;
+    s->capacity = (int64_t)std::ceil((double)numParticles * s->opt.capacity_factor);
+    if (s->capacity < 1) s->capacity = 1;
+    *out = s;  // from here on the caller can read last_error and must destroy
+    if (s->device < 0 || s->device >= ndev) { s->err = "invalid device ordinal"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    {
+        cudaDeviceProp prop;
+        AK_CUDA(s, cudaGetDeviceProperties(&prop, s->device));
+        if (prop.major < 10) { s->err = "this library is built for sm_100a (Blackwell) only"; return AKUA_ERR_NO_DEVICE; }
+    }
+    AK_CUDA(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)s->capacity;
+    AK_CUDA(s, dalloc(&s->pos, cap)); AK_CUDA(s, dalloc(&s->posAlt, cap));
+    AK_CUDA(s, dalloc(&s->vel, cap)); AK_CUDA(s, dalloc(&s->velAlt, cap));
+    AK_CUDA(s, dalloc(&s->xs, cap));  AK_CUDA(s, dalloc(&s->xsAlt, cap));
+    AK_CUDA(s, dalloc(&s->id, cap));  AK_CUDA(s, dalloc(&s->idAlt, cap));
+    AK_CUDA(s, dalloc(&s->density, cap)); AK_CUDA(s, dalloc(&s->lambda, cap)); AK_CUDA(s, dalloc(&s->omegaLen, cap));
+    AK_CUDA(s, dalloc(&s->omega, cap)); AK_CUDA(s, dalloc(&s->dpos, cap));
+    AK_CUDA(s, dalloc(&s->color, cap)); AK_CUDA(s, dalloc(&s->size, cap));
+    AK_CUDA(s, dalloc(&s->keysUnsorted, cap));
+    AK_CUDA(s, dalloc(&s->keyA, cap)); AK_CUDA(s, dalloc(&s->keyB, cap));
+    AK_CUDA(s, dalloc(&s->valA, cap)); AK_CUDA(s, dalloc(&s->valB, cap));
+    s->keysSorted = s->keyA; s->perm = s->valA;
+    s->nbrStride = (uint32_t)((cap + 31) / 32 * 32);
+    AK_CUDA(s, dalloc(&s->nbrList, (size_t)s->nbrStride * (size_t)cfg->maxNeighbours));
+    AK_CUDA(s, dalloc(&s->nbrCount, cap));
+    s->sortWs.maxTiles = rsort::tiles_for(cap);
+    AK_CUDA(s, dalloc(&s->sortWs.tileHist, (size_t)256 * s->sortWs.maxTiles));
+    AK_CUDA(s, dalloc(&s->sortWs.binTotal, 256));
+    AK_CUDA(s, dalloc(&s->partSum, 1024)); AK_CUDA(s, dalloc(&s->partMax, 1024));
+    for (float4* p : {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->omega, s->dpos, s->color})
+        AK_CUDA(s, cudaMemsetAsync(p, 0, cap * sizeof(float4), s->stream));
+    for (float* p : {s->density, s->lambda, s->omegaLen, s->size}) AK_CUDA(s, cudaMemsetAsync(p, 0, cap * sizeof(float), s->stream));
+    for (uint32_t* p : {s->id, s->idAlt, s->keysUnsorted, s->keyA, s->keyB, s->valA, s->valB, s->nbrCount})
+        AK_CUDA(s, cudaMemsetAsync(p, 0, cap * sizeof(uint32_t), s->stream));
+    s->grid.cellSize = cfg->smoothRadius;             // NeighbourSearchCUDA.cu:163
+    s->grid.lookupCellSize = cfg->spatialHashCellSize;  // NeighbourSearchCUDA.cu:177
+    if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) {
+        // tableSize = maxNeighbours * numParticles as an int (PBFSolver.cpp:15); undefined in the reference beyond INT_MAX.
+        int64_t ts = (int64_t)cfg->maxNeighbours * numParticles;
+        if (ts <= 0 || ts > 0x7fffffffLL) { s->err = "REFERENCE_HASH: maxNeighbours*numParticles must be in [1, 2^31) (the reference's int tableSize); use LINEAR_CELL"; return AKUA_ERR_INVALID; }
+        s->grid.tableSize = (uint32_t)ts;
+        s->keyBits = bitsFor((uint64_t)ts - 1);
+        s->ctr.num_cells = ts;
+        AK_CUDA(s, dalloc(&s->bucketStart, (size_t)ts));
+        k_fill_u32<<<148 * 8, kBlock, 0, s->stream>>>(s->bucketStart, (uint64_t)ts, 0xffffffffu);
+        AK_LAUNCH_CHECK(s, "k_fill_u32");
+    } else if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) {
+        s->err = "unknown key_mode"; return AKUA_ERR_INVALID;
+    }
+    for (int p = 0; p < PH_COUNT; p++) AK_CUDA(s, cudaEventCreate(&s->ev[p]));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return AKUA_OK;
+}
+
+void akua_pbf_destroy(akua_pbf_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->id, s->idAlt, s->density, s->lambda,
+                    s->omegaLen, s->omega, s->dpos, s->color, s->size, s->keysUnsorted, s->keyA, s->keyB, s->valA, s->valB,
+                    s->bucketStart, s->cellRange, s->nbrList, s->nbrCount, s->sortWs.tileHist, s->sortWs.binTotal,
+                    s->aosStage, s->partSum, s->partMax};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int p = 0; p < PH_COUNT; p++) if (s->ev[p]) cudaEventDestroy(s->ev[p]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int akua_pbf_step(akua_pbf_solver* s, float dt, const float boxMin[3], const float boxMax[3]) {
+    if (!s) return AKUA_ERR_INVALID;
+    return stepImpl(s, dt, s->cfg.solverIterations, boxMin, boxMax);
+}
+int akua_pbf_step_iters(akua_pbf_solver* s, float dt, int32_t iters, const float boxMin[3], const float boxMax[3]) {
+    if (!s) return AKUA_ERR_INVALID;
+    return stepImpl(s, dt, iters, boxMin, boxMax);
+}
+int akua_pbf_set_gravity(akua_pbf_solver* s, const float g[3]) {
+    if (!s || !g) return AKUA_ERR_INVALID;
+    s->cfg.gravity[0] = g[0]; s->cfg.gravity[1] = g[1]; s->cfg.gravity[2] = g[2];
+    return AKUA_OK;
+}
+int akua_pbf_sync(akua_pbf_solver* s) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return AKUA_OK;
+}
+const char* akua_pbf_last_error(const akua_pbf_solver* s) { return s ? s->err.c_str() : "null solver"; }
+int64_t akua_pbf_num_particles(const akua_pbf_solver* s) { return s ? s->n : -1; }
+
+int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
+    if (!s || !src || n != s->n) { if (s) s->err = "upload_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (n == 0) return AKUA_OK;
+    int rc = ensureStage(s);
+    if (rc) return rc;
+    AK_CUDA(s, cudaMemcpyAsync(s->aosStage, src, (size_t)n * 108, cudaMemcpyHostToDevice, s->stream));
+    s->ctr.h2d_bytes += n * 108;
+    k_unpack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((const uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega,
+        s->omegaLen, s->dpos, s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+    AK_LAUNCH_CHECK(s, "k_unpack_aos");
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));  // `src` may be reused by the caller as soon as we return
+    return AKUA_OK;
+}
+int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
+    if (!s || !dst || n != s->n) { if (s) s->err = "download_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (n == 0) return AKUA_OK;
+    int rc = ensureStage(s);
+    if (rc) return rc;
+    k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
+        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+    AK_LAUNCH_CHECK(s, "k_pack_aos");
+    AK_CUDA(s, cudaMemcpyAsync(dst, s->aosStage, (size_t)n * 108, cudaMemcpyDeviceToHost, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->ctr.d2h_bytes += n * 108;
+    return AKUA_OK;
+}
+
+int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n) {
+    if (!s || !pos_xyz || n != s->n) { if (s) s->err = "upload_soa: bad arguments"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (n == 0) return AKUA_OK;
+    // Host-side widening to float4, then two async copies. (Setup path; the per-step e2e path is AoS-108.)
+    std::vector<float4> p4((size_t)n), v4((size_t)n);
+    std::vector<uint32_t> ids((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        float m = mass ? mass[i] : 1.0f;
+        p4[i] = make_float4(pos_xyz[3 * i], pos_xyz[3 * i + 1], pos_xyz[3 * i + 2], m);
+        v4[i] = vel_xyz ? make_float4(vel_xyz[3 * i], vel_xyz[3 * i + 1], vel_xyz[3 * i + 2], 0.f) : make_float4(0, 0, 0, 0);
+        ids[i] = (uint32_t)i;
+    }
+    AK_CUDA(s, cudaMemcpyAsync(s->pos, p4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(s->xs, p4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(s->vel, v4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(s->id, ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->ctr.h2d_bytes += n * 52;
+    return AKUA_OK;
+}
+int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t* id, int64_t n) {
+    if (!s || n != s->n) { if (s) s->err = "download_soa: bad arguments"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (pos4) { AK_CUDA(s, cudaMemcpyAsync(pos4, s->pos, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 16; }
+    if (vel4) { AK_CUDA(s, cudaMemcpyAsync(vel4, s->vel, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 16; }
+    if (id)   { AK_CUDA(s, cudaMemcpyAsync(id, s->id, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 4; }
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return AKUA_OK;
+}
+const float* akua_pbf_positions_device(akua_pbf_solver* s) { return s ? reinterpret_cast<const float*>(s->pos) : nullptr; }
+const float* akua_pbf_velocities_device(akua_pbf_solver* s) { return s ? reinterpret_cast<const float*>(s->vel) : nullptr; }
+
+void* akua_pbf_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void akua_pbf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- phase-level operators ----
+int akua_pbf_phase_predict(akua_pbf_solver* s, float dt) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    return phasePredictKey(s, dt, true, false);
+}
+int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    const float* bmin = boxMin ? boxMin : s->lastBoxMin;
+    const float* bmax = boxMax ? boxMax : s->lastBoxMax;
+    if (s->opt.key_mode == AKUA_KEY_LINEAR_CELL && !boxMin && !s->haveBox) { s->err = "phase_neighbours: LINEAR_CELL needs a box"; return AKUA_ERR_INVALID; }
+    if (boxMin && boxMax) rememberBox(s, boxMin, boxMax);
+    int rc = layoutGrid(s, bmin, bmax);
+    if (rc) return rc;
+    if ((rc = phasePredictKey(s, 0.0f, false, true))) return rc;  // keys from the current x* (K2)
+    return phaseSortReorderLists(s);
+}
+int akua_pbf_phase_solve(akua_pbf_solver* s, int32_t iters, const float boxMin[3], const float boxMax[3]) {
+    if (!s || !boxMin || !boxMax || iters < 0) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    rememberBox(s, boxMin, boxMax);
+    bool committed;
+    return phaseSolve(s, iters, boxMin, boxMax, false, 0.0f, &committed);
+}
+int akua_pbf_phase_update(akua_pbf_solver* s, float dt) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    return phaseUpdate(s, dt);
+}
+int akua_pbf_phase_damping(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]) {
+    if (!s || !boxMin || !boxMax) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    return phaseDamping(s, boxMin, boxMax);
+}
+int akua_pbf_phase_vorticity_viscosity(akua_pbf_solver* s, float dt) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    return phasePost(s, dt);
+}
+
+// ---- debug taps ----
+int64_t akua_pbf_debug_size(akua_pbf_solver* s, int32_t which) {
+    if (!s) return -1;
+    const int64_t n = s->n;
+    switch (which) {
+        case AKUA_DBG_KEYS_UNSORTED: case AKUA_DBG_KEYS_SORTED: case AKUA_DBG_PERM: case AKUA_DBG_ID:
+        case AKUA_DBG_NBR_COUNT: case AKUA_DBG_DENSITY: case AKUA_DBG_LAMBDA: return n * 4;
+        case AKUA_DBG_BUCKET_START: return s->opt.key_mode == AKUA_KEY_REFERENCE_HASH ? (int64_t)s->grid.tableSize * 4 : -1;
+        case AKUA_DBG_CELL_RANGE: return s->opt.key_mode == AKUA_KEY_LINEAR_CELL ? s->ctr.num_cells * 8 : -1;
+        case AKUA_DBG_NBR_LIST: return n * (int64_t)s->cfg.maxNeighbours * 4;
+        case AKUA_DBG_XSTAR: case AKUA_DBG_POSITION: case AKUA_DBG_VELOCITY: case AKUA_DBG_VORTICITY:
+        case AKUA_DBG_DELTA_P: return n * 16;
+        default: return -1;
+    }
+}
+int akua_pbf_debug_get(akua_pbf_solver* s, int32_t which, void* dst, int64_t dst_bytes) {
+    if (!s || !dst) return AKUA_ERR_INVALID;
+    const int64_t need = akua_pbf_debug_size(s, which);
+    if (need < 0 || dst_bytes < need) { s->err = "debug_get: array not available or destination too small"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (need == 0) return AKUA_OK;
+    const void* src = nullptr;
+    switch (which) {
+        case AKUA_DBG_KEYS_UNSORTED: src = s->keysUnsorted; break;
+        case AKUA_DBG_KEYS_SORTED: src = s->keysSorted; break;
+        case AKUA_DBG_PERM: src = s->perm; break;
+        case AKUA_DBG_ID: src = s->id; break;
+        case AKUA_DBG_BUCKET_START: src = s->bucketStart; break;
+        case AKUA_DBG_CELL_RANGE: src = s->cellRange; break;
+        case AKUA_DBG_NBR_COUNT: src = s->nbrCount; break;
+        case AKUA_DBG_DENSITY: src = s->density; break;
+        case AKUA_DBG_LAMBDA: src = s->lambda; break;
+        case AKUA_DBG_XSTAR: src = s->xs; break;
+        case AKUA_DBG_POSITION: src = s->pos; break;
+        case AKUA_DBG_VELOCITY: src = s->vel; break;
+        case AKUA_DBG_VORTICITY: src = s->omega; break;
+        case AKUA_DBG_DELTA_P: src = s->dpos; break;
+        case AKUA_DBG_NBR_LIST: {
+            uint32_t* tmp = nullptr;
+            AK_CUDA(s, cudaMalloc(&tmp, (size_t)need));
+            uint64_t total = (uint64_t)s->n * s->cfg.maxNeighbours;
+            k_list_to_rowmajor<<<gridFor(total), kBlock, 0, s->stream>>>(s->nbrList, s->nbrCount, s->nbrStride, (uint32_t)s->n,
+                (uint32_t)s->cfg.maxNeighbours, tmp);
+            AK_LAUNCH_CHECK(s, "k_list_to_rowmajor");
+            cudaError_t e = cudaMemcpyAsync(dst, tmp, (size_t)need, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+            cudaFree(tmp);
+            if (e != cudaSuccess) { s->err = std::string("debug_get: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
+            s->ctr.d2h_bytes += need;
+            return AKUA_OK;
+        }
+        default: return AKUA_ERR_INVALID;
+    }
+    AK_CUDA(s, cudaMemcpyAsync(dst, src, (size_t)need, cudaMemcpyDeviceToHost, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->ctr.d2h_bytes += need;
+    return AKUA_OK;
+}
+
+int akua_pbf_density_error(akua_pbf_solver* s, float* mean, float* maxv) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    const uint32_t n = (uint32_t)s->n;
+    if (n == 0) { if (mean) *mean = 0; if (maxv) *maxv = 0; return AKUA_OK; }
+    uint32_t blocks = gridFor(n);
+    if (blocks > 1024) blocks = 1024;
+    k_density_error<<<blocks, kBlock, 0, s->stream>>>(s->density, n, 1.0f / s->cfg.restDensity, s->partSum, s->partMax);
+    AK_LAUNCH_CHECK(s, "k_density_error");
+    std::vector<float> hs(blocks), hm(blocks);
+    AK_CUDA(s, cudaMemcpyAsync(hs.data(), s->partSum, blocks * 4, cudaMemcpyDeviceToHost, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(hm.data(), s->partMax, blocks * 4, cudaMemcpyDeviceToHost, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    double sum = 0; float mx = 0;
+    for (uint32_t b = 0; b < blocks; b++) { sum += hs[b]; mx = std::fmax(mx, hm[b]); }
+    if (mean) *mean = (float)(sum / n);
+    if (maxv) *maxv = mx;
+    return AKUA_OK;
+}
+
+int akua_pbf_get_counters(const akua_pbf_solver* s, akua_pbf_counters* out) {
+    if (!s || !out) return AKUA_ERR_INVALID;
+    *out = s->ctr;
+    return AKUA_OK;
+}
+int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on) {
+    if (!s) return AKUA_ERR_INVALID;
+    s->timing = on != 0;
+    s->timingValid = false;
+    return AKUA_OK;
+}
+int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[7]) {
+    if (!s || !ms) return AKUA_ERR_INVALID;
+    if (!s->timingValid) { s->err = "no timed step recorded (call akua_pbf_enable_timing first)"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    AK_CUDA(s, cudaEventSynchronize(s->ev[PH_END]));
+    for (int p = 0; p < 6; p++) AK_CUDA(s, cudaEventElapsedTime(&ms[p], s->ev[p], s->ev[p + 1]));
+    AK_CUDA(s, cudaEventElapsedTime(&ms[6], s->ev[PH_PREDICT], s->ev[PH_END]));
+    return AKUA_OK;
+}
+
+}  // extern "C"

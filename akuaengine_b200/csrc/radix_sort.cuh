@@ -1,0 +1,212 @@
+// radix_sort.cuh — hand-written stable LSD radix sort of (key32, index32) pairs for sm_100a.
+//
+// Replaces thrust::sort of whole 108-byte Particle structs by hash (reference: src/CUDA/NeighbourSearchCUDA.cu:167-170,
+// a CUB merge sort moving 216 B per particle per merge level) with a sort of 8-byte pairs followed by one gather.
+// Stable, so equal keys keep their input order — the same order the reference's (de-facto stable) merge sort leaves.
+//
+// One pass per 8-bit digit, three launches per pass, no spin-waits between CTAs (nothing here can hang):
+//   count   : one CTA per 4096-key tile -> 256-bin histogram, written bin-major  tileHist[bin][tile]
+//   scan    : one CTA per bin           -> exclusive scan of that bin's row over tiles, row total -> binTotal[bin]
+//   scatter : one CTA per tile          -> stable in-tile ranks (warp match + per-warp counters), keys/indices staged in
+//                                          shared memory in digit order, then written out as contiguous runs
+// HBM traffic per pass: count reads 4 B, scatter reads 8 B (4 B on the first pass: indices are implicit) and writes 8 B
+// per key; the histogram rows are ~1/16 of a key each.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace akua {
+namespace rsort {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096 keys per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kWarpSpan = 32 * kItems;    // keys handled by one warp (contiguous -> stability)
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__global__ void __launch_bounds__(kThreads) k_count(const uint32_t* __restrict__ keys, uint32_t n, int shift,
+                                                    uint32_t* __restrict__ tileHist, uint32_t numTiles) {
+    __shared__ uint32_t hist[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * (uint32_t)kTile;
+#pragma unroll 4
+    for (int r = 0; r < kItems; r++) {
+        uint32_t idx = base + r * kThreads + tid;
+        bool valid = idx < n;
+        uint32_t d = valid ? ((keys[idx] >> shift) & 255u) : 256u;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    tileHist[(size_t)tid * numTiles + blockIdx.x] = hist[tid];
+}
+
+// Block-wide exclusive scan helper for 256 threads. Returns the exclusive prefix; *total gets the block sum.
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* smem8, uint32_t* total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) smem8[warp] = incl;
+    __syncthreads();
+    uint32_t warpOff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+        uint32_t s = smem8[w];
+        if (w < warp) warpOff += s;
+        tot += s;
+    }
+    __syncthreads();  // smem8 may be reused by the caller
+    *total = tot;
+    return incl - v + warpOff;
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan(uint32_t* __restrict__ tileHist, uint32_t numTiles,
+                                                   uint32_t* __restrict__ binTotal) {
+    __shared__ uint32_t s8[kWarps];
+    uint32_t* row = tileHist + (size_t)blockIdx.x * numTiles;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < numTiles; base += kThreads) {
+        uint32_t idx = base + threadIdx.x;
+        uint32_t v = idx < numTiles ? row[idx] : 0u;
+        uint32_t tot;
+        uint32_t ex = block_excl_scan_256(v, s8, &tot);
+        if (idx < numTiles) row[idx] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) binTotal[blockIdx.x] = carry;
+}
+
+template <bool FIRST>  // FIRST: input indices are implicit (idx itself)
+__global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict__ keysIn,
+                                                      const uint32_t* __restrict__ valsIn,
+                                                      uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+                                                      uint32_t n, int shift, const uint32_t* __restrict__ tileHist,
+                                                      uint32_t numTiles, const uint32_t* __restrict__ binTotal) {
+    __shared__ uint32_t warpCnt[kWarps][256];  // per-warp running digit counts, then exclusive warp prefixes
+    __shared__ uint32_t tileBase[256];         // exclusive prefix of this tile's digit counts (slot of a digit's run in smem)
+    __shared__ uint32_t globalBase[256];       // where this tile's run of each digit starts in the output
+    __shared__ uint32_t s8[kWarps];
+    __shared__ uint32_t stageKey[kTile];
+    __shared__ uint32_t stageVal[kTile];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < kWarps * 256; i += kThreads) (&warpCnt[0][0])[i] = 0;
+    {
+        uint32_t tot;
+        uint32_t ex = block_excl_scan_256(binTotal[tid], s8, &tot);  // syncs inside
+        globalBase[tid] = ex + tileHist[(size_t)tid * numTiles + blockIdx.x];
+    }
+    __syncthreads();
+
+    uint32_t key[kItems], rank[kItems];
+    const uint32_t wbase = blockIdx.x * (uint32_t)kTile + warp * (uint32_t)kWarpSpan;
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int r = 0; r < kItems; r++) {
+        uint32_t idx = wbase + r * 32 + lane;
+        bool valid = idx < n;
+        key[r] = valid ? keysIn[idx] : 0xffffffffu;
+        uint32_t d = valid ? ((key[r] >> shift) & 255u) : 256u;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pre = valid ? warpCnt[warp][d] : 0u;
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) warpCnt[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = pre + __popc(peers & lt);
+    }
+    __syncthreads();
+    // thread `tid` owns digit `tid`: exclusive prefix over warps, digit total for the tile
+    uint32_t digitTotal = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+        uint32_t c = warpCnt[w][tid];
+        warpCnt[w][tid] = digitTotal;
+        digitTotal += c;
+    }
+    {
+        uint32_t tot;
+        uint32_t ex = block_excl_scan_256(digitTotal, s8, &tot);  // syncs inside
+        tileBase[tid] = ex;
+    }
+    __syncthreads();
+    // stage in digit order (stable)
+#pragma unroll
+    for (int r = 0; r < kItems; r++) {
+        uint32_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
+            uint32_t d = (key[r] >> shift) & 255u;
+            uint32_t slot = tileBase[d] + warpCnt[warp][d] + rank[r];
+            stageKey[slot] = key[r];
+            stageVal[slot] = FIRST ? idx : valsIn[idx];
+        }
+    }
+    __syncthreads();
+    // contiguous runs out: slot s holds digit d(s); its destination is globalBase[d] + (s - tileBase[d])
+    const uint32_t tileBeg = blockIdx.x * (uint32_t)kTile;
+    const uint32_t tileCount = min((uint32_t)kTile, n - tileBeg);
+#pragma unroll 4
+    for (int r = 0; r < kItems; r++) {
+        uint32_t s = r * kThreads + tid;
+        if (s < tileCount) {
+            uint32_t k = stageKey[s];
+            uint32_t d = (k >> shift) & 255u;
+            uint32_t dst = globalBase[d] + (s - tileBase[d]);
+            keysOut[dst] = k;
+            valsOut[dst] = stageVal[s];
+        }
+    }
+}
+
+struct Workspace {
+    uint32_t* tileHist = nullptr;  // [256][maxTiles]
+    uint32_t* binTotal = nullptr;  // [256]
+    uint32_t maxTiles = 0;
+};
+
+inline uint32_t tiles_for(uint64_t n) { return (uint32_t)((n + kTile - 1) / kTile); }
+inline int passes_for_bits(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
+
+// Sorts n (key, index) pairs. keysIn is preserved. Results land in (*keysOut, *valsOut), which point into bufA or bufB.
+// Returns the number of kernel launches issued.
+inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
+                      uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
+                      uint32_t** valsOut) {
+    const uint32_t numTiles = tiles_for(n);
+    const int passes = passes_for_bits(keyBits);
+    const uint32_t* kin = keysIn;
+    const uint32_t* vin = nullptr;
+    uint32_t* kout = keyA;
+    uint32_t* vout = valA;
+    int launches = 0;
+    for (int p = 0; p < passes; p++) {
+        int shift = 8 * p;
+        k_count<<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
+        k_scan<<<256, kThreads, 0, st>>>(ws.tileHist, numTiles, ws.binTotal);
+        if (p == 0)
+            k_scatter<true><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal);
+        else
+            k_scatter<false><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal);
+        launches += 3;
+        kin = kout;
+        vin = vout;
+        if (kout == keyA) { kout = keyB; vout = valB; } else { kout = keyA; vout = valA; }
+    }
+    *keysOut = const_cast<uint32_t*>(kin);
+    *valsOut = const_cast<uint32_t*>(vin);
+    return launches;
+}
+
+}  // namespace rsort
+}  // namespace akua

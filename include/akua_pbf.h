@@ -1,0 +1,188 @@
+/* akua_pbf.h — C ABI of the B200-native PBF simulation step (drop-in for AkuaEngine's src/Simulation solver surface).
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference repository root).
+ * Plain pointers and sizes only; no C++ / torch / glm types cross this boundary. All functions return 0 on success and
+ * a non-zero akua_status otherwise (the reference's wrappers return void and ignore CUDA errors; see
+ * akua_pbf_last_error). Nothing throws across the ABI. A solver handle is single-caller and not re-entrant, like the
+ * reference's PBFSolver (one caller: Application::run, src/Application/Application.cpp:63-70).
+ *
+ * The library is CUDA-only (sm_100a). There is no CPU fallback: akua_pbf_create fails with AKUA_ERR_NO_DEVICE when
+ * no CUDA device is usable.
+ */
+#ifndef AKUA_PBF_H
+#define AKUA_PBF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AKUA_PBF_ABI_VERSION 1
+
+typedef struct akua_pbf_solver akua_pbf_solver; /* opaque; replaces AkuaEngine::PBFSolver (PBFSolver.h:12-27) */
+
+typedef enum akua_status {
+    AKUA_OK = 0,
+    AKUA_ERR_INVALID = 1,   /* bad argument / unsupported configuration */
+    AKUA_ERR_NO_DEVICE = 2, /* no usable CUDA device (no CPU fallback exists) */
+    AKUA_ERR_CUDA = 3,      /* a CUDA call or kernel failed; see akua_pbf_last_error */
+    AKUA_ERR_ALLOC = 4,
+    AKUA_ERR_COMM = 5
+} akua_status;
+
+/* Mirrors AkuaEngine::LambdaCorrParams field-for-field (include/AkuaEngine/Simulation/PBFConfig.h:10-15).
+ * `enabled` is carried for layout parity only: the reference never reads it (src/CUDA/ConstraintSolverCUDA.cu:123-126
+ * always applies the term), and neither does this library. Use k = 0 to switch artificial pressure off. */
+typedef struct akua_corr_params {
+    int32_t enabled; /* bool in the reference */
+    float k;         /* 0.0001f */
+    float n;         /* 4.0f */
+    float delta_q;   /* 0.03f */
+} akua_corr_params;
+
+/* Mirrors AkuaEngine::PBFConfig field-for-field and in order (PBFConfig.h:18-29); glm::vec3 gravity -> float[3]. */
+typedef struct akua_pbf_config {
+    float restDensity;         /* 7600 */
+    float particle_spacing;    /* 0.05 (scene construction only; the solver does not read it) */
+    float smoothRadius;        /* 0.1  */
+    float spatialHashCellSize; /* 0.1; must equal smoothRadius (the reference silently breaks otherwise:
+                                  NeighbourSearchCUDA.cu:163 hashes with smoothRadius, :177 looks up with cellSize) */
+    float relaxation;          /* 600  */
+    float vorticityEpsilon;    /* 1e-5 */
+    float viscosity;           /* 0.01 */
+    int32_t maxNeighbours;     /* 128  */
+    int32_t solverIterations;  /* 4    */
+    float gravity[3];          /* 0,-9.8,0 */
+} akua_pbf_config;
+
+/* How particles are keyed for the neighbour search. Neighbour SETS are identical in both modes (when the neighbour cap
+ * does not bite and no two of a particle's 27 cells collide in the reference's hash); order inside a set, and therefore
+ * float summation order, differs. */
+typedef enum akua_key_mode {
+    /* key = reference hash (NeighbourSearchCUDA.cu:15-27) mod tableSize = maxNeighbours*n (PBFSolver.cpp:15).
+     * Keys, sorted permutation, bucket-start table and neighbour lists are bit-identical to the reference. */
+    AKUA_KEY_REFERENCE_HASH = 0,
+    /* key = dense linear cell index (x-major, z-fastest) over a grid covering the box; spatially coherent order. */
+    AKUA_KEY_LINEAR_CELL = 1
+} akua_key_mode;
+
+/* Knobs that exist only on the B200 side (no reference counterpart). Zero-initialise, then akua_pbf_default_options. */
+typedef struct akua_pbf_options {
+    int32_t key_mode;        /* akua_key_mode; default AKUA_KEY_LINEAR_CELL */
+    int32_t device;          /* CUDA device ordinal; default 0 */
+    int32_t use_graph;       /* capture the step into a CUDA graph and replay it (default 1) */
+    int32_t fast_math;       /* 0 = IEEE sqrt/div in the SPH kernels (default); 1 = MUFU rsqrt/rcp approximations */
+    float capacity_factor;   /* device arrays are sized for capacity_factor * n particles (ghosts, migration); default 1 */
+    int32_t reserved[8];
+} akua_pbf_options;
+
+void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */
+void akua_pbf_default_corr(akua_corr_params* corr);   /* LambdaCorrParams{} defaults */
+void akua_pbf_default_options(akua_pbf_options* opt);
+int akua_pbf_abi_version(void);
+
+/* PBFSolver::PBFSolver(int numParticles, const PBFConfig&, const LambdaCorrParams&) — PBFSolver.h:14,
+ * src/Simulation/PBFSolver.cpp:13-20. All device memory is allocated here; step() allocates nothing. `opt` may be NULL. */
+int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_config* cfg,
+                    const akua_corr_params* corr, const akua_pbf_options* opt);
+void akua_pbf_destroy(akua_pbf_solver* s);
+
+/* void PBFSolver::step(const InteropResource&, float deltaTime, glm::vec3 boxMin, glm::vec3 boxMax) — PBFSolver.h:17,
+ * src/Simulation/PBFSolver.cpp:22-78. The particle buffer is owned by the solver (see upload/download) instead of
+ * being passed as a GL-interop handle. Iteration count comes from config.solverIterations (PBFSolver.cpp:48).
+ * Asynchronous on the solver's stream; akua_pbf_sync waits. */
+int akua_pbf_step(akua_pbf_solver* s, float deltaTime, const float boxMin[3], const float boxMax[3]);
+/* step(dt, solverIterations) shape named by the north-star: same as akua_pbf_step with an explicit iteration count. */
+int akua_pbf_step_iters(akua_pbf_solver* s, float deltaTime, int32_t solverIterations, const float boxMin[3],
+                        const float boxMax[3]);
+/* void PBFSolver::setGravity(glm::vec3) — PBFSolver.h:18,29-31 */
+int akua_pbf_set_gravity(akua_pbf_solver* s, const float gravity[3]);
+int akua_pbf_sync(akua_pbf_solver* s);
+const char* akua_pbf_last_error(const akua_pbf_solver* s);
+int64_t akua_pbf_num_particles(const akua_pbf_solver* s);
+
+/* ---- particle buffer interchange (replaces the caller-owned VBO of Particle[N], Renderer.cpp:185-219) ----
+ * AoS-108 is the reference's `Particle` (include/AkuaEngine/Simulation/Particle.h:8-31): position@0 velocity@12
+ * new_position@24 new_velocity@36 position_delta@48 vorticity@60 mass@72 density@76 lambda@80 hash@84 color@88 size@104.
+ * upload: `src` is a HOST pointer to n structs. All solver-visible fields are imported; upload order defines particle ids.
+ * download: `dst` is a HOST pointer; particles come back in the solver's current (key-sorted) order, exactly as the
+ * reference leaves its VBO after the in-place sort (NeighbourSearchCUDA.cu:167-170). Fields the reference overwrites
+ * before reading on the next step and this solver does not keep (new_velocity) are filled with their commit-time
+ * equivalents (new_velocity := velocity). */
+int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n);
+int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n);
+/* Lean interchange: xyz triples + mass (mass may be NULL => 1.0). Host pointers. */
+int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n);
+/* pos4/vel4 are n float4 (xyz + mass / xyz + density); id is the upload index of each returned particle. Any may be NULL. */
+int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t* id, int64_t n);
+/* Zero-copy consumers (the "optional OpenGL consumer": a renderer can cudaMemcpy / map from these). DEVICE pointers to
+ * n float4, valid until the next step. */
+const float* akua_pbf_positions_device(akua_pbf_solver* s);
+const float* akua_pbf_velocities_device(akua_pbf_solver* s);
+
+/* Page-locked host memory for the interchange buffers (so uploads/downloads run at full PCIe rate). */
+void* akua_pbf_host_alloc(int64_t bytes);
+void akua_pbf_host_free(void* p);
+
+/* ---- phase-level operators: the six free functions PBFSolver::step calls, same decomposition, same order ----
+ * They double as the teacher-forced parity hooks (upload the oracle's pre-phase state, run one phase, compare). */
+/* predictNewPositionCUDA — include/AkuaEngine/CUDA/IntegrationCUDA.h:12, src/CUDA/IntegrationCUDA.cu:199-214 */
+int akua_pbf_phase_predict(akua_pbf_solver* s, float deltaTime);
+/* findParticleNeighboursCUDA — NeighbourSearchCUDA.h:12-21, src/CUDA/NeighbourSearchCUDA.cu:134-187.
+ * Uses the box of the last step/solve call (or the grid given at creation) to lay out the LINEAR_CELL grid. */
+int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]);
+/* runConstraintSolverCUDA — ConstraintSolverCUDA.h:14-27, src/CUDA/ConstraintSolverCUDA.cu:173-222 */
+int akua_pbf_phase_solve(akua_pbf_solver* s, int32_t solverIterations, const float boxMin[3], const float boxMax[3]);
+/* updatePositionAndVelocityCUDA — IntegrationCUDA.h:13, src/CUDA/IntegrationCUDA.cu:216-230 */
+int akua_pbf_phase_update(akua_pbf_solver* s, float deltaTime);
+/* applyBoundaryVelocityDampingCUDA(…, restitution 0, friction 0.95) — IntegrationCUDA.h:14-21, PBFSolver.cpp:64 */
+int akua_pbf_phase_damping(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]);
+/* applyVorticityAndViscosityCUDA — IntegrationCUDA.h:22-32, src/CUDA/IntegrationCUDA.cu:253-286 */
+int akua_pbf_phase_vorticity_viscosity(akua_pbf_solver* s, float deltaTime);
+
+/* ---- debug taps (no reference counterpart; required to check integer parity) ---- */
+typedef enum akua_debug_which {
+    AKUA_DBG_KEYS_UNSORTED = 0, /* u32[n]  key of each particle in pre-sort order (= Particle::hash after K2) */
+    AKUA_DBG_KEYS_SORTED = 1,   /* u32[n]  (= Particle::hash after the sort) */
+    AKUA_DBG_PERM = 2,          /* u32[n]  sorted slot -> pre-sort slot */
+    AKUA_DBG_ID = 3,            /* u32[n]  sorted slot -> upload index */
+    AKUA_DBG_BUCKET_START = 4,  /* u32[tableSize] hashToFirstParticleIndex (REFERENCE_HASH mode; UINT32_MAX = empty) */
+    AKUA_DBG_CELL_RANGE = 5,    /* u32[2*numCells] (start,end) per linear cell (LINEAR_CELL mode) */
+    AKUA_DBG_NBR_COUNT = 6,     /* u32[n] */
+    AKUA_DBG_NBR_LIST = 7,      /* u32[n*maxNeighbours], row-major like the reference's neighbourArray */
+    AKUA_DBG_DENSITY = 8,       /* f32[n] */
+    AKUA_DBG_LAMBDA = 9,        /* f32[n] */
+    AKUA_DBG_XSTAR = 10,        /* f32[4n] predicted position, w = mass */
+    AKUA_DBG_POSITION = 11,     /* f32[4n] */
+    AKUA_DBG_VELOCITY = 12,     /* f32[4n] w = density */
+    AKUA_DBG_VORTICITY = 13,    /* f32[4n] w = |omega| */
+    AKUA_DBG_DELTA_P = 14       /* f32[4n] last position_delta */
+} akua_debug_which;
+/* Copies the selected array to host memory `dst` (dst_bytes must be large enough). Synchronises. */
+int akua_pbf_debug_get(akua_pbf_solver* s, int32_t which, void* dst, int64_t dst_bytes);
+int64_t akua_pbf_debug_size(akua_pbf_solver* s, int32_t which); /* bytes needed for akua_pbf_debug_get, <0 if n/a */
+
+/* Per-step density-constraint error |rho_i/rho0 - 1| over all particles, from the last density pass (north-star
+ * acceptance criterion for long runs). Synchronises. */
+int akua_pbf_density_error(akua_pbf_solver* s, float* mean, float* max);
+
+/* ---- instrumentation ---- */
+typedef struct akua_pbf_counters {
+    int64_t kernel_launches;  /* kernels of this library launched (or replayed inside a graph) since creation */
+    int64_t steps;
+    int64_t sort_passes_last; /* radix passes used by the last neighbour phase */
+    int64_t num_cells;        /* linear grid cells (LINEAR_CELL) or tableSize (REFERENCE_HASH) */
+    int64_t h2d_bytes, d2h_bytes; /* bytes moved by upload_* / download_* / debug_get since creation */
+} akua_pbf_counters;
+int akua_pbf_get_counters(const akua_pbf_solver* s, akua_pbf_counters* out);
+/* Timing of the phases of the LAST akua_pbf_step call, from CUDA events recorded on the solver's stream when
+ * enabled with akua_pbf_enable_timing(s, 1) (disables graph replay). ms[]: 0 predict+key, 1 sort, 2 reorder+ranges,
+ * 3 neighbour lists, 4 constraint solve (all iterations), 5 post-solve (vorticity, confinement, XSPH), 6 whole step. */
+int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on);
+int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[7]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKUA_PBF_H */

@@ -101,7 +101,7 @@ ABI_SYMBOLS = [
     "akua_pbf_velocities_device", "akua_pbf_host_alloc", "akua_pbf_host_free", "akua_pbf_phase_predict",
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
-    "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing",
+    "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_stream",
 ]
 
 _lib = None
@@ -163,6 +163,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.akua_pbf_enable_timing.argtypes = [vp, C.c_int32]
     lib.akua_pbf_last_step_timing.argtypes = [vp, f3]
+    lib.akua_pbf_stream.argtypes = [vp]
+    lib.akua_pbf_stream.restype = vp
     if path is None:
         _lib = lib
     return lib
@@ -351,11 +353,16 @@ class PBFSolver:
         self._ck(self._lib.akua_pbf_get_counters(self._h, C.byref(c)), "get_counters")
         return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the solver, e.g. for torch.cuda.ExternalStream."""
+        return int(self._lib.akua_pbf_stream(self._h) or 0)
+
     def enable_timing(self, on=True):
         self._ck(self._lib.akua_pbf_enable_timing(self._h, int(on)), "enable_timing")
 
     def last_step_timing(self) -> dict:
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 10)()
         self._ck(self._lib.akua_pbf_last_step_timing(self._h, ms), "last_step_timing")
-        names = ["predict_key", "sort", "reorder_ranges", "neighbour_lists", "solve", "post", "step"]
+        names = ["predict_key", "sort", "reorder_ranges", "neighbour_lists", "solve", "post", "step", "pass_a_sum",
+                 "pass_b_sum", "timed_iterations"]
         return dict(zip(names, [float(x) for x in ms]))

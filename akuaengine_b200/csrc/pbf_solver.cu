@@ -68,7 +68,9 @@ struct akua_pbf_solver {
     float lastBoxMin[3] = {0, 0, 0}, lastBoxMax[3] = {0, 0, 0};
     bool timing = false;
     cudaEvent_t ev[PH_COUNT] = {};
-    float lastMs[7] = {0, 0, 0, 0, 0, 0, 0};
+    static constexpr int kMaxTimedIters = 16;
+    cudaEvent_t evPass[kMaxTimedIters][3] = {};  // before A, between A and B, after B
+    int timedIters = 0;
     bool timingValid = false;
 };
 
@@ -250,10 +252,14 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
     const SphParams P = makeSph(s);
     const BoxParams B = makeBox(bmin, bmax);
     const bool fast = s->opt.fast_math != 0;
+    s->timedIters = 0;
     for (int it = 0; it < iterations; it++) {
+        const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
+        if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
         if (fast) k_density_lambda<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
         else      k_density_lambda<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
         AK_LAUNCH_CHECK(s, "k_density_lambda");
+        if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
         const bool fin = commit && it == iterations - 1;
 #define AK_DELTA(F, L) k_delta_apply<F, L><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
             s->nbrCount, s->nbrStride, n, P, B, s->dpos, s->pos, s->vel, s->density, dt)
@@ -261,6 +267,7 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
         else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
 #undef AK_DELTA
         AK_LAUNCH_CHECK(s, "k_delta_apply");
+        if (timeIt) { cudaEventRecord(s->evPass[it][2], s->stream); s->timedIters = it + 1; }
         std::swap(s->xs, s->xsAlt);
         if (fin) *committed = true;
     }
@@ -415,6 +422,8 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
         s->err = "unknown key_mode"; return AKUA_ERR_INVALID;
     }
     for (int p = 0; p < PH_COUNT; p++) AK_CUDA(s, cudaEventCreate(&s->ev[p]));
+    for (int i = 0; i < akua_pbf_solver::kMaxTimedIters; i++)
+        for (int k = 0; k < 3; k++) AK_CUDA(s, cudaEventCreate(&s->evPass[i][k]));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
 }
@@ -429,6 +438,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
                     s->aosStage, s->partSum, s->partMax};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int p = 0; p < PH_COUNT; p++) if (s->ev[p]) cudaEventDestroy(s->ev[p]);
+    for (int i = 0; i < akua_pbf_solver::kMaxTimedIters; i++)
+        for (int k = 0; k < 3; k++) if (s->evPass[i][k]) cudaEventDestroy(s->evPass[i][k]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -655,13 +666,22 @@ int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on) {
     s->timingValid = false;
     return AKUA_OK;
 }
-int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[7]) {
+void* akua_pbf_stream(akua_pbf_solver* s) { return s ? (void*)s->stream : nullptr; }
+int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[10]) {
     if (!s || !ms) return AKUA_ERR_INVALID;
     if (!s->timingValid) { s->err = "no timed step recorded (call akua_pbf_enable_timing first)"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     AK_CUDA(s, cudaEventSynchronize(s->ev[PH_END]));
     for (int p = 0; p < 6; p++) AK_CUDA(s, cudaEventElapsedTime(&ms[p], s->ev[p], s->ev[p + 1]));
     AK_CUDA(s, cudaEventElapsedTime(&ms[6], s->ev[PH_PREDICT], s->ev[PH_END]));
+    ms[7] = ms[8] = 0.0f;
+    ms[9] = (float)s->timedIters;
+    for (int it = 0; it < s->timedIters; it++) {
+        float a = 0, b = 0;
+        AK_CUDA(s, cudaEventElapsedTime(&a, s->evPass[it][0], s->evPass[it][1]));
+        AK_CUDA(s, cudaEventElapsedTime(&b, s->evPass[it][1], s->evPass[it][2]));
+        ms[7] += a; ms[8] += b;
+    }
     return AKUA_OK;
 }
 

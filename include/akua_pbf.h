@@ -178,9 +178,13 @@ typedef struct akua_pbf_counters {
 int akua_pbf_get_counters(const akua_pbf_solver* s, akua_pbf_counters* out);
 /* Timing of the phases of the LAST akua_pbf_step call, from CUDA events recorded on the solver's stream when
  * enabled with akua_pbf_enable_timing(s, 1) (disables graph replay). ms[]: 0 predict+key, 1 sort, 2 reorder+ranges,
- * 3 neighbour lists, 4 constraint solve (all iterations), 5 post-solve (vorticity, confinement, XSPH), 6 whole step. */
+ * 3 neighbour lists, 4 constraint solve (all iterations), 5 post-solve (vorticity, confinement, XSPH), 6 whole step,
+ * 7 sum of the density+lambda launches (pass A), 8 sum of the delta-p+apply launches (pass B), 9 launches per pass. */
 int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on);
-int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[7]);
+int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[10]);
+/* The CUDA stream (cudaStream_t) all of this solver's work is issued on, so callers can record their own events on it
+ * or order other work after it. */
+void* akua_pbf_stream(akua_pbf_solver* s);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol akua_pbf.h declares,
+struct layouts match the reference's, and the product has no CPU fallback."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(akua_lib):
+    header = (REPO / "include" / "akua_pbf.h").read_text()
+    declared = set(re.findall(r"\b(akua_pbf_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(akua_lib, name), f"libakua_pbf.so does not export {name}"
+    from akuaengine_b200 import ABI_SYMBOLS
+    assert declared == set(ABI_SYMBOLS)
+    assert akua_lib.akua_pbf_abi_version() == 1
+
+
+def test_struct_layouts_mirror_reference(akua_lib):
+    from akuaengine_b200 import PARTICLE_DTYPE, LambdaCorrParams, PBFConfig
+    # include/AkuaEngine/Simulation/Particle.h:8-31 offsets
+    want = {"position": 0, "velocity": 12, "new_position": 24, "new_velocity": 36, "position_delta": 48, "vorticity": 60,
+            "mass": 72, "density": 76, "lambda": 80, "hash": 84, "color": 88, "size": 104}
+    assert PARTICLE_DTYPE.itemsize == 108
+    for k, off in want.items():
+        assert PARTICLE_DTYPE.fields[k][1] == off
+    assert C.sizeof(PBFConfig) == 48 and C.sizeof(LambdaCorrParams) == 16
+    # defaults come from the library and equal the reference's (PBFConfig.h:10-29)
+    cfg, corr = PBFConfig(), LambdaCorrParams()
+    c2, k2 = PBFConfig(), LambdaCorrParams()
+    akua_lib.akua_pbf_default_config(C.byref(c2))
+    akua_lib.akua_pbf_default_corr(C.byref(k2))
+    for f, _ in PBFConfig._fields_:
+        a, b = getattr(cfg, f), getattr(c2, f)
+        assert (list(a) == list(b)) if f == "gravity" else (a == b), f
+    assert (c2.restDensity, c2.smoothRadius, c2.maxNeighbours, c2.solverIterations) == (7600.0, np.float32(0.1), 128, 4)
+    assert list(c2.gravity) == [0.0, np.float32(-9.8), 0.0]
+    assert (k2.enabled, k2.k, k2.n, k2.delta_q) == (1, np.float32(1e-4), 4.0, np.float32(0.03))
+    assert (corr.k, corr.n) == (k2.k, k2.n)
+
+
+def test_invalid_arguments_are_rejected_without_a_device(akua_lib):
+    from akuaengine_b200 import LambdaCorrParams, PBFConfig
+    h = C.c_void_p()
+    cfg, corr = PBFConfig(), LambdaCorrParams()
+    assert akua_lib.akua_pbf_create(None, 10, C.byref(cfg), C.byref(corr), None) == 1
+    assert akua_lib.akua_pbf_create(C.byref(h), -1, C.byref(cfg), C.byref(corr), None) == 1
+    bad = PBFConfig(spatialHashCellSize=0.2)  # reference silently breaks when cell size != smoothing radius
+    assert akua_lib.akua_pbf_create(C.byref(h), 10, C.byref(bad), C.byref(corr), None) == 1
+    assert akua_lib.akua_pbf_step(None, 0.01, None, None) == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device construction must fail loudly (never route through oracle/ or any CPU path)."""
+    from conftest import HAS_GPU
+    from akuaengine_b200 import AkuaError, PBFSolver
+    if HAS_GPU:
+        pytest.skip("GPU present")
+    with pytest.raises(AkuaError):
+        PBFSolver(100)
+
+
+def test_product_never_imports_oracle():
+    for f in list((REPO / "akuaengine_b200").rglob("*.py")) + list((REPO / "akuaengine_b200" / "csrc").glob("*")):
+        txt = f.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt and "pbf_oracle" not in txt, f
+
+
+def test_missing_library_is_loud(tmp_path):
+    from akuaengine_b200 import AkuaError, load_library
+    with pytest.raises(AkuaError):
+        load_library(tmp_path / "nope.so")

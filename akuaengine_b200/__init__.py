@@ -112,6 +112,9 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    import os
+    if path is None and os.environ.get("AKUA_PBF_LIB"):
+        path = os.environ["AKUA_PBF_LIB"]  # alternative build of the same library (tuning experiments)
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise AkuaError(f"{p} not found: the CUDA library is not built. Run `python -m akuaengine_b200.build` "
@@ -208,7 +211,7 @@ class PBFSolver:
     """
 
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
-                 key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = False, use_graph: bool = True,
+                 key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
                  capacity_factor: float = 1.0):
         self._lib = load_library()
         self.config = config or PBFConfig()

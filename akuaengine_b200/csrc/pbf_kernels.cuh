@@ -3,12 +3,22 @@
 // Each kernel cites the reference kernel(s) it replaces (paths relative to the reference repository root). The
 // reference's 13 kernels run one thread per particle over a 108-byte AoS with a per-particle neighbour list that
 // round-trips through host memory; here the state is SoA float4 (x,y,z,mass) / (vx,vy,vz,density), the neighbour list is a
-// column-major (ELL) device array so that the k-th neighbours of 32 consecutive particles are one 128-byte line, and
-// the per-iteration kernels are fused so that each neighbour's position is gathered once per sweep:
+// column-major (ELL) device array in groups of four (entry k of particle i lives in uint4 number (k/4)*stride + i, lane
+// k%4), so that one coalesced 16-byte load per thread fetches four neighbour indices, the four gathers they feed are
+// issued together, and the next group is prefetched while the current one is evaluated. The per-iteration kernels
+// are fused so that each neighbour's position is gathered once per sweep:
 //   pass A = K5+K6  (density, both lambda loops)            pass B = K7+K8 (+K9+K10 on the last iteration)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#ifndef AKUA_SWEEP_BLOCK
+#define AKUA_SWEEP_BLOCK 128
+#endif
+#ifndef AKUA_SWEEP_MINBLOCKS
+#define AKUA_SWEEP_MINBLOCKS 8
+#endif
+#define AKUA_SWEEP_BOUNDS __launch_bounds__(AKUA_SWEEP_BLOCK, AKUA_SWEEP_MINBLOCKS)
 
 namespace akua {
 
@@ -53,7 +63,7 @@ __device__ __forceinline__ float poly6(float d2, const SphParams& P) {  // Smoot
 template <bool FAST>
 __device__ __forceinline__ float spiky_scale(float d2, const SphParams& P) {
     float r, invr;
-    if (FAST) { invr = rsqrtf(d2); r = d2 * invr; }
+    if (FAST) { invr = rsqrtf(fmaxf(d2, 1e-30f)); r = d2 * invr; }  // d2 == 0 (coincident / masked self slot) -> r = 0 -> s = 0
     else      { r = sqrtf(d2); invr = 1.0f / r; }
     float t = P.h - r;
     float s = P.spikyCoef * (t * t) * invr;
@@ -74,6 +84,42 @@ __device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams& G) {
     int y = clampi(c.y - G.gridMin.y, 0, G.gridDim.y - 1);
     int z = clampi(c.z - G.gridMin.z, 0, G.gridDim.z - 1);
     return (uint32_t)((x * G.gridDim.y + y) * G.gridDim.z + z);
+}
+
+// ------------------------------------------------------------------------------------------------ neighbour list access
+__device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
+    return ((size_t)(k >> 2) * stride + i) * 4 + (k & 3);
+}
+// Streaming 16-byte load of four neighbour indices: read once per sweep, so keep it out of L1 (the gathers want L1).
+__device__ __forceinline__ uint4 ld_list4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// Drives one neighbour sweep for particle i: `load(j)` gathers whatever the sweep needs of neighbour j, `acc(payload,
+// valid)` accumulates it. Indices come four at a time; the four gathers are independent and issued back to back, and
+// the next index group is already in flight while the current one is evaluated. Tail slots of the last group hold the
+// particle's own index (always cached) and are masked out through `valid`. Neighbours are visited in list order, so
+// every accumulator sees its terms in the reference's order.
+template <typename Payload, typename LoadF, typename AccF>
+__device__ __forceinline__ void neighbour_sweep(const uint32_t* __restrict__ list, uint32_t i, uint32_t c,
+                                                uint32_t stride, LoadF load, AccF acc) {
+    if (c == 0) return;
+    const uint4* lp = reinterpret_cast<const uint4*>(list) + i;
+    const uint32_t groups = (c + 3) >> 2;
+    uint4 cur = ld_list4(lp);
+    for (uint32_t g = 0; g < groups; g++) {
+        uint4 nxt = cur;
+        if (g + 1 < groups) nxt = ld_list4(lp + (size_t)(g + 1) * stride);
+        Payload p0 = load(cur.x), p1 = load(cur.y), p2 = load(cur.z), p3 = load(cur.w);
+        const uint32_t k = g * 4;
+        acc(p0, true);
+        acc(p1, k + 1 < c);
+        acc(p2, k + 2 < c);
+        acc(p3, k + 3 < c);
+        cur = nxt;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K1 + K2
@@ -145,7 +191,7 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ p, uint
 // ------------------------------------------------------------------------------------------------ K4
 // kernel_find_neighbours (NeighbourSearchCUDA.cu:72-130): 27-cell scan in the reference's order (dx outer, dz inner,
 // bucket order = sorted order), strict d2 < h*h, self skipped, capped at maxNeighbours. The list is written
-// column-major: entry k of particle i lives at list[k*stride + i].
+// column-major in groups of four (list_slot); the unused tail of the last group is padded with the particle's own index.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restrict__ xs,
                                                           const uint32_t* __restrict__ keysSorted,
@@ -171,7 +217,7 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
                         if (keysSorted[cand] != hash) break;
                         float4 xj = __ldg(&xs[cand]);
                         float d2 = dist2(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
-                        if (d2 < h2) { list[(size_t)count * stride + i] = cand; count++; }
+                        if (d2 < h2) { list[list_slot(i, count, stride)] = cand; count++; }
                         cand++;
                     }
                 }
@@ -197,19 +243,20 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
                     if (cand == i) continue;
                     float4 xj = __ldg(&xs[cand]);
                     float d2 = dist2(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z);
-                    if (d2 < h2) { list[(size_t)count * stride + i] = cand; count++; }
+                    if (d2 < h2) { list[list_slot(i, count, stride)] = cand; count++; }
                 }
             }
         }
     }
     cnt[i] = count;
+    for (uint32_t k = count; k < ((count + 3u) & ~3u); k++) list[list_slot(i, k, stride)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------ pass A = K5 + K6
 // kernel_calculate_densities (ConstraintSolverCUDA.cu:16-42) + kernel_calculate_lambdas (:51-97), one neighbour loop.
 // Each accumulator sees its terms in the reference's order, so fusing the loops does not change the sums.
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
+__global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
                                                         const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
                                                         float* __restrict__ density, float* __restrict__ lambda,
                                                         SphParams P) {
@@ -219,21 +266,20 @@ __global__ void __launch_bounds__(256) k_density_lambda(const float4* __restrict
     const uint32_t c = cnt[i];
     float rho = xi.w * P.selfW;
     float gx = 0.f, gy = 0.f, gz = 0.f, sum = 0.f;
-    const uint32_t* lp = list + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < c; k++) {
-        uint32_t j = lp[(size_t)k * stride];
-        float4 xj = __ldg(&xs[j]);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float d2 = dist2(dx, dy, dz);
-        rho = fmaf(xj.w, poly6(d2, P), rho);
-        float s = spiky_scale<FAST>(d2, P);
-        float ax = s * dx, ay = s * dy, az = s * dz;        // grad W_spiky
-        gx = fmaf(xj.w, ax, gx); gy = fmaf(xj.w, ay, gy); gz = fmaf(xj.w, az, gz);
-        float q = -P.invRestDensity * xj.w;                  // grad_pj C_i = q * gradW
-        float bx = q * ax, by = q * ay, bz = q * az;
-        sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
-    }
+    neighbour_sweep<float4>(list, i, c, stride,
+        [&](uint32_t j) { return __ldg(&xs[j]); },
+        [&](const float4& xj, bool valid) {
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            float d2 = dist2(dx, dy, dz);
+            float m = valid ? xj.w : 0.0f;                       // masked tail slots contribute exactly nothing
+            rho = fmaf(m, poly6(d2, P), rho);
+            float s = spiky_scale<FAST>(d2, P);
+            float ax = s * dx, ay = s * dy, az = s * dz;        // grad W_spiky
+            gx = fmaf(m, ax, gx); gy = fmaf(m, ay, gy); gz = fmaf(m, az, gz);
+            float q = -P.invRestDensity * m;                     // grad_pj C_i = q * gradW
+            float bx = q * ax, by = q * ay, bz = q * az;
+            sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
+        });
     gx *= P.invRestDensity; gy *= P.invRestDensity; gz *= P.invRestDensity;
     float C = rho * P.invRestDensity - 1.0f;
     float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
@@ -282,7 +328,7 @@ __device__ __forceinline__ void damp_velocity(float px, float py, float pz, floa
 // corrected x* goes to the other half of a double buffer. FINAL additionally commits: kernel_update_position_and_velocity
 // (IntegrationCUDA.cu:38-49) and kernel_apply_boundary_velocity_damping (:75-102), both per-particle.
 template <bool FAST, bool FINAL>
-__global__ void __launch_bounds__(256) k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
+__global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
                                                      const float* __restrict__ lambda, const uint32_t* __restrict__ list,
                                                      const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
                                                      SphParams P, BoxParams B, float4* __restrict__ dposOut,
@@ -294,22 +340,21 @@ __global__ void __launch_bounds__(256) k_delta_apply(const float4* __restrict__ 
     const float li = lambda[i];
     const uint32_t c = cnt[i];
     float px = 0.f, py = 0.f, pz = 0.f;
-    const uint32_t* lp = list + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < c; k++) {
-        uint32_t j = lp[(size_t)k * stride];
-        float4 xj = __ldg(&xsIn[j]);
-        float lj = __ldg(&lambda[j]);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float d2 = dist2(dx, dy, dz);
-        float ratio = poly6(d2, P) * P.invPoly6Dq;
-        float pw;
-        if (P.corrNIsFour) { float r2 = ratio * ratio; pw = r2 * r2; }
-        else pw = powf(ratio, P.corrN);
-        float corr = -P.corrK * pw;
-        float coef = (li + lj + corr) * xj.w * spiky_scale<FAST>(d2, P);
-        px = fmaf(coef, dx, px); py = fmaf(coef, dy, py); pz = fmaf(coef, dz, pz);
-    }
+    struct NB { float4 x; float l; };
+    neighbour_sweep<NB>(list, i, c, stride,
+        [&](uint32_t j) { NB r; r.x = __ldg(&xsIn[j]); r.l = __ldg(&lambda[j]); return r; },
+        [&](const NB& nb, bool valid) {
+            float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
+            float d2 = dist2(dx, dy, dz);
+            float ratio = poly6(d2, P) * P.invPoly6Dq;
+            float pw;
+            if (P.corrNIsFour) { float r2 = ratio * ratio; pw = r2 * r2; }
+            else pw = powf(ratio, P.corrN);
+            float corr = -P.corrK * pw;
+            float coef = (li + nb.l + corr) * nb.x.w * spiky_scale<FAST>(d2, P);
+            coef = valid ? coef : 0.0f;
+            px = fmaf(coef, dx, px); py = fmaf(coef, dy, py); pz = fmaf(coef, dz, pz);
+        });
     px *= P.invRestDensity; py *= P.invRestDensity; pz *= P.invRestDensity;
     if (dposOut) dposOut[i] = make_float4(px, py, pz, 0.f);
     float x = collide_axis(xi.x + px, B.bmin.x, B.bmax.x, B);
@@ -347,7 +392,7 @@ __global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos,
 // ------------------------------------------------------------------------------------------------ K11
 // kernel_compute_vorticities, IntegrationCUDA.cu:104-128. Also stores |omega| so K12 gathers 4 B per neighbour, not 12.
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
+__global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                                    uint32_t stride, uint32_t n, float4* __restrict__ omega,
                                                    float* __restrict__ omegaLen, SphParams P) {
@@ -356,19 +401,18 @@ __global__ void __launch_bounds__(256) k_vorticity(const float4* __restrict__ xs
     const float4 xi = xs[i], vi = vel[i];
     const uint32_t c = cnt[i];
     float wx = 0.f, wy = 0.f, wz = 0.f;
-    const uint32_t* lp = list + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < c; k++) {
-        uint32_t j = lp[(size_t)k * stride];
-        float4 xj = __ldg(&xs[j]);
-        float4 vj = __ldg(&vel[j]);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float s = spiky_scale<FAST>(dist2(dx, dy, dz), P);
-        float gx = s * dx, gy = s * dy, gz = s * dz;
-        float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-        float cx = uy * gz - uz * gy, cy = uz * gx - ux * gz, cz = ux * gy - uy * gx;  // MathUtilsCUDA.h:12-18
-        wx = fmaf(-xj.w, cx, wx); wy = fmaf(-xj.w, cy, wy); wz = fmaf(-xj.w, cz, wz);
-    }
+    struct NB { float4 x, v; };
+    neighbour_sweep<NB>(list, i, c, stride,
+        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.v = __ldg(&vel[j]); return r; },
+        [&](const NB& nb, bool valid) {
+            float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
+            float s = spiky_scale<FAST>(dist2(dx, dy, dz), P);
+            float gx = s * dx, gy = s * dy, gz = s * dz;
+            float ux = nb.v.x - vi.x, uy = nb.v.y - vi.y, uz = nb.v.z - vi.z;
+            float cx = uy * gz - uz * gy, cy = uz * gx - ux * gz, cz = ux * gy - uy * gx;  // MathUtilsCUDA.h:12-18
+            float m = valid ? -nb.x.w : 0.0f;
+            wx = fmaf(m, cx, wx); wy = fmaf(m, cy, wy); wz = fmaf(m, cz, wz);
+        });
     float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
     omega[i] = make_float4(wx, wy, wz, len);
     omegaLen[i] = len;
@@ -378,7 +422,7 @@ __global__ void __launch_bounds__(256) k_vorticity(const float4* __restrict__ xs
 // kernel_apply_vorticity_confinement, IntegrationCUDA.cu:130-165. Reads neighbours' |omega|, writes only its own
 // velocity: race-free in place.
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
+__global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
                                                      const float* __restrict__ omegaLen, const float* __restrict__ density,
                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                                      uint32_t stride, uint32_t n, float4* __restrict__ vel, SphParams P,
@@ -389,16 +433,15 @@ __global__ void __launch_bounds__(256) k_confinement(const float4* __restrict__ 
     const uint32_t c = cnt[i];
     const float invDensity = 1.0f / density[i];
     float ex = 0.f, ey = 0.f, ez = 0.f;
-    const uint32_t* lp = list + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < c; k++) {
-        uint32_t j = lp[(size_t)k * stride];
-        float4 xj = __ldg(&xs[j]);
-        float lj = __ldg(&omegaLen[j]);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float coef = xj.w * (oi.w - lj) * spiky_scale<FAST>(dist2(dx, dy, dz), P);
-        ex = fmaf(coef, dx, ex); ey = fmaf(coef, dy, ey); ez = fmaf(coef, dz, ez);
-    }
+    struct NB { float4 x; float l; };
+    neighbour_sweep<NB>(list, i, c, stride,
+        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.l = __ldg(&omegaLen[j]); return r; },
+        [&](const NB& nb, bool valid) {
+            float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
+            float coef = nb.x.w * (oi.w - nb.l) * spiky_scale<FAST>(dist2(dx, dy, dz), P);
+            coef = valid ? coef : 0.0f;
+            ex = fmaf(coef, dx, ex); ey = fmaf(coef, dy, ey); ez = fmaf(coef, dz, ez);
+        });
     ex *= invDensity; ey *= invDensity; ez *= invDensity;
     float len = sqrtf(fmaf(ez, ez, fmaf(ex, ex, ey * ey)));
     if (len < 1e-5f) return;
@@ -413,7 +456,7 @@ __global__ void __launch_bounds__(256) k_confinement(const float4* __restrict__ 
 // kernel_apply_xsph_viscosity, IntegrationCUDA.cu:167-195 — as a Jacobi sweep (velIn -> velOut). The reference updates
 // velocity in place while neighbours read it (a data race, :187,:194); Jacobi is one of its legal outcomes and is
 // deterministic.
-__global__ void __launch_bounds__(256) k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
+__global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                               uint32_t stride, uint32_t n, float4* __restrict__ velOut, SphParams P,
                                               float cvisc) {
@@ -422,17 +465,16 @@ __global__ void __launch_bounds__(256) k_xsph(const float4* __restrict__ xs, con
     const float4 xi = xs[i], vi = velIn[i];
     const uint32_t c = cnt[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    const uint32_t* lp = list + i;
-#pragma unroll 4
-    for (uint32_t k = 0; k < c; k++) {
-        uint32_t j = lp[(size_t)k * stride];
-        float4 xj = __ldg(&xs[j]);
-        float4 vj = __ldg(&velIn[j]);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float w = poly6(dist2(dx, dy, dz), P);
-        float mr = xj.w / vj.w;  // m_j / rho_j
-        ax = fmaf(mr * (vj.x - vi.x), w, ax); ay = fmaf(mr * (vj.y - vi.y), w, ay); az = fmaf(mr * (vj.z - vi.z), w, az);
-    }
+    struct NB { float4 x, v; };
+    neighbour_sweep<NB>(list, i, c, stride,
+        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.v = __ldg(&velIn[j]); return r; },
+        [&](const NB& nb, bool valid) {
+            float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
+            float w = poly6(dist2(dx, dy, dz), P);
+            float mr = nb.x.w / nb.v.w;  // m_j / rho_j
+            w = valid ? w : 0.0f;
+            ax = fmaf(mr * (nb.v.x - vi.x), w, ax); ay = fmaf(mr * (nb.v.y - vi.y), w, ay); az = fmaf(mr * (nb.v.z - vi.z), w, az);
+        });
     velOut[i] = make_float4(fmaf(cvisc, ax, vi.x), fmaf(cvisc, ay, vi.y), fmaf(cvisc, az, vi.z), vi.w);
 }
 
@@ -509,7 +551,7 @@ __global__ void __launch_bounds__(256) k_list_to_rowmajor(const uint32_t* __rest
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint64_t)n * maxN) return;
     uint32_t i = (uint32_t)(t / maxN), k = (uint32_t)(t % maxN);
-    out[t] = k < cnt[i] ? list[(size_t)k * stride + i] : 0u;
+    out[t] = k < cnt[i] ? list[list_slot(i, k, stride)] : 0u;
 }
 
 // |rho/rho0 - 1| partial sums / maxima per CTA

@@ -20,7 +20,12 @@ using namespace akua;
 
 namespace {
 
+#ifndef AKUA_SWEEP_BLOCK
+#define AKUA_SWEEP_BLOCK 128
+#endif
 constexpr int kBlock = 256;
+constexpr int kSweepBlock = AKUA_SWEEP_BLOCK;
+inline uint32_t sweepGrid(uint64_t n) { return (uint32_t)((n + kSweepBlock - 1) / kSweepBlock); }
 inline uint32_t gridFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
 
 enum Phase { PH_PREDICT = 0, PH_SORT, PH_REORDER, PH_LISTS, PH_SOLVE, PH_POST, PH_END, PH_COUNT };
@@ -256,12 +261,12 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
     for (int it = 0; it < iterations; it++) {
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
-        if (fast) k_density_lambda<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
-        else      k_density_lambda<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+        if (fast) k_density_lambda<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+        else      k_density_lambda<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
         AK_LAUNCH_CHECK(s, "k_density_lambda");
         if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
         const bool fin = commit && it == iterations - 1;
-#define AK_DELTA(F, L) k_delta_apply<F, L><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
+#define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
             s->nbrCount, s->nbrStride, n, P, B, s->dpos, s->pos, s->vel, s->density, dt)
         if (fast) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
         else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
@@ -293,13 +298,13 @@ int phasePost(akua_pbf_solver* s, float dt) {
     if (n == 0) return AKUA_OK;
     const SphParams P = makeSph(s);
     const bool fast = s->opt.fast_math != 0;
-    if (fast) k_vorticity<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
-    else      k_vorticity<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
+    if (fast) k_vorticity<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
+    else      k_vorticity<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
     AK_LAUNCH_CHECK(s, "k_vorticity");
-    if (fast) k_confinement<true><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
-    else      k_confinement<false><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    if (fast) k_confinement<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    else      k_confinement<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
     AK_LAUNCH_CHECK(s, "k_confinement");
-    k_xsph<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->velAlt, P, s->cfg.viscosity);
+    k_xsph<<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->velAlt, P, s->cfg.viscosity);
     AK_LAUNCH_CHECK(s, "k_xsph");
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
@@ -351,7 +356,7 @@ void akua_pbf_default_corr(akua_corr_params* c) {  // PBFConfig.h:10-15
 void akua_pbf_default_options(akua_pbf_options* o) {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));
-    o->key_mode = AKUA_KEY_LINEAR_CELL; o->device = 0; o->use_graph = 1; o->fast_math = 0; o->capacity_factor = 1.0f;
+    o->key_mode = AKUA_KEY_LINEAR_CELL; o->device = 0; o->use_graph = 1; o->fast_math = 1; o->capacity_factor = 1.0f;
 }
 
 int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_config* cfg, const akua_corr_params* corr,
@@ -395,7 +400,7 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     AK_CUDA(s, dalloc(&s->valA, cap)); AK_CUDA(s, dalloc(&s->valB, cap));
     s->keysSorted = s->keyA; s->perm = s->valA;
     s->nbrStride = (uint32_t)((cap + 31) / 32 * 32);
-    AK_CUDA(s, dalloc(&s->nbrList, (size_t)s->nbrStride * (size_t)cfg->maxNeighbours));
+    AK_CUDA(s, dalloc(&s->nbrList, (size_t)s->nbrStride * (size_t)((cfg->maxNeighbours + 3) / 4 * 4)));
     AK_CUDA(s, dalloc(&s->nbrCount, cap));
     s->sortWs.maxTiles = rsort::tiles_for(cap);
     AK_CUDA(s, dalloc(&s->sortWs.tileHist, (size_t)256 * s->sortWs.maxTiles));
@@ -411,6 +416,7 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) {
         // tableSize = maxNeighbours * numParticles as an int (PBFSolver.cpp:15); undefined in the reference beyond INT_MAX.
         int64_t ts = (int64_t)cfg->maxNeighbours * numParticles;
+        if (numParticles == 0) ts = 1;  // the reference would compute `% 0`; nothing is ever hashed with n = 0
         if (ts <= 0 || ts > 0x7fffffffLL) { s->err = "REFERENCE_HASH: maxNeighbours*numParticles must be in [1, 2^31) (the reference's int tableSize); use LINEAR_CELL"; return AKUA_ERR_INVALID; }
         s->grid.tableSize = (uint32_t)ts;
         s->keyBits = bitsFor((uint64_t)ts - 1);

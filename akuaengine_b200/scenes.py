@@ -34,28 +34,26 @@ def particles_from_positions(pos: np.ndarray, mass: float = 1.0) -> np.ndarray:
 
 def dam_break(n_side: int = 30):
     """README scene at n_side=30 (27 000 particles); n_side=100 -> 1 M; 252 -> 16 M. Returns (particles, boxMin, boxMax)."""
-    s = n_side / 30.0
-    box_min = np.array([1.5, 0.0, 1.5], dtype=F)
-    box_max = np.array([4.5, 4.0, 4.5], dtype=F)
-    if n_side == 30:
-        origin = np.array([2.0, 1.0, 2.0], dtype=F)
-    else:
-        ext = (box_max - box_min) * F(s)
-        box_min = np.zeros(3, dtype=F)
-        box_max = ext.astype(F)
-        origin = (np.array([0.5, 1.0, 0.5], dtype=F) * F(s)).astype(F)
+    s = F(n_side / 30.0)
+    # every scene constant of Application.cpp:14-15,162 is scaled by s, so the block keeps its place in the box and the
+    # box keeps its distance from the world origin (see DESIGN.md: the reference's hash double-counts neighbours in cells
+    # with two zero coordinates, so scenes stay clear of the origin planes in x and z like the README scene does)
+    box_min = (np.array([1.5, 0.0, 1.5], dtype=F) * s).astype(F)
+    box_max = (np.array([4.5, 4.0, 4.5], dtype=F) * s).astype(F)
+    origin = (np.array([2.0, 1.0, 2.0], dtype=F) * s).astype(F)
     pos = _lattice(n_side, n_side, n_side, origin)
     return particles_from_positions(pos), box_min, box_max
 
 
 def tank(nx: int, ny: int, nz: int):
-    """Tank-slosh scene (config 4): lattice filling the lower part of a box (0,0,0)-(1.25 Lx, 2 Ly, 1.05 Lz);
+    """Tank-slosh scene (config 4): lattice filling the lower part of a box of size (1.25 Lx, 2 Ly, 1.05 Lz);
     the slosh is driven through setGravity (see tank_gravity)."""
     sp = 0.05
     L = np.array([nx, ny, nz], dtype=np.float64) * sp
-    box_min = np.zeros(3, dtype=F)
-    box_max = np.array([1.25 * L[0], 2.0 * L[1], 1.05 * L[2]], dtype=F)
-    origin = np.array([0.05, 0.05, 0.05], dtype=F)
+    off = np.array([1.5, 0.0, 1.5])  # keep clear of the origin planes in x and z, like the README box
+    box_min = off.astype(F)
+    box_max = (off + np.array([1.25 * L[0], 2.0 * L[1], 1.05 * L[2]])).astype(F)
+    origin = (off + 0.05).astype(F)
     pos = _lattice(nx, ny, nz, origin)
     return particles_from_positions(pos), box_min, box_max
 

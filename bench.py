@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=100, help="lattice side: 30 -> 27 K (config 1), 100 -> 1 M (config 2), 252 -> 16 M (config 3)")
     ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
-    ap.add_argument("--fast-math", type=int, default=0)
+    ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

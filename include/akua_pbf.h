@@ -72,7 +72,8 @@ typedef struct akua_pbf_options {
     int32_t key_mode;        /* akua_key_mode; default AKUA_KEY_LINEAR_CELL */
     int32_t device;          /* CUDA device ordinal; default 0 */
     int32_t use_graph;       /* capture the step into a CUDA graph and replay it (default 1) */
-    int32_t fast_math;       /* 0 = IEEE sqrt/div in the SPH kernels (default); 1 = MUFU rsqrt/rcp approximations */
+    int32_t fast_math;       /* 1 (default) = r and 1/r of the spiky gradient from one MUFU rsqrt (max 2 ulp, the same error
+                                class as the reference's own powf calls); 0 = IEEE sqrtf and division */
     float capacity_factor;   /* device arrays are sized for capacity_factor * n particles (ghosts, migration); default 1 */
     int32_t reserved[8];
 } akua_pbf_options;

@@ -51,7 +51,7 @@ def make_solver(n, params, key_mode, **kw):
     return PBFSolver(n, cfg, corr, key_mode=key_mode, **kw)
 
 
-def phase_report(trace: dict, key_mode: int, fast_math: bool = False) -> dict:
+def phase_report(trace: dict, key_mode: int, fast_math: bool = True) -> dict:
     """Runs every phase of one step teacher-forced from `trace` (a fixture of tests/golden/make_golden.py or the same
     structure produced live from an oracle) and returns a dict of error measures."""
     init = trace["init"]
@@ -176,7 +176,7 @@ def phase_report(trace: dict, key_mode: int, fast_math: bool = False) -> dict:
 
 
 def trajectory_report(init, bmin, bmax, params, dt, golden: dict, steps=(1, 10), key_mode=KEY_LINEAR_CELL,
-                      fast_math=False) -> dict:
+                      fast_math=True) -> dict:
     """Free-running steps of the CUDA solver compared with golden step snapshots (matched by particle id)."""
     n = len(init)
     s = make_solver(n, params, key_mode, fast_math=fast_math)

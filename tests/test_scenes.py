@@ -22,8 +22,8 @@ def test_dam_break_readme_scene():
 def test_scaled_dam_break_and_tank():
     p, bmin, bmax = scenes.dam_break(100)
     assert len(p) == 1_000_000
-    assert np.allclose(bmax, [10.0, 13.3333, 10.0], atol=1e-3) and np.all(bmin == 0)
-    assert p["position"].min() > 0 and np.all(p["position"].max(0) < bmax)
+    assert np.allclose(bmin, [5.0, 0.0, 5.0], atol=1e-5) and np.allclose(bmax, [15.0, 13.3333, 15.0], atol=1e-3)
+    assert np.all(p["position"].min(0) > bmin) and np.all(p["position"].max(0) < bmax)
     q, bmin, bmax = scenes.tank(40, 20, 10)
     assert len(q) == 8000 and np.all(q["position"].max(0) < bmax)
     g = scenes.tank_gravity(15.0)

@@ -1,0 +1,27 @@
+"""Times alternative builds of libakua_pbf.so (tuning experiments): python tools/time_variants.py build/*.so"""
+import json, os, subprocess, sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parents[1]
+CODE = r'''
+import sys, json, time
+sys.path.insert(0, %r)
+from akuaengine_b200 import PBFSolver, scenes, KEY_LINEAR_CELL
+n_side = int(sys.argv[1]); fast = int(sys.argv[2])
+p, bmin, bmax = scenes.dam_break(n_side)
+s = PBFSolver(len(p), key_mode=KEY_LINEAR_CELL, fast_math=bool(fast))
+s.upload_particles(p)
+for _ in range(20): s.step(0.0083, bmin, bmax)
+s.sync(); t = time.perf_counter()
+for _ in range(30): s.step(0.0083, bmin, bmax)
+s.sync(); wall = (time.perf_counter() - t) / 30
+s.enable_timing(True); s.step(0.0083, bmin, bmax); ph = s.last_step_timing()
+print(json.dumps({"ms": round(wall*1e3, 4), "A": round(ph["pass_a_sum"]/4*1e3), "B": round(ph["pass_b_sum"]/4*1e3), "lists": round(ph["neighbour_lists"]*1e3), "post": round(ph["post"]*1e3), "sort": round(ph["sort"]*1e3)}))
+''' % str(REPO)
+libs = sys.argv[1:] or [""]
+for n_side in (100,):
+    for fast in (0, 1):
+        for lib in libs:
+            env = dict(os.environ)
+            if lib: env["AKUA_PBF_LIB"] = str(Path(lib).resolve())
+            r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
+            print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s}", r.stdout.strip() or r.stderr[-300:], flush=True)

@@ -501,6 +501,16 @@ int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
     return AKUA_OK;
 }
 
+int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t n) {
+    if (!s || !device_dst || n != s->n) { if (s) s->err = "export_aos108_device: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (n == 0) return AKUA_OK;
+    k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)device_dst, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
+        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+    AK_LAUNCH_CHECK(s, "k_pack_aos");
+    return AKUA_OK;
+}
+
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n) {
     if (!s || !pos_xyz || n != s->n) { if (s) s->err = "upload_soa: bad arguments"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));

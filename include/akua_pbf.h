@@ -113,6 +113,10 @@ int64_t akua_pbf_num_particles(const akua_pbf_solver* s);
  * equivalents (new_velocity := velocity). */
 int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n);
 int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n);
+/* Optional OpenGL consumer (replaces the in-place VBO update): writes the AoS-108 buffer straight into DEVICE memory,
+ * e.g. the pointer obtained from cudaGraphicsResourceGetMappedPointer on the renderer's VBO (layout the reference's
+ * renderer binds: position@0, color@88, size@104, stride 108 — src/Rendering/Renderer.cpp:201-213). Asynchronous. */
+int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t n);
 /* Lean interchange: xyz triples + mass (mass may be NULL => 1.0). Host pointers. */
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n);
 /* pos4/vel4 are n float4 (xyz + mass / xyz + density); id is the upload index of each returned particle. Any may be NULL. */

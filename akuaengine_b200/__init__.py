@@ -102,6 +102,7 @@ ABI_SYMBOLS = [
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
     "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_stream",
+    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats",
 ]
 
 _lib = None
@@ -169,6 +170,12 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_last_step_timing.argtypes = [vp, f3]
     lib.akua_pbf_stream.argtypes = [vp]
     lib.akua_pbf_stream.restype = vp
+    lib.akua_pbf_comm_unique_id.argtypes = [vp, C.c_int64]
+    lib.akua_pbf_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    lib.akua_pbf_set_slab.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.akua_pbf_upload_ids.argtypes = [vp, vp, C.c_int64]
+    lib.akua_pbf_slab_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.akua_slab_partition.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     if path is None:
         _lib = lib
     return lib
@@ -271,20 +278,24 @@ class PBFSolver:
         self._ck(self._lib.akua_pbf_sync(self._h), "sync")
 
     # -- particle buffer
+    @property
+    def n(self) -> int:
+        """Live particle count (== numParticles on a single GPU; the owned count of this rank in slab mode)."""
+        return int(self._lib.akua_pbf_num_particles(self._h))
+
     def upload_particles(self, particles: np.ndarray):
-        assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous and len(particles) == self.numParticles
+        assert particles.dtype == PARTICLE_DTYPE and particles.flags.c_contiguous
         self._ck(self._lib.akua_pbf_upload_aos108(self._h, particles.ctypes.data, len(particles)), "upload_aos108")
 
     def download_particles(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
-            out = np.empty(self.numParticles, dtype=PARTICLE_DTYPE)
-        assert out.dtype == PARTICLE_DTYPE and out.flags.c_contiguous and len(out) == self.numParticles
+            out = np.empty(self.n, dtype=PARTICLE_DTYPE)
+        assert out.dtype == PARTICLE_DTYPE and out.flags.c_contiguous and len(out) == self.n
         self._ck(self._lib.akua_pbf_download_aos108(self._h, out.ctypes.data, len(out)), "download_aos108")
         return out
 
     def upload(self, pos, vel=None, mass=None):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
-        assert len(pos) == self.numParticles
         vel_p = None
         if vel is not None:
             vel = np.ascontiguousarray(vel, dtype=np.float32).reshape(-1, 3)
@@ -296,7 +307,7 @@ class PBFSolver:
         self._ck(self._lib.akua_pbf_upload_soa(self._h, pos.ctypes.data, vel_p, mass_p, len(pos)), "upload_soa")
 
     def download(self):
-        n = self.numParticles
+        n = self.n
         pos4 = np.empty((n, 4), np.float32)
         vel4 = np.empty((n, 4), np.float32)
         pid = np.empty(n, np.uint32)
@@ -342,7 +353,7 @@ class PBFSolver:
         if which in (DBG.XSTAR, DBG.POSITION, DBG.VELOCITY, DBG.VORTICITY, DBG.DELTA_P):
             return out.reshape(-1, 4)
         if which == DBG.NBR_LIST:
-            return out.reshape(self.numParticles, self.config.maxNeighbours)
+            return out.reshape(self.n, self.config.maxNeighbours)
         if which == DBG.CELL_RANGE:
             return out.reshape(-1, 2)
         return out
@@ -356,6 +367,33 @@ class PBFSolver:
         c = Counters()
         self._ck(self._lib.akua_pbf_get_counters(self._h, C.byref(c)), "get_counters")
         return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    # -- multi-GPU (x-slab) plumbing; see akuaengine_b200/slab.py for the torch.distributed driver
+    @staticmethod
+    def comm_unique_id() -> np.ndarray:
+        buf = np.zeros(128, np.uint8)
+        rc = load_library().akua_pbf_comm_unique_id(buf.ctypes.data, 128)
+        if rc != 0:
+            raise AkuaError(f"akua_pbf_comm_unique_id failed (status {rc}): is libnccl.so.2 loadable?")
+        return buf
+
+    def comm_init(self, rank: int, nranks: int, unique_id: np.ndarray):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self._ck(self._lib.akua_pbf_comm_init(self._h, rank, nranks, uid.ctypes.data), "comm_init")
+
+    def set_slab(self, xCellLo: int, xCellHi: int):
+        self._ck(self._lib.akua_pbf_set_slab(self._h, int(xCellLo), int(xCellHi)), "set_slab")
+
+    def upload_ids(self, ids: np.ndarray):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self._lib.akua_pbf_upload_ids(self._h, ids.ctypes.data, len(ids)), "upload_ids")
+
+    def slab_stats(self) -> dict:
+        out = (C.c_int64 * 8)()
+        self._ck(self._lib.akua_pbf_slab_stats(self._h, out), "slab_stats")
+        names = ["owned", "ghost_left", "ghost_right", "plane_left", "plane_right", "exchanges", "bytes_sent", "migrated_in"]
+        return dict(zip(names, [int(x) for x in out]))
 
     def stream_ptr(self) -> int:
         """cudaStream_t of the solver, e.g. for torch.cuda.ExternalStream."""

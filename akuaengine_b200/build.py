@@ -15,7 +15,8 @@ REPO_DIR = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libakua_pbf.so"
 SOURCES = [CSRC / "pbf_solver.cu"]
-HEADERS = [CSRC / "pbf_kernels.cuh", CSRC / "radix_sort.cuh", REPO_DIR / "include" / "akua_pbf.h"]
+HEADERS = [CSRC / "pbf_kernels.cuh", CSRC / "radix_sort.cuh", CSRC / "slab_kernels.cuh", CSRC / "pbf_slab.inl",
+           REPO_DIR / "include" / "akua_pbf.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -40,7 +41,7 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES)]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

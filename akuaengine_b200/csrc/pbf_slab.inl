@@ -1,0 +1,216 @@
+// pbf_slab.inl — host side of the x-slab multi-GPU step (included by pbf_solver.cu inside its anonymous namespace).
+//
+// One process per GPU. Rank r owns the particles whose predicted position x* lies in grid x-planes [xLo, xHi) (absolute
+// cell coordinates floor(x/h); the first / last rank own everything below / above). Layout of every per-particle array
+// during a step:   [ owned, key-sorted | ghost plane from the left rank | ghost plane from the right rank ].
+// Because keys are x-major, the planes a rank sends are the first and last contiguous stretch of its owned range, and
+// what it receives is already sorted: no pack/unpack kernels and no re-sort on the per-iteration path, only
+// ncclSend/ncclRecv of array slices on the solver's stream. Exchanges per step (1-cell halo): x* once for the neighbour
+// search; lambda after pass A and x* after pass B in every iteration; v after the commit; |omega| after K11; v after K12.
+// Migration happens once per step, right after the prediction: leavers are compacted deterministically into send
+// buffers and get a sentinel key that sorts them out of the owned range; arrivals are appended before the sort.
+// NCCL is loaded with dlopen so single-GPU users need no NCCL at all.
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+const char* loadNccl() {
+    if (g_nccl.lib) return nullptr;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return "cannot dlopen libnccl.so.2";
+#define AK_SYM(field, name) \
+    *(void**)(&g_nccl.field) = dlsym(lib, name); \
+    if (!g_nccl.field) return "libnccl is missing " name;
+    AK_SYM(GetUniqueId, "ncclGetUniqueId") AK_SYM(CommInitRank, "ncclCommInitRank") AK_SYM(CommDestroy, "ncclCommDestroy")
+    AK_SYM(Send, "ncclSend") AK_SYM(Recv, "ncclRecv") AK_SYM(GroupStart, "ncclGroupStart") AK_SYM(GroupEnd, "ncclGroupEnd")
+    AK_SYM(GetErrorString, "ncclGetErrorString")
+#undef AK_SYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+
+#define AK_NCCL(s, call)                                                                          \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) {                                                                  \
+            (s)->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_);                     \
+            return AKUA_ERR_COMM;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+// Sends [sendLoff, +sendLcnt) to the left rank and [sendRoff, +sendRcnt) to the right rank, receives recvLcnt elements
+// from the left at recvLoff and recvRcnt from the right at recvRoff. One grouped NCCL call, on the solver's stream.
+int slabExchange(akua_pbf_solver* s, void* base, size_t elemBytes, size_t sendLoff, size_t sendLcnt, size_t sendRoff,
+                 size_t sendRcnt, size_t recvLoff, size_t recvLcnt, size_t recvRoff, size_t recvRcnt) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    char* b = static_cast<char*>(base);
+    ncclComm_t comm = (ncclComm_t)sl.comm;
+    AK_NCCL(s, g_nccl.GroupStart());
+    if (hasL && sendLcnt) AK_NCCL(s, g_nccl.Send(b + sendLoff * elemBytes, sendLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, s->stream));
+    if (hasR && sendRcnt) AK_NCCL(s, g_nccl.Send(b + sendRoff * elemBytes, sendRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, s->stream));
+    if (hasL && recvLcnt) AK_NCCL(s, g_nccl.Recv(b + recvLoff * elemBytes, recvLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, s->stream));
+    if (hasR && recvRcnt) AK_NCCL(s, g_nccl.Recv(b + recvRoff * elemBytes, recvRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, s->stream));
+    AK_NCCL(s, g_nccl.GroupEnd());
+    sl.exchanges++;
+    sl.bytesSent += (hasL ? sendLcnt : 0) * elemBytes + (hasR ? sendRcnt : 0) * elemBytes;
+    return AKUA_OK;
+}
+
+// Ghost-plane exchange of one SoA array for the current step's plane sizes.
+template <typename T>
+int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
+    if (!s->slab.enabled) return AKUA_OK;
+    const SlabState& sl = s->slab;
+    const size_t nOwn = (size_t)s->n;
+    return slabExchange(s, arr, sizeof(T), 0, sl.nPlaneL, nOwn - sl.nPlaneR, sl.nPlaneR, nOwn, sl.nGhostL, nOwn + sl.nGhostL,
+                        sl.nGhostR);
+}
+
+// Exchanges two u32 counters with each neighbour: counts[srcL], counts[srcR] go left / right; what the neighbours sent
+// lands in counts[dstL] (from the left rank) and counts[dstR] (from the right rank). Then copies all 8 counters to the
+// host and waits — the one host synchronisation this costs.
+int slabSwapCounts(akua_pbf_solver* s, int srcL, int srcR, int dstL, int dstR) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    ncclComm_t comm = (ncclComm_t)sl.comm;
+    AK_NCCL(s, g_nccl.GroupStart());
+    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcL, 4, ncclUint8, sl.rank - 1, comm, s->stream));
+    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcR, 4, ncclUint8, sl.rank + 1, comm, s->stream));
+    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstL, 4, ncclUint8, sl.rank - 1, comm, s->stream));
+    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstR, 4, ncclUint8, sl.rank + 1, comm, s->stream));
+    AK_NCCL(s, g_nccl.GroupEnd());
+    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (!hasL) sl.hCounts[dstL] = 0;
+    if (!hasR) sl.hCounts[dstR] = 0;
+    return AKUA_OK;
+}
+
+int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
+    SlabState& sl = s->slab;
+    if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
+    int rc = layoutGrid(s, bmin, bmax);
+    if (rc) return rc;
+    const GridParams& G = s->grid;
+    const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
+    // ownership in grid-relative x planes; the end ranks own the clamped border planes too
+    int xLo = sl.rank == 0 ? 0 : std::min(std::max(sl.xLoAbs - G.gridMin.x, 0), G.gridDim.x);
+    int xHi = sl.rank + 1 == sl.nranks ? G.gridDim.x : std::min(std::max(sl.xHiAbs - G.gridMin.x, 0), G.gridDim.x);
+    if (xHi <= xLo) { s->err = "slab is empty in the current grid (box does not cover this rank's x range)"; return AKUA_ERR_INVALID; }
+    const uint32_t sentinel = (uint32_t)s->ctr.num_cells;  // one past the last valid key
+    const int sortBits = bitsFor((uint64_t)sentinel);
+    uint32_t n = (uint32_t)s->n;
+
+    // ---- 1. predict + key (PBFSolver.cpp:30 + K2) ----
+    mark(s, PH_PREDICT);
+    if ((rc = phasePredictKey(s, dt, true, true))) return rc;
+
+    // ---- 2. migration: leavers out (sentinel key), arrivals appended ----
+    mark(s, PH_SORT);
+    const uint32_t blocks = std::max(1u, gridFor(n));
+    if (blocks > sl.migBlocksCap) { s->err = "slab: migration scratch too small"; return AKUA_ERR_INVALID; }
+    slab::k_mig_count<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt);
+    AK_LAUNCH_CHECK(s, "k_mig_count");
+    slab::k_mig_scan<<<1, kBlock, 0, s->stream>>>(sl.blockCnt, blocks, sl.dCounts);
+    AK_LAUNCH_CHECK(s, "k_mig_scan");
+    slab::k_mig_pack<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sentinel, s->pos,
+                                                       s->vel, s->xs, s->id, sl.sendL, sl.sendR, sl.migCap);
+    AK_LAUNCH_CHECK(s, "k_mig_pack");
+    if ((rc = slabSwapCounts(s, 0, 1, 4, 5))) return rc;  // my leavers (0: left, 1: right) -> neighbours' arrivals
+    const uint32_t outL = sl.hCounts[0], outR = sl.hCounts[1], inL = sl.hCounts[4], inR = sl.hCounts[5];
+    if (sl.rank == 0 && outL) { s->err = "slab: internal error (leavers beyond the first rank)"; return AKUA_ERR_INVALID; }
+    if (outL > sl.migCap || outR > sl.migCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    if ((uint64_t)n + inL + inR > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    {
+        const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+        ncclComm_t comm = (ncclComm_t)sl.comm;
+        AK_NCCL(s, g_nccl.GroupStart());
+        if (hasL && outL) AK_NCCL(s, g_nccl.Send(sl.sendL, (size_t)outL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, s->stream));
+        if (hasR && outR) AK_NCCL(s, g_nccl.Send(sl.sendR, (size_t)outR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, s->stream));
+        if (hasL && inL) AK_NCCL(s, g_nccl.Recv(sl.recvL, (size_t)inL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, s->stream));
+        if (hasR && inR) AK_NCCL(s, g_nccl.Recv(sl.recvR, (size_t)inR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, s->stream));
+        AK_NCCL(s, g_nccl.GroupEnd());
+        sl.exchanges++;
+        sl.bytesSent += ((size_t)outL + outR) * sizeof(slab::MigRecord);
+    }
+    if (inL) { slab::k_mig_unpack<<<gridFor(inL), kBlock, 0, s->stream>>>(sl.recvL, inL, n, s->pos, s->vel, s->xs, s->id, s->keysUnsorted, G); AK_LAUNCH_CHECK(s, "k_mig_unpack"); }
+    if (inR) { slab::k_mig_unpack<<<gridFor(inR), kBlock, 0, s->stream>>>(sl.recvR, inR, n + inL, s->pos, s->vel, s->xs, s->id, s->keysUnsorted, G); AK_LAUNCH_CHECK(s, "k_mig_unpack"); }
+    const uint32_t nPre = n + inL + inR;
+    const uint32_t nOwn = nPre - outL - outR;
+    sl.migratedIn += inL + inR; sl.migratedOut += outL + outR;
+
+    // ---- 3. sort everything resident (leavers end up past nOwn), reorder the owned range, owned cell ranges ----
+    AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
+    if (nPre) {
+        int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, nPre, sortBits, s->sortWs, s->stream,
+                                         &s->keysSorted, &s->perm);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
+        s->ctr.kernel_launches += launches;
+        s->ctr.sort_passes_last = launches / 3;
+    }
+    mark(s, PH_REORDER);
+    s->n = nOwn;
+    if (nOwn) {
+        k_reorder_ranges<KEY_LINEAR><<<gridFor(nOwn), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, nOwn, s->pos, s->vel, s->xs, s->id,
+            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
+        AK_LAUNCH_CHECK(s, "k_reorder_ranges");
+    }
+    std::swap(s->pos, s->posAlt); std::swap(s->vel, s->velAlt); std::swap(s->xs, s->xsAlt); std::swap(s->id, s->idAlt);
+
+    // ---- 4. ghost planes: sizes, then x* of the neighbours' boundary planes, keyed and ranged in place ----
+    slab::k_plane_counts<<<1, 32, 0, s->stream>>>(s->keysSorted, nOwn, planeCells, xLo, xHi, sl.dCounts);
+    AK_LAUNCH_CHECK(s, "k_plane_counts");
+    if ((rc = slabSwapCounts(s, 2, 3, 6, 7))) return rc;  // my first/last plane sizes -> neighbours' ghost sizes
+    sl.nPlaneL = sl.rank > 0 ? sl.hCounts[2] : 0;
+    sl.nPlaneR = sl.rank + 1 < sl.nranks ? sl.hCounts[3] : 0;
+    sl.nGhostL = sl.hCounts[6];
+    sl.nGhostR = sl.hCounts[7];
+    const uint64_t nTot = (uint64_t)nOwn + sl.nGhostL + sl.nGhostR;
+    if (nTot > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by ghosts (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    if ((rc = slabExchangePlanes(s, s->xs))) return rc;
+    const uint32_t nGhost = sl.nGhostL + sl.nGhostR;
+    if (nGhost) {
+        float3 g0 = make_float3(0, 0, 0);
+        k_predict_key<KEY_LINEAR><<<gridFor(nGhost), kBlock, 0, s->stream>>>(nullptr, nullptr, s->xs + nOwn, s->keysSorted + nOwn, nGhost, 0.0f, g0, G, 0);
+        AK_LAUNCH_CHECK(s, "k_predict_key(ghosts)");
+        slab::k_ranges<<<gridFor(nGhost), kBlock, 0, s->stream>>>(s->keysSorted, nOwn, (uint32_t)nTot, s->cellRange);
+        AK_LAUNCH_CHECK(s, "k_ranges(ghosts)");
+    }
+
+    // ---- 5. neighbour lists of the owned particles (candidates include the ghost planes) ----
+    mark(s, PH_LISTS);
+    if (nOwn) {
+        k_build_neighbours<KEY_LINEAR><<<gridFor(nOwn), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, nOwn,
+            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
+        AK_LAUNCH_CHECK(s, "k_build_neighbours");
+    }
+
+    // ---- 6. constraint solve and post-solve on the owned range, with the per-pass ghost exchanges inside ----
+    mark(s, PH_SOLVE);
+    bool committed = false;
+    if ((rc = phaseSolve(s, iterations, bmin, bmax, true, dt, &committed))) return rc;
+    if (!committed) {
+        if ((rc = phaseUpdate(s, dt))) return rc;
+        if ((rc = phaseDamping(s, bmin, bmax))) return rc;
+        if ((rc = slabExchangePlanes(s, s->vel))) return rc;
+    }
+    mark(s, PH_POST);
+    if ((rc = phasePost(s, dt))) return rc;
+    mark(s, PH_END);
+    s->timingValid = s->timing;
+    s->ctr.steps++;
+    return AKUA_OK;
+}

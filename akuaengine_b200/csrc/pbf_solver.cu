@@ -8,7 +8,12 @@
 #include "../../include/akua_pbf.h"
 #include "pbf_kernels.cuh"
 #include "radix_sort.cuh"
+#include "slab_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library itself is dlopen'ed by akua_pbf_comm_init (pbf_slab.inl)
+
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -32,8 +37,24 @@ enum Phase { PH_PREDICT = 0, PH_SORT, PH_REORDER, PH_LISTS, PH_SOLVE, PH_POST, P
 
 }  // namespace
 
+// x-slab multi-GPU state (pbf_slab.inl)
+struct SlabState {
+    bool enabled = false;
+    int rank = 0, nranks = 1;
+    void* comm = nullptr;                  // ncclComm_t
+    int xLoAbs = 0, xHiAbs = 0;            // owned absolute x cells [lo, hi)
+    uint32_t* dCounts = nullptr;           // device u32[8]: 0,1 leavers L/R; 2,3 my plane sizes; 4,5 arrivals; 6,7 ghost sizes
+    uint32_t* hCounts = nullptr;           // pinned mirror
+    uint32_t* blockCnt = nullptr;          // [2][migBlocksCap]
+    uint32_t migBlocksCap = 0;
+    slab::MigRecord *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
+    uint32_t migCap = 0;
+    uint32_t nPlaneL = 0, nPlaneR = 0, nGhostL = 0, nGhostR = 0;
+    int64_t exchanges = 0, bytesSent = 0, migratedIn = 0, migratedOut = 0;
+};
+
 struct akua_pbf_solver {
-    int64_t n = 0;         // live particles
+    int64_t n = 0;         // live (owned) particles
     int64_t capacity = 0;  // array capacity
     akua_pbf_config cfg{};
     akua_corr_params corr{};
@@ -77,6 +98,7 @@ struct akua_pbf_solver {
     cudaEvent_t evPass[kMaxTimedIters][3] = {};  // before A, between A and B, after B
     int timedIters = 0;
     bool timingValid = false;
+    SlabState slab;
 };
 
 namespace {
@@ -248,12 +270,15 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
+template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);  // pbf_slab.inl; no-op unless slab mode
+
 // `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
 int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const float* bmax, bool commit, float dt,
                bool* committed) {
     const uint32_t n = (uint32_t)s->n;
     *committed = false;
-    if (n == 0) return AKUA_OK;
+    if (n == 0 && !s->slab.enabled) return AKUA_OK;  // a slab rank without particles still takes part in the exchanges
+    int rc;
     const SphParams P = makeSph(s);
     const BoxParams B = makeBox(bmin, bmax);
     const bool fast = s->opt.fast_math != 0;
@@ -261,17 +286,24 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
     for (int it = 0; it < iterations; it++) {
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
-        if (fast) k_density_lambda<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
-        else      k_density_lambda<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
-        AK_LAUNCH_CHECK(s, "k_density_lambda");
+        if (n) {
+            if (fast) k_density_lambda<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+            else      k_density_lambda<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
+            AK_LAUNCH_CHECK(s, "k_density_lambda");
+        }
+        if ((rc = slabExchangePlanes(s, s->lambda))) return rc;   // ghosts' lambda for pass B
         if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
         const bool fin = commit && it == iterations - 1;
 #define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
             s->nbrCount, s->nbrStride, n, P, B, s->dpos, s->pos, s->vel, s->density, dt)
-        if (fast) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
-        else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
+        if (n) {
+            if (fast) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
+            else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
+            AK_LAUNCH_CHECK(s, "k_delta_apply");
+        }
 #undef AK_DELTA
-        AK_LAUNCH_CHECK(s, "k_delta_apply");
+        if ((rc = slabExchangePlanes(s, s->xsAlt))) return rc;    // ghosts' corrected x* for the next sweep
+        if (fin && (rc = slabExchangePlanes(s, s->vel))) return rc;  // ghosts' committed velocity (+density) for K11
         if (timeIt) { cudaEventRecord(s->evPass[it][2], s->stream); s->timedIters = it + 1; }
         std::swap(s->xs, s->xsAlt);
         if (fin) *committed = true;
@@ -295,26 +327,36 @@ int phaseDamping(akua_pbf_solver* s, const float* bmin, const float* bmax) {
 }
 int phasePost(akua_pbf_solver* s, float dt) {
     const uint32_t n = (uint32_t)s->n;
-    if (n == 0) return AKUA_OK;
+    if (n == 0 && !s->slab.enabled) return AKUA_OK;
+    int rc;
     const SphParams P = makeSph(s);
     const bool fast = s->opt.fast_math != 0;
+    if (n == 0) {  // slab rank without particles: exchanges only
+        if ((rc = slabExchangePlanes(s, s->omegaLen))) return rc;
+        return slabExchangePlanes(s, s->vel);
+    }
     if (fast) k_vorticity<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
     else      k_vorticity<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
     AK_LAUNCH_CHECK(s, "k_vorticity");
+    if ((rc = slabExchangePlanes(s, s->omegaLen))) return rc;     // ghosts' |omega| for K12
     if (fast) k_confinement<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
     else      k_confinement<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
     AK_LAUNCH_CHECK(s, "k_confinement");
+    if ((rc = slabExchangePlanes(s, s->vel))) return rc;          // ghosts' post-confinement velocity for K13
     k_xsph<<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->velAlt, P, s->cfg.viscosity);
     AK_LAUNCH_CHECK(s, "k_xsph");
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
 
+#include "pbf_slab.inl"
+
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
     if (!s || !bmin || !bmax) return AKUA_ERR_INVALID;
     if (iterations < 0) { s->err = "solverIterations must be >= 0"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     rememberBox(s, bmin, bmax);
+    if (s->slab.enabled) return stepSlab(s, dt, iterations, bmin, bmax);
     int rc = layoutGrid(s, bmin, bmax);
     if (rc) return rc;
     mark(s, PH_PREDICT);
@@ -443,6 +485,13 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
                     s->bucketStart, s->cellRange, s->nbrList, s->nbrCount, s->sortWs.tileHist, s->sortWs.binTotal,
                     s->aosStage, s->partSum, s->partMax};
     for (void* p : ptrs) if (p) cudaFree(p);
+    {
+        SlabState& sl = s->slab;
+        void* sp[] = {sl.dCounts, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR};
+        for (void* p : sp) if (p) cudaFree(p);
+        if (sl.hCounts) cudaFreeHost(sl.hCounts);
+        if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
+    }
     for (int p = 0; p < PH_COUNT; p++) if (s->ev[p]) cudaEventDestroy(s->ev[p]);
     for (int i = 0; i < akua_pbf_solver::kMaxTimedIters; i++)
         for (int k = 0; k < 3; k++) if (s->evPass[i][k]) cudaEventDestroy(s->evPass[i][k]);
@@ -473,8 +522,9 @@ const char* akua_pbf_last_error(const akua_pbf_solver* s) { return s ? s->err.c_
 int64_t akua_pbf_num_particles(const akua_pbf_solver* s) { return s ? s->n : -1; }
 
 int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
-    if (!s || !src || n != s->n) { if (s) s->err = "upload_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    if (!s || !src || n < 0 || n > s->capacity) { if (s) s->err = "upload_aos108: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
+    s->n = n;  // the live particle count follows the upload (slab ranks upload their own share)
     if (n == 0) return AKUA_OK;
     int rc = ensureStage(s);
     if (rc) return rc;
@@ -512,8 +562,9 @@ int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t 
 }
 
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n) {
-    if (!s || !pos_xyz || n != s->n) { if (s) s->err = "upload_soa: bad arguments"; return AKUA_ERR_INVALID; }
+    if (!s || !pos_xyz || n < 0 || n > s->capacity) { if (s) s->err = "upload_soa: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
+    s->n = n;
     if (n == 0) return AKUA_OK;
     // Host-side widening to float4, then two async copies. (Setup path; the per-step e2e path is AoS-108.)
     std::vector<float4> p4((size_t)n), v4((size_t)n);
@@ -550,6 +601,80 @@ void* akua_pbf_host_alloc(int64_t bytes) {
     return p;
 }
 void akua_pbf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- multi-GPU (x-slab) ----
+int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n) {
+    if (!s || !ids || n != s->n) { if (s) s->err = "upload_ids: n must equal the live particle count"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    if (n == 0) return AKUA_OK;
+    AK_CUDA(s, cudaMemcpyAsync(s->id, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return AKUA_OK;
+}
+int akua_pbf_comm_unique_id(void* out, int64_t out_bytes) {
+    if (!out || out_bytes < (int64_t)sizeof(ncclUniqueId)) return AKUA_ERR_INVALID;
+    if (loadNccl()) return AKUA_ERR_COMM;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return AKUA_ERR_COMM;
+    std::memcpy(out, &id, sizeof(id));
+    return AKUA_OK;
+}
+int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id) {
+    if (!s || !unique_id || nranks < 1 || rank < 0 || rank >= nranks) return AKUA_ERR_INVALID;
+    if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "comm_init: slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
+    if (const char* e = loadNccl()) { s->err = e; return AKUA_ERR_COMM; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    SlabState& sl = s->slab;
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclComm_t comm = nullptr;
+    AK_NCCL(s, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    sl.comm = comm; sl.rank = rank; sl.nranks = nranks;
+    sl.migCap = (uint32_t)std::max<int64_t>(4096, s->capacity / 8);
+    sl.migBlocksCap = gridFor((uint64_t)s->capacity) + 1;
+    AK_CUDA(s, dalloc(&sl.dCounts, 8));
+    AK_CUDA(s, cudaMemsetAsync(sl.dCounts, 0, 8 * sizeof(uint32_t), s->stream));
+    AK_CUDA(s, cudaMallocHost((void**)&sl.hCounts, 8 * sizeof(uint32_t)));
+    AK_CUDA(s, dalloc(&sl.blockCnt, (size_t)2 * sl.migBlocksCap));
+    AK_CUDA(s, dalloc(&sl.sendL, sl.migCap)); AK_CUDA(s, dalloc(&sl.sendR, sl.migCap));
+    AK_CUDA(s, dalloc(&sl.recvL, sl.migCap)); AK_CUDA(s, dalloc(&sl.recvR, sl.migCap));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    return AKUA_OK;
+}
+int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi) {
+    if (!s || !s->slab.comm) { if (s) s->err = "set_slab: call akua_pbf_comm_init first"; return AKUA_ERR_INVALID; }
+    if (xCellHi <= xCellLo) { s->err = "set_slab: empty interval"; return AKUA_ERR_INVALID; }
+    s->slab.xLoAbs = xCellLo; s->slab.xHiAbs = xCellHi; s->slab.enabled = true;
+    return AKUA_OK;
+}
+int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
+    if (!s || !out) return AKUA_ERR_INVALID;
+    const SlabState& sl = s->slab;
+    out[0] = s->n; out[1] = sl.nGhostL; out[2] = sl.nGhostR; out[3] = sl.nPlaneL; out[4] = sl.nPlaneR;
+    out[5] = sl.exchanges; out[6] = sl.bytesSent; out[7] = sl.migratedIn;
+    return AKUA_OK;
+}
+// Balanced x-slab boundaries from a histogram of particles per absolute x cell column (pure host code, no CUDA):
+// bounds[r] .. bounds[r+1] is rank r's interval of columns (indices into hist); bounds[0] = 0, bounds[nranks] = ncols.
+int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds) {
+    if (!hist || !bounds || ncols < nranks || nranks < 1) return AKUA_ERR_INVALID;
+    int64_t total = 0;
+    for (int c = 0; c < ncols; c++) total += hist[c];
+    bounds[0] = 0;
+    int64_t cum = 0;
+    int c = 0;
+    for (int r = 1; r < nranks; r++) {
+        const int64_t target = (total * r + nranks / 2) / nranks;
+        while (c < ncols && cum + hist[c] <= target) { cum += hist[c]; c++; }
+        // keep every slab at least one column wide and leave room for the remaining ranks
+        int lo = bounds[r - 1] + 1, hi = ncols - (nranks - r);
+        int b = std::min(std::max(c, lo), hi);
+        while (c < b) { cum += hist[c]; c++; }
+        bounds[r] = b;
+    }
+    bounds[nranks] = ncols;
+    return AKUA_OK;
+}
 
 // ---- phase-level operators ----
 int akua_pbf_phase_predict(akua_pbf_solver* s, float dt) {

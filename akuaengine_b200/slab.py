@@ -1,0 +1,87 @@
+"""x-slab multi-GPU driver glue (one process per GPU, torch.distributed for the rendezvous only).
+
+The data path — migration, ghost-plane exchange over NCCL/NVLink — lives in the CUDA library (csrc/pbf_slab.inl). This
+module only (1) chooses balanced slab boundaries from an all-reduced x-column histogram (host code in the library:
+akua_slab_partition), (2) distributes the NCCL unique id, and (3) uploads each rank's share.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import PARTICLE_DTYPE, PBFSolver, load_library
+
+INT_MIN, INT_MAX = -(2 ** 31), 2 ** 31 - 1
+
+
+def x_columns(pos_x: np.ndarray, h: float) -> np.ndarray:
+    """Absolute x cell of each particle, exactly as the kernels compute it: floor of an IEEE float32 division."""
+    return np.floor(pos_x.astype(np.float32) / np.float32(h)).astype(np.int64)
+
+
+def partition_columns(hist: np.ndarray, nranks: int) -> np.ndarray:
+    """Balanced contiguous column intervals; returns nranks + 1 indices into `hist` (library host code, no GPU needed)."""
+    hist = np.ascontiguousarray(hist, dtype=np.int64)
+    bounds = np.zeros(nranks + 1, np.int32)
+    rc = load_library().akua_slab_partition(hist.ctypes.data_as(C.POINTER(C.c_int64)), len(hist), nranks,
+                                            bounds.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise ValueError(f"akua_slab_partition failed (status {rc}): need at least one column per rank")
+    return bounds
+
+
+def global_histogram(cols_local: np.ndarray, dist=None):
+    """(col_min, histogram over [col_min, col_max]) of all ranks' particles. `dist` = torch.distributed or None."""
+    lo = int(cols_local.min()) if len(cols_local) else INT_MAX
+    hi = int(cols_local.max()) if len(cols_local) else INT_MIN
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([-lo, hi], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lo, hi = -int(t[0]), int(t[1])
+        hist = torch.from_numpy(np.bincount(cols_local - lo, minlength=hi - lo + 1).astype(np.int64)).to(dev)
+        dist.all_reduce(hist)
+        return lo, hist.cpu().numpy()
+    return lo, np.bincount(cols_local - lo, minlength=hi - lo + 1).astype(np.int64)
+
+
+def slab_interval(rank: int, nranks: int, col_min: int, bounds: np.ndarray):
+    """Absolute x-cell interval [lo, hi) of a rank."""
+    return col_min + int(bounds[rank]), col_min + int(bounds[rank + 1])
+
+
+def broadcast_unique_id(dist, rank: int) -> np.ndarray:
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    uid = PBFSolver.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)
+    t = torch.from_numpy(uid).to(dev)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
+def setup_slab_solver(particles: np.ndarray, ids: np.ndarray, dist, rank: int, nranks: int, device: int, h: float = 0.1,
+                      capacity_factor: float = 1.5, **solver_kw) -> PBFSolver:
+    """`particles` / `ids`: any subset of the scene held by this rank (e.g. a 1/nranks share, or everything on every rank
+    with `ids` selecting a share); the routine keeps what falls into this rank's slab. Every particle of the scene must be
+    held by exactly one rank whose slab it falls into — the simplest way is for every rank to pass the whole scene."""
+    assert particles.dtype == PARTICLE_DTYPE
+    cols = x_columns(particles["position"][:, 0], h)
+    col_min, hist = global_histogram(cols, None)  # callers pass the whole scene: the histogram is already global
+    bounds = partition_columns(hist, nranks)
+    lo, hi = slab_interval(rank, nranks, col_min, bounds)
+    mine = (cols >= lo) & (cols < hi)
+    if rank == 0:
+        mine |= cols < lo
+    if rank == nranks - 1:
+        mine |= cols >= hi
+    own = np.ascontiguousarray(particles[mine])
+    cap_n = max(int(len(particles) / nranks), len(own), 1)
+    solver = PBFSolver(cap_n, device=device, capacity_factor=capacity_factor, **solver_kw)
+    if nranks > 1:
+        solver.comm_init(rank, nranks, broadcast_unique_id(dist, rank))
+        solver.set_slab(lo, hi)
+    solver.upload_particles(own)
+    solver.upload_ids(np.ascontiguousarray(ids[mine], dtype=np.uint32))
+    return solver

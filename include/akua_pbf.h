@@ -106,7 +106,8 @@ int64_t akua_pbf_num_particles(const akua_pbf_solver* s);
 /* ---- particle buffer interchange (replaces the caller-owned VBO of Particle[N], Renderer.cpp:185-219) ----
  * AoS-108 is the reference's `Particle` (include/AkuaEngine/Simulation/Particle.h:8-31): position@0 velocity@12
  * new_position@24 new_velocity@36 position_delta@48 vorticity@60 mass@72 density@76 lambda@80 hash@84 color@88 size@104.
- * upload: `src` is a HOST pointer to n structs. All solver-visible fields are imported; upload order defines particle ids.
+ * upload: `src` is a HOST pointer to n <= capacity structs. All solver-visible fields are imported; upload order defines
+ * particle ids and n becomes the live particle count.
  * download: `dst` is a HOST pointer; particles come back in the solver's current (key-sorted) order, exactly as the
  * reference leaves its VBO after the in-place sort (NeighbourSearchCUDA.cu:167-170). Fields the reference overwrites
  * before reading on the next step and this solver does not keep (new_velocity) are filled with their commit-time
@@ -125,6 +126,26 @@ int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t
  * n float4, valid until the next step. */
 const float* akua_pbf_positions_device(akua_pbf_solver* s);
 const float* akua_pbf_velocities_device(akua_pbf_solver* s);
+
+/* ---- multi-GPU: x-slab domain decomposition, one process per GPU (no reference counterpart) ----
+ * Each rank creates its own solver (capacity_factor > 1 leaves room for ghosts and arrivals), then:
+ *   rank 0: akua_pbf_comm_unique_id(buf, 128) and broadcasts buf by any means (torch.distributed, MPI, a file);
+ *   all:    akua_pbf_comm_init(s, rank, nranks, buf)  — loads NCCL with dlopen and builds the communicator;
+ *           akua_pbf_set_slab(s, xCellLo, xCellHi)    — owned interval of absolute x cells floor(x / smoothRadius);
+ *                                                        contiguous across ranks; the end ranks own everything beyond;
+ *           upload the owned particles (upload_* sets the live count; akua_pbf_upload_ids gives them global ids);
+ *           akua_pbf_step(...) with the SAME box on every rank. It migrates particles whose predicted position left the
+ *           slab, exchanges ghost planes over NCCL/NVLink (x*, lambda per iteration; v, |omega| post-solve) and steps
+ *           the owned particles. Downloads return the owned particles; akua_pbf_num_particles is the owned count. */
+int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
+int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
+int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);
+int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
+/* out: 0 owned, 1 ghosts from left, 2 ghosts from right, 3 first-plane size, 4 last-plane size, 5 exchanges so far,
+ * 6 bytes sent so far, 7 particles migrated in so far */
+int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]);
+/* Balanced slab boundaries from a per-x-column particle histogram. Pure host code (callable without a GPU). */
+int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds /* nranks + 1 */);
 
 /* Page-locked host memory for the interchange buffers (so uploads/downloads run at full PCIe rate). */
 void* akua_pbf_host_alloc(int64_t bytes);

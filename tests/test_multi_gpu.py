@@ -1,0 +1,85 @@
+"""x-slab multi-GPU path: (a) host-side partition logic with world_size-2 gloo on CPU, (b) the real 2-GPU run against
+the single-GPU result (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+def test_partition_is_balanced_and_contiguous(akua_lib):
+    from akuaengine_b200.slab import partition_columns
+    rng = np.random.default_rng(0)
+    hist = rng.integers(0, 1000, 57).astype(np.int64)
+    for nranks in (1, 2, 3, 4, 8):
+        b = partition_columns(hist, nranks)
+        assert b[0] == 0 and b[-1] == len(hist) and np.all(np.diff(b) >= 1)
+        loads = np.array([hist[b[r]:b[r + 1]].sum() for r in range(nranks)])
+        assert loads.sum() == hist.sum()
+        assert loads.max() <= hist.sum() / nranks + hist.max()  # within one column of perfect balance
+    # degenerate: everything in one column still gives every rank a (possibly empty) column interval
+    h2 = np.zeros(8, np.int64); h2[3] = 100
+    b = partition_columns(h2, 4)
+    assert np.all(np.diff(b) >= 1) and b[-1] == 8
+    with pytest.raises(ValueError):
+        partition_columns(np.ones(2, np.int64), 4)
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(REPO))
+    from akuaengine_b200 import scenes
+    from akuaengine_b200.slab import global_histogram, partition_columns, slab_interval, x_columns
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    particles, bmin, bmax = scenes.dam_break(24)
+    share = particles[rank::world]                      # each rank starts with an arbitrary 1/world share
+    cols = x_columns(share["position"][:, 0], 0.1)
+    col_min, hist = global_histogram(cols, dist)        # all-reduced over gloo
+    bounds = partition_columns(hist, world)
+    lo, hi = slab_interval(rank, world, col_min, bounds)
+    all_cols = x_columns(particles["position"][:, 0], 0.1)
+    mine = int(((all_cols >= lo) & (all_cols < hi)).sum())
+    t = torch.tensor([mine, lo, hi], dtype=torch.int64)
+    got = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(got, t)
+    if rank == 0:
+        np.save(Path(out_dir) / "res.npy", np.stack([g.numpy() for g in got]))
+        np.save(Path(out_dir) / "hist.npy", hist)
+    dist.destroy_process_group()
+
+
+def test_slab_partition_over_gloo_world2(tmp_path, akua_lib):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(tmp_path / "res.npy")
+    hist = np.load(tmp_path / "hist.npy")
+    assert hist.sum() == 24 ** 3                       # the all-reduced histogram saw every particle exactly once
+    assert res[:, 0].sum() == 24 ** 3                  # slabs partition the scene
+    assert res[0, 2] == res[1, 1]                      # contiguous intervals
+    assert abs(int(res[0, 0]) - int(res[1, 0])) <= hist.max()
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["dam", "tank"])
+def test_two_gpu_slab_matches_single_gpu(scene):
+    if _gpu_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(REPO / "tests" / "mgpu_worker.py"), "--scene", scene, "--steps", "8"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

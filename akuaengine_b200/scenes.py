@@ -45,6 +45,57 @@ def dam_break(n_side: int = 30):
     return particles_from_positions(pos), box_min, box_max
 
 
+def dam_break_wide_positions(n_side: int, mult: int):
+    """Weak-scaling extension of dam_break: the scene is `mult` times as long in x (box and block), i.e. a
+    (mult*n_side) x n_side x n_side lattice — `mult` x the particles of dam_break(n_side), for x-slab runs on `mult` GPUs.
+    Returns (positions float32 [N,3], boxMin, boxMax); mult = 1 is exactly dam_break(n_side)."""
+    s = F(n_side / 30.0)
+    box_min = (np.array([1.5, 0.0, 1.5], dtype=F) * s).astype(F)
+    box_max = (np.array([4.5, 4.0, 4.5], dtype=F) * s).astype(F)
+    box_max[0] = F(box_min[0] + (box_max[0] - box_min[0]) * F(mult))
+    origin = (np.array([2.0, 1.0, 2.0], dtype=F) * s).astype(F)
+    return _lattice(n_side * mult, n_side, n_side, origin), box_min, box_max
+
+
+def lattice_x_columns(nx: int, origin_x, h: float = 0.1, spacing: float = 0.05):
+    """Absolute x cell (floor of the float32 division, as the kernels compute it) of each lattice x index."""
+    xs = F(origin_x) + np.arange(nx, dtype=F) * F(spacing)
+    return np.floor(xs / F(h)).astype(np.int64)
+
+
+def lattice_slab(nx: int, ny: int, nz: int, origin, ix0: int, ix1: int, spacing: float = 0.05):
+    """Positions and global lattice ids of the x-index range [ix0, ix1) of an nx*ny*nz lattice (same values and the
+    same x-outer / z-inner numbering as the full lattice), so each rank can generate only its own slab."""
+    sp = F(spacing)
+    xs = (F(origin[0]) + np.arange(nx, dtype=F) * sp)[ix0:ix1]
+    ys = F(origin[1]) + np.arange(ny, dtype=F) * sp
+    zs = F(origin[2]) + np.arange(nz, dtype=F) * sp
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    pos = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(F)
+    ids = (np.arange(ix0 * ny * nz, ix1 * ny * nz, dtype=np.int64)).astype(np.uint32)
+    return pos, ids
+
+
+def dam_break_wide_layout(n_side: int, mult: int):
+    """(lattice dims, origin, boxMin, boxMax) of dam_break_wide_positions without generating it."""
+    s = F(n_side / 30.0)
+    box_min = (np.array([1.5, 0.0, 1.5], dtype=F) * s).astype(F)
+    box_max = (np.array([4.5, 4.0, 4.5], dtype=F) * s).astype(F)
+    box_max[0] = F(box_min[0] + (box_max[0] - box_min[0]) * F(mult))
+    origin = (np.array([2.0, 1.0, 2.0], dtype=F) * s).astype(F)
+    return (n_side * mult, n_side, n_side), origin, box_min, box_max
+
+
+def tank_layout(nx: int, ny: int, nz: int):
+    sp = 0.05
+    L = np.array([nx, ny, nz], dtype=np.float64) * sp
+    off = np.array([1.5, 0.0, 1.5])
+    box_min = off.astype(F)
+    box_max = (off + np.array([1.25 * L[0], 2.0 * L[1], 1.05 * L[2]])).astype(F)
+    origin = (off + 0.05).astype(F)
+    return (nx, ny, nz), origin, box_min, box_max
+
+
 def tank(nx: int, ny: int, nz: int):
     """Tank-slosh scene (config 4): lattice filling the lower part of a box of size (1.25 Lx, 2 Ly, 1.05 Lz);
     the slosh is driven through setGravity (see tank_gravity)."""

@@ -115,15 +115,60 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU/oracle arm)")
     torch.cuda.set_device(local)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     key_mode = KEY_LINEAR_CELL if args.key_mode == "linear" else KEY_REFERENCE_HASH
-    particles, bmin, bmax = scenes.dam_break(args.n_side)
-    n = len(particles)
-    solver = PBFSolver(n, key_mode=key_mode, device=local, fast_math=bool(args.fast_math))
-    solver.upload_particles(particles)
+    gravity = None
+    if args.workload == "tank":
+        # config 4: tank slosh; --tank-per-gpu => weak scaling (nx grows with the GPU count), --tank-total => strong
+        if args.tank_total:
+            dims = [int(v) for v in args.tank_total.split(",")]
+            scaling = "strong"
+        else:
+            dims = [int(v) for v in args.tank_per_gpu.split(",")]
+            dims[0] *= world
+            scaling = "weak"
+        (nx, ny, nz), origin, bmin, bmax = scenes.tank_layout(*dims)
+        gravity = scenes.tank_gravity(15.0)
+        scene_name = f"tank slosh {nx}x{ny}x{nz} lattice, gravity tilted 15 deg (SURVEY.md §8d config 4)"
+    else:
+        (nx, ny, nz), origin, bmin, bmax = scenes.dam_break_wide_layout(args.n_side, world)
+        scaling = "weak"
+        scene_name = (f"dam break {args.n_side}^3 lattice (SURVEY.md §8d config {'2' if args.n_side == 100 else 'n/a'})"
+                      + (f", {world}x as long in x for {world} GPUs" if world > 1 else ""))
+    n_total = nx * ny * nz
+    if world == 1:
+        pos, ids = scenes.lattice_slab(nx, ny, nz, origin, 0, nx)
+        particles = scenes.particles_from_positions(pos)
+        del pos
+        n = len(particles)
+        solver = PBFSolver(n, key_mode=key_mode, device=local, fast_math=bool(args.fast_math))
+        solver.upload_particles(particles)
+    else:
+        # x-slab partition (one slab per GPU); ghost planes + migration go over NCCL/NVLink inside akua_pbf_step
+        # (csrc/pbf_slab.inl). Each rank generates only its own slab of the lattice.
+        from akuaengine_b200.slab import partition_columns, broadcast_unique_id
+        cols1d = scenes.lattice_x_columns(nx, origin[0])
+        col_min = int(cols1d.min())
+        hist = np.bincount(cols1d - col_min).astype(np.int64) * (ny * nz)
+        bounds = partition_columns(hist, world)
+        lo, hi = col_min + int(bounds[rank]), col_min + int(bounds[rank + 1])
+        sel = np.nonzero((cols1d >= lo) & (cols1d < hi))[0]
+        pos, ids = scenes.lattice_slab(nx, ny, nz, origin, int(sel[0]), int(sel[-1]) + 1)
+        particles = scenes.particles_from_positions(pos)
+        del pos
+        n = len(particles)
+        solver = PBFSolver(max(n, n_total // world), key_mode=key_mode, device=local, fast_math=bool(args.fast_math),
+                           capacity_factor=1.6)
+        solver.comm_init(rank, world, broadcast_unique_id(dist, rank))
+        solver.set_slab(lo, hi)
+        solver.upload_particles(particles)
+        solver.upload_ids(ids)
+    del particles
+    if gravity is not None:
+        solver.setGravity(gravity)
     stream = torch.cuda.ExternalStream(solver.stream_ptr(), device=local)
 
     def barrier():
@@ -164,22 +209,38 @@ def run_ours(args):
     mean_err, max_err = solver.density_error()
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------------
-    pin = PinnedBuffer((n,), PARTICLE_DTYPE)
-    solver.download_particles(pin.array)
+    cap = int(max(n, solver.n) * 1.6) + 1024
+    pin = PinnedBuffer((cap,), PARTICLE_DTYPE)
+    pin_ids = np.empty(cap, np.uint32)
+
+    def e2e_step():
+        m = solver.n                      # owned count can change through migration in slab mode
+        solver.upload_particles(pin.array[:m])
+        if world > 1:
+            solver.upload_ids(pin_ids[:m])
+        solver.step(DT, bmin, bmax)
+        m = solver.n
+        solver.download_particles(pin.array[:m])
+        if world > 1:
+            pin_ids[:m] = solver.debug(3)
+        return m
+
+    m = solver.n
+    solver.download_particles(pin.array[:m])
+    pin_ids[:m] = solver.debug(3)
     for _ in range(3):
-        solver.upload_particles(pin.array); solver.step(DT, bmin, bmax); solver.download_particles(pin.array)
+        e2e_step()
     barrier()
     e2e_steps = max(3, min(args.steps, 20))
     t0 = time.perf_counter()
     e0.record(stream)
+    moved = 0
     for _ in range(e2e_steps):
-        solver.upload_particles(pin.array)
-        solver.step(DT, bmin, bmax)
-        solver.download_particles(pin.array)
+        moved += e2e_step()
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
-    finite = bool(np.isfinite(pin.array["position"]).all())
+    finite = bool(np.isfinite(pin.array["position"][:solver.n]).all())
     pin.free()
 
     # ---- max over ranks -----------------------------------------------------------------------------------------
@@ -188,7 +249,9 @@ def run_ours(args):
         t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(t[0]), float(t[1])
-    total_particles = n * world
+    total_particles = n_total
+    n_owned_end = solver.n
+    slab_stats = solver.slab_stats() if world > 1 else None
     value = total_particles * ITERS / (ms_step * 1e-3)
     e2e_value = total_particles * ITERS / (e2e_ms * 1e-3)
 
@@ -197,16 +260,17 @@ def run_ours(args):
     out = {
         "metric": "particle-iterations/sec", "value": value, "unit": "particle-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"dam break {n} particles ({args.n_side}^3 lattice, SURVEY.md §8d config "
-                               f"{'2' if args.n_side == 100 else 'n/a'}), dt={DT}, {ITERS} solver iterations, artificial pressure + "
-                               "vorticity confinement + XSPH, box " + str([float(x) for x in bmax]),
-                   "particles_per_gpu": n, "key_mode": args.key_mode, "fast_math": bool(args.fast_math),
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{scene_name}: {n_total} particles, dt={DT}, {ITERS} solver iterations, artificial pressure + "
+                               "vorticity confinement + XSPH, box " + str([float(x) for x in bmin]) + "-" + str([float(x) for x in bmax]),
+                   "particles_total": n_total, "particles_rank0": n, "key_mode": args.key_mode, "fast_math": bool(args.fast_math),
                    "l2": "no explicit flush: per-step working set (neighbour lists ~100 B/particle + 7 float4 arrays) "
                          f"= ~{(100 + 7 * 16 + 24) * n / 1e6:.0f} MB vs 126 MB L2",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (x-slab exchange: see DESIGN.md)"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"{world} x-slabs (one per GPU), 1-cell ghost planes + per-step migration over NCCL send/recv inside "
+                   "akua_pbf_step"},
         "e2e": {"value": e2e_value, "unit": "particle-iterations/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "h2d_bytes_per_step": 108 * n, "d2h_bytes_per_step": 108 * n,
+                "h2d_bytes_per_step": 108 * n_total, "d2h_bytes_per_step": 108 * n_total,
                 "what": "akua_pbf_upload_aos108(pinned host) + akua_pbf_step + akua_pbf_download_aos108(pinned host) per step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -222,6 +286,8 @@ def run_ours(args):
         "density_error": {"mean": mean_err, "max": max_err},
         "finite": finite,
     }
+    if world > 1:
+        out["slab_rank0"] = {"owned_start": n, "owned_end": n_owned_end, **slab_stats}
     prof = REPO / "profiles" / "r01_ncu_pass_b_traffic.json"
     if prof.exists():
         try:
@@ -320,6 +386,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=100, help="lattice side: 30 -> 27 K (config 1), 100 -> 1 M (config 2), 252 -> 16 M (config 3)")
     ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
+    ap.add_argument("--workload", default="dam", choices=["dam", "tank"])
+    ap.add_argument("--tank-per-gpu", default="200,200,200", help="tank lattice per GPU (weak scaling): nx,ny,nz")
+    ap.add_argument("--tank-total", default="", help="tank lattice in total (strong scaling), e.g. 400,400,400 = 64 M")
     ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

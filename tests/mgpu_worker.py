@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--scene", default="dam")
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--side", type=int, default=40)
+    ap.add_argument("--vx", type=float, default=0.0, help="initial x velocity of every particle (forces migration)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -34,6 +35,7 @@ def main():
     else:
         particles, bmin, bmax = scenes.tank(2 * args.side, args.side // 2, args.side)
     n = len(particles)
+    particles["velocity"][:, 0] = np.float32(args.vx)
     ids = np.arange(n, dtype=np.uint32)
     if args.scene == "tank":
         g = scenes.tank_gravity(15.0)
@@ -50,6 +52,9 @@ def main():
     all_owned = [torch.zeros_like(owned) for _ in range(world)]
     dist.all_gather(all_owned, owned)
     all_owned = [int(t) for t in all_owned]
+    migt = torch.tensor([st["migrated_in"]], device="cuda", dtype=torch.int64)
+    all_mig = [torch.zeros_like(migt) for _ in range(world)]
+    dist.all_gather(all_mig, migt)
     mx = max(all_owned)
     pack = torch.zeros((mx, 9), dtype=torch.float64, device="cuda")
     pack[:solver.n, 0:4] = torch.from_numpy(pos4.astype(np.float64)).cuda()
@@ -82,6 +87,10 @@ def main():
             print("FAIL: slab result differs from the single-GPU result"); ok = False
         if world > 1 and st["exchanges"] == 0:
             print("FAIL: no exchanges happened"); ok = False
+        mig = sum(int(t) for t in all_mig)
+        print("particles migrated between ranks:", mig)
+        if args.vx != 0.0 and world > 1 and mig == 0:
+            print("FAIL: expected migration with an initial x velocity"); ok = False
         ref.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

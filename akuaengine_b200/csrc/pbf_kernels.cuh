@@ -86,6 +86,16 @@ __device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams& G) {
     return (uint32_t)((x * G.gridDim.y + y) * G.gridDim.z + z);
 }
 
+// Index span of a sweep launch: thread t handles particle base + t (+ skip once t >= split). One launch can thus cover
+// the whole owned range (single GPU), the interior of a slab, or its two boundary planes (multi-GPU overlap).
+struct Span { uint32_t count, base, split, skip; };
+__device__ __forceinline__ bool span_index(const Span& sp, uint32_t& i) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sp.count) return false;
+    i = sp.base + t + (t >= sp.split ? sp.skip : 0u);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ neighbour list access
 __device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
     return ((size_t)(k >> 2) * stride + i) * 4 + (k & 3);
@@ -257,11 +267,11 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
 // Each accumulator sees its terms in the reference's order, so fusing the loops does not change the sums.
 template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
-                                                        const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
+                                                        const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                         float* __restrict__ density, float* __restrict__ lambda,
                                                         SphParams P) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i;
+    if (!span_index(sp, i)) return;
     const float4 xi = xs[i];
     const uint32_t c = cnt[i];
     float rho = xi.w * P.selfW;
@@ -330,12 +340,12 @@ __device__ __forceinline__ void damp_velocity(float px, float py, float pz, floa
 template <bool FAST, bool FINAL>
 __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
                                                      const float* __restrict__ lambda, const uint32_t* __restrict__ list,
-                                                     const uint32_t* __restrict__ cnt, uint32_t stride, uint32_t n,
+                                                     const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                      SphParams P, BoxParams B, float4* __restrict__ dposOut,
                                                      float4* __restrict__ pos, float4* __restrict__ vel,
                                                      const float* __restrict__ density, float dt) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i;
+    if (!span_index(sp, i)) return;
     const float4 xi = xsIn[i];
     const float li = lambda[i];
     const uint32_t c = cnt[i];
@@ -394,10 +404,10 @@ __global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos,
 template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
-                                                   uint32_t stride, uint32_t n, float4* __restrict__ omega,
+                                                   uint32_t stride, Span sp, float4* __restrict__ omega,
                                                    float* __restrict__ omegaLen, SphParams P) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i;
+    if (!span_index(sp, i)) return;
     const float4 xi = xs[i], vi = vel[i];
     const uint32_t c = cnt[i];
     float wx = 0.f, wy = 0.f, wz = 0.f;
@@ -425,10 +435,10 @@ template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
                                                      const float* __restrict__ omegaLen, const float* __restrict__ density,
                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
-                                                     uint32_t stride, uint32_t n, float4* __restrict__ vel, SphParams P,
+                                                     uint32_t stride, Span sp, float4* __restrict__ vel, SphParams P,
                                                      float dt, float eps) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i;
+    if (!span_index(sp, i)) return;
     const float4 xi = xs[i], oi = omega[i];
     const uint32_t c = cnt[i];
     const float invDensity = 1.0f / density[i];
@@ -458,10 +468,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
 // deterministic.
 __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
-                                              uint32_t stride, uint32_t n, float4* __restrict__ velOut, SphParams P,
+                                              uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
                                               float cvisc) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i;
+    if (!span_index(sp, i)) return;
     const float4 xi = xs[i], vi = velIn[i];
     const uint32_t c = cnt[i];
     float ax = 0.f, ay = 0.f, az = 0.f;

@@ -49,33 +49,90 @@ const char* loadNccl() {
         }                                                                                         \
     } while (0)
 
+cudaEvent_t slabNextEvent(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    cudaEvent_t e = sl.evPool[sl.evNext];
+    sl.evNext = (sl.evNext + 1) % SlabState::kEvents;
+    return e;
+}
+// comm stream waits for everything issued on the main stream so far
+int slabCommAfterMain(akua_pbf_solver* s) {
+    cudaEvent_t e = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(e, s->stream));
+    AK_CUDA(s, cudaStreamWaitEvent(s->slab.commStream, e, 0));
+    return AKUA_OK;
+}
+
 // Sends [sendLoff, +sendLcnt) to the left rank and [sendRoff, +sendRcnt) to the right rank, receives recvLcnt elements
-// from the left at recvLoff and recvRcnt from the right at recvRoff. One grouped NCCL call, on the solver's stream.
+// from the left at recvLoff and recvRcnt from the right at recvRoff. One grouped NCCL call on the comm stream.
 int slabExchange(akua_pbf_solver* s, void* base, size_t elemBytes, size_t sendLoff, size_t sendLcnt, size_t sendRoff,
                  size_t sendRcnt, size_t recvLoff, size_t recvLcnt, size_t recvRoff, size_t recvRcnt) {
     SlabState& sl = s->slab;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
     char* b = static_cast<char*>(base);
     ncclComm_t comm = (ncclComm_t)sl.comm;
+    cudaStream_t st = sl.commStream;
     AK_NCCL(s, g_nccl.GroupStart());
-    if (hasL && sendLcnt) AK_NCCL(s, g_nccl.Send(b + sendLoff * elemBytes, sendLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, s->stream));
-    if (hasR && sendRcnt) AK_NCCL(s, g_nccl.Send(b + sendRoff * elemBytes, sendRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, s->stream));
-    if (hasL && recvLcnt) AK_NCCL(s, g_nccl.Recv(b + recvLoff * elemBytes, recvLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, s->stream));
-    if (hasR && recvRcnt) AK_NCCL(s, g_nccl.Recv(b + recvRoff * elemBytes, recvRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, s->stream));
+    if (hasL && sendLcnt) AK_NCCL(s, g_nccl.Send(b + sendLoff * elemBytes, sendLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR && sendRcnt) AK_NCCL(s, g_nccl.Send(b + sendRoff * elemBytes, sendRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, st));
+    if (hasL && recvLcnt) AK_NCCL(s, g_nccl.Recv(b + recvLoff * elemBytes, recvLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR && recvRcnt) AK_NCCL(s, g_nccl.Recv(b + recvRoff * elemBytes, recvRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, st));
     AK_NCCL(s, g_nccl.GroupEnd());
     sl.exchanges++;
     sl.bytesSent += (hasL ? sendLcnt : 0) * elemBytes + (hasR ? sendRcnt : 0) * elemBytes;
     return AKUA_OK;
 }
-
-// Ghost-plane exchange of one SoA array for the current step's plane sizes.
 template <typename T>
-int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
-    if (!s->slab.enabled) return AKUA_OK;
+int slabPlanesOnComm(akua_pbf_solver* s, T* arr) {
     const SlabState& sl = s->slab;
     const size_t nOwn = (size_t)s->n;
     return slabExchange(s, arr, sizeof(T), 0, sl.nPlaneL, nOwn - sl.nPlaneR, sl.nPlaneR, nOwn, sl.nGhostL, nOwn + sl.nGhostL,
                         sl.nGhostR);
+}
+// Asynchronous ghost-plane exchange: ordered after the main stream's work so far, runs on the comm stream; `*done`
+// must be waited on (cudaStreamWaitEvent) before the main stream touches the received ghosts.
+template <typename T>
+int slabExchangeAsync(akua_pbf_solver* s, T* arr, cudaEvent_t* done) {
+    int rc;
+    if ((rc = slabCommAfterMain(s))) return rc;
+    if ((rc = slabPlanesOnComm(s, arr))) return rc;
+    *done = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(*done, s->slab.commStream));
+    return AKUA_OK;
+}
+template <typename T, typename U>
+int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, cudaEvent_t* done) {
+    int rc;
+    if ((rc = slabCommAfterMain(s))) return rc;
+    if ((rc = slabPlanesOnComm(s, a))) return rc;
+    if ((rc = slabPlanesOnComm(s, b))) return rc;
+    *done = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(*done, s->slab.commStream));
+    return AKUA_OK;
+}
+// Blocking flavour: the main stream waits for the exchange.
+template <typename T>
+int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
+    if (!s->slab.enabled) return AKUA_OK;
+    cudaEvent_t done;
+    int rc = slabExchangeAsync(s, arr, &done);
+    if (rc) return rc;
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, done, 0));
+    return AKUA_OK;
+}
+// Interior / boundary index spans of the owned range for the current step's plane sizes.
+SweepSpans sweepSpans(const akua_pbf_solver* s) {
+    const SlabState& sl = s->slab;
+    const uint32_t n = (uint32_t)s->n, pl = sl.nPlaneL, pr = sl.nPlaneR;
+    SweepSpans sp;
+    if ((uint64_t)pl + pr >= n) {  // slab only one or two planes wide: everything is boundary
+        sp.boundary = Span{n, 0u, 0xffffffffu, 0u};
+        sp.interior = Span{0u, 0u, 0xffffffffu, 0u};
+    } else {
+        sp.boundary = Span{pl + pr, 0u, pl, n - pr - pl};
+        sp.interior = Span{n - pl - pr, pl, 0xffffffffu, 0u};
+    }
+    return sp;
 }
 
 // Exchanges two u32 counters with each neighbour: counts[srcL], counts[srcR] go left / right; what the neighbours sent
@@ -85,14 +142,17 @@ int slabSwapCounts(akua_pbf_solver* s, int srcL, int srcR, int dstL, int dstR) {
     SlabState& sl = s->slab;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
     ncclComm_t comm = (ncclComm_t)sl.comm;
+    cudaStream_t st = sl.commStream;
+    int rc;
+    if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.GroupStart());
-    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcL, 4, ncclUint8, sl.rank - 1, comm, s->stream));
-    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcR, 4, ncclUint8, sl.rank + 1, comm, s->stream));
-    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstL, 4, ncclUint8, sl.rank - 1, comm, s->stream));
-    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstR, 4, ncclUint8, sl.rank + 1, comm, s->stream));
+    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcL, 4, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcR, 4, ncclUint8, sl.rank + 1, comm, st));
+    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstL, 4, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstR, 4, ncclUint8, sl.rank + 1, comm, st));
     AK_NCCL(s, g_nccl.GroupEnd());
-    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    AK_CUDA(s, cudaStreamSynchronize(st));
     if (!hasL) sl.hCounts[dstL] = 0;
     if (!hasR) sl.hCounts[dstR] = 0;
     return AKUA_OK;
@@ -136,12 +196,18 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     {
         const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
         ncclComm_t comm = (ncclComm_t)sl.comm;
+        cudaStream_t st = sl.commStream;   // already ordered after the pack kernel by the count swap's host sync
         AK_NCCL(s, g_nccl.GroupStart());
-        if (hasL && outL) AK_NCCL(s, g_nccl.Send(sl.sendL, (size_t)outL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, s->stream));
-        if (hasR && outR) AK_NCCL(s, g_nccl.Send(sl.sendR, (size_t)outR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, s->stream));
-        if (hasL && inL) AK_NCCL(s, g_nccl.Recv(sl.recvL, (size_t)inL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, s->stream));
-        if (hasR && inR) AK_NCCL(s, g_nccl.Recv(sl.recvR, (size_t)inR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, s->stream));
+        if (hasL && outL) AK_NCCL(s, g_nccl.Send(sl.sendL, (size_t)outL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, st));
+        if (hasR && outR) AK_NCCL(s, g_nccl.Send(sl.sendR, (size_t)outR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, st));
+        if (hasL && inL) AK_NCCL(s, g_nccl.Recv(sl.recvL, (size_t)inL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, st));
+        if (hasR && inR) AK_NCCL(s, g_nccl.Recv(sl.recvR, (size_t)inR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, st));
         AK_NCCL(s, g_nccl.GroupEnd());
+        {
+            cudaEvent_t e = slabNextEvent(s);
+            AK_CUDA(s, cudaEventRecord(e, st));
+            AK_CUDA(s, cudaStreamWaitEvent(s->stream, e, 0));
+        }
         sl.exchanges++;
         sl.bytesSent += ((size_t)outL + outR) * sizeof(slab::MigRecord);
     }
@@ -198,14 +264,15 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         AK_LAUNCH_CHECK(s, "k_build_neighbours");
     }
 
+    sl.pending = nullptr;
     // ---- 6. constraint solve and post-solve on the owned range, with the per-pass ghost exchanges inside ----
     mark(s, PH_SOLVE);
     bool committed = false;
     if ((rc = phaseSolve(s, iterations, bmin, bmax, true, dt, &committed))) return rc;
-    if (!committed) {
+    if (!committed) {  // solverIterations == 0
         if ((rc = phaseUpdate(s, dt))) return rc;
         if ((rc = phaseDamping(s, bmin, bmax))) return rc;
-        if ((rc = slabExchangePlanes(s, s->vel))) return rc;
+        if ((rc = slabExchangeAsync(s, s->vel, &sl.pending))) return rc;
     }
     mark(s, PH_POST);
     if ((rc = phasePost(s, dt))) return rc;

@@ -30,6 +30,7 @@ namespace {
 #endif
 constexpr int kBlock = 256;
 constexpr int kSweepBlock = AKUA_SWEEP_BLOCK;
+inline Span fullSpan(uint32_t n) { return Span{n, 0u, 0xffffffffu, 0u}; }
 inline uint32_t sweepGrid(uint64_t n) { return (uint32_t)((n + kSweepBlock - 1) / kSweepBlock); }
 inline uint32_t gridFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
 
@@ -51,6 +52,11 @@ struct SlabState {
     uint32_t migCap = 0;
     uint32_t nPlaneL = 0, nPlaneR = 0, nGhostL = 0, nGhostR = 0;
     int64_t exchanges = 0, bytesSent = 0, migratedIn = 0, migratedOut = 0;
+    cudaStream_t commStream = nullptr;     // high-priority stream all NCCL traffic is issued on
+    static constexpr int kEvents = 64;
+    cudaEvent_t evPool[kEvents] = {};
+    int evNext = 0;
+    cudaEvent_t pending = nullptr;         // completion of the last asynchronous x* (/v) ghost exchange
 };
 
 struct akua_pbf_solver {
@@ -270,40 +276,90 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
-template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);  // pbf_slab.inl; no-op unless slab mode
+// ---- slab-mode plumbing used by the sweeps below (definitions in pbf_slab.inl) ----
+template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);           // blocking w.r.t. the main stream
+template <typename T> int slabExchangeAsync(akua_pbf_solver* s, T* arr, cudaEvent_t* done);  // on the comm stream
+template <typename T, typename U> int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, cudaEvent_t* done);
+struct SweepSpans { Span interior, boundary; };
+SweepSpans sweepSpans(const akua_pbf_solver* s);
+
+// ---- sweep launchers over an index span ----
+int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P) {
+    if (!sp.count) return AKUA_OK;
+    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P);
+    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P);
+    AK_LAUNCH_CHECK(s, "k_density_lambda");
+    return AKUA_OK;
+}
+int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams& B, bool fin, float dt) {
+    if (!sp.count) return AKUA_OK;
+#define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
+            s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, dt)
+    if (s->opt.fast_math) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
+    else                  { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
+#undef AK_DELTA
+    AK_LAUNCH_CHECK(s, "k_delta_apply");
+    return AKUA_OK;
+}
+int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P) {
+    if (!sp.count) return AKUA_OK;
+    if (s->opt.fast_math) k_vorticity<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P);
+    else                  k_vorticity<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P);
+    AK_LAUNCH_CHECK(s, "k_vorticity");
+    return AKUA_OK;
+}
+int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt) {
+    if (!sp.count) return AKUA_OK;
+    if (s->opt.fast_math) k_confinement<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    else                  k_confinement<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    AK_LAUNCH_CHECK(s, "k_confinement");
+    return AKUA_OK;
+}
+int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P) {
+    if (!sp.count) return AKUA_OK;
+    k_xsph<<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity);
+    AK_LAUNCH_CHECK(s, "k_xsph");
+    return AKUA_OK;
+}
 
 // `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
+// Slab mode: every sweep is split into the slab interior (needs no ghost data) and its two boundary planes. The
+// boundary planes run as soon as the ghost data they need has arrived and their results go out on the comm stream
+// while the interior of the NEXT sweep runs on the main stream — every exchange is hidden behind an interior launch.
 int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const float* bmax, bool commit, float dt,
                bool* committed) {
     const uint32_t n = (uint32_t)s->n;
     *committed = false;
-    if (n == 0 && !s->slab.enabled) return AKUA_OK;  // a slab rank without particles still takes part in the exchanges
+    const bool slabMode = s->slab.enabled;
+    if (n == 0 && !slabMode) return AKUA_OK;  // a slab rank without particles still takes part in the exchanges
     int rc;
     const SphParams P = makeSph(s);
     const BoxParams B = makeBox(bmin, bmax);
-    const bool fast = s->opt.fast_math != 0;
+    SweepSpans sp{fullSpan(n), Span{0, 0, 0, 0}};
+    if (slabMode) sp = sweepSpans(s);
     s->timedIters = 0;
     for (int it = 0; it < iterations; it++) {
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
-        if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
-        if (n) {
-            if (fast) k_density_lambda<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
-            else      k_density_lambda<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, n, s->density, s->lambda, P);
-            AK_LAUNCH_CHECK(s, "k_density_lambda");
-        }
-        if ((rc = slabExchangePlanes(s, s->lambda))) return rc;   // ghosts' lambda for pass B
-        if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
         const bool fin = commit && it == iterations - 1;
-#define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
-            s->nbrCount, s->nbrStride, n, P, B, s->dpos, s->pos, s->vel, s->density, dt)
-        if (n) {
-            if (fast) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
-            else      { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
-            AK_LAUNCH_CHECK(s, "k_delta_apply");
+        if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
+        if ((rc = launchPassA(s, sp.interior, P))) return rc;
+        if (slabMode) {
+            if (s->slab.pending) { AK_CUDA(s, cudaStreamWaitEvent(s->stream, s->slab.pending, 0)); s->slab.pending = nullptr; }  // ghosts' x*
+            if ((rc = launchPassA(s, sp.boundary, P))) return rc;
+            cudaEvent_t evL;
+            if ((rc = slabExchangeAsync(s, s->lambda, &evL))) return rc;      // ghosts' lambda, hidden behind pass B (interior)
+            if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
+            AK_CUDA(s, cudaStreamWaitEvent(s->stream, evL, 0));
+            if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt))) return rc;
+            // ghosts' corrected x* (and, after the commit, v + rho for K11), hidden behind the next interior sweep
+            if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
+            else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
+            if (rc) return rc;
+        } else {
+            if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
         }
-#undef AK_DELTA
-        if ((rc = slabExchangePlanes(s, s->xsAlt))) return rc;    // ghosts' corrected x* for the next sweep
-        if (fin && (rc = slabExchangePlanes(s, s->vel))) return rc;  // ghosts' committed velocity (+density) for K11
         if (timeIt) { cudaEventRecord(s->evPass[it][2], s->stream); s->timedIters = it + 1; }
         std::swap(s->xs, s->xsAlt);
         if (fin) *committed = true;
@@ -327,24 +383,31 @@ int phaseDamping(akua_pbf_solver* s, const float* bmin, const float* bmax) {
 }
 int phasePost(akua_pbf_solver* s, float dt) {
     const uint32_t n = (uint32_t)s->n;
-    if (n == 0 && !s->slab.enabled) return AKUA_OK;
+    const bool slabMode = s->slab.enabled;
+    if (n == 0 && !slabMode) return AKUA_OK;
     int rc;
     const SphParams P = makeSph(s);
-    const bool fast = s->opt.fast_math != 0;
-    if (n == 0) {  // slab rank without particles: exchanges only
-        if ((rc = slabExchangePlanes(s, s->omegaLen))) return rc;
-        return slabExchangePlanes(s, s->vel);
+    if (!slabMode) {
+        const Span all = fullSpan(n);
+        if ((rc = launchVorticity(s, all, P))) return rc;
+        if ((rc = launchConfinement(s, all, P, dt))) return rc;
+        if ((rc = launchXsph(s, all, P))) return rc;
+        std::swap(s->vel, s->velAlt);
+        return AKUA_OK;
     }
-    if (fast) k_vorticity<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
-    else      k_vorticity<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->omega, s->omegaLen, P);
-    AK_LAUNCH_CHECK(s, "k_vorticity");
-    if ((rc = slabExchangePlanes(s, s->omegaLen))) return rc;     // ghosts' |omega| for K12
-    if (fast) k_confinement<true><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
-    else      k_confinement<false><<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, n, s->vel, P, dt, s->cfg.vorticityEpsilon);
-    AK_LAUNCH_CHECK(s, "k_confinement");
-    if ((rc = slabExchangePlanes(s, s->vel))) return rc;          // ghosts' post-confinement velocity for K13
-    k_xsph<<<sweepGrid(n), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, n, s->velAlt, P, s->cfg.viscosity);
-    AK_LAUNCH_CHECK(s, "k_xsph");
+    const SweepSpans sp = sweepSpans(s);
+    cudaEvent_t evW, evV;
+    if ((rc = launchVorticity(s, sp.interior, P))) return rc;
+    if (s->slab.pending) { AK_CUDA(s, cudaStreamWaitEvent(s->stream, s->slab.pending, 0)); s->slab.pending = nullptr; }  // ghosts' final x*, v
+    if ((rc = launchVorticity(s, sp.boundary, P))) return rc;
+    if ((rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;         // ghosts' |omega| for K12
+    if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, evW, 0));
+    if ((rc = launchConfinement(s, sp.boundary, P, dt))) return rc;
+    if ((rc = slabExchangeAsync(s, s->vel, &evV))) return rc;              // ghosts' post-confinement v for K13
+    if ((rc = launchXsph(s, sp.interior, P))) return rc;
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, evV, 0));
+    if ((rc = launchXsph(s, sp.boundary, P))) return rc;
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
@@ -490,6 +553,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         void* sp[] = {sl.dCounts, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR};
         for (void* p : sp) if (p) cudaFree(p);
         if (sl.hCounts) cudaFreeHost(sl.hCounts);
+        if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
+        for (int e = 0; e < SlabState::kEvents; e++) if (sl.evPool[e]) cudaEventDestroy(sl.evPool[e]);
         if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
     }
     for (int p = 0; p < PH_COUNT; p++) if (s->ev[p]) cudaEventDestroy(s->ev[p]);
@@ -632,6 +697,12 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     sl.comm = comm; sl.rank = rank; sl.nranks = nranks;
     sl.migCap = (uint32_t)std::max<int64_t>(4096, s->capacity / 8);
     sl.migBlocksCap = gridFor((uint64_t)s->capacity) + 1;
+    {
+        int lo = 0, hi = 0;
+        AK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
+        for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
+    }
     AK_CUDA(s, dalloc(&sl.dCounts, 8));
     AK_CUDA(s, cudaMemsetAsync(sl.dCounts, 0, 8 * sizeof(uint32_t), s->stream));
     AK_CUDA(s, cudaMallocHost((void**)&sl.hCounts, 8 * sizeof(uint32_t)));
@@ -696,6 +767,7 @@ int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const f
 }
 int akua_pbf_phase_solve(akua_pbf_solver* s, int32_t iters, const float boxMin[3], const float boxMax[3]) {
     if (!s || !boxMin || !boxMax || iters < 0) return AKUA_ERR_INVALID;
+    if (s->slab.enabled) { s->err = "phase-level operators are single-GPU only; use akua_pbf_step in slab mode"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     rememberBox(s, boxMin, boxMax);
     bool committed;
@@ -713,6 +785,7 @@ int akua_pbf_phase_damping(akua_pbf_solver* s, const float boxMin[3], const floa
 }
 int akua_pbf_phase_vorticity_viscosity(akua_pbf_solver* s, float dt) {
     if (!s) return AKUA_ERR_INVALID;
+    if (s->slab.enabled) { s->err = "phase-level operators are single-GPU only; use akua_pbf_step in slab mode"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     return phasePost(s, dt);
 }

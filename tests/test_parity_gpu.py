@@ -265,7 +265,7 @@ def test_set_gravity_and_step_iters_and_errors():
     with pytest.raises(AkuaError):
         s.step(0.01, bmax, bmin)  # inverted box
     with pytest.raises(AkuaError):
-        s._ck(s._lib.akua_pbf_upload_aos108(s._h, init.ctypes.data, len(init) - 1), "upload")  # wrong count
+        s._ck(s._lib.akua_pbf_upload_aos108(s._h, init.ctypes.data, len(init) + 1), "upload")  # beyond capacity
     s.close()
 
 

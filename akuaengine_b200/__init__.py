@@ -82,7 +82,7 @@ class PBFOptions(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("steps", C.c_int64), ("sort_passes_last", C.c_int64),
-                ("num_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("num_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("graph_replays", C.c_int64)]
 
 
 class DBG:
@@ -96,6 +96,7 @@ class DBG:
 ABI_SYMBOLS = [
     "akua_pbf_abi_version", "akua_pbf_default_config", "akua_pbf_default_corr", "akua_pbf_default_options",
     "akua_pbf_create", "akua_pbf_destroy", "akua_pbf_step", "akua_pbf_step_iters", "akua_pbf_set_gravity",
+    "akua_pbf_advance", "akua_pbf_run_steps",
     "akua_pbf_sync", "akua_pbf_last_error", "akua_pbf_num_particles", "akua_pbf_upload_aos108",
     "akua_pbf_download_aos108", "akua_pbf_export_aos108_device", "akua_pbf_upload_soa", "akua_pbf_download_soa", "akua_pbf_positions_device",
     "akua_pbf_velocities_device", "akua_pbf_host_alloc", "akua_pbf_host_free", "akua_pbf_phase_predict",
@@ -137,6 +138,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_step.argtypes = [vp, C.c_float, f3, f3]
     lib.akua_pbf_step_iters.argtypes = [vp, C.c_float, C.c_int32, f3, f3]
     lib.akua_pbf_set_gravity.argtypes = [vp, f3]
+    lib.akua_pbf_advance.argtypes = [vp, C.c_float, C.c_float, C.c_int32, f3, f3, C.POINTER(C.c_int32)]
+    lib.akua_pbf_run_steps.argtypes = [vp, C.c_int32, C.c_float, f3, f3]
     lib.akua_pbf_sync.argtypes = [vp]
     lib.akua_pbf_last_error.argtypes = [vp]
     lib.akua_pbf_last_error.restype = C.c_char_p
@@ -269,6 +272,16 @@ class PBFSolver:
         else:
             self._ck(self._lib.akua_pbf_step_iters(self._h, deltaTime, int(solverIterations), _vec3(boxMin),
                                                    _vec3(boxMax)), "step")
+
+    def advance(self, frameTime: float, deltaTime: float, boxMin, boxMax, maxStepsPerFrame: int = 3) -> int:
+        """Fixed-timestep accumulator loop of Application::run (Application.cpp:63-70); returns the steps taken."""
+        n = C.c_int32(0)
+        self._ck(self._lib.akua_pbf_advance(self._h, frameTime, deltaTime, maxStepsPerFrame, _vec3(boxMin), _vec3(boxMax),
+                                            C.byref(n)), "advance")
+        return int(n.value)
+
+    def run_steps(self, steps: int, deltaTime: float, boxMin, boxMax):
+        self._ck(self._lib.akua_pbf_run_steps(self._h, int(steps), deltaTime, _vec3(boxMin), _vec3(boxMax)), "run_steps")
 
     def setGravity(self, gravity):
         self.config.gravity[:] = [float(x) for x in gravity]

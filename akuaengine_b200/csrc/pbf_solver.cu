@@ -105,6 +105,22 @@ struct akua_pbf_solver {
     int timedIters = 0;
     bool timingValid = false;
     SlabState slab;
+    // CUDA-graph replay of the whole step (single-GPU path). The step's kernel arguments depend on which half of each
+    // double buffer is current, so up to kGraphSlots graphs are cached, keyed by the pre-step state + parameters.
+    struct GraphEntry {
+        bool used = false;
+        uint64_t key[16] = {};
+        cudaGraphExec_t exec = nullptr;
+        // host-side state after the step (the pointer swaps and flags the captured calls performed)
+        float4 *pos, *posAlt, *vel, *velAlt, *xs, *xsAlt;
+        uint32_t *id, *idAlt, *keysSorted, *perm;
+        bool bucketsDirty;
+        int64_t launches, sortPasses;
+    };
+    static constexpr int kGraphSlots = 4;
+    GraphEntry graphs[kGraphSlots];
+    int graphNext = 0;
+    float accumulator = 0.0f;  // fixed-timestep driver (akua_pbf_advance)
 };
 
 namespace {
@@ -414,14 +430,75 @@ int phasePost(akua_pbf_solver* s, float dt) {
 
 #include "pbf_slab.inl"
 
+int stepEager(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax);
+
+void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax, uint64_t key[16]) {
+    auto f2 = [](float a, float b) { uint32_t x, y; std::memcpy(&x, &a, 4); std::memcpy(&y, &b, 4); return ((uint64_t)x << 32) | y; };
+    key[0] = (uint64_t)s->pos; key[1] = (uint64_t)s->vel; key[2] = (uint64_t)s->xs; key[3] = (uint64_t)s->id;
+    key[4] = (uint64_t)s->keysSorted; key[5] = (uint64_t)s->n; key[6] = ((uint64_t)iterations << 1) | (s->bucketsDirty ? 1 : 0);
+    key[7] = f2(dt, s->cfg.gravity[0]); key[8] = f2(s->cfg.gravity[1], s->cfg.gravity[2]);
+    key[9] = f2(bmin[0], bmin[1]); key[10] = f2(bmin[2], bmax[0]); key[11] = f2(bmax[1], bmax[2]);
+    key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math; key[15] = 0;
+}
+
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
     if (!s || !bmin || !bmax) return AKUA_ERR_INVALID;
     if (iterations < 0) { s->err = "solverIterations must be >= 0"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     rememberBox(s, bmin, bmax);
     if (s->slab.enabled) return stepSlab(s, dt, iterations, bmin, bmax);
-    int rc = layoutGrid(s, bmin, bmax);
+    int rc = layoutGrid(s, bmin, bmax);  // may (re)allocate the cell table: stays outside any capture
     if (rc) return rc;
+    if (!s->opt.use_graph || s->timing || s->n == 0) return stepEager(s, dt, iterations, bmin, bmax);
+    uint64_t key[16];
+    graphKey(s, dt, iterations, bmin, bmax, key);
+    akua_pbf_solver::GraphEntry* hit = nullptr;
+    for (auto& g : s->graphs)
+        if (g.used && std::memcmp(g.key, key, sizeof(key)) == 0) { hit = &g; break; }
+    if (!hit) {
+        // capture this step (the launches below are recorded, not executed), instantiate, then replay it
+        akua_pbf_solver::GraphEntry& g = s->graphs[s->graphNext];
+        s->graphNext = (s->graphNext + 1) % akua_pbf_solver::kGraphSlots;
+        if (g.used && g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        g.used = false;
+        // pre-state, restored before the replay so that capture + replay advance the state exactly once
+        float4 *pos = s->pos, *posAlt = s->posAlt, *vel = s->vel, *velAlt = s->velAlt, *xs = s->xs, *xsAlt = s->xsAlt;
+        uint32_t *id = s->id, *idAlt = s->idAlt, *ks = s->keysSorted, *pm = s->perm;
+        const bool dirty = s->bucketsDirty;
+        const int64_t launches0 = s->ctr.kernel_launches, steps0 = s->ctr.steps;
+        AK_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        rc = stepEager(s, dt, iterations, bmin, bmax);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != AKUA_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc == AKUA_OK) { s->err = std::string("graph capture: ") + cudaGetErrorString(ce); rc = AKUA_ERR_CUDA; }
+            cudaGetLastError();
+            return rc;
+        }
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { s->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return AKUA_ERR_CUDA; }
+        std::memcpy(g.key, key, sizeof(key));
+        g.pos = s->pos; g.posAlt = s->posAlt; g.vel = s->vel; g.velAlt = s->velAlt; g.xs = s->xs; g.xsAlt = s->xsAlt;
+        g.id = s->id; g.idAlt = s->idAlt; g.keysSorted = s->keysSorted; g.perm = s->perm; g.bucketsDirty = s->bucketsDirty;
+        g.launches = s->ctr.kernel_launches - launches0; g.sortPasses = s->ctr.sort_passes_last;
+        g.used = true;
+        s->pos = pos; s->posAlt = posAlt; s->vel = vel; s->velAlt = velAlt; s->xs = xs; s->xsAlt = xsAlt;
+        s->id = id; s->idAlt = idAlt; s->keysSorted = ks; s->perm = pm; s->bucketsDirty = dirty;
+        s->ctr.kernel_launches = launches0; s->ctr.steps = steps0;
+        hit = &g;
+    }
+    AK_CUDA(s, cudaGraphLaunch(hit->exec, s->stream));
+    s->pos = hit->pos; s->posAlt = hit->posAlt; s->vel = hit->vel; s->velAlt = hit->velAlt; s->xs = hit->xs; s->xsAlt = hit->xsAlt;
+    s->id = hit->id; s->idAlt = hit->idAlt; s->keysSorted = hit->keysSorted; s->perm = hit->perm; s->bucketsDirty = hit->bucketsDirty;
+    s->ctr.kernel_launches += hit->launches; s->ctr.sort_passes_last = hit->sortPasses; s->ctr.steps++;
+    s->ctr.graph_replays++;
+    return AKUA_OK;
+}
+
+int stepEager(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
+    int rc;
     mark(s, PH_PREDICT);
     if ((rc = phasePredictKey(s, dt, true, true))) return rc;            // PBFSolver.cpp:30 (+ K2)
     mark(s, PH_SORT);
@@ -507,7 +584,7 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     s->nbrStride = (uint32_t)((cap + 31) / 32 * 32);
     AK_CUDA(s, dalloc(&s->nbrList, (size_t)s->nbrStride * (size_t)((cfg->maxNeighbours + 3) / 4 * 4)));
     AK_CUDA(s, dalloc(&s->nbrCount, cap));
-    s->sortWs.maxTiles = rsort::tiles_for(cap);
+    s->sortWs.maxTiles = rsort::max_tiles_for_capacity(cap);
     AK_CUDA(s, dalloc(&s->sortWs.tileHist, (size_t)256 * s->sortWs.maxTiles));
     AK_CUDA(s, dalloc(&s->sortWs.binTotal, 256));
     AK_CUDA(s, dalloc(&s->partSum, 1024)); AK_CUDA(s, dalloc(&s->partMax, 1024));
@@ -547,6 +624,7 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
                     s->omegaLen, s->omega, s->dpos, s->color, s->size, s->keysUnsorted, s->keyA, s->keyB, s->valA, s->valB,
                     s->bucketStart, s->cellRange, s->nbrList, s->nbrCount, s->sortWs.tileHist, s->sortWs.binTotal,
                     s->aosStage, s->partSum, s->partMax};
+    for (auto& g : s->graphs) if (g.used && g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : ptrs) if (p) cudaFree(p);
     {
         SlabState& sl = s->slab;
@@ -571,6 +649,29 @@ int akua_pbf_step(akua_pbf_solver* s, float dt, const float boxMin[3], const flo
 int akua_pbf_step_iters(akua_pbf_solver* s, float dt, int32_t iters, const float boxMin[3], const float boxMax[3]) {
     if (!s) return AKUA_ERR_INVALID;
     return stepImpl(s, dt, iters, boxMin, boxMax);
+}
+// Fixed-timestep driver: the accumulator loop of Application::run (src/Application/Application.cpp:37-70), headless.
+int akua_pbf_advance(akua_pbf_solver* s, float frameTime, float deltaTime, int32_t maxStepsPerFrame, const float boxMin[3],
+                     const float boxMax[3], int32_t* stepsDone) {
+    if (!s || !(deltaTime > 0.0f) || frameTime < 0.0f) return AKUA_ERR_INVALID;
+    s->accumulator += frameTime;
+    int n = 0;
+    while (s->accumulator >= deltaTime && n < maxStepsPerFrame) {   // Application.cpp:63-70
+        int rc = stepImpl(s, deltaTime, s->cfg.solverIterations, boxMin, boxMax);
+        if (rc) return rc;
+        s->accumulator -= deltaTime;
+        n++;
+    }
+    if (stepsDone) *stepsDone = n;
+    return AKUA_OK;
+}
+int akua_pbf_run_steps(akua_pbf_solver* s, int32_t steps, float deltaTime, const float boxMin[3], const float boxMax[3]) {
+    if (!s || steps < 0) return AKUA_ERR_INVALID;
+    for (int i = 0; i < steps; i++) {
+        int rc = stepImpl(s, deltaTime, s->cfg.solverIterations, boxMin, boxMax);
+        if (rc) return rc;
+    }
+    return AKUA_OK;
 }
 int akua_pbf_set_gravity(akua_pbf_solver* s, const float g[3]) {
     if (!s || !g) return AKUA_ERR_INVALID;

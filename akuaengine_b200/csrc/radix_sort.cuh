@@ -15,14 +15,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 namespace akua {
 namespace rsort {
 
 constexpr int kThreads = 256;
-constexpr int kItems = 16;
-constexpr int kTile = kThreads * kItems;  // 4096 keys per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kWarpSpan = 32 * kItems;    // keys handled by one warp (contiguous -> stability)
+// Keys per thread is a template parameter: 16 (4096-key tiles) for large inputs, 4 (1024-key tiles) below ~8 M keys so
+// that the count / scatter grids still fill 148 SMs several times over (at 1 M keys a 4096-key tiling is only 245 CTAs).
+constexpr int kItemsLarge = 16, kItemsSmall = 4;
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -30,8 +32,10 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+template <int kItems>
 __global__ void __launch_bounds__(kThreads) k_count(const uint32_t* __restrict__ keys, uint32_t n, int shift,
                                                     uint32_t* __restrict__ tileHist, uint32_t numTiles) {
+    constexpr int kTile = kThreads * kItems;
     __shared__ uint32_t hist[256];
     const int tid = threadIdx.x, lane = tid & 31;
     hist[tid] = 0;
@@ -88,12 +92,14 @@ __global__ void __launch_bounds__(kThreads) k_scan(uint32_t* __restrict__ tileHi
     if (threadIdx.x == 0) binTotal[blockIdx.x] = carry;
 }
 
-template <bool FIRST>  // FIRST: input indices are implicit (idx itself)
+template <bool FIRST, int kItems>  // FIRST: input indices are implicit (idx itself)
 __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict__ keysIn,
                                                       const uint32_t* __restrict__ valsIn,
                                                       uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                       uint32_t n, int shift, const uint32_t* __restrict__ tileHist,
                                                       uint32_t numTiles, const uint32_t* __restrict__ binTotal) {
+    constexpr int kTile = kThreads * kItems;
+    constexpr int kWarpSpan = 32 * kItems;  // keys handled by one warp (contiguous -> stability)
     __shared__ uint32_t warpCnt[kWarps][256];  // per-warp running digit counts, then exclusive warp prefixes
     __shared__ uint32_t tileBase[256];         // exclusive prefix of this tile's digit counts (slot of a digit's run in smem)
     __shared__ uint32_t globalBase[256];       // where this tile's run of each digit starts in the output
@@ -175,7 +181,17 @@ struct Workspace {
     uint32_t maxTiles = 0;
 };
 
-inline uint32_t tiles_for(uint64_t n) { return (uint32_t)((n + kTile - 1) / kTile); }
+constexpr uint64_t kSmallLimit = 8u << 20;
+inline int items_for(uint64_t n) { return n < kSmallLimit ? kItemsSmall : kItemsLarge; }
+inline uint32_t tiles_for(uint64_t n) { uint64_t t = (uint64_t)kThreads * items_for(n); return (uint32_t)((n + t - 1) / t); }
+// workspace must hold the tiling of any n <= capacity (the small tiling of a small n can need more tiles than the
+// large tiling of the capacity)
+inline uint32_t max_tiles_for_capacity(uint64_t cap) {
+    uint64_t small = std::min<uint64_t>(cap, kSmallLimit - 1);
+    uint64_t a = (small + (uint64_t)kThreads * kItemsSmall - 1) / ((uint64_t)kThreads * kItemsSmall);
+    uint64_t b = (cap + (uint64_t)kThreads * kItemsLarge - 1) / ((uint64_t)kThreads * kItemsLarge);
+    return (uint32_t)std::max<uint64_t>(std::max(a, b), 1);
+}
 inline int passes_for_bits(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
 
 // Sorts n (key, index) pairs. keysIn is preserved. Results land in (*keysOut, *valsOut), which point into bufA or bufB.
@@ -184,6 +200,7 @@ inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, ui
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
                       uint32_t** valsOut) {
     const uint32_t numTiles = tiles_for(n);
+    const bool small = items_for(n) == kItemsSmall;
     const int passes = passes_for_bits(keyBits);
     const uint32_t* kin = keysIn;
     const uint32_t* vin = nullptr;
@@ -192,12 +209,13 @@ inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, ui
     int launches = 0;
     for (int p = 0; p < passes; p++) {
         int shift = 8 * p;
-        k_count<<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
+        if (small) k_count<kItemsSmall><<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
+        else       k_count<kItemsLarge><<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
         k_scan<<<256, kThreads, 0, st>>>(ws.tileHist, numTiles, ws.binTotal);
-        if (p == 0)
-            k_scatter<true><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal);
-        else
-            k_scatter<false><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal);
+#define AK_SCATTER(F, I) k_scatter<F, I><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal)
+        if (p == 0) { if (small) AK_SCATTER(true, kItemsSmall); else AK_SCATTER(true, kItemsLarge); }
+        else        { if (small) AK_SCATTER(false, kItemsSmall); else AK_SCATTER(false, kItemsLarge); }
+#undef AK_SCATTER
         launches += 3;
         kin = kout;
         vin = vout;

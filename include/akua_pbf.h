@@ -97,6 +97,13 @@ int akua_pbf_step(akua_pbf_solver* s, float deltaTime, const float boxMin[3], co
 /* step(dt, solverIterations) shape named by the north-star: same as akua_pbf_step with an explicit iteration count. */
 int akua_pbf_step_iters(akua_pbf_solver* s, float deltaTime, int32_t solverIterations, const float boxMin[3],
                         const float boxMax[3]);
+/* Headless fixed-timestep driver: the accumulator loop of Application::run (src/Application/Application.cpp:37-70).
+ * accumulator += frameTime; while (accumulator >= deltaTime && steps < maxStepsPerFrame) step. MAX_STEPS_PER_FRAME is 3
+ * in the reference (Application.cpp:19). Steps replay a captured CUDA graph when options.use_graph is set. */
+int akua_pbf_advance(akua_pbf_solver* s, float frameTime, float deltaTime, int32_t maxStepsPerFrame, const float boxMin[3],
+                     const float boxMax[3], int32_t* stepsDone);
+/* `steps` back-to-back steps of deltaTime (asynchronous). */
+int akua_pbf_run_steps(akua_pbf_solver* s, int32_t steps, float deltaTime, const float boxMin[3], const float boxMax[3]);
 /* void PBFSolver::setGravity(glm::vec3) — PBFSolver.h:18,29-31 */
 int akua_pbf_set_gravity(akua_pbf_solver* s, const float gravity[3]);
 int akua_pbf_sync(akua_pbf_solver* s);
@@ -200,6 +207,7 @@ typedef struct akua_pbf_counters {
     int64_t sort_passes_last; /* radix passes used by the last neighbour phase */
     int64_t num_cells;        /* linear grid cells (LINEAR_CELL) or tableSize (REFERENCE_HASH) */
     int64_t h2d_bytes, d2h_bytes; /* bytes moved by upload_* / download_* / debug_get since creation */
+    int64_t graph_replays;    /* steps executed by replaying a captured CUDA graph */
 } akua_pbf_counters;
 int akua_pbf_get_counters(const akua_pbf_solver* s, akua_pbf_counters* out);
 /* Timing of the phases of the LAST akua_pbf_step call, from CUDA events recorded on the solver's stream when

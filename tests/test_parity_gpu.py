@@ -172,7 +172,7 @@ def test_origin_corner_hash_quirk():
             assert len(mine) == len(set(mine)) and set(mine) == ref_sets[pid]
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 33, 4095, 4096, 4097, 70001])
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 1023, 1024, 1025, 4095, 4096, 4097, 70001])
 @pytest.mark.parametrize("mode", MODES)
 def test_sort_and_ranges_on_ragged_sizes(n, mode):
     """Radix sort + range detection at sizes around the sort tile (4096) and warp boundaries, incl. empty input."""
@@ -220,6 +220,41 @@ def test_hash_and_linear_modes_agree_on_a_trajectory():
         s.close()
     assert np.abs(outs[0][0][:, :3] - outs[1][0][:, :3]).max() / pl.H < 2e-4
     assert np.abs(outs[0][1][:, :3] - outs[1][1][:, :3]).max() / (pl.H / 0.0083) < 2e-4
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_graph_replay_is_bit_identical_to_eager_launches(mode):
+    """The CUDA-graph replay of the step (options.use_graph) must leave exactly the state the eager launches leave."""
+    init, bmin, bmax = scenes.dam_break(16)
+    outs = []
+    for use_graph in (False, True):
+        s = PBFSolver(len(init), key_mode=mode, use_graph=use_graph)
+        s.upload_particles(init)
+        for k in range(7):
+            if k == 4:
+                s.setGravity([1.0, -9.8, 0.5])  # parameter change: the cached graphs must not be reused
+            s.step(0.0083, bmin, bmax)
+        outs.append(s.download_particles())
+        c = s.counters()
+        assert c["steps"] == 7 and (c["graph_replays"] == 7 if use_graph else c["graph_replays"] == 0)
+        assert c["kernel_launches"] > 7 * 15
+        s.close()
+    assert outs[0].tobytes() == outs[1].tobytes()
+
+
+def test_fixed_timestep_driver_matches_reference_accumulator_loop():
+    """akua_pbf_advance = the accumulator loop of Application::run (Application.cpp:63-70), MAX_STEPS_PER_FRAME = 3."""
+    init, bmin, bmax = scenes.dam_break(10)
+    s = PBFSolver(len(init)); s.upload_particles(init)
+    dt = 0.0083
+    assert s.advance(0.020, dt, bmin, bmax) == 2          # 0.020 -> two steps, 0.0034 left
+    assert s.advance(0.005, dt, bmin, bmax) == 1          # 0.0084 -> one step
+    assert s.advance(0.100, dt, bmin, bmax) == 3          # capped at 3 steps per frame
+    assert s.counters()["steps"] == 6
+    ref = PBFSolver(len(init)); ref.upload_particles(init)
+    ref.run_steps(6, dt, bmin, bmax)
+    assert s.download_particles().tobytes() == ref.download_particles().tobytes()
+    s.close(); ref.close()
 
 
 def test_aos108_roundtrip_and_payload_follow_particles():

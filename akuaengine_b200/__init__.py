@@ -96,7 +96,7 @@ class DBG:
 ABI_SYMBOLS = [
     "akua_pbf_abi_version", "akua_pbf_default_config", "akua_pbf_default_corr", "akua_pbf_default_options",
     "akua_pbf_create", "akua_pbf_destroy", "akua_pbf_step", "akua_pbf_step_iters", "akua_pbf_set_gravity",
-    "akua_pbf_advance", "akua_pbf_run_steps",
+    "akua_pbf_advance", "akua_pbf_run_steps", "akua_pbf_checkpoint_save", "akua_pbf_checkpoint_load",
     "akua_pbf_sync", "akua_pbf_last_error", "akua_pbf_num_particles", "akua_pbf_upload_aos108",
     "akua_pbf_download_aos108", "akua_pbf_export_aos108_device", "akua_pbf_upload_soa", "akua_pbf_download_soa", "akua_pbf_positions_device",
     "akua_pbf_velocities_device", "akua_pbf_host_alloc", "akua_pbf_host_free", "akua_pbf_phase_predict",
@@ -140,6 +140,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_set_gravity.argtypes = [vp, f3]
     lib.akua_pbf_advance.argtypes = [vp, C.c_float, C.c_float, C.c_int32, f3, f3, C.POINTER(C.c_int32)]
     lib.akua_pbf_run_steps.argtypes = [vp, C.c_int32, C.c_float, f3, f3]
+    lib.akua_pbf_checkpoint_save.argtypes = [vp, C.c_char_p]
+    lib.akua_pbf_checkpoint_load.argtypes = [vp, C.c_char_p]
     lib.akua_pbf_sync.argtypes = [vp]
     lib.akua_pbf_last_error.argtypes = [vp]
     lib.akua_pbf_last_error.restype = C.c_char_p
@@ -282,6 +284,12 @@ class PBFSolver:
 
     def run_steps(self, steps: int, deltaTime: float, boxMin, boxMax):
         self._ck(self._lib.akua_pbf_run_steps(self._h, int(steps), deltaTime, _vec3(boxMin), _vec3(boxMax)), "run_steps")
+
+    def save_checkpoint(self, path):
+        self._ck(self._lib.akua_pbf_checkpoint_save(self._h, str(path).encode()), "checkpoint_save")
+
+    def load_checkpoint(self, path):
+        self._ck(self._lib.akua_pbf_checkpoint_load(self._h, str(path).encode()), "checkpoint_load")
 
     def setGravity(self, gravity):
         self.config.gravity[:] = [float(x) for x in gravity]

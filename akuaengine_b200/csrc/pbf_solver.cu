@@ -768,6 +768,82 @@ void* akua_pbf_host_alloc(int64_t bytes) {
 }
 void akua_pbf_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// ---- checkpoint / resume (the reference keeps its state only in the GL VBO) ----
+namespace {
+struct CkptHeader {
+    char magic[8];          // "AKUAPBF1"
+    int64_t n;
+    akua_pbf_config cfg;
+    akua_corr_params corr;
+    int64_t steps;
+    float accumulator;
+    int32_t key_mode;
+};
+}
+int akua_pbf_checkpoint_save(akua_pbf_solver* s, const char* path) {
+    if (!s || !path) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    const size_t n = (size_t)s->n;
+    std::vector<float4> pos(n), vel(n), color(n);
+    std::vector<float> size(n);
+    std::vector<uint32_t> id(n);
+    if (n) {
+        AK_CUDA(s, cudaMemcpy(pos.data(), s->pos, n * 16, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(vel.data(), s->vel, n * 16, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(id.data(), s->id, n * 4, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(color.data(), s->color, n * 16, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(size.data(), s->size, n * 4, cudaMemcpyDeviceToHost));
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { s->err = std::string("checkpoint_save: cannot open ") + path; return AKUA_ERR_INVALID; }
+    CkptHeader h{};
+    std::memcpy(h.magic, "AKUAPBF1", 8);
+    h.n = (int64_t)n; h.cfg = s->cfg; h.corr = s->corr; h.steps = s->ctr.steps; h.accumulator = s->accumulator;
+    h.key_mode = s->opt.key_mode;
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
+    ok = ok && (n == 0 || (std::fwrite(pos.data(), 16, n, f) == n && std::fwrite(vel.data(), 16, n, f) == n &&
+                           std::fwrite(id.data(), 4, n, f) == n && std::fwrite(color.data(), 16, n, f) == n &&
+                           std::fwrite(size.data(), 4, n, f) == n));
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { s->err = "checkpoint_save: short write"; return AKUA_ERR_INVALID; }
+    return AKUA_OK;
+}
+int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
+    if (!s || !path) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { s->err = std::string("checkpoint_load: cannot open ") + path; return AKUA_ERR_INVALID; }
+    CkptHeader h{};
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "AKUAPBF1", 8) != 0) {
+        std::fclose(f); s->err = "checkpoint_load: not an AKUAPBF1 file"; return AKUA_ERR_INVALID;
+    }
+    if (h.n < 0 || h.n > s->capacity) { std::fclose(f); s->err = "checkpoint_load: particle count exceeds solver capacity"; return AKUA_ERR_INVALID; }
+    const size_t n = (size_t)h.n;
+    std::vector<float4> pos(n), vel(n), color(n);
+    std::vector<float> size(n);
+    std::vector<uint32_t> id(n);
+    bool ok = n == 0 || (std::fread(pos.data(), 16, n, f) == n && std::fread(vel.data(), 16, n, f) == n &&
+                         std::fread(id.data(), 4, n, f) == n && std::fread(color.data(), 16, n, f) == n &&
+                         std::fread(size.data(), 4, n, f) == n);
+    std::fclose(f);
+    if (!ok) { s->err = "checkpoint_load: truncated file"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (n) {
+        AK_CUDA(s, cudaMemcpy(s->pos, pos.data(), n * 16, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemcpy(s->xs, pos.data(), n * 16, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemcpy(s->vel, vel.data(), n * 16, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemcpy(s->id, id.data(), n * 4, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemcpy(s->color, color.data(), n * 16, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemcpy(s->size, size.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    s->n = h.n;
+    s->cfg.gravity[0] = h.cfg.gravity[0]; s->cfg.gravity[1] = h.cfg.gravity[1]; s->cfg.gravity[2] = h.cfg.gravity[2];
+    s->accumulator = h.accumulator;
+    s->ctr.steps = h.steps;
+    return AKUA_OK;
+}
+
 // ---- multi-GPU (x-slab) ----
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n) {
     if (!s || !ids || n != s->n) { if (s) s->err = "upload_ids: n must equal the live particle count"; return AKUA_ERR_INVALID; }

@@ -134,6 +134,13 @@ int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t
 const float* akua_pbf_positions_device(akua_pbf_solver* s);
 const float* akua_pbf_velocities_device(akua_pbf_solver* s);
 
+/* ---- checkpoint / resume ----
+ * Saves / restores the simulation state a step depends on: positions (+mass), velocities (+density), particle ids,
+ * payload (color, size), gravity, step count and the fixed-timestep accumulator. Particle order is preserved, so a run
+ * resumed from a checkpoint continues bit-identically. Synchronises. */
+int akua_pbf_checkpoint_save(akua_pbf_solver* s, const char* path);
+int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path);
+
 /* ---- multi-GPU: x-slab domain decomposition, one process per GPU (no reference counterpart) ----
  * Each rank creates its own solver (capacity_factor > 1 leaves room for ghosts and arrivals), then:
  *   rank 0: akua_pbf_comm_unique_id(buf, 128) and broadcasts buf by any means (torch.distributed, MPI, a file);

@@ -257,6 +257,38 @@ def test_fixed_timestep_driver_matches_reference_accumulator_loop():
     s.close(); ref.close()
 
 
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    init, bmin, bmax = scenes.dam_break(12)
+    a = PBFSolver(len(init)); a.upload_particles(init)
+    a.run_steps(5, 0.0083, bmin, bmax)
+    a.save_checkpoint(tmp_path / "state.akpbf")
+    a.run_steps(5, 0.0083, bmin, bmax)
+    want = a.download_particles(); a.close()
+    b = PBFSolver(len(init)); b.load_checkpoint(tmp_path / "state.akpbf")
+    assert b.counters()["steps"] == 5
+    b.run_steps(5, 0.0083, bmin, bmax)
+    got = b.download_particles(); b.close()
+    for f in ("position", "velocity", "color", "size", "mass"):
+        assert np.array_equal(got[f], want[f]), f
+    from akuaengine_b200 import AkuaError
+    c = PBFSolver(10)
+    with pytest.raises(AkuaError):
+        c.load_checkpoint(tmp_path / "state.akpbf")   # more particles than this solver's capacity
+    with pytest.raises(AkuaError):
+        c.load_checkpoint(tmp_path / "missing.akpbf")
+    c.close()
+
+
+def test_scene_runner_reports_density_error(tmp_path):
+    import io
+    from akuaengine_b200.run import run
+    out = io.StringIO()
+    res = run({"scene": "dam_break", "n_side": 10, "steps": 20, "report_every": 5,
+               "gravity_schedule": [[0.0, 0, -9.8, 0], [0.05, 2.0, -9.8, 0]]}, out=out)
+    assert len(res["report"]) == 4 and res["summary"]["steps"] == 20
+    assert all(0 <= r["density_err_mean"] < 0.2 for r in res["report"])
+
+
 def test_aos108_roundtrip_and_payload_follow_particles():
     init, bmin, bmax = scenes.dam_break(12)
     init = with_ids(init)

@@ -939,8 +939,14 @@ int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const f
     if (boxMin && boxMax) rememberBox(s, boxMin, boxMax);
     int rc = layoutGrid(s, bmin, bmax);
     if (rc) return rc;
+    mark(s, PH_PREDICT);
     if ((rc = phasePredictKey(s, 0.0f, false, true))) return rc;  // keys from the current x* (K2)
-    return phaseSortReorderLists(s);
+    mark(s, PH_SORT);
+    if ((rc = phaseSortReorderLists(s))) return rc;
+    mark(s, PH_SOLVE); mark(s, PH_POST); mark(s, PH_END);            // so akua_pbf_last_step_timing covers this call too
+    s->timedIters = 0;
+    s->timingValid = s->timing;
+    return AKUA_OK;
 }
 int akua_pbf_phase_solve(akua_pbf_solver* s, int32_t iters, const float boxMin[3], const float boxMax[3]) {
     if (!s || !boxMin || !boxMax || iters < 0) return AKUA_ERR_INVALID;

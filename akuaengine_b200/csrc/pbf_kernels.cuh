@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
                                                   const float4* __restrict__ omega, const float4* __restrict__ dpos,
                                                   const float* __restrict__ density, const float* __restrict__ lambda,
                                                   const uint32_t* __restrict__ keys, const float4* __restrict__ color,
-                                                  const float* __restrict__ size, const uint32_t* __restrict__ id) {
+                                                  const float* __restrict__ size, const uint32_t* __restrict__ id,
+                                                  int payloadById) {
     __shared__ uint32_t sm[256 * kAosWords];
     const uint32_t base = blockIdx.x * 256u;
     const uint32_t count = min(256u, n - base);
@@ -536,8 +537,9 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
         const uint32_t i = base + threadIdx.x;
         float* f = reinterpret_cast<float*>(sm + threadIdx.x * kAosWords);
         float4 p = pos[i], v = vel[i], x = xs[i], o = omega[i], d = dpos[i];
+        // slab mode: ids are global and the payload is not migrated -> the scene defaults of Application.cpp:186-187
         uint32_t pid = id[i];
-        float4 c = color[pid];
+        float4 c = payloadById ? color[pid] : make_float4(0.f, 0.f, 1.f, 1.f);
         f[0] = p.x; f[1] = p.y; f[2] = p.z;
         f[3] = v.x; f[4] = v.y; f[5] = v.z;
         f[6] = x.x; f[7] = x.y; f[8] = x.z;
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
         f[18] = p.w; f[19] = density[i]; f[20] = lambda[i];
         sm[threadIdx.x * kAosWords + 21] = keys[i];
         f[22] = c.x; f[23] = c.y; f[24] = c.z; f[25] = c.w;
-        f[26] = size[pid];
+        f[26] = payloadById ? size[pid] : 50.0f;
     }
     __syncthreads();
     uint32_t* dst = aos + (size_t)base * kAosWords;

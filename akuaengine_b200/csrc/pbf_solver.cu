@@ -709,7 +709,7 @@ int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
     int rc = ensureStage(s);
     if (rc) return rc;
     k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
-        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id, s->slab.enabled ? 0 : 1);
     AK_LAUNCH_CHECK(s, "k_pack_aos");
     AK_CUDA(s, cudaMemcpyAsync(dst, s->aosStage, (size_t)n * 108, cudaMemcpyDeviceToHost, s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -722,7 +722,7 @@ int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t 
     AK_CUDA(s, cudaSetDevice(s->device));
     if (n == 0) return AKUA_OK;
     k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)device_dst, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
-        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id, s->slab.enabled ? 0 : 1);
     AK_LAUNCH_CHECK(s, "k_pack_aos");
     return AKUA_OK;
 }

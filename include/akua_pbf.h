@@ -150,7 +150,9 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path);
  *           upload the owned particles (upload_* sets the live count; akua_pbf_upload_ids gives them global ids);
  *           akua_pbf_step(...) with the SAME box on every rank. It migrates particles whose predicted position left the
  *           slab, exchanges ghost planes over NCCL/NVLink (x*, lambda per iteration; v, |omega| post-solve) and steps
- *           the owned particles. Downloads return the owned particles; akua_pbf_num_particles is the owned count. */
+ *           the owned particles. Downloads return the owned particles; akua_pbf_num_particles is the owned count.
+ *           The render payload (color, size) is not migrated between ranks: AoS downloads in slab mode carry the
+ *           reference scene's defaults (blue, 50 — Application.cpp:186-187); ids are what identifies a particle. */
 int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);

@@ -303,7 +303,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, n_side=None, steps=2):
+def cpu_baseline(args, n_side=None, steps=8):
     """The CPU port (oracle/pbf_oracle.cpp, OpenMP) on a bounded sample of the same workload."""
     from akuaengine_b200 import scenes
     from oracle import PortOracle, param_block

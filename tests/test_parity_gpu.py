@@ -408,3 +408,28 @@ def test_config2_1m_vs_live_reference_1_and_10_steps():
             golden[f"step{k}_velocity"] = p["velocity"].copy(); golden[f"step{k}_density"] = p["density"].copy()
     ref.close()
     check_traj(pl.trajectory_report(init, bmin, bmax, params, dt, golden, key_mode=KEY_LINEAR_CELL))
+
+
+def test_config3_16m_vs_live_reference_1_step():
+    """Config 3 (16 003 008 particles, the largest size the reference's int tableSize allows) against the unmodified
+    reference kernels run live: positions / velocities after one full step, matched by particle id."""
+    from oracle import REF_LIB, RefOracle, param_block
+    if not REF_LIB.exists():
+        pytest.skip("oracle/_ref/libakua_ref.so not present")
+    init, bmin, bmax = scenes.dam_break(252)
+    init = with_ids(init)                      # ids < 2^24 are exact in a float
+    params = param_block()
+    dt = 0.0083
+    ref = RefOracle(init, params)
+    ref.step(dt, bmin, bmax)
+    p = ref.download()
+    ref.close()
+    golden = {"step1_id": pl.ids_of(p), "step1_position": p["position"].copy(), "step1_velocity": p["velocity"].copy(),
+              "step1_density": p["density"].copy()}
+    del p
+    rep = pl.trajectory_report(init, bmin, bmax, params, dt, golden, steps=(1,), key_mode=KEY_LINEAR_CELL)
+    # coordinates reach 37.8 here: one float32 ulp of a position is 3.8e-6 m = 3.8e-5 h, so the 1-step tolerance is the
+    # larger of 2e-5 h and two position ulps (velocities inherit it through v = (x* - x) / dt)
+    tol = max(STEP1_TOL, 2.0 * float(np.spacing(np.float32(bmax.max()))) / pl.H)
+    assert rep["step1_pos_max_rel_h"] < tol and rep["step1_vel_max_rel"] < tol, rep
+    assert rep["step1_pos_rms_rel_h"] < 1e-6 and rep["step1_vel_rms_rel"] < 1e-6, rep

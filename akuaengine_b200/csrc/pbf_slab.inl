@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -34,7 +35,7 @@ const char* loadNccl() {
     if (!g_nccl.field) return "libnccl is missing " name;
     AK_SYM(GetUniqueId, "ncclGetUniqueId") AK_SYM(CommInitRank, "ncclCommInitRank") AK_SYM(CommDestroy, "ncclCommDestroy")
     AK_SYM(Send, "ncclSend") AK_SYM(Recv, "ncclRecv") AK_SYM(GroupStart, "ncclGroupStart") AK_SYM(GroupEnd, "ncclGroupEnd")
-    AK_SYM(GetErrorString, "ncclGetErrorString")
+    AK_SYM(GetErrorString, "ncclGetErrorString") AK_SYM(AllReduce, "ncclAllReduce")
 #undef AK_SYM
     g_nccl.lib = lib;
     return nullptr;
@@ -279,5 +280,60 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     mark(s, PH_END);
     s->timingValid = s->timing;
     s->ctr.steps++;
+    return AKUA_OK;
+}
+
+// Re-balances the slab boundaries from the current per-x-plane particle counts of all ranks (collective: every rank
+// calls it at the same step). The owned particles are sorted by x plane after a step, so each rank histograms its own
+// planes with binary searches, the histograms are summed with one ncclAllReduce, and every rank computes the same new
+// boundaries (akua_slab_partition). A boundary may only move inside the two slabs it separates, and by no more
+// particles than the migration buffers hold, so the ordinary per-step migration of the NEXT step performs the transfer.
+int slabRebalance(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.enabled || !s->haveBox) { s->err = "rebalance: slab mode with at least one completed step required"; return AKUA_ERR_INVALID; }
+    const GridParams& G = s->grid;
+    const int gx = G.gridDim.x, R = sl.nranks;
+    const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
+    const size_t words = (size_t)gx + R;  // [0,gx): plane counts; [gx, gx+R): current lower bounds (grid-relative)
+    if (words > sl.histCap) {
+        if (sl.dHist) cudaFree(sl.dHist);
+        if (sl.hHist) cudaFreeHost(sl.hHist);
+        sl.dHist = nullptr; sl.hHist = nullptr;
+        AK_CUDA(s, dalloc(&sl.dHist, words));
+        AK_CUDA(s, cudaMallocHost((void**)&sl.hHist, words * sizeof(unsigned long long)));
+        sl.histCap = words;
+    }
+    AK_CUDA(s, cudaMemsetAsync(sl.dHist, 0, words * sizeof(unsigned long long), s->stream));
+    const uint32_t n = (uint32_t)s->n;
+    slab::k_plane_hist<<<(gx + 255) / 256, 256, 0, s->stream>>>(s->keysSorted, n, planeCells, gx, sl.dHist);
+    AK_LAUNCH_CHECK(s, "k_plane_hist");
+    const int curLo = sl.rank == 0 ? 0 : std::min(std::max(sl.xLoAbs - G.gridMin.x, 0), gx);
+    unsigned long long lo64 = (unsigned long long)curLo;
+    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
+    int rc;
+    if ((rc = slabCommAfterMain(s))) return rc;
+    AK_NCCL(s, g_nccl.AllReduce(sl.dHist, sl.dHist, words, ncclUint64, ncclSum, (ncclComm_t)sl.comm, sl.commStream));
+    AK_CUDA(s, cudaMemcpyAsync(sl.hHist, sl.dHist, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.commStream));
+    AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
+    std::vector<int64_t> hist(gx);
+    for (int x = 0; x < gx; x++) hist[x] = (int64_t)sl.hHist[x];
+    std::vector<int32_t> bounds(R + 1), old(R + 1);
+    if (akua_slab_partition(hist.data(), gx, R, bounds.data()) != AKUA_OK) { s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID; }
+    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[gx + r];
+    old[0] = 0; old[R] = gx;
+    // clamp: boundary r (between ranks r-1 and r) stays strictly inside (old[r-1], old[r+1]) and moves at most
+    // migCap/2 particles
+    const int64_t maxMove = (int64_t)sl.migCap / 2;
+    for (int r = 1; r < R; r++) {
+        int b = std::min(std::max(bounds[r], old[r - 1] + 1), old[r + 1] - 1);
+        int64_t moved = 0;
+        if (b > old[r]) { int x = old[r]; while (x < b && moved + hist[x] <= maxMove) { moved += hist[x]; x++; } b = x; }
+        else if (b < old[r]) { int x = old[r]; while (x > b && moved + hist[x - 1] <= maxMove) { moved += hist[x - 1]; x--; } b = x; }
+        bounds[r] = b;
+    }
+    // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
+    sl.xLoAbs = G.gridMin.x + bounds[sl.rank];
+    sl.xHiAbs = G.gridMin.x + bounds[sl.rank + 1];
+    sl.rebalances++;
     return AKUA_OK;
 }

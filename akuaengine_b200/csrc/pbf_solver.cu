@@ -57,6 +57,9 @@ struct SlabState {
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
     cudaEvent_t pending = nullptr;         // completion of the last asynchronous x* (/v) ghost exchange
+    unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
+    size_t histCap = 0;
+    int64_t rebalances = 0;
 };
 
 struct akua_pbf_solver {
@@ -631,6 +634,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         void* sp[] = {sl.dCounts, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR};
         for (void* p : sp) if (p) cudaFree(p);
         if (sl.hCounts) cudaFreeHost(sl.hCounts);
+        if (sl.dHist) cudaFree(sl.dHist);
+        if (sl.hHist) cudaFreeHost(sl.hHist);
         if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
         for (int e = 0; e < SlabState::kEvents; e++) if (sl.evPool[e]) cudaEventDestroy(sl.evPool[e]);
         if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
@@ -894,6 +899,11 @@ int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi) {
     if (xCellHi <= xCellLo) { s->err = "set_slab: empty interval"; return AKUA_ERR_INVALID; }
     s->slab.xLoAbs = xCellLo; s->slab.xHiAbs = xCellHi; s->slab.enabled = true;
     return AKUA_OK;
+}
+int akua_pbf_rebalance(akua_pbf_solver* s) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    return slabRebalance(s);
 }
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
     if (!s || !out) return AKUA_ERR_INVALID;

@@ -109,6 +109,23 @@ __global__ void k_plane_counts(const uint32_t* __restrict__ keysSorted, uint32_t
     }
     counts[2 + t] = t == 0 ? lo : nOwn - lo;
 }
+// Per-x-plane population of the owned (key-sorted) particles: hist[x] = #{ i : key_i / planeCells == x }, by two binary
+// searches per plane (one thread per plane). Used to re-balance the slab boundaries.
+__global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells,
+                                                    int gx, unsigned long long* __restrict__ hist) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= gx) return;
+    auto lower = [&](uint64_t bound) {
+        uint32_t lo = 0, hi = nOwn;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)keysSorted[mid] < bound) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    hist[x] = (unsigned long long)(lower((uint64_t)(x + 1) * planeCells) - lower((uint64_t)x * planeCells));
+}
+
 // Cell ranges of a contiguous, already key-sorted block [begin, end) (ghost planes received from a neighbour).
 __global__ void __launch_bounds__(256) k_ranges(const uint32_t* __restrict__ keysSorted, uint32_t begin, uint32_t end,
                                                 uint2* __restrict__ cellRange) {

@@ -62,7 +62,7 @@ def broadcast_unique_id(dist, rank: int) -> np.ndarray:
 
 
 def setup_slab_solver(particles: np.ndarray, ids: np.ndarray, dist, rank: int, nranks: int, device: int, h: float = 0.1,
-                      capacity_factor: float = 1.5, **solver_kw) -> PBFSolver:
+                      capacity_factor: float = 1.5, skew: float = 0.0, **solver_kw) -> PBFSolver:
     """`particles` / `ids`: any subset of the scene held by this rank (e.g. a 1/nranks share, or everything on every rank
     with `ids` selecting a share); the routine keeps what falls into this rank's slab. Every particle of the scene must be
     held by exactly one rank whose slab it falls into — the simplest way is for every rank to pass the whole scene."""
@@ -70,6 +70,9 @@ def setup_slab_solver(particles: np.ndarray, ids: np.ndarray, dist, rank: int, n
     cols = x_columns(particles["position"][:, 0], h)
     col_min, hist = global_histogram(cols, None)  # callers pass the whole scene: the histogram is already global
     bounds = partition_columns(hist, nranks)
+    if skew:  # deliberately unbalanced start (tests of akua_pbf_rebalance): interior boundaries pulled towards column 0
+        for r in range(1, nranks):
+            bounds[r] = max(r, int(bounds[r] * (1.0 - skew)))
     lo, hi = slab_interval(rank, nranks, col_min, bounds)
     mine = (cols >= lo) & (cols < hi)
     if rank == 0:
@@ -77,7 +80,7 @@ def setup_slab_solver(particles: np.ndarray, ids: np.ndarray, dist, rank: int, n
     if rank == nranks - 1:
         mine |= cols >= hi
     own = np.ascontiguousarray(particles[mine])
-    cap_n = max(int(len(particles) / nranks), len(own), 1)
+    cap_n = max(int(len(particles) / nranks), len(own), 1) if not skew else len(particles)
     solver = PBFSolver(cap_n, device=device, capacity_factor=capacity_factor, **solver_kw)
     if nranks > 1:
         solver.comm_init(rank, nranks, broadcast_unique_id(dist, rank))

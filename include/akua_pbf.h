@@ -157,6 +157,10 @@ int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
+/* Collective (every rank, same step): moves the slab boundaries towards equal particle counts using the current
+ * per-x-plane populations (one small ncclAllReduce); the following step's migration transfers the particles. Call every
+ * few dozen steps for scenes whose fluid moves along x (dam break). */
+int akua_pbf_rebalance(akua_pbf_solver* s);
 /* out: 0 owned, 1 ghosts from left, 2 ghosts from right, 3 first-plane size, 4 last-plane size, 5 exchanges so far,
  * 6 bytes sent so far, 7 particles migrated in so far */
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]);

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--side", type=int, default=40)
     ap.add_argument("--vx", type=float, default=0.0, help="initial x velocity of every particle (forces migration)")
+    ap.add_argument("--rebalance-every", type=int, default=0)
+    ap.add_argument("--skew", type=float, default=0.0, help="start from deliberately unbalanced slabs (fraction moved to rank 0)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -39,12 +41,14 @@ def main():
     ids = np.arange(n, dtype=np.uint32)
     if args.scene == "tank":
         g = scenes.tank_gravity(15.0)
-    solver = setup_slab_solver(particles, ids, dist, rank, world, local, H, capacity_factor=2.0)
+    solver = setup_slab_solver(particles, ids, dist, rank, world, local, H, capacity_factor=2.0, skew=args.skew)
     if args.scene == "tank":
         solver.setGravity(g)
     counts0 = solver.n
-    for _ in range(args.steps):
+    for k in range(args.steps):
         solver.step(DT, bmin, bmax)
+        if args.rebalance_every and (k + 1) % args.rebalance_every == 0:
+            solver.rebalance()
     pos4, vel4, pid = solver.download()
     st = solver.slab_stats()
     # gather everything on rank 0
@@ -85,6 +89,11 @@ def main():
         print(f"slab({world}) vs single GPU after {args.steps} steps: dpos/h={dp:.3e} dvel/(h/dt)={dv:.3e} drho/rho0={drho:.3e} tol={tol}")
         if not (dp < tol and dv < tol):
             print("FAIL: slab result differs from the single-GPU result"); ok = False
+        if args.rebalance_every and world > 1:
+            imb = max(all_owned) / (sum(all_owned) / world)
+            print(f"imbalance after rebalancing: {imb:.3f}")
+            if imb > 1.15:
+                print("FAIL: slabs not balanced after rebalancing"); ok = False
         if world > 1 and st["exchanges"] == 0:
             print("FAIL: no exchanges happened"); ok = False
         mig = sum(int(t) for t in all_mig)

@@ -75,11 +75,12 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene,vx,steps", [("dam", 0.0, 8), ("tank", 0.0, 8), ("dam", 1.5, 20)])
-def test_two_gpu_slab_matches_single_gpu(scene, vx, steps):
+@pytest.mark.parametrize("scene,vx,steps,extra", [("dam", 0.0, 8, []), ("tank", 0.0, 8, []), ("dam", 1.5, 20, []),
+                                                  ("dam", 0.0, 30, ["--rebalance-every", "5", "--skew", "0.5"])])
+def test_two_gpu_slab_matches_single_gpu(scene, vx, steps, extra):
     if _gpu_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(REPO / "tests" / "mgpu_worker.py"), "--scene", scene, "--steps", str(steps), "--vx", str(vx)]
+           "--master-port", "29533", str(REPO / "tests" / "mgpu_worker.py"), "--scene", scene, "--steps", str(steps), "--vx", str(vx), *extra]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

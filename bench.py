@@ -277,6 +277,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "k_delta_apply (constraint pass B)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": PASS_B_BYTES, "launch_ms": pass_b_ms,
+                     "launch_ms_source": "CUDA events recorded on the solver's stream around every pass-A / pass-B launch of "
+                                         "10 further steps run right after the timed region (event pairs per launch "
+                                         "would perturb the graph-replayed timed region itself)",
                      "pass_a": {"kernel": "k_density_lambda", "launch_ms": pass_a_ms,
                                 "achieved": PASS_A_BYTES * n / (pass_a_ms * 1e-3) / 1e9},
                      "whole_step": {"algorithmic_bytes_per_particle": STEP_BYTES,

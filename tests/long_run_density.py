@@ -1,6 +1,6 @@
-"""Long-run statistics (north-star acceptance criterion): mean / max density-constraint error |rho/rho0 - 1| per step of
+"""TEST INFRASTRUCTURE (imports oracle/). Long-run statistics (north-star acceptance criterion): mean / max density-constraint error |rho/rho0 - 1| per step of
 the README dam break, this library vs the unmodified reference kernels (oracle/_ref), both on the GPU.
-    python tools/long_run_density.py [steps] > profiles/r01_long_run_density_error.json"""
+    python tests/long_run_density.py [steps] > profiles/r01_long_run_density_error.json"""
 import json
 import sys
 from pathlib import Path

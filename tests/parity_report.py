@@ -1,5 +1,5 @@
-"""Diagnostic run for a GPU box: golden generation, port-vs-reference check, CUDA-vs-reference parity, quick timings.
-Usage (under gpurun): python tools/parity_report.py [--golden] [--timing]"""
+"""TEST INFRASTRUCTURE (imports oracle/). Diagnostic run for a GPU box: golden generation, port-vs-reference check, CUDA-vs-reference parity, quick timings.
+Usage (under gpurun): python tests/parity_report.py [--golden] [--timing]"""
 import json
 import sys
 import time

@@ -439,13 +439,11 @@ def test_long_run_density_error_statistics_agree_with_reference():
     """North-star criterion for long runs: mean / max density-constraint error |rho/rho0 - 1| agree with the reference.
     Trajectories diverge chaotically after a few dozen steps (the reference even diverges from its own re-run: its XSPH
     kernel is a data race), so the statistics are compared, with thresholds set from the reference-vs-reference noise
-    floor measured by tools/long_run_density.py (profiles/r01_long_run_density_error.json: per-step mean error differs
+    floor measured by tests/long_run_density.py (profiles/r01_long_run_density_error.json: per-step mean error differs
     by 0.7 % on average / 2.5 % at most between two reference runs, the max error by 9 % on average)."""
     from oracle import REF_LIB
     if not REF_LIB.exists():
         pytest.skip("oracle/_ref/libakua_ref.so not present")
-    import sys
-    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
     from long_run_density import curves
     c = curves(200)
     ref_mean, ref_max = np.array(c["reference"]["mean"]), np.array(c["reference"]["max"])

@@ -136,10 +136,10 @@ SweepSpans sweepSpans(const akua_pbf_solver* s) {
     return sp;
 }
 
-// Exchanges two u32 counters with each neighbour: counts[srcL], counts[srcR] go left / right; what the neighbours sent
-// lands in counts[dstL] (from the left rank) and counts[dstR] (from the right rank). Then copies all 8 counters to the
-// host and waits — the one host synchronisation this costs.
-int slabSwapCounts(akua_pbf_solver* s, int srcL, int srcR, int dstL, int dstR) {
+// The one count exchange of a step: three u32 to each neighbour (assembled by k_mig_scan at dCounts[16..18] for the left
+// rank, [20..22] for the right rank), three from each (landing at [24..26] from the left, [28..30] from the right), then
+// all 32 counters go to the host — the only host synchronisation of the step.
+int slabSwapCounts(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
     ncclComm_t comm = (ncclComm_t)sl.comm;
@@ -147,15 +147,15 @@ int slabSwapCounts(akua_pbf_solver* s, int srcL, int srcR, int dstL, int dstR) {
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.GroupStart());
-    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcL, 4, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + srcR, 4, ncclUint8, sl.rank + 1, comm, st));
-    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstL, 4, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + dstR, 4, ncclUint8, sl.rank + 1, comm, st));
+    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + 16, 12, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + 20, 12, ncclUint8, sl.rank + 1, comm, st));
+    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + 24, 12, ncclUint8, sl.rank - 1, comm, st));
+    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + 28, 12, ncclUint8, sl.rank + 1, comm, st));
     AK_NCCL(s, g_nccl.GroupEnd());
-    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     AK_CUDA(s, cudaStreamSynchronize(st));
-    if (!hasL) sl.hCounts[dstL] = 0;
-    if (!hasR) sl.hCounts[dstR] = 0;
+    if (!hasL) sl.hCounts[24] = sl.hCounts[25] = sl.hCounts[26] = 0;
+    if (!hasR) sl.hCounts[28] = sl.hCounts[29] = sl.hCounts[30] = 0;
     return AKUA_OK;
 }
 
@@ -182,15 +182,27 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     mark(s, PH_SORT);
     const uint32_t blocks = std::max(1u, gridFor(n));
     if (blocks > sl.migBlocksCap) { s->err = "slab: migration scratch too small"; return AKUA_ERR_INVALID; }
-    slab::k_mig_count<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt);
+    if (xHi - xLo < 2 && sl.nranks > 1) { s->err = "slab must be at least two x planes wide"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaMemsetAsync(sl.dCounts + 2, 0, 4 * sizeof(uint32_t), s->stream));   // the four plane populations
+    slab::k_mig_count<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sl.dCounts + 2);
     AK_LAUNCH_CHECK(s, "k_mig_count");
-    slab::k_mig_scan<<<1, kBlock, 0, s->stream>>>(sl.blockCnt, blocks, sl.dCounts);
+    slab::k_mig_scan<<<1, 1024, 0, s->stream>>>(sl.blockCnt, blocks, sl.dCounts);
     AK_LAUNCH_CHECK(s, "k_mig_scan");
     slab::k_mig_pack<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sentinel, s->pos,
                                                        s->vel, s->xs, s->id, sl.sendL, sl.sendR, sl.migCap);
     AK_LAUNCH_CHECK(s, "k_mig_pack");
-    if ((rc = slabSwapCounts(s, 0, 1, 4, 5))) return rc;  // my leavers (0: left, 1: right) -> neighbours' arrivals
-    const uint32_t outL = sl.hCounts[0], outR = sl.hCounts[1], inL = sl.hCounts[4], inR = sl.hCounts[5];
+    if ((rc = slabSwapCounts(s))) return rc;
+    const uint32_t* hc = sl.hCounts;
+    if (hc[31]) { s->err = "slab: boundary-plane size prediction failed in the previous step (a particle crossed more than one slab?)"; return AKUA_ERR_INVALID; }
+    const uint32_t outL = hc[0], outR = hc[1], inL = hc[24], inR = hc[28];
+    // Post-migration plane sizes, known before the sort: my boundary planes = stayers + arrivals that land in them;
+    // a neighbour's facing plane (= my ghosts) = its stayers there + my leavers that land there. (Arrivals from the far
+    // side cannot reach the near plane: slabs are >= 2 planes wide and the stepper moves particles by << one slab.)
+    const bool hasLn = sl.rank > 0, hasRn = sl.rank + 1 < sl.nranks;
+    sl.nPlaneL = hasLn ? hc[2] + hc[25] : 0;
+    sl.nPlaneR = hasRn ? hc[3] + hc[29] : 0;
+    sl.nGhostL = hasLn ? hc[26] + hc[4] : 0;
+    sl.nGhostR = hasRn ? hc[30] + hc[5] : 0;
     if (sl.rank == 0 && outL) { s->err = "slab: internal error (leavers beyond the first rank)"; return AKUA_ERR_INVALID; }
     if (outL > sl.migCap || outR > sl.migCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
     if ((uint64_t)n + inL + inR > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
@@ -238,13 +250,9 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     std::swap(s->pos, s->posAlt); std::swap(s->vel, s->velAlt); std::swap(s->xs, s->xsAlt); std::swap(s->id, s->idAlt);
 
     // ---- 4. ghost planes: sizes, then x* of the neighbours' boundary planes, keyed and ranged in place ----
-    slab::k_plane_counts<<<1, 32, 0, s->stream>>>(s->keysSorted, nOwn, planeCells, xLo, xHi, sl.dCounts);
-    AK_LAUNCH_CHECK(s, "k_plane_counts");
-    if ((rc = slabSwapCounts(s, 2, 3, 6, 7))) return rc;  // my first/last plane sizes -> neighbours' ghost sizes
-    sl.nPlaneL = sl.rank > 0 ? sl.hCounts[2] : 0;
-    sl.nPlaneR = sl.rank + 1 < sl.nranks ? sl.hCounts[3] : 0;
-    sl.nGhostL = sl.hCounts[6];
-    sl.nGhostR = sl.hCounts[7];
+    slab::k_plane_verify<<<1, 32, 0, s->stream>>>(s->keysSorted, nOwn, planeCells, xLo, xHi, sl.nPlaneL, sl.nPlaneR,
+                                                 hasLn ? 1 : 0, hasRn ? 1 : 0, sl.dCounts);
+    AK_LAUNCH_CHECK(s, "k_plane_verify");
     const uint64_t nTot = (uint64_t)nOwn + sl.nGhostL + sl.nGhostR;
     if (nTot > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by ghosts (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
     if ((rc = slabExchangePlanes(s, s->xs))) return rc;
@@ -325,10 +333,12 @@ int slabRebalance(akua_pbf_solver* s) {
     // migCap/2 particles
     const int64_t maxMove = (int64_t)sl.migCap / 2;
     for (int r = 1; r < R; r++) {
-        int b = std::min(std::max(bounds[r], old[r - 1] + 1), old[r + 1] - 1);
+        // stay inside the two old slabs and keep every slab at least two planes wide
+        int b = std::min(std::max(bounds[r], std::max(old[r - 1] + 1, bounds[r - 1] + 2)), old[r + 1] - 2);
         int64_t moved = 0;
         if (b > old[r]) { int x = old[r]; while (x < b && moved + hist[x] <= maxMove) { moved += hist[x]; x++; } b = x; }
         else if (b < old[r]) { int x = old[r]; while (x > b && moved + hist[x - 1] <= maxMove) { moved += hist[x - 1]; x--; } b = x; }
+        if (b < bounds[r - 1] + 2) b = std::min(bounds[r - 1] + 2, old[r + 1] - 2);
         bounds[r] = b;
     }
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval

@@ -44,7 +44,8 @@ struct SlabState {
     int rank = 0, nranks = 1;
     void* comm = nullptr;                  // ncclComm_t
     int xLoAbs = 0, xHiAbs = 0;            // owned absolute x cells [lo, hi)
-    uint32_t* dCounts = nullptr;           // device u32[8]: 0,1 leavers L/R; 2,3 my plane sizes; 4,5 arrivals; 6,7 ghost sizes
+    uint32_t* dCounts = nullptr;           // device u32[32]: 0,1 leavers L/R; 2..5 plane populations; 16..22 outgoing, 24..30
+                                           // incoming count messages; 31 sticky prediction-error flag
     uint32_t* hCounts = nullptr;           // pinned mirror
     uint32_t* blockCnt = nullptr;          // [2][migBlocksCap]
     uint32_t migBlocksCap = 0;
@@ -885,9 +886,9 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
         for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
     }
-    AK_CUDA(s, dalloc(&sl.dCounts, 8));
-    AK_CUDA(s, cudaMemsetAsync(sl.dCounts, 0, 8 * sizeof(uint32_t), s->stream));
-    AK_CUDA(s, cudaMallocHost((void**)&sl.hCounts, 8 * sizeof(uint32_t)));
+    AK_CUDA(s, dalloc(&sl.dCounts, 32));
+    AK_CUDA(s, cudaMemsetAsync(sl.dCounts, 0, 32 * sizeof(uint32_t), s->stream));
+    AK_CUDA(s, cudaMallocHost((void**)&sl.hCounts, 32 * sizeof(uint32_t)));
     AK_CUDA(s, dalloc(&sl.blockCnt, (size_t)2 * sl.migBlocksCap));
     AK_CUDA(s, dalloc(&sl.sendL, sl.migCap)); AK_CUDA(s, dalloc(&sl.sendR, sl.migCap));
     AK_CUDA(s, dalloc(&sl.recvL, sl.migCap)); AK_CUDA(s, dalloc(&sl.recvR, sl.migCap));
@@ -924,8 +925,9 @@ int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int3
     for (int r = 1; r < nranks; r++) {
         const int64_t target = (total * r + nranks / 2) / nranks;
         while (c < ncols && cum + hist[c] <= target) { cum += hist[c]; c++; }
-        // keep every slab at least one column wide and leave room for the remaining ranks
-        int lo = bounds[r - 1] + 1, hi = ncols - (nranks - r);
+        // keep every slab at least two columns wide (one when there are too few columns) and leave room for the rest
+        const int minW = ncols >= 2 * nranks ? 2 : 1;
+        int lo = bounds[r - 1] + minW, hi = ncols - minW * (nranks - r);
         int b = std::min(std::max(c, lo), hi);
         while (c < b) { cum += hist[c]; c++; }
         bounds[r] = b;

@@ -20,15 +20,32 @@ __device__ __forceinline__ int dest_of(uint32_t key, uint32_t planeCells, int xL
     return cx < xLo ? 0 : (cx >= xHi ? 2 : 1);
 }
 
-// Pass 1: per-CTA counts of leavers in each direction (deterministic compaction, no atomics).
+// Pass 1: per-CTA counts of leavers in each direction (deterministic compaction, no atomics on the compaction path),
+// plus the four plane populations that let every rank PREDICT its post-migration boundary-plane and ghost-plane sizes
+// from one count exchange (extra[0] stayers in my first plane, [1] stayers in my last plane, [2] leavers to the left that
+// land in the left rank's last plane, [3] leavers to the right that land in the right rank's first plane).
 __global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, uint32_t n, uint32_t planeCells,
-                                                   int xLo, int xHi, uint32_t* __restrict__ blockCnt /*[2][blocks]*/) {
-    __shared__ uint32_t sL[8], sR[8];
+                                                   int xLo, int xHi, uint32_t* __restrict__ blockCnt /*[2][blocks]*/,
+                                                   uint32_t* __restrict__ extra /*[4], zeroed*/) {
+    __shared__ uint32_t sL[8], sR[8], sE[4];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    int d = i < n ? dest_of(keys[i], planeCells, xLo, xHi) : 1;
+    if (threadIdx.x < 4) sE[threadIdx.x] = 0;
+    __syncthreads();
+    int cx = i < n ? (int)(keys[i] / planeCells) : xLo + 1;
+    int d = i < n ? (cx < xLo ? 0 : (cx >= xHi ? 2 : 1)) : 1;
     uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
+    uint32_t b0 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xLo);
+    uint32_t b1 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xHi - 1);
+    uint32_t b2 = __ballot_sync(0xffffffffu, d == 0 && cx == xLo - 1);
+    uint32_t b3 = __ballot_sync(0xffffffffu, d == 2 && cx == xHi);
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sL[warp] = __popc(bl); sR[warp] = __popc(br); }
+    if (lane == 0) {
+        sL[warp] = __popc(bl); sR[warp] = __popc(br);
+        if (b0) atomicAdd(&sE[0], (uint32_t)__popc(b0));
+        if (b1) atomicAdd(&sE[1], (uint32_t)__popc(b1));
+        if (b2) atomicAdd(&sE[2], (uint32_t)__popc(b2));
+        if (b3) atomicAdd(&sE[3], (uint32_t)__popc(b3));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t a = 0, b = 0;
@@ -36,22 +53,50 @@ __global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ 
         blockCnt[blockIdx.x] = a;
         blockCnt[gridDim.x + blockIdx.x] = b;
     }
+    if (threadIdx.x < 4 && sE[threadIdx.x]) atomicAdd(&extra[threadIdx.x], sE[threadIdx.x]);
 }
-// Pass 2 (one CTA): exclusive scan of the per-CTA counts in place; totals -> counts[0] (left), counts[1] (right).
-__global__ void __launch_bounds__(256) k_mig_scan(uint32_t* __restrict__ blockCnt, uint32_t blocks, uint32_t* __restrict__ counts) {
-    __shared__ uint32_t s8[8];
-    for (int dir = 0; dir < 2; dir++) {
-        uint32_t* row = blockCnt + (size_t)dir * blocks;
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base < blocks; base += 256) {
-            uint32_t idx = base + threadIdx.x;
-            uint32_t v = idx < blocks ? row[idx] : 0u, tot;
-            uint32_t ex = rsort::block_excl_scan_256(v, s8, &tot);
-            if (idx < blocks) row[idx] = carry + ex;
-            carry += tot;
+// Pass 2 (one CTA of 1024 threads): exclusive scan of the per-CTA counts in place, both directions at once; totals ->
+// counts[0] (left), counts[1] (right).
+__global__ void __launch_bounds__(1024) k_mig_scan(uint32_t* __restrict__ blockCnt, uint32_t blocks, uint32_t* __restrict__ counts) {
+    __shared__ uint32_t wsum[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t carry0 = 0, carry1 = 0;
+    for (uint32_t base = 0; base < blocks; base += 1024) {
+        const uint32_t idx = base + tid;
+        const uint32_t v0 = idx < blocks ? blockCnt[idx] : 0u, v1 = idx < blocks ? blockCnt[blocks + idx] : 0u;
+        uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
         }
-        if (threadIdx.x == 0) counts[dir] = carry;
+        if (lane == 31) { wsum[0][warp] = i0; wsum[1][warp] = i1; }
         __syncthreads();
+        if (warp == 0) {
+            uint32_t a = wsum[0][lane], b = wsum[1][lane], ia = a, ib = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t0 = __shfl_up_sync(0xffffffffu, ia, o), t1 = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) { ia += t0; ib += t1; }
+            }
+            wsum[0][lane] = ia - a; wsum[1][lane] = ib - b;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t off0 = wsum[0][warp], off1 = wsum[1][warp];
+        if (idx < blocks) { blockCnt[idx] = carry0 + off0 + i0 - v0; blockCnt[blocks + idx] = carry1 + off1 + i1 - v1; }
+        // chunk totals = exclusive offset of the last warp + its inclusive sum
+        __shared__ uint32_t tot[2];
+        if (tid == 1023) { tot[0] = off0 + i0; tot[1] = off1 + i1; }
+        __syncthreads();
+        carry0 += tot[0]; carry1 += tot[1];
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = carry0; counts[1] = carry1; }
+    // messages for the single count exchange: to the left rank {leavers, leavers landing in its last plane, my
+    // first-plane stayers} at counts[16..18]; to the right rank the mirror image at counts[20..22]
+    if (threadIdx.x == 0) {
+        counts[16] = counts[0]; counts[17] = counts[4]; counts[18] = counts[2];
+        counts[20] = counts[1]; counts[21] = counts[5]; counts[22] = counts[3];
     }
 }
 // Pass 3: leavers are copied (in index order) into the send buffers and get the sentinel key, which sorts them past the
@@ -94,20 +139,21 @@ __global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict_
     pos[i] = r.pos; vel[i] = r.vel; xs[i] = r.xs; id[i] = r.meta.x;
     keys[i] = linear_key(cell_of(r.xs.x, r.xs.y, r.xs.z, G.cellSize), G);
 }
-// counts[2] = number of owned particles in the first owned x-plane, counts[3] = in the last one (binary searches in the
-// sorted keys; two threads).
-__global__ void k_plane_counts(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells, int xLo, int xHi,
-                               uint32_t* __restrict__ counts) {
+// Verifies the predicted boundary-plane sizes against the sorted keys (binary searches; two threads): a mismatch sets
+// the sticky error word counts[31], which the host sees at the next step's count exchange.
+__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells, int xLo, int xHi,
+                               uint32_t predictFirst, uint32_t predictLast, int hasL, int hasR, uint32_t* __restrict__ counts) {
     int t = threadIdx.x;
     if (t > 1) return;
-    // first key of plane xLo+1 (t = 0) or of plane xHi-1 (t = 1)
     uint64_t bound = (uint64_t)(t == 0 ? (xLo + 1) : (xHi - 1)) * planeCells;
     uint32_t lo = 0, hi = nOwn;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if ((uint64_t)keysSorted[mid] < bound) lo = mid + 1; else hi = mid;
     }
-    counts[2 + t] = t == 0 ? lo : nOwn - lo;
+    uint32_t actual = t == 0 ? lo : nOwn - lo;
+    if (t == 0 && hasL && actual != predictFirst) counts[31] = 1;
+    if (t == 1 && hasR && actual != predictLast) counts[31] = 1;
 }
 // Per-x-plane population of the owned (key-sorted) particles: hist[x] = #{ i : key_i / planeCells == x }, by two binary
 // searches per plane (one thread per plane). Used to re-balance the slab boundaries.

@@ -17,10 +17,10 @@ def test_partition_is_balanced_and_contiguous(akua_lib):
     hist = rng.integers(0, 1000, 57).astype(np.int64)
     for nranks in (1, 2, 3, 4, 8):
         b = partition_columns(hist, nranks)
-        assert b[0] == 0 and b[-1] == len(hist) and np.all(np.diff(b) >= 1)
+        assert b[0] == 0 and b[-1] == len(hist) and np.all(np.diff(b) >= 2)   # slabs are at least two planes wide
         loads = np.array([hist[b[r]:b[r + 1]].sum() for r in range(nranks)])
         assert loads.sum() == hist.sum()
-        assert loads.max() <= hist.sum() / nranks + hist.max()  # within one column of perfect balance
+        assert loads.max() <= hist.sum() / nranks + 2 * hist.max()  # within two columns of perfect balance
     # degenerate: everything in one column still gives every rank a (possibly empty) column interval
     h2 = np.zeros(8, np.int64); h2[3] = 100
     b = partition_columns(h2, 4)

@@ -419,7 +419,10 @@ class PBFSolver:
         out = (C.c_int64 * 8)()
         self._ck(self._lib.akua_pbf_slab_stats(self._h, out), "slab_stats")
         names = ["owned", "ghost_left", "ghost_right", "plane_left", "plane_right", "exchanges", "bytes_sent", "migrated_in"]
-        return dict(zip(names, [int(x) for x in out]))
+        d = dict(zip(names, [int(x) for x in out]))
+        d["transport"] = "cuda-ipc p2p" if d["bytes_sent"] < 0 else "nccl"
+        d["bytes_sent"] = abs(d["bytes_sent"])
+        return d
 
     def stream_ptr(self) -> int:
         """cudaStream_t of the solver, e.g. for torch.cuda.ExternalStream."""

@@ -96,6 +96,66 @@ __device__ __forceinline__ bool span_index(const Span& sp, uint32_t& i) {
     return true;
 }
 
+// Fused compute + halo push (multi-GPU, CUDA-IPC transport): a boundary particle's result is also stored straight into the
+// neighbouring rank's ghost region through the peer-mapped pointer (NVLink P2P store), so no separate copy or
+// collective follows the sweep. dstL / dstR already point at the ghost region's first element; null = nothing to push.
+struct PeerPush {
+    void* dstL = nullptr;   // left rank: particles [0, nL) of this rank's owned range
+    void* dstR = nullptr;   // right rank: particles [startR, nOwn)
+    uint32_t nL = 0, startR = 0xffffffffu;
+};
+template <typename T>
+__device__ __forceinline__ void peer_push(const PeerPush& pp, uint32_t i, const T& v) {
+    if (pp.dstL && i < pp.nL) static_cast<T*>(pp.dstL)[i] = v;
+    if (pp.dstR && i >= pp.startR) static_cast<T*>(pp.dstR)[i - pp.startR] = v;
+}
+
+// In-kernel halo synchronisation for the fused path: a boundary sweep first waits (one thread per CTA, bounded spin) until
+// both neighbours have published the epoch of the ghost data it is about to read, and, when it has pushed its own
+// results, the LAST CTA to finish publishes this exchange's epoch in the neighbours' flag words. No extra kernels, no
+// copy engine, no collective: compute, communication and synchronisation are one launch.
+struct HaloSync {
+    const uint32_t* waitFlags = nullptr;   // this rank's flag words: [0] written by the left rank, [1] by the right rank
+    int waitL = 0, waitR = 0;
+    uint32_t waitEpoch = 0;
+    uint32_t* signalL = nullptr;           // neighbours' flag words to publish into (null: no neighbour / nothing pushed)
+    uint32_t* signalR = nullptr;
+    uint32_t signalEpoch = 0;
+    uint32_t* doneCounter = nullptr;       // CTA completion counter for this launch (zero before and after)
+    uint32_t* errWord = nullptr;
+};
+__device__ __forceinline__ void halo_wait(const HaloSync& hs) {
+    if (!hs.waitFlags) return;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int side = 0; side < 2; side++) {
+            if (!(side == 0 ? hs.waitL : hs.waitR)) continue;
+            const volatile uint32_t* f = hs.waitFlags + side;
+            while ((int32_t)(*f - hs.waitEpoch) < 0) {
+                if (clock64() - t0 > 4000000000LL) { *hs.errWord = 2; break; }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+// Call with ALL threads of the CTA (no early returns before it) once the CTA's pushes are issued.
+__device__ __forceinline__ void halo_signal(const HaloSync& hs) {
+    if (!hs.doneCounter) return;
+    __syncthreads();   // every thread's pushes happen-before thread 0's fence below (fences are cumulative)
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const uint32_t done = atomicAdd(hs.doneCounter, 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence_system();
+            if (hs.signalL) *(volatile uint32_t*)hs.signalL = hs.signalEpoch;
+            if (hs.signalR) *(volatile uint32_t*)hs.signalR = hs.signalEpoch;
+            *hs.doneCounter = 0;
+            __threadfence_system();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ neighbour list access
 __device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
     return ((size_t)(k >> 2) * stride + i) * 4 + (k & 3);
@@ -269,9 +329,11 @@ template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
                                                         const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                         float* __restrict__ density, float* __restrict__ lambda,
-                                                        SphParams P) {
+                                                        SphParams P, PeerPush pushLambda, HaloSync hs) {
+    halo_wait(hs);
     uint32_t i;
-    if (!span_index(sp, i)) return;
+    const bool live = span_index(sp, i);
+    if (live) {
     const float4 xi = xs[i];
     const uint32_t c = cnt[i];
     float rho = xi.w * P.selfW;
@@ -295,6 +357,9 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
     float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
     density[i] = rho;
     lambda[i] = lam;
+    peer_push(pushLambda, i, lam);
+    }
+    halo_signal(hs);
 }
 
 // ------------------------------------------------------------------------------------------------ K8 / K9 / K10 pieces
@@ -343,9 +408,12 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
                                                      const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                      SphParams P, BoxParams B, float4* __restrict__ dposOut,
                                                      float4* __restrict__ pos, float4* __restrict__ vel,
-                                                     const float* __restrict__ density, float dt) {
+                                                     const float* __restrict__ density, float dt, PeerPush pushX,
+                                                     PeerPush pushV, HaloSync hs) {
+    halo_wait(hs);
     uint32_t i;
-    if (!span_index(sp, i)) return;
+    const bool live = span_index(sp, i);
+    if (live) {
     const float4 xi = xsIn[i];
     const float li = lambda[i];
     const uint32_t c = cnt[i];
@@ -371,13 +439,18 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
     float y = collide_axis(xi.y + py, B.bmin.y, B.bmax.y, B);
     float z = collide_axis(xi.z + pz, B.bmin.z, B.bmax.z, B);
     xsOut[i] = make_float4(x, y, z, xi.w);
+    peer_push(pushX, i, make_float4(x, y, z, xi.w));
     if (FINAL) {
         float4 p = pos[i];
         float vx = (x - p.x) / dt, vy = (y - p.y) / dt, vz = (z - p.z) / dt;
         damp_velocity(x, y, z, vx, vy, vz, B);
         pos[i] = make_float4(x, y, z, xi.w);
-        vel[i] = make_float4(vx, vy, vz, density[i]);
+        const float4 vout = make_float4(vx, vy, vz, density[i]);
+        vel[i] = vout;
+        peer_push(pushV, i, vout);
     }
+    }
+    halo_signal(hs);
 }
 
 // Stand-alone K9 / K10 for the phase-level API (and solverIterations == 0).
@@ -405,9 +478,11 @@ template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                                    uint32_t stride, Span sp, float4* __restrict__ omega,
-                                                   float* __restrict__ omegaLen, SphParams P) {
+                                                   float* __restrict__ omegaLen, SphParams P, PeerPush pushLen, HaloSync hs) {
+    halo_wait(hs);
     uint32_t i;
-    if (!span_index(sp, i)) return;
+    const bool live = span_index(sp, i);
+    if (live) {
     const float4 xi = xs[i], vi = vel[i];
     const uint32_t c = cnt[i];
     float wx = 0.f, wy = 0.f, wz = 0.f;
@@ -426,6 +501,9 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
     float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
     omega[i] = make_float4(wx, wy, wz, len);
     omegaLen[i] = len;
+    peer_push(pushLen, i, len);
+    }
+    halo_signal(hs);
 }
 
 // ------------------------------------------------------------------------------------------------ K12
@@ -436,9 +514,11 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
                                                      const float* __restrict__ omegaLen, const float* __restrict__ density,
                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                                      uint32_t stride, Span sp, float4* __restrict__ vel, SphParams P,
-                                                     float dt, float eps) {
+                                                     float dt, float eps, PeerPush pushV, HaloSync hs) {
+    halo_wait(hs);
     uint32_t i;
-    if (!span_index(sp, i)) return;
+    const bool live = span_index(sp, i);
+    if (live) {
     const float4 xi = xs[i], oi = omega[i];
     const uint32_t c = cnt[i];
     const float invDensity = 1.0f / density[i];
@@ -454,12 +534,16 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
         });
     ex *= invDensity; ey *= invDensity; ez *= invDensity;
     float len = sqrtf(fmaf(ez, ez, fmaf(ex, ex, ey * ey)));
-    if (len < 1e-5f) return;
+    if (len >= 1e-5f) {
     float nx = ex / len, ny = ey / len, nz = ez / len;
     float fx = eps * (ny * oi.z - nz * oi.y), fy = eps * (nz * oi.x - nx * oi.z), fz = eps * (nx * oi.y - ny * oi.x);
     float4 v = vel[i];
     v.x = fmaf(dt, fx, v.x); v.y = fmaf(dt, fy, v.y); v.z = fmaf(dt, fz, v.z);
     vel[i] = v;
+    peer_push(pushV, i, v);   // unchanged velocities were already pushed by the committing pass B
+    }
+    }
+    halo_signal(hs);
 }
 
 // ------------------------------------------------------------------------------------------------ K13
@@ -469,7 +553,8 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
 __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                               uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
-                                              float cvisc) {
+                                              float cvisc, HaloSync hs) {
+    halo_wait(hs);
     uint32_t i;
     if (!span_index(sp, i)) return;
     const float4 xi = xs[i], vi = velIn[i];

@@ -64,62 +64,159 @@ int slabCommAfterMain(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
-// Sends [sendLoff, +sendLcnt) to the left rank and [sendRoff, +sendRcnt) to the right rank, receives recvLcnt elements
-// from the left at recvLoff and recvRcnt from the right at recvRoff. One grouped NCCL call on the comm stream.
-int slabExchange(akua_pbf_solver* s, void* base, size_t elemBytes, size_t sendLoff, size_t sendLcnt, size_t sendRoff,
-                 size_t sendRcnt, size_t recvLoff, size_t recvLcnt, size_t recvRoff, size_t recvRcnt) {
-    SlabState& sl = s->slab;
-    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    char* b = static_cast<char*>(base);
-    ncclComm_t comm = (ncclComm_t)sl.comm;
-    cudaStream_t st = sl.commStream;
-    AK_NCCL(s, g_nccl.GroupStart());
-    if (hasL && sendLcnt) AK_NCCL(s, g_nccl.Send(b + sendLoff * elemBytes, sendLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR && sendRcnt) AK_NCCL(s, g_nccl.Send(b + sendRoff * elemBytes, sendRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, st));
-    if (hasL && recvLcnt) AK_NCCL(s, g_nccl.Recv(b + recvLoff * elemBytes, recvLcnt * elemBytes, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR && recvRcnt) AK_NCCL(s, g_nccl.Recv(b + recvRoff * elemBytes, recvRcnt * elemBytes, ncclUint8, sl.rank + 1, comm, st));
-    AK_NCCL(s, g_nccl.GroupEnd());
-    sl.exchanges++;
-    sl.bytesSent += (hasL ? sendLcnt : 0) * elemBytes + (hasR ? sendRcnt : 0) * elemBytes;
-    return AKUA_OK;
+// ---- ghost-plane exchange --------------------------------------------------------------------------------------------
+// Ghost planes live at FIXED offsets at the top of every per-particle array (ghostBaseL for the plane received from the
+// left rank, ghostBaseR for the one from the right), so neither side needs the other's particle count.
+// Two transports:
+//   * CUDA IPC (default when the neighbours' allocations can be opened): the plane is copied straight from this rank's
+//     array into the neighbour's ghost region over NVLink by the copy engine (cudaMemcpyAsync to the peer-mapped pointer)
+//     and the exchange's epoch is published in the neighbour's flag word; the neighbour's main stream runs a bounded
+//     spin-wait kernel (k_wait_flags) before the kernel that reads the ghosts. No NCCL kernel, no SM time, no rendezvous.
+//   * NCCL send/recv (fallback; AKUA_SLAB_P2P=0): one grouped call per exchange.
+// A SlabTicket is what the main stream has to wait for before it touches the ghosts of an exchange.
+template <typename T> T* peerOf(const akua_pbf_solver* s, const SlabPeer& peer, T* mine) {
+    const SlabState& sl = s->slab;
+    const void* m = mine;
+    if (m == sl.xsBuf[0]) return reinterpret_cast<T*>(peer.xsBuf[0]);
+    if (m == sl.xsBuf[1]) return reinterpret_cast<T*>(peer.xsBuf[1]);
+    if (m == sl.velBuf[0]) return reinterpret_cast<T*>(peer.velBuf[0]);
+    if (m == sl.velBuf[1]) return reinterpret_cast<T*>(peer.velBuf[1]);
+    if (m == s->lambda) return reinterpret_cast<T*>(peer.lambda);
+    if (m == s->omegaLen) return reinterpret_cast<T*>(peer.omegaLen);
+    return nullptr;
 }
 template <typename T>
 int slabPlanesOnComm(akua_pbf_solver* s, T* arr) {
-    const SlabState& sl = s->slab;
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
     const size_t nOwn = (size_t)s->n;
-    return slabExchange(s, arr, sizeof(T), 0, sl.nPlaneL, nOwn - sl.nPlaneR, sl.nPlaneR, nOwn, sl.nGhostL, nOwn + sl.nGhostL,
-                        sl.nGhostR);
+    cudaStream_t st = sl.commStream;
+    if (sl.p2p) {
+        // my first plane -> the left rank's "from the right" ghost region; my last plane -> the right rank's "from the left"
+        if (hasL && sl.nPlaneL) {
+            T* dst = peerOf(s, sl.peerL, arr);
+            if (!dst) { s->err = "slab p2p: array has no peer mapping"; return AKUA_ERR_COMM; }
+            AK_CUDA(s, cudaMemcpyAsync(dst + sl.peerL.ghostBaseR, arr, (size_t)sl.nPlaneL * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        }
+        if (hasR && sl.nPlaneR) {
+            T* dst = peerOf(s, sl.peerR, arr);
+            if (!dst) { s->err = "slab p2p: array has no peer mapping"; return AKUA_ERR_COMM; }
+            AK_CUDA(s, cudaMemcpyAsync(dst + sl.peerR.ghostBaseL, arr + (nOwn - sl.nPlaneR), (size_t)sl.nPlaneR * sizeof(T),
+                                       cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
+        ncclComm_t comm = (ncclComm_t)sl.comm;
+        AK_NCCL(s, g_nccl.GroupStart());
+        if (hasL && sl.nPlaneL) AK_NCCL(s, g_nccl.Send(arr, (size_t)sl.nPlaneL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
+        if (hasR && sl.nPlaneR) AK_NCCL(s, g_nccl.Send(arr + (nOwn - sl.nPlaneR), (size_t)sl.nPlaneR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
+        if (hasL && sl.nGhostL) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseL, (size_t)sl.nGhostL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
+        if (hasR && sl.nGhostR) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseR, (size_t)sl.nGhostR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
+        AK_NCCL(s, g_nccl.GroupEnd());
+    }
+    sl.exchanges++;
+    sl.bytesSent += ((hasL ? sl.nPlaneL : 0) + (hasR ? sl.nPlaneR : 0)) * sizeof(T);
+    return AKUA_OK;
 }
-// Asynchronous ghost-plane exchange: ordered after the main stream's work so far, runs on the comm stream; `*done`
-// must be waited on (cudaStreamWaitEvent) before the main stream touches the received ghosts.
+// Closes an exchange on the comm stream: publishes the epoch to the neighbours (p2p) and records the local event.
+int slabFinishExchange(akua_pbf_solver* s, SlabTicket* t) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    t->epoch = 0;
+    t->valid = true;
+    if (sl.p2p) {
+        t->epoch = ++sl.epoch;
+        if (hasL) { slab::k_signal_flag<<<1, 1, 0, sl.commStream>>>(sl.peerL.flags + 1, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
+        if (hasR) { slab::k_signal_flag<<<1, 1, 0, sl.commStream>>>(sl.peerR.flags + 0, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
+    }
+    t->ev = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(t->ev, sl.commStream));
+    return AKUA_OK;
+}
+// Asynchronous ghost-plane exchange: ordered after the main stream's work so far, runs on the comm stream.
 template <typename T>
-int slabExchangeAsync(akua_pbf_solver* s, T* arr, cudaEvent_t* done) {
+int slabExchangeAsync(akua_pbf_solver* s, T* arr, SlabTicket* t) {
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     if ((rc = slabPlanesOnComm(s, arr))) return rc;
-    *done = slabNextEvent(s);
-    AK_CUDA(s, cudaEventRecord(*done, s->slab.commStream));
-    return AKUA_OK;
+    return slabFinishExchange(s, t);
 }
 template <typename T, typename U>
-int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, cudaEvent_t* done) {
+int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, SlabTicket* t) {
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     if ((rc = slabPlanesOnComm(s, a))) return rc;
     if ((rc = slabPlanesOnComm(s, b))) return rc;
-    *done = slabNextEvent(s);
-    AK_CUDA(s, cudaEventRecord(*done, s->slab.commStream));
+    return slabFinishExchange(s, t);
+}
+// Main stream: do not run past this point before the exchange behind `t` has delivered this rank's ghosts (and has
+// finished reading this rank's planes).
+int slabWait(akua_pbf_solver* s, const SlabTicket& t) {
+    SlabState& sl = s->slab;
+    if (!t.valid) return AKUA_OK;
+    if (t.ev) AK_CUDA(s, cudaStreamWaitEvent(s->stream, t.ev, 0));
+    if (sl.p2p) {
+        const int hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+        if (hasL || hasR) {
+            slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags, hasL, hasR, t.epoch, sl.dCounts + 31, 4000000000LL);
+            AK_LAUNCH_CHECK(s, "k_wait_flags");
+        }
+    }
     return AKUA_OK;
+}
+// Fused path: the boundary kernel that just ran on the main stream already stored its planes into the neighbours' ghost
+// regions (PeerPush); all that is left is to publish the epoch, in stream order right behind that kernel.
+int slabSignalAfterKernel(akua_pbf_solver* s, SlabTicket* t) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    t->valid = true; t->ev = nullptr; t->epoch = ++sl.epoch;
+    if (hasL) { slab::k_signal_flag<<<1, 1, 0, s->stream>>>(sl.peerL.flags + 1, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
+    if (hasR) { slab::k_signal_flag<<<1, 1, 0, s->stream>>>(sl.peerR.flags + 0, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
+    sl.exchanges++;
+    return AKUA_OK;
+}
+int slabHalo(akua_pbf_solver* s, const SlabTicket& waitFor, SlabTicket* out, bool launchHappens, HaloSync* hs) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    *hs = HaloSync{};
+    hs->errWord = sl.dCounts + 31;
+    if (!launchHappens) {
+        // no boundary particles on this rank: nothing reads ghosts, but the neighbours still expect the epoch
+        if (out) return slabSignalAfterKernel(s, out);
+        return AKUA_OK;
+    }
+    if (waitFor.valid) {
+        if (waitFor.ev) AK_CUDA(s, cudaStreamWaitEvent(s->stream, waitFor.ev, 0));
+        hs->waitFlags = sl.flags; hs->waitL = hasL ? 1 : 0; hs->waitR = hasR ? 1 : 0; hs->waitEpoch = waitFor.epoch;
+    }
+    if (out) {
+        out->valid = true; out->ev = nullptr; out->epoch = ++sl.epoch;
+        hs->signalL = hasL ? sl.peerL.flags + 1 : nullptr;
+        hs->signalR = hasR ? sl.peerR.flags + 0 : nullptr;
+        hs->signalEpoch = out->epoch;
+        hs->doneCounter = sl.flags + 3;
+        sl.exchanges++;
+    }
+    return AKUA_OK;
+}
+template <typename T>
+PeerPush slabPush(const akua_pbf_solver* s, T* arr) {
+    const SlabState& sl = s->slab;
+    PeerPush pp;
+    if (!sl.p2p) return pp;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    const uint32_t nOwn = (uint32_t)s->n;
+    if (hasL && sl.nPlaneL) { T* d = peerOf(s, sl.peerL, arr); if (d) { pp.dstL = d + sl.peerL.ghostBaseR; pp.nL = sl.nPlaneL; } }
+    if (hasR && sl.nPlaneR) { T* d = peerOf(s, sl.peerR, arr); if (d) { pp.dstR = d + sl.peerR.ghostBaseL; pp.startR = nOwn - sl.nPlaneR; } }
+    return pp;
 }
 // Blocking flavour: the main stream waits for the exchange.
 template <typename T>
 int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
     if (!s->slab.enabled) return AKUA_OK;
-    cudaEvent_t done;
-    int rc = slabExchangeAsync(s, arr, &done);
+    SlabTicket t;
+    int rc = slabExchangeAsync(s, arr, &t);
     if (rc) return rc;
-    AK_CUDA(s, cudaStreamWaitEvent(s->stream, done, 0));
-    return AKUA_OK;
+    return slabWait(s, t);
 }
 // Interior / boundary index spans of the owned range for the current step's plane sizes.
 SweepSpans sweepSpans(const akua_pbf_solver* s) {
@@ -193,6 +290,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     AK_LAUNCH_CHECK(s, "k_mig_pack");
     if ((rc = slabSwapCounts(s))) return rc;
     const uint32_t* hc = sl.hCounts;
+    if (hc[31] == 2) { s->err = "slab p2p: timed out waiting for a neighbour's ghost planes in the previous step"; return AKUA_ERR_COMM; }
     if (hc[31]) { s->err = "slab: boundary-plane size prediction failed in the previous step (a particle crossed more than one slab?)"; return AKUA_ERR_INVALID; }
     const uint32_t outL = hc[0], outR = hc[1], inL = hc[24], inR = hc[28];
     // Post-migration plane sizes, known before the sort: my boundary planes = stayers + arrivals that land in them;
@@ -205,7 +303,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     sl.nGhostR = hasRn ? hc[30] + hc[5] : 0;
     if (sl.rank == 0 && outL) { s->err = "slab: internal error (leavers beyond the first rank)"; return AKUA_ERR_INVALID; }
     if (outL > sl.migCap || outR > sl.migCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
-    if ((uint64_t)n + inL + inR > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    if ((uint64_t)n + inL + inR > (uint64_t)sl.ghostBaseL) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
     {
         const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
         ncclComm_t comm = (ncclComm_t)sl.comm;
@@ -253,15 +351,17 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     slab::k_plane_verify<<<1, 32, 0, s->stream>>>(s->keysSorted, nOwn, planeCells, xLo, xHi, sl.nPlaneL, sl.nPlaneR,
                                                  hasLn ? 1 : 0, hasRn ? 1 : 0, sl.dCounts);
     AK_LAUNCH_CHECK(s, "k_plane_verify");
-    const uint64_t nTot = (uint64_t)nOwn + sl.nGhostL + sl.nGhostR;
-    if (nTot > (uint64_t)s->capacity) { s->err = "slab: particle capacity exceeded by ghosts (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    if (sl.nGhostL > sl.ghostCap || sl.nGhostR > sl.ghostCap || sl.nPlaneL > sl.ghostCap || sl.nPlaneR > sl.ghostCap) {
+        s->err = "slab: boundary plane larger than the ghost region (raise capacity_factor)"; return AKUA_ERR_ALLOC;
+    }
     if ((rc = slabExchangePlanes(s, s->xs))) return rc;
-    const uint32_t nGhost = sl.nGhostL + sl.nGhostR;
-    if (nGhost) {
+    for (int side = 0; side < 2; side++) {   // ghost planes: keys from the received x*, then their cell ranges
+        const uint32_t cntG = side == 0 ? sl.nGhostL : sl.nGhostR, base = side == 0 ? sl.ghostBaseL : sl.ghostBaseR;
+        if (!cntG) continue;
         float3 g0 = make_float3(0, 0, 0);
-        k_predict_key<KEY_LINEAR><<<gridFor(nGhost), kBlock, 0, s->stream>>>(nullptr, nullptr, s->xs + nOwn, s->keysSorted + nOwn, nGhost, 0.0f, g0, G, 0);
+        k_predict_key<KEY_LINEAR><<<gridFor(cntG), kBlock, 0, s->stream>>>(nullptr, nullptr, s->xs + base, s->keysSorted + base, cntG, 0.0f, g0, G, 0);
         AK_LAUNCH_CHECK(s, "k_predict_key(ghosts)");
-        slab::k_ranges<<<gridFor(nGhost), kBlock, 0, s->stream>>>(s->keysSorted, nOwn, (uint32_t)nTot, s->cellRange);
+        slab::k_ranges<<<gridFor(cntG), kBlock, 0, s->stream>>>(s->keysSorted, base, base + cntG, s->cellRange);
         AK_LAUNCH_CHECK(s, "k_ranges(ghosts)");
     }
 
@@ -273,7 +373,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         AK_LAUNCH_CHECK(s, "k_build_neighbours");
     }
 
-    sl.pending = nullptr;
+    sl.pending = SlabTicket{};
     // ---- 6. constraint solve and post-solve on the owned range, with the per-pass ghost exchanges inside ----
     mark(s, PH_SOLVE);
     bool committed = false;

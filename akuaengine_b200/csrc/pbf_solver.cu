@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,6 +40,16 @@ enum Phase { PH_PREDICT = 0, PH_SORT, PH_REORDER, PH_LISTS, PH_SOLVE, PH_POST, P
 }  // namespace
 
 // x-slab multi-GPU state (pbf_slab.inl)
+struct SlabPeer {            // a neighbour's allocations, opened through CUDA IPC
+    bool open = false;
+    float4* xsBuf[2] = {nullptr, nullptr};
+    float4* velBuf[2] = {nullptr, nullptr};
+    float* lambda = nullptr;
+    float* omegaLen = nullptr;
+    uint32_t* flags = nullptr;
+    uint32_t ghostBaseL = 0, ghostBaseR = 0;
+};
+struct SlabTicket { bool valid = false; cudaEvent_t ev = nullptr; uint32_t epoch = 0; };
 struct SlabState {
     bool enabled = false;
     int rank = 0, nranks = 1;
@@ -57,7 +68,18 @@ struct SlabState {
     static constexpr int kEvents = 64;
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
-    cudaEvent_t pending = nullptr;         // completion of the last asynchronous x* (/v) ghost exchange
+    SlabTicket pending;                    // the last asynchronous x* (/v) ghost exchange, not yet waited for
+    // fixed ghost regions at the top of every per-particle array
+    uint32_t ghostBaseL = 0, ghostBaseR = 0, ghostCap = 0;
+    // CUDA IPC transport
+    bool p2p = false;
+    bool fusedPush = false;                // p2p only: boundary kernels store straight into the neighbours' ghost regions
+                                           // (AKUA_SLAB_FUSED_PUSH=1); default: copy-engine pushes on the comm stream
+    SlabPeer peerL, peerR;
+    void* xsBuf[2] = {nullptr, nullptr};   // this rank's two x* / velocity allocations (pointer identity across swaps)
+    void* velBuf[2] = {nullptr, nullptr};
+    uint32_t* flags = nullptr;             // [0] epoch published by the left rank, [1] by the right rank
+    uint32_t epoch = 0;
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
     int64_t rebalances = 0;
@@ -298,46 +320,57 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
 
 // ---- slab-mode plumbing used by the sweeps below (definitions in pbf_slab.inl) ----
 template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);           // blocking w.r.t. the main stream
-template <typename T> int slabExchangeAsync(akua_pbf_solver* s, T* arr, cudaEvent_t* done);  // on the comm stream
-template <typename T, typename U> int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, cudaEvent_t* done);
+template <typename T> int slabExchangeAsync(akua_pbf_solver* s, T* arr, SlabTicket* t);  // on the comm stream
+template <typename T, typename U> int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, SlabTicket* t);
+int slabWait(akua_pbf_solver* s, const SlabTicket& t);
+template <typename T> PeerPush slabPush(const akua_pbf_solver* s, T* arr);        // null pushes unless the p2p transport is on
+int slabSignalAfterKernel(akua_pbf_solver* s, SlabTicket* t);                   // publish "boundary results pushed" to both peers
+// Fused path: builds the in-kernel wait (on `waitFor`) / signal (new ticket in *out when non-null) block of a boundary launch.
+int slabHalo(akua_pbf_solver* s, const SlabTicket& waitFor, SlabTicket* out, bool launchHappens, HaloSync* hs);
 struct SweepSpans { Span interior, boundary; };
 SweepSpans sweepSpans(const akua_pbf_solver* s);
 
 // ---- sweep launchers over an index span ----
-int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P) {
+int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P);
-    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P);
+    const PeerPush pl = push ? slabPush(s, s->lambda) : PeerPush{};
+    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P, pl, hs);
+    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P, pl, hs);
     AK_LAUNCH_CHECK(s, "k_density_lambda");
     return AKUA_OK;
 }
-int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams& B, bool fin, float dt) {
+int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams& B, bool fin, float dt, bool push = false,
+                const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
+    const PeerPush px = push ? slabPush(s, s->xsAlt) : PeerPush{};
+    const PeerPush pv = (push && fin) ? slabPush(s, s->vel) : PeerPush{};
 #define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
-            s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, dt)
+            s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, dt, px, pv, hs)
     if (s->opt.fast_math) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
     else                  { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
 #undef AK_DELTA
     AK_LAUNCH_CHECK(s, "k_delta_apply");
     return AKUA_OK;
 }
-int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P) {
+int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    if (s->opt.fast_math) k_vorticity<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P);
-    else                  k_vorticity<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P);
+    const PeerPush pw = push ? slabPush(s, s->omegaLen) : PeerPush{};
+    if (s->opt.fast_math) k_vorticity<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P, pw, hs);
+    else                  k_vorticity<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P, pw, hs);
     AK_LAUNCH_CHECK(s, "k_vorticity");
     return AKUA_OK;
 }
-int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt) {
+int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    if (s->opt.fast_math) k_confinement<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon);
-    else                  k_confinement<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon);
+    const PeerPush pv = push ? slabPush(s, s->vel) : PeerPush{};
+    if (s->opt.fast_math) k_confinement<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon, pv, hs);
+    else                  k_confinement<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon, pv, hs);
     AK_LAUNCH_CHECK(s, "k_confinement");
     return AKUA_OK;
 }
-int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P) {
+int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    k_xsph<<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity);
+    k_xsph<<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
     AK_LAUNCH_CHECK(s, "k_xsph");
     return AKUA_OK;
 }
@@ -364,18 +397,42 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
         if ((rc = launchPassA(s, sp.interior, P))) return rc;
         if (slabMode) {
-            if (s->slab.pending) { AK_CUDA(s, cudaStreamWaitEvent(s->stream, s->slab.pending, 0)); s->slab.pending = nullptr; }  // ghosts' x*
-            if ((rc = launchPassA(s, sp.boundary, P))) return rc;
-            cudaEvent_t evL;
-            if ((rc = slabExchangeAsync(s, s->lambda, &evL))) return rc;      // ghosts' lambda, hidden behind pass B (interior)
-            if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
-            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
-            AK_CUDA(s, cudaStreamWaitEvent(s->stream, evL, 0));
-            if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt))) return rc;
-            // ghosts' corrected x* (and, after the commit, v + rho for K11), hidden behind the next interior sweep
-            if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
-            else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
-            if (rc) return rc;
+            if (s->slab.p2p) {
+                // CUDA-IPC transport. Every boundary launch waits IN-KERNEL for the epoch of the ghosts it reads. Its own
+                // planes reach the neighbours either by copy-engine pushes on the comm stream (default) or, with
+                // fusedPush, by P2P stores from the boundary kernel itself whose last CTA publishes the epoch.
+                const bool fused = s->slab.fusedPush;
+                const bool any = sp.boundary.count != 0;
+                HaloSync hs;
+                SlabTicket tkL;
+                if ((rc = slabHalo(s, s->slab.pending, fused ? &tkL : nullptr, any, &hs))) return rc;   // waits x* (, signals lambda)
+                s->slab.pending = SlabTicket{};
+                if ((rc = launchPassA(s, sp.boundary, P, fused, hs))) return rc;
+                if (!fused && (rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;
+                if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+                if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
+                if ((rc = slabHalo(s, tkL, fused ? &s->slab.pending : nullptr, any, &hs))) return rc;   // waits lambda (, signals x*, v)
+                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt, fused, hs))) return rc;
+                if (!fused) {
+                    if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
+                    else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
+                    if (rc) return rc;
+                }
+            } else {
+                if ((rc = slabWait(s, s->slab.pending))) return rc;                // ghosts' x*
+                s->slab.pending = SlabTicket{};
+                if ((rc = launchPassA(s, sp.boundary, P))) return rc;
+                SlabTicket tkL;
+                if ((rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;      // ghosts' lambda, hidden behind pass B (interior)
+                if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+                if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
+                if ((rc = slabWait(s, tkL))) return rc;
+                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt))) return rc;
+                // ghosts' corrected x* (and, after the commit, v + rho for K11), hidden behind the next interior sweep
+                if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
+                else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
+                if (rc) return rc;
+            }
         } else {
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
             if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
@@ -416,18 +473,36 @@ int phasePost(akua_pbf_solver* s, float dt) {
         return AKUA_OK;
     }
     const SweepSpans sp = sweepSpans(s);
-    cudaEvent_t evW, evV;
-    if ((rc = launchVorticity(s, sp.interior, P))) return rc;
-    if (s->slab.pending) { AK_CUDA(s, cudaStreamWaitEvent(s->stream, s->slab.pending, 0)); s->slab.pending = nullptr; }  // ghosts' final x*, v
-    if ((rc = launchVorticity(s, sp.boundary, P))) return rc;
-    if ((rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;         // ghosts' |omega| for K12
-    if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
-    AK_CUDA(s, cudaStreamWaitEvent(s->stream, evW, 0));
-    if ((rc = launchConfinement(s, sp.boundary, P, dt))) return rc;
-    if ((rc = slabExchangeAsync(s, s->vel, &evV))) return rc;              // ghosts' post-confinement v for K13
-    if ((rc = launchXsph(s, sp.interior, P))) return rc;
-    AK_CUDA(s, cudaStreamWaitEvent(s->stream, evV, 0));
-    if ((rc = launchXsph(s, sp.boundary, P))) return rc;
+    SlabTicket evW, evV;
+    if (s->slab.p2p) {
+        HaloSync hs;
+        const bool any = sp.boundary.count != 0, fused = s->slab.fusedPush;
+        if ((rc = launchVorticity(s, sp.interior, P))) return rc;
+        if ((rc = slabHalo(s, s->slab.pending, fused ? &evW : nullptr, any, &hs))) return rc;   // waits final x*, v
+        s->slab.pending = SlabTicket{};
+        if ((rc = launchVorticity(s, sp.boundary, P, fused, hs))) return rc;
+        if (!fused && (rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;             // ghosts' |omega| for K12
+        if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
+        if ((rc = slabHalo(s, evW, fused ? &evV : nullptr, any, &hs))) return rc;               // waits |omega|
+        if ((rc = launchConfinement(s, sp.boundary, P, dt, fused, hs))) return rc;
+        if (!fused && (rc = slabExchangeAsync(s, s->vel, &evV))) return rc;                  // ghosts' post-confinement v for K13
+        if ((rc = launchXsph(s, sp.interior, P))) return rc;
+        if ((rc = slabHalo(s, evV, nullptr, any, &hs))) return rc;                              // waits post-confinement v
+        if ((rc = launchXsph(s, sp.boundary, P, hs))) return rc;
+    } else {
+        if ((rc = launchVorticity(s, sp.interior, P))) return rc;
+        if ((rc = slabWait(s, s->slab.pending))) return rc;                     // ghosts' final x*, v
+        s->slab.pending = SlabTicket{};
+        if ((rc = launchVorticity(s, sp.boundary, P))) return rc;
+        if ((rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;         // ghosts' |omega| for K12
+        if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
+        if ((rc = slabWait(s, evW))) return rc;
+        if ((rc = launchConfinement(s, sp.boundary, P, dt))) return rc;
+        if ((rc = slabExchangeAsync(s, s->vel, &evV))) return rc;              // ghosts' post-confinement v for K13
+        if ((rc = launchXsph(s, sp.interior, P))) return rc;
+        if ((rc = slabWait(s, evV))) return rc;
+        if ((rc = launchXsph(s, sp.boundary, P))) return rc;
+    }
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
@@ -634,6 +709,10 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         SlabState& sl = s->slab;
         void* sp[] = {sl.dCounts, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR};
         for (void* p : sp) if (p) cudaFree(p);
+        for (SlabPeer* p : {&sl.peerL, &sl.peerR})
+            if (p->open) for (void* q : {(void*)p->xsBuf[0], (void*)p->xsBuf[1], (void*)p->velBuf[0], (void*)p->velBuf[1],
+                                         (void*)p->lambda, (void*)p->omegaLen, (void*)p->flags}) cudaIpcCloseMemHandle(q);
+        if (sl.flags) cudaFree(sl.flags);
         if (sl.hCounts) cudaFreeHost(sl.hCounts);
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
@@ -892,6 +971,66 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     AK_CUDA(s, dalloc(&sl.blockCnt, (size_t)2 * sl.migBlocksCap));
     AK_CUDA(s, dalloc(&sl.sendL, sl.migCap)); AK_CUDA(s, dalloc(&sl.sendR, sl.migCap));
     AK_CUDA(s, dalloc(&sl.recvL, sl.migCap)); AK_CUDA(s, dalloc(&sl.recvR, sl.migCap));
+    // fixed ghost regions: the top two eighths of every per-particle array
+    sl.ghostCap = (uint32_t)(s->capacity / 8);
+    sl.ghostBaseL = (uint32_t)s->capacity - 2 * sl.ghostCap;
+    sl.ghostBaseR = (uint32_t)s->capacity - sl.ghostCap;
+    if (s->n > (int64_t)sl.ghostBaseL) { s->err = "comm_init: capacity_factor too small for the ghost regions (use >= 1.4)"; return AKUA_ERR_INVALID; }
+    sl.xsBuf[0] = s->xs; sl.xsBuf[1] = s->xsAlt; sl.velBuf[0] = s->vel; sl.velBuf[1] = s->velAlt;
+    AK_CUDA(s, dalloc(&sl.flags, 4));
+    AK_CUDA(s, cudaMemsetAsync(sl.flags, 0, 4 * sizeof(uint32_t), s->stream));
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    // ---- CUDA IPC: open the neighbours' arrays so that ghost planes can be copied straight into them ----
+    const char* env = std::getenv("AKUA_SLAB_P2P");
+    const bool wantP2p = !(env && env[0] == '0') && nranks > 1;
+    struct PeerMsg { cudaIpcMemHandle_t h[7]; uint32_t ghostBaseL, ghostBaseR, ok, pad; };
+    PeerMsg mine{};
+    mine.ghostBaseL = sl.ghostBaseL; mine.ghostBaseR = sl.ghostBaseR; mine.ok = wantP2p ? 1u : 0u;
+    if (wantP2p) {
+        void* arrs[7] = {sl.xsBuf[0], sl.xsBuf[1], sl.velBuf[0], sl.velBuf[1], s->lambda, s->omegaLen, sl.flags};
+        for (int k = 0; k < 7; k++)
+            if (cudaIpcGetMemHandle(&mine.h[k], arrs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); break; }
+    }
+    if (nranks > 1) {
+        PeerMsg* dmsg = nullptr;   // [0] mine, [1] from left, [2] from right
+        AK_CUDA(s, dalloc(&dmsg, 3));
+        AK_CUDA(s, cudaMemcpy(dmsg, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        const bool hasL = rank > 0, hasR = rank + 1 < nranks;
+        AK_NCCL(s, g_nccl.GroupStart());
+        if (hasL) AK_NCCL(s, g_nccl.Send(dmsg, sizeof(PeerMsg), ncclUint8, rank - 1, comm, sl.commStream));
+        if (hasR) AK_NCCL(s, g_nccl.Send(dmsg, sizeof(PeerMsg), ncclUint8, rank + 1, comm, sl.commStream));
+        if (hasL) AK_NCCL(s, g_nccl.Recv(dmsg + 1, sizeof(PeerMsg), ncclUint8, rank - 1, comm, sl.commStream));
+        if (hasR) AK_NCCL(s, g_nccl.Recv(dmsg + 2, sizeof(PeerMsg), ncclUint8, rank + 1, comm, sl.commStream));
+        AK_NCCL(s, g_nccl.GroupEnd());
+        AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
+        PeerMsg got[2]{};
+        AK_CUDA(s, cudaMemcpy(got, dmsg + 1, 2 * sizeof(PeerMsg), cudaMemcpyDeviceToHost));
+        cudaFree(dmsg);
+        bool ok = mine.ok != 0 && (!hasL || got[0].ok) && (!hasR || got[1].ok);
+        auto openPeer = [&](const PeerMsg& m, SlabPeer& p) {
+            void* ptr[7] = {};
+            for (int k = 0; k < 7; k++)
+                if (cudaIpcOpenMemHandle(&ptr[k], m.h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+            p.xsBuf[0] = (float4*)ptr[0]; p.xsBuf[1] = (float4*)ptr[1]; p.velBuf[0] = (float4*)ptr[2]; p.velBuf[1] = (float4*)ptr[3];
+            p.lambda = (float*)ptr[4]; p.omegaLen = (float*)ptr[5]; p.flags = (uint32_t*)ptr[6];
+            p.ghostBaseL = m.ghostBaseL; p.ghostBaseR = m.ghostBaseR; p.open = true;
+            return true;
+        };
+        if (ok && hasL) ok = openPeer(got[0], sl.peerL);
+        if (ok && hasR) ok = openPeer(got[1], sl.peerR);
+        // all ranks must agree on the transport: a tiny all-reduce (min) over the local verdicts
+        uint32_t* dflag = nullptr;
+        AK_CUDA(s, dalloc(&dflag, 1));
+        uint32_t v = ok ? 1u : 0u;
+        AK_CUDA(s, cudaMemcpy(dflag, &v, 4, cudaMemcpyHostToDevice));
+        AK_NCCL(s, g_nccl.AllReduce(dflag, dflag, 1, ncclUint32, ncclMin, comm, sl.commStream));
+        AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
+        AK_CUDA(s, cudaMemcpy(&v, dflag, 4, cudaMemcpyDeviceToHost));
+        cudaFree(dflag);
+        sl.p2p = v != 0;
+        const char* fp = std::getenv("AKUA_SLAB_FUSED_PUSH");
+        sl.fusedPush = sl.p2p && fp && fp[0] == '1';
+    }
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
 }
@@ -910,7 +1049,7 @@ int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
     if (!s || !out) return AKUA_ERR_INVALID;
     const SlabState& sl = s->slab;
     out[0] = s->n; out[1] = sl.nGhostL; out[2] = sl.nGhostR; out[3] = sl.nPlaneL; out[4] = sl.nPlaneR;
-    out[5] = sl.exchanges; out[6] = sl.bytesSent; out[7] = sl.migratedIn;
+    out[5] = sl.exchanges; out[6] = sl.p2p ? -sl.bytesSent : sl.bytesSent; out[7] = sl.migratedIn;  // negative bytes: p2p transport
     return AKUA_OK;
 }
 // Balanced x-slab boundaries from a histogram of particles per absolute x cell column (pure host code, no CUDA):

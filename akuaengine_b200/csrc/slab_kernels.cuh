@@ -172,6 +172,30 @@ __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__
     hist[x] = (unsigned long long)(lower((uint64_t)(x + 1) * planeCells) - lower((uint64_t)x * planeCells));
 }
 
+// ---- peer-to-peer signalling (CUDA IPC path) ----
+// After a rank has copied its boundary plane straight into the neighbour's ghost region (peer-mapped memory over NVLink),
+// it publishes the exchange's epoch in the neighbour's flag word; the neighbour's stream runs k_wait_flags before the
+// kernel that reads the ghosts. Epochs only grow, so "flag >= epoch" (wrap-safe) is the wait condition. The wait is
+// bounded: on timeout it raises the sticky error word instead of hanging the GPU.
+__global__ void k_signal_flag(uint32_t* __restrict__ peerFlag, uint32_t epoch) {
+    __threadfence_system();
+    *(volatile uint32_t*)peerFlag = epoch;
+    __threadfence_system();
+}
+__global__ void k_wait_flags(const uint32_t* __restrict__ flags, int waitL, int waitR, uint32_t epoch,
+                             uint32_t* __restrict__ errWord, long long timeoutCycles) {
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? waitL : waitR)) continue;
+        const volatile uint32_t* f = flags + side;
+        while ((int32_t)(*f - epoch) < 0) {
+            if (clock64() - t0 > timeoutCycles) { *errWord = 2; return; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
 // Cell ranges of a contiguous, already key-sorted block [begin, end) (ghost planes received from a neighbour).
 __global__ void __launch_bounds__(256) k_ranges(const uint32_t* __restrict__ keysSorted, uint32_t begin, uint32_t end,
                                                 uint2* __restrict__ cellRange) {

@@ -162,7 +162,9 @@ int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
  * few dozen steps for scenes whose fluid moves along x (dam break). */
 int akua_pbf_rebalance(akua_pbf_solver* s);
 /* out: 0 owned, 1 ghosts from left, 2 ghosts from right, 3 first-plane size, 4 last-plane size, 5 exchanges so far,
- * 6 bytes sent so far, 7 particles migrated in so far */
+ * 6 bytes sent so far (NEGATIVE when the CUDA-IPC peer-to-peer transport is in use, positive for NCCL send/recv),
+ * 7 particles migrated in so far. Transport: ghost planes are copied straight into the neighbour's arrays through
+ * CUDA IPC when every rank could open its neighbours' allocations (environment AKUA_SLAB_P2P=0 forces NCCL). */
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]);
 /* Balanced slab boundaries from a per-x-column particle histogram. Pure host code (callable without a GPU). */
 int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds /* nranks + 1 */);

@@ -146,6 +146,8 @@ struct akua_pbf_solver {
     static constexpr int kGraphSlots = 4;
     GraphEntry graphs[kGraphSlots];
     int graphNext = 0;
+    int graphMissStreak = 0;     // consecutive steps whose parameters matched no cached graph
+    int graphCooldown = 0;       // steps to run eagerly after a burst of misses (callers that change dt / box every step)
     float accumulator = 0.0f;  // fixed-timestep driver (akua_pbf_advance)
 };
 
@@ -534,6 +536,13 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     akua_pbf_solver::GraphEntry* hit = nullptr;
     for (auto& g : s->graphs)
         if (g.used && std::memcmp(g.key, key, sizeof(key)) == 0) { hit = &g; break; }
+    if (hit) s->graphMissStreak = 0;
+    else if (s->graphCooldown > 0) { s->graphCooldown--; return stepEager(s, dt, iterations, bmin, bmax); }
+    else if (++s->graphMissStreak > 6) {
+        // parameters keep changing (adaptive dt, moving box): capturing a graph per step costs more than it saves
+        s->graphMissStreak = 0; s->graphCooldown = 64;
+        return stepEager(s, dt, iterations, bmin, bmax);
+    }
     if (!hit) {
         // capture this step (the launches below are recorded, not executed), instantiate, then replay it
         akua_pbf_solver::GraphEntry& g = s->graphs[s->graphNext];

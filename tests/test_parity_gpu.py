@@ -242,6 +242,24 @@ def test_graph_replay_is_bit_identical_to_eager_launches(mode):
     assert outs[0].tobytes() == outs[1].tobytes()
 
 
+def test_graph_cache_backs_off_when_parameters_change_every_step():
+    """A caller that changes dt every step must not pay a graph capture per step: after a burst of misses the solver
+    runs eagerly for a while; results stay identical to the never-graphed run."""
+    init, bmin, bmax = scenes.dam_break(12)
+    outs = []
+    for use_graph in (True, False):
+        s = PBFSolver(len(init), use_graph=use_graph)
+        s.upload_particles(init)
+        for k in range(30):
+            s.step(0.008 + 1e-5 * k, bmin, bmax)
+        outs.append(s.download_particles())
+        c = s.counters()
+        if use_graph:
+            assert c["graph_replays"] < 12 and c["steps"] == 30
+        s.close()
+    assert outs[0].tobytes() == outs[1].tobytes()
+
+
 def test_fixed_timestep_driver_matches_reference_accumulator_loop():
     """akua_pbf_advance = the accumulator loop of Application::run (Application.cpp:63-70), MAX_STEPS_PER_FRAME = 3."""
     init, bmin, bmax = scenes.dam_break(10)

@@ -64,8 +64,10 @@ struct SlabState {
     uint32_t migCap = 0;
     uint32_t nPlaneL = 0, nPlaneR = 0, nGhostL = 0, nGhostR = 0;
     int64_t exchanges = 0, bytesSent = 0, migratedIn = 0, migratedOut = 0;
-    cudaStream_t commStream = nullptr;     // high-priority stream all NCCL traffic is issued on
-    static constexpr int kEvents = 64;
+    cudaStream_t commStream = nullptr;     // high-priority stream all exchange traffic is issued on
+    cudaStream_t bndStream = nullptr;      // boundary-plane sweeps run here, concurrently with the interior sweeps
+    bool useBndStream = false;
+    static constexpr int kEvents = 256;
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
     SlabTicket pending;                    // the last asynchronous x* (/v) ghost exchange, not yet waited for
@@ -377,6 +379,26 @@ int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P, const HaloSync& 
     return AKUA_OK;
 }
 
+// Slab mode runs the small boundary-plane launches on a second stream so that they execute concurrently with the big
+// interior launches instead of adding their latency to the critical path. BndScope redirects s->stream for the duration of
+// a boundary section; slabJoin makes each of the two streams wait for the other (needed wherever a sweep reads what the
+// previous sweep wrote across the interior / boundary split).
+cudaEvent_t slabNextEvent(akua_pbf_solver* s);
+struct BndScope {
+    akua_pbf_solver* s; cudaStream_t saved;
+    explicit BndScope(akua_pbf_solver* s_) : s(s_), saved(s_->stream) { if (s->slab.useBndStream) s->stream = s->slab.bndStream; }
+    ~BndScope() { s->stream = saved; }
+};
+int slabJoin(akua_pbf_solver* s) {
+    if (!s->slab.enabled || !s->slab.useBndStream) return AKUA_OK;
+    cudaEvent_t a = slabNextEvent(s), b = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(a, s->stream));
+    AK_CUDA(s, cudaEventRecord(b, s->slab.bndStream));
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, b, 0));
+    AK_CUDA(s, cudaStreamWaitEvent(s->slab.bndStream, a, 0));
+    return AKUA_OK;
+}
+
 // `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
 // Slab mode: every sweep is split into the slab interior (needs no ghost data) and its two boundary planes. The
 // boundary planes run as soon as the ghost data they need has arrived and their results go out on the comm stream
@@ -397,44 +419,39 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
         const bool fin = commit && it == iterations - 1;
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
+        if (it == 0 && (rc = slabJoin(s))) return rc;   // boundary stream catches up with the list build
         if ((rc = launchPassA(s, sp.interior, P))) return rc;
         if (slabMode) {
-            if (s->slab.p2p) {
-                // CUDA-IPC transport. Every boundary launch waits IN-KERNEL for the epoch of the ghosts it reads. Its own
-                // planes reach the neighbours either by copy-engine pushes on the comm stream (default) or, with
-                // fusedPush, by P2P stores from the boundary kernel itself whose last CTA publishes the epoch.
-                const bool fused = s->slab.fusedPush;
-                const bool any = sp.boundary.count != 0;
+            // CUDA-IPC transport: every boundary launch waits IN-KERNEL for the epoch of the ghosts it reads; its own planes
+            // reach the neighbours by copy-engine pushes on the comm stream (default) or, with fusedPush, by P2P stores from
+            // the boundary kernel itself whose last CTA publishes the epoch. NCCL transport: event waits + send/recv.
+            const bool p2p = s->slab.p2p, fused = s->slab.fusedPush, any = sp.boundary.count != 0;
+            SlabTicket tkL;
+            {   // ---- pass A on the boundary planes (boundary stream), lambda goes out
+                BndScope scope(s);
                 HaloSync hs;
-                SlabTicket tkL;
-                if ((rc = slabHalo(s, s->slab.pending, fused ? &tkL : nullptr, any, &hs))) return rc;   // waits x* (, signals lambda)
+                if (p2p) { if ((rc = slabHalo(s, s->slab.pending, fused ? &tkL : nullptr, any, &hs))) return rc; }
+                else if ((rc = slabWait(s, s->slab.pending))) return rc;                       // ghosts' x*
                 s->slab.pending = SlabTicket{};
-                if ((rc = launchPassA(s, sp.boundary, P, fused, hs))) return rc;
-                if (!fused && (rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;
-                if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
-                if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
-                if ((rc = slabHalo(s, tkL, fused ? &s->slab.pending : nullptr, any, &hs))) return rc;   // waits lambda (, signals x*, v)
-                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt, fused, hs))) return rc;
-                if (!fused) {
+                if ((rc = launchPassA(s, sp.boundary, P, p2p && fused, hs))) return rc;
+                if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;
+            }
+            if ((rc = slabJoin(s))) return rc;   // pass B reads lambda across the interior / boundary split
+            if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;                 // hides the lambda exchange
+            {   // ---- pass B on the boundary planes, corrected x* (and after the commit v + rho) go out
+                BndScope scope(s);
+                HaloSync hs;
+                if (p2p) { if ((rc = slabHalo(s, tkL, fused ? &s->slab.pending : nullptr, any, &hs))) return rc; }
+                else if ((rc = slabWait(s, tkL))) return rc;
+                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt, p2p && fused, hs))) return rc;
+                if (!(p2p && fused)) {
                     if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
                     else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
                     if (rc) return rc;
                 }
-            } else {
-                if ((rc = slabWait(s, s->slab.pending))) return rc;                // ghosts' x*
-                s->slab.pending = SlabTicket{};
-                if ((rc = launchPassA(s, sp.boundary, P))) return rc;
-                SlabTicket tkL;
-                if ((rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;      // ghosts' lambda, hidden behind pass B (interior)
-                if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
-                if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
-                if ((rc = slabWait(s, tkL))) return rc;
-                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt))) return rc;
-                // ghosts' corrected x* (and, after the commit, v + rho for K11), hidden behind the next interior sweep
-                if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
-                else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
-                if (rc) return rc;
             }
+            if ((rc = slabJoin(s))) return rc;   // the next sweep reads x* across the split
         } else {
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
             if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
@@ -476,35 +493,38 @@ int phasePost(akua_pbf_solver* s, float dt) {
     }
     const SweepSpans sp = sweepSpans(s);
     SlabTicket evW, evV;
-    if (s->slab.p2p) {
+    const bool p2p = s->slab.p2p, fused = s->slab.fusedPush, any = sp.boundary.count != 0;
+    if ((rc = slabJoin(s))) return rc;
+    if ((rc = launchVorticity(s, sp.interior, P))) return rc;
+    {
+        BndScope scope(s);
         HaloSync hs;
-        const bool any = sp.boundary.count != 0, fused = s->slab.fusedPush;
-        if ((rc = launchVorticity(s, sp.interior, P))) return rc;
-        if ((rc = slabHalo(s, s->slab.pending, fused ? &evW : nullptr, any, &hs))) return rc;   // waits final x*, v
+        if (p2p) { if ((rc = slabHalo(s, s->slab.pending, fused ? &evW : nullptr, any, &hs))) return rc; }
+        else if ((rc = slabWait(s, s->slab.pending))) return rc;                              // ghosts' final x*, v
         s->slab.pending = SlabTicket{};
-        if ((rc = launchVorticity(s, sp.boundary, P, fused, hs))) return rc;
-        if (!fused && (rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;             // ghosts' |omega| for K12
-        if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
-        if ((rc = slabHalo(s, evW, fused ? &evV : nullptr, any, &hs))) return rc;               // waits |omega|
-        if ((rc = launchConfinement(s, sp.boundary, P, dt, fused, hs))) return rc;
-        if (!fused && (rc = slabExchangeAsync(s, s->vel, &evV))) return rc;                  // ghosts' post-confinement v for K13
-        if ((rc = launchXsph(s, sp.interior, P))) return rc;
-        if ((rc = slabHalo(s, evV, nullptr, any, &hs))) return rc;                              // waits post-confinement v
-        if ((rc = launchXsph(s, sp.boundary, P, hs))) return rc;
-    } else {
-        if ((rc = launchVorticity(s, sp.interior, P))) return rc;
-        if ((rc = slabWait(s, s->slab.pending))) return rc;                     // ghosts' final x*, v
-        s->slab.pending = SlabTicket{};
-        if ((rc = launchVorticity(s, sp.boundary, P))) return rc;
-        if ((rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;         // ghosts' |omega| for K12
-        if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
-        if ((rc = slabWait(s, evW))) return rc;
-        if ((rc = launchConfinement(s, sp.boundary, P, dt))) return rc;
-        if ((rc = slabExchangeAsync(s, s->vel, &evV))) return rc;              // ghosts' post-confinement v for K13
-        if ((rc = launchXsph(s, sp.interior, P))) return rc;
-        if ((rc = slabWait(s, evV))) return rc;
-        if ((rc = launchXsph(s, sp.boundary, P))) return rc;
+        if ((rc = launchVorticity(s, sp.boundary, P, p2p && fused, hs))) return rc;
+        if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;      // ghosts' |omega| for K12
     }
+    if ((rc = slabJoin(s))) return rc;
+    if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
+    {
+        BndScope scope(s);
+        HaloSync hs;
+        if (p2p) { if ((rc = slabHalo(s, evW, fused ? &evV : nullptr, any, &hs))) return rc; }
+        else if ((rc = slabWait(s, evW))) return rc;
+        if ((rc = launchConfinement(s, sp.boundary, P, dt, p2p && fused, hs))) return rc;
+        if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->vel, &evV))) return rc;           // ghosts' post-confinement v for K13
+    }
+    if ((rc = slabJoin(s))) return rc;
+    if ((rc = launchXsph(s, sp.interior, P))) return rc;
+    {
+        BndScope scope(s);
+        HaloSync hs;
+        if (p2p) { if ((rc = slabHalo(s, evV, nullptr, any, &hs))) return rc; }
+        else if ((rc = slabWait(s, evV))) return rc;
+        if ((rc = launchXsph(s, sp.boundary, P, hs))) return rc;
+    }
+    if ((rc = slabJoin(s))) return rc;   // the step ends on the main stream
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
@@ -726,6 +746,7 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
         if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
+        if (sl.bndStream) { cudaStreamSynchronize(sl.bndStream); cudaStreamDestroy(sl.bndStream); }
         for (int e = 0; e < SlabState::kEvents; e++) if (sl.evPool[e]) cudaEventDestroy(sl.evPool[e]);
         if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
     }
@@ -972,6 +993,9 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         int lo = 0, hi = 0;
         AK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
+        AK_CUDA(s, cudaStreamCreateWithPriority(&sl.bndStream, cudaStreamNonBlocking, hi));
+        const char* eb = std::getenv("AKUA_SLAB_BND_STREAM");
+        sl.useBndStream = !(eb && eb[0] == '0');
         for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
     }
     AK_CUDA(s, dalloc(&sl.dCounts, 32));

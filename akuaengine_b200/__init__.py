@@ -18,10 +18,13 @@ from .build import LIB_PATH, build_library  # noqa: F401
 __all__ = [
     "PBFConfig", "LambdaCorrParams", "PBFOptions", "PBFSolver", "PARTICLE_DTYPE", "AkuaError", "load_library",
     "KEY_REFERENCE_HASH", "KEY_LINEAR_CELL", "DBG", "PinnedBuffer",
+    "GATHER_AUTO", "GATHER_PLAIN", "GATHER_PACKED", "GATHER_RECORDS", "GATHER_PACKED_RECORDS",
 ]
 
 KEY_REFERENCE_HASH = 0
 KEY_LINEAR_CELL = 1
+# akua_gather_layout (include/akua_pbf.h): how the sweeps fetch a neighbour; results are bit-identical in every layout
+GATHER_AUTO, GATHER_PLAIN, GATHER_PACKED, GATHER_RECORDS, GATHER_PACKED_RECORDS = 0, 1, 2, 3, 4
 
 # include/AkuaEngine/Simulation/Particle.h:8-31 — packed, 108 bytes
 PARTICLE_DTYPE = np.dtype([
@@ -77,7 +80,7 @@ class PBFConfig(C.Structure):
 
 class PBFOptions(C.Structure):
     _fields_ = [("key_mode", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("fast_math", C.c_int32),
-                ("capacity_factor", C.c_float), ("reserved", C.c_int32 * 8)]
+                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class Counters(C.Structure):
@@ -226,7 +229,7 @@ class PBFSolver:
 
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
-                 capacity_factor: float = 1.0):
+                 capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO):
         self._lib = load_library()
         self.config = config or PBFConfig()
         self.corrParams = corrParams or LambdaCorrParams()
@@ -235,6 +238,7 @@ class PBFSolver:
         self._lib.akua_pbf_default_options(C.byref(opt))
         opt.key_mode, opt.device, opt.fast_math, opt.use_graph = int(key_mode), int(device), int(fast_math), int(use_graph)
         opt.capacity_factor = float(capacity_factor)
+        opt.gather_layout = int(gather_layout)
         self.options = opt
         self._h = C.c_void_p()
         rc = self._lib.akua_pbf_create(C.byref(self._h), self.numParticles, C.byref(self.config),

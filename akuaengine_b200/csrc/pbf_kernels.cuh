@@ -33,6 +33,7 @@ struct SphParams {
     float relaxation;
     float corrK, corrN, invPoly6Dq;  // artificial pressure: -k * (W(d2)/W(dq^2))^n
     int corrNIsFour;
+    float uniformMass;  // packed-gather sweeps only: the one mass every particle has (checked at upload)
 };
 
 struct GridParams {
@@ -166,6 +167,18 @@ __device__ __forceinline__ uint4 ld_list4(const uint4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+// Post-solve gather record: committed position (w = mass) and velocity (w = density) of one particle side by side, so that
+// K11 / K13 fetch a neighbour with ONE 32-byte gather (LDG.E.256, sm_100+) instead of two 16-byte gathers into two arrays.
+// The gathers are bound by L1 data-stage wavefronts (a quarter-warp of scattered 16-byte reads collides on the L1 banks:
+// ~9.8 wavefronts per request measured, profiles/r01_ncu_final_summary.txt), so one wider request beats two.
+struct __align__(32) PosVel { float4 x, v; };
+__device__ __forceinline__ PosVel ld_posvel(const PosVel* p) {
+    PosVel r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.x.x), "=f"(r.x.y), "=f"(r.x.z), "=f"(r.x.w), "=f"(r.v.x), "=f"(r.v.y), "=f"(r.v.z), "=f"(r.v.w)
+                 : "l"(p));
+    return r;
 }
 // Drives one neighbour sweep for particle i: `load(j)` gathers whatever the sweep needs of neighbour j, `acc(payload,
 // valid)` accumulates it. Indices come four at a time; the four gathers are independent and issued back to back, and
@@ -329,7 +342,8 @@ template <bool FAST>
 __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
                                                         const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                         float* __restrict__ density, float* __restrict__ lambda,
-                                                        SphParams P, PeerPush pushLambda, HaloSync hs) {
+                                                        float4* __restrict__ xl, SphParams P, PeerPush pushLambda,
+                                                        HaloSync hs) {
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
@@ -357,6 +371,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
     float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
     density[i] = rho;
     lambda[i] = lam;
+    if (xl) xl[i] = make_float4(xi.x, xi.y, xi.z, lam);   // packed-gather layout: pass B fetches x* and lambda in one gather
     peer_push(pushLambda, i, lam);
     }
     halo_signal(hs);
@@ -402,25 +417,35 @@ __device__ __forceinline__ void damp_velocity(float px, float py, float pz, floa
 // kernel_calculate_position_delta (ConstraintSolverCUDA.cu:99-130) + kernel_correct_position (:159-169); Jacobi, so the
 // corrected x* goes to the other half of a double buffer. FINAL additionally commits: kernel_update_position_and_velocity
 // (IntegrationCUDA.cu:38-49) and kernel_apply_boundary_velocity_damping (:75-102), both per-particle.
-template <bool FAST, bool FINAL>
+// PACK (every particle has the mass P.uniformMass): x* and lambda of a neighbour come from ONE gather of pass A's packed
+// (x*, lambda) array `xl` instead of a 16-byte and a 4-byte gather; the arithmetic is the same expression on the same values.
+template <bool FAST, bool FINAL, bool PACK>
 __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
-                                                     const float* __restrict__ lambda, const uint32_t* __restrict__ list,
+                                                     const float* __restrict__ lambda, const float4* __restrict__ xl,
+                                                     const uint32_t* __restrict__ list,
                                                      const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                      SphParams P, BoxParams B, float4* __restrict__ dposOut,
                                                      float4* __restrict__ pos, float4* __restrict__ vel,
-                                                     const float* __restrict__ density, float dt, PeerPush pushX,
-                                                     PeerPush pushV, HaloSync hs) {
+                                                     const float* __restrict__ density, PosVel* __restrict__ pvOut,
+                                                     float dt, PeerPush pushX, PeerPush pushV, HaloSync hs) {
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
     if (live) {
-    const float4 xi = xsIn[i];
-    const float li = lambda[i];
+    float4 xi;
+    float li;
+    if (PACK) { const float4 t = xl[i]; li = t.w; xi = make_float4(t.x, t.y, t.z, P.uniformMass); }
+    else      { xi = xsIn[i]; li = lambda[i]; }
     const uint32_t c = cnt[i];
     float px = 0.f, py = 0.f, pz = 0.f;
     struct NB { float4 x; float l; };
     neighbour_sweep<NB>(list, i, c, stride,
-        [&](uint32_t j) { NB r; r.x = __ldg(&xsIn[j]); r.l = __ldg(&lambda[j]); return r; },
+        [&](uint32_t j) {
+            NB r;
+            if (PACK) { r.x = __ldg(&xl[j]); r.l = r.x.w; r.x.w = P.uniformMass; }
+            else      { r.x = __ldg(&xsIn[j]); r.l = __ldg(&lambda[j]); }
+            return r;
+        },
         [&](const NB& nb, bool valid) {
             float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
             float d2 = dist2(dx, dy, dz);
@@ -447,10 +472,21 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
         pos[i] = make_float4(x, y, z, xi.w);
         const float4 vout = make_float4(vx, vy, vz, density[i]);
         vel[i] = vout;
+        if (pvOut) { PosVel r; r.x = make_float4(x, y, z, xi.w); r.v = vout; pvOut[i] = r; }   // post-solve gather records
         peer_push(pushV, i, vout);
     }
     }
     halo_signal(hs);
+}
+
+// (position, velocity) -> post-solve gather records, for callers that commit outside the fused final pass B (phase-level
+// API, solverIterations == 0).
+__global__ void __launch_bounds__(256) k_build_posvel(const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                                      uint32_t n, PosVel* __restrict__ pv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PosVel r; r.x = pos[i]; r.v = vel[i];
+    pv[i] = r;
 }
 
 // Stand-alone K9 / K10 for the phase-level API (and solverIterations == 0).
@@ -474,22 +510,30 @@ __global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos,
 
 // ------------------------------------------------------------------------------------------------ K11
 // kernel_compute_vorticities, IntegrationCUDA.cu:104-128. Also stores |omega| so K12 gathers 4 B per neighbour, not 12.
-template <bool FAST>
+// REC: neighbour position + velocity come from one 32-byte record gather (PosVel). `xw` (optional) receives the packed
+// (x, |omega|) array K12's PACK variant gathers from.
+template <bool FAST, bool REC>
 __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
+                                                   const PosVel* __restrict__ pv,
                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                                    uint32_t stride, Span sp, float4* __restrict__ omega,
-                                                   float* __restrict__ omegaLen, SphParams P, PeerPush pushLen, HaloSync hs) {
+                                                   float* __restrict__ omegaLen, float4* __restrict__ xw, SphParams P,
+                                                   PeerPush pushLen, HaloSync hs) {
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
     if (live) {
-    const float4 xi = xs[i], vi = vel[i];
+    float4 xi, vi;
+    if (REC) { const PosVel t = pv[i]; xi = t.x; vi = t.v; }
+    else     { xi = xs[i]; vi = vel[i]; }
     const uint32_t c = cnt[i];
     float wx = 0.f, wy = 0.f, wz = 0.f;
-    struct NB { float4 x, v; };
-    neighbour_sweep<NB>(list, i, c, stride,
-        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.v = __ldg(&vel[j]); return r; },
-        [&](const NB& nb, bool valid) {
+    neighbour_sweep<PosVel>(list, i, c, stride,
+        [&](uint32_t j) {
+            if (REC) return ld_posvel(pv + j);
+            PosVel r; r.x = __ldg(&xs[j]); r.v = __ldg(&vel[j]); return r;
+        },
+        [&](const PosVel& nb, bool valid) {
             float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
             float s = spiky_scale<FAST>(dist2(dx, dy, dz), P);
             float gx = s * dx, gy = s * dy, gz = s * dz;
@@ -501,6 +545,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
     float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
     omega[i] = make_float4(wx, wy, wz, len);
     omegaLen[i] = len;
+    if (xw) xw[i] = make_float4(xi.x, xi.y, xi.z, len);
     peer_push(pushLen, i, len);
     }
     halo_signal(hs);
@@ -508,24 +553,33 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
 
 // ------------------------------------------------------------------------------------------------ K12
 // kernel_apply_vorticity_confinement, IntegrationCUDA.cu:130-165. Reads neighbours' |omega|, writes only its own
-// velocity: race-free in place.
-template <bool FAST>
+// velocity: race-free in place. PACK (uniform mass): position and |omega| of a neighbour come from one gather of `xw`.
+// `pvOut` (optional): the updated velocity is mirrored into the post-solve gather records K13 reads.
+template <bool FAST, bool PACK>
 __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
-                                                     const float* __restrict__ omegaLen, const float* __restrict__ density,
+                                                     const float* __restrict__ omegaLen, const float4* __restrict__ xw,
+                                                     const float* __restrict__ density,
                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
-                                                     uint32_t stride, Span sp, float4* __restrict__ vel, SphParams P,
+                                                     uint32_t stride, Span sp, float4* __restrict__ vel,
+                                                     PosVel* __restrict__ pvOut, SphParams P,
                                                      float dt, float eps, PeerPush pushV, HaloSync hs) {
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
     if (live) {
-    const float4 xi = xs[i], oi = omega[i];
+    const float4 xi = PACK ? xw[i] : xs[i];
+    const float4 oi = omega[i];
     const uint32_t c = cnt[i];
     const float invDensity = 1.0f / density[i];
     float ex = 0.f, ey = 0.f, ez = 0.f;
     struct NB { float4 x; float l; };
     neighbour_sweep<NB>(list, i, c, stride,
-        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.l = __ldg(&omegaLen[j]); return r; },
+        [&](uint32_t j) {
+            NB r;
+            if (PACK) { r.x = __ldg(&xw[j]); r.l = r.x.w; r.x.w = P.uniformMass; }
+            else      { r.x = __ldg(&xs[j]); r.l = __ldg(&omegaLen[j]); }
+            return r;
+        },
         [&](const NB& nb, bool valid) {
             float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
             float coef = nb.x.w * (oi.w - nb.l) * spiky_scale<FAST>(dist2(dx, dy, dz), P);
@@ -540,6 +594,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
     float4 v = vel[i];
     v.x = fmaf(dt, fx, v.x); v.y = fmaf(dt, fy, v.y); v.z = fmaf(dt, fz, v.z);
     vel[i] = v;
+    if (pvOut) pvOut[i].v = v;
     peer_push(pushV, i, v);   // unchanged velocities were already pushed by the committing pass B
     }
     }
@@ -549,21 +604,27 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
 // ------------------------------------------------------------------------------------------------ K13
 // kernel_apply_xsph_viscosity, IntegrationCUDA.cu:167-195 — as a Jacobi sweep (velIn -> velOut). The reference updates
 // velocity in place while neighbours read it (a data race, :187,:194); Jacobi is one of its legal outcomes and is
-// deterministic.
+// deterministic. REC: one 32-byte record gather per neighbour instead of two 16-byte gathers.
+template <bool REC>
 __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
+                                              const PosVel* __restrict__ pv,
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                               uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
                                               float cvisc, HaloSync hs) {
     halo_wait(hs);
     uint32_t i;
     if (!span_index(sp, i)) return;
-    const float4 xi = xs[i], vi = velIn[i];
+    float4 xi, vi;
+    if (REC) { const PosVel t = pv[i]; xi = t.x; vi = t.v; }
+    else     { xi = xs[i]; vi = velIn[i]; }
     const uint32_t c = cnt[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
-    struct NB { float4 x, v; };
-    neighbour_sweep<NB>(list, i, c, stride,
-        [&](uint32_t j) { NB r; r.x = __ldg(&xs[j]); r.v = __ldg(&velIn[j]); return r; },
-        [&](const NB& nb, bool valid) {
+    neighbour_sweep<PosVel>(list, i, c, stride,
+        [&](uint32_t j) {
+            if (REC) return ld_posvel(pv + j);
+            PosVel r; r.x = __ldg(&xs[j]); r.v = __ldg(&velIn[j]); return r;
+        },
+        [&](const PosVel& nb, bool valid) {
             float dx = xi.x - nb.x.x, dy = xi.y - nb.x.y, dz = xi.z - nb.x.z;
             float w = poly6(dist2(dx, dy, dz), P);
             float mr = nb.x.w / nb.v.w;  // m_j / rho_j
@@ -649,6 +710,28 @@ __global__ void __launch_bounds__(256) k_list_to_rowmajor(const uint32_t* __rest
     if (t >= (uint64_t)n * maxN) return;
     uint32_t i = (uint32_t)(t / maxN), k = (uint32_t)(t % maxN);
     out[t] = k < cnt[i] ? list[list_slot(i, k, stride)] : 0u;
+}
+
+// min / max of the particle masses (pos.w) as order-preserving u32 codes: out[0] = min code, out[1] = max code
+__device__ __forceinline__ uint32_t float_order_code(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) k_mass_range(const float4* __restrict__ pos, uint32_t n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t slo[8], shi[8];
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t c = float_order_code(pos[i].w);
+        lo = min(lo, c); hi = max(hi, c);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        atomicMin(&out[0], lo); atomicMax(&out[1], hi);
+    }
 }
 
 // |rho/rho0 - 1| partial sums / maxima per CTA

@@ -104,6 +104,15 @@ struct akua_pbf_solver {
     uint32_t *id = nullptr, *idAlt = nullptr;  // upload index of each particle
     float *density = nullptr, *lambda = nullptr, *omegaLen = nullptr;
     float4 *omega = nullptr, *dpos = nullptr;
+    // gather layouts of the sweeps (options.gather_layout; single-GPU path): packed (x*, lambda) written by pass A for
+    // pass B, packed (x, |omega|) written by K11 for K12 — both need every particle to have the same mass — and the 32-byte
+    // (position, velocity) records K11 / K13 gather from
+    float4 *xl = nullptr, *xw = nullptr;
+    PosVel* pv = nullptr;
+    bool massUniform = false;     // established by the uploads
+    float uniformMass = 0.0f;
+    bool pvFresh = false;         // pv holds the committed (pos, vel) of this step (written by the final pass B)
+    uint32_t *dMassRange = nullptr, *hMassRange = nullptr;   // order-preserving u32 encodings of min / max mass
     // payload in upload order (the solver never reads it: Particle::color / ::size)
     float4* color = nullptr;
     float* size = nullptr;
@@ -200,6 +209,7 @@ SphParams makeSph(const akua_pbf_solver* s) {
     float wdq = dq2 > P.h2 ? 0.0f : P.poly6Coef * (tq * tq * tq);
     P.invPoly6Dq = 1.0f / wdq;
     P.corrNIsFour = (s->corr.n == 4.0f) ? 1 : 0;
+    P.uniformMass = s->uniformMass;
     return P;
 }
 
@@ -335,11 +345,23 @@ struct SweepSpans { Span interior, boundary; };
 SweepSpans sweepSpans(const akua_pbf_solver* s);
 
 // ---- sweep launchers over an index span ----
+// Gather layouts (akua_pbf_options::gather_layout). Slab mode keeps the plain per-array layout: its halo exchanges move
+// ghost planes array by array.
+inline bool usePack(const akua_pbf_solver* s) {
+    const int g = s->opt.gather_layout;
+    return s->massUniform && !s->slab.enabled && (g == AKUA_GATHER_AUTO || g == AKUA_GATHER_PACKED || g == AKUA_GATHER_PACKED_RECORDS);
+}
+inline bool useRec(const akua_pbf_solver* s) {
+    const int g = s->opt.gather_layout;
+    return !s->slab.enabled && (g == AKUA_GATHER_RECORDS || g == AKUA_GATHER_PACKED_RECORDS);
+}
+
 int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
     const PeerPush pl = push ? slabPush(s, s->lambda) : PeerPush{};
-    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P, pl, hs);
-    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, P, pl, hs);
+    float4* xl = usePack(s) ? s->xl : nullptr;
+    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
+    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
     AK_LAUNCH_CHECK(s, "k_density_lambda");
     return AKUA_OK;
 }
@@ -348,33 +370,49 @@ int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams
     if (!sp.count) return AKUA_OK;
     const PeerPush px = push ? slabPush(s, s->xsAlt) : PeerPush{};
     const PeerPush pv = (push && fin) ? slabPush(s, s->vel) : PeerPush{};
-#define AK_DELTA(F, L) k_delta_apply<F, L><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->nbrList, \
-            s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, dt, px, pv, hs)
-    if (s->opt.fast_math) { if (fin) AK_DELTA(true, true); else AK_DELTA(true, false); }
-    else                  { if (fin) AK_DELTA(false, true); else AK_DELTA(false, false); }
+    PosVel* rec = (fin && useRec(s)) ? s->pv : nullptr;
+#define AK_DELTA(F, L, K) k_delta_apply<F, L, K><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->xl, \
+            s->nbrList, s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, rec, dt, px, pv, hs)
+    if (usePack(s)) {
+        if (s->opt.fast_math) { if (fin) AK_DELTA(true, true, true); else AK_DELTA(true, false, true); }
+        else                  { if (fin) AK_DELTA(false, true, true); else AK_DELTA(false, false, true); }
+    } else {
+        if (s->opt.fast_math) { if (fin) AK_DELTA(true, true, false); else AK_DELTA(true, false, false); }
+        else                  { if (fin) AK_DELTA(false, true, false); else AK_DELTA(false, false, false); }
+    }
 #undef AK_DELTA
     AK_LAUNCH_CHECK(s, "k_delta_apply");
+    if (rec) s->pvFresh = true;
     return AKUA_OK;
 }
 int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
     const PeerPush pw = push ? slabPush(s, s->omegaLen) : PeerPush{};
-    if (s->opt.fast_math) k_vorticity<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P, pw, hs);
-    else                  k_vorticity<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->omega, s->omegaLen, P, pw, hs);
+    float4* xw = usePack(s) ? s->xw : nullptr;
+#define AK_VORT(F, R) k_vorticity<F, R><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, \
+            s->nbrStride, sp, s->omega, s->omegaLen, xw, P, pw, hs)
+    if (useRec(s)) { if (s->opt.fast_math) AK_VORT(true, true); else AK_VORT(false, true); }
+    else           { if (s->opt.fast_math) AK_VORT(true, false); else AK_VORT(false, false); }
+#undef AK_VORT
     AK_LAUNCH_CHECK(s, "k_vorticity");
     return AKUA_OK;
 }
 int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
     const PeerPush pv = push ? slabPush(s, s->vel) : PeerPush{};
-    if (s->opt.fast_math) k_confinement<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon, pv, hs);
-    else                  k_confinement<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->density, s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, P, dt, s->cfg.vorticityEpsilon, pv, hs);
+    PosVel* rec = useRec(s) ? s->pv : nullptr;
+#define AK_CONF(F, K) k_confinement<F, K><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->xw, s->density, \
+            s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, rec, P, dt, s->cfg.vorticityEpsilon, pv, hs)
+    if (usePack(s)) { if (s->opt.fast_math) AK_CONF(true, true); else AK_CONF(false, true); }
+    else            { if (s->opt.fast_math) AK_CONF(true, false); else AK_CONF(false, false); }
+#undef AK_CONF
     AK_LAUNCH_CHECK(s, "k_confinement");
     return AKUA_OK;
 }
 int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    k_xsph<<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
+    if (useRec(s)) k_xsph<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
+    else           k_xsph<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
     AK_LAUNCH_CHECK(s, "k_xsph");
     return AKUA_OK;
 }
@@ -485,6 +523,11 @@ int phasePost(akua_pbf_solver* s, float dt) {
     const SphParams P = makeSph(s);
     if (!slabMode) {
         const Span all = fullSpan(n);
+        if (useRec(s) && !s->pvFresh) {   // committed outside the fused final pass B (phase-level API, 0 iterations)
+            k_build_posvel<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, n, s->pv);
+            AK_LAUNCH_CHECK(s, "k_build_posvel");
+        }
+        s->pvFresh = false;               // K12 / K13 leave the records behind the committed state
         if ((rc = launchVorticity(s, all, P))) return rc;
         if ((rc = launchConfinement(s, all, P, dt))) return rc;
         if ((rc = launchXsph(s, all, P))) return rc;
@@ -539,7 +582,9 @@ void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* b
     key[4] = (uint64_t)s->keysSorted; key[5] = (uint64_t)s->n; key[6] = ((uint64_t)iterations << 1) | (s->bucketsDirty ? 1 : 0);
     key[7] = f2(dt, s->cfg.gravity[0]); key[8] = f2(s->cfg.gravity[1], s->cfg.gravity[2]);
     key[9] = f2(bmin[0], bmin[1]); key[10] = f2(bmin[2], bmax[0]); key[11] = f2(bmax[1], bmax[2]);
-    key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math; key[15] = 0;
+    key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math;
+    uint32_t mbits; std::memcpy(&mbits, &s->uniformMass, 4);
+    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u);
 }
 
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
@@ -626,6 +671,24 @@ int stepEager(akua_pbf_solver* s, float dt, int iterations, const float* bmin, c
     return AKUA_OK;
 }
 
+// Uniform-mass detection for the packed gather layouts: min / max of pos.w through an order-preserving u32 encoding,
+// fetched with the copy the upload already waits for. A NaN mass encodes above +inf on one side only -> "not uniform".
+int massRangeAsync(akua_pbf_solver* s) {
+    const uint32_t n = (uint32_t)s->n;
+    AK_CUDA(s, cudaMemsetAsync(s->dMassRange, 0xff, sizeof(uint32_t), s->stream));
+    AK_CUDA(s, cudaMemsetAsync(s->dMassRange + 1, 0, sizeof(uint32_t), s->stream));
+    k_mass_range<<<std::min<uint32_t>(gridFor(n), 148 * 8), kBlock, 0, s->stream>>>(s->pos, n, s->dMassRange);
+    AK_LAUNCH_CHECK(s, "k_mass_range");
+    AK_CUDA(s, cudaMemcpyAsync(s->hMassRange, s->dMassRange, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    return AKUA_OK;
+}
+void massRangeFinish(akua_pbf_solver* s) {   // after the stream synchronisation
+    const uint32_t lo = s->hMassRange[0], hi = s->hMassRange[1];
+    s->massUniform = s->n > 0 && lo == hi;
+    const uint32_t bits = (lo & 0x80000000u) ? (lo ^ 0x80000000u) : ~lo;   // decode
+    std::memcpy(&s->uniformMass, &bits, 4);
+}
+
 }  // namespace
 
 // ======================================================================================================== C ABI
@@ -685,6 +748,22 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     AK_CUDA(s, dalloc(&s->density, cap)); AK_CUDA(s, dalloc(&s->lambda, cap)); AK_CUDA(s, dalloc(&s->omegaLen, cap));
     AK_CUDA(s, dalloc(&s->omega, cap)); AK_CUDA(s, dalloc(&s->dpos, cap));
     AK_CUDA(s, dalloc(&s->color, cap)); AK_CUDA(s, dalloc(&s->size, cap));
+    if (const char* e = std::getenv("AKUA_GATHER_LAYOUT")) s->opt.gather_layout = std::atoi(e);   // tuning experiments
+    if (s->opt.gather_layout < AKUA_GATHER_AUTO || s->opt.gather_layout > AKUA_GATHER_PACKED_RECORDS) { s->err = "unknown gather_layout"; return AKUA_ERR_INVALID; }
+    {
+        const int g = s->opt.gather_layout;
+        if (g != AKUA_GATHER_PLAIN && g != AKUA_GATHER_RECORDS) {
+            AK_CUDA(s, dalloc(&s->xl, cap)); AK_CUDA(s, dalloc(&s->xw, cap));
+            AK_CUDA(s, cudaMemsetAsync(s->xl, 0, cap * sizeof(float4), s->stream));
+            AK_CUDA(s, cudaMemsetAsync(s->xw, 0, cap * sizeof(float4), s->stream));
+        }
+        if (g == AKUA_GATHER_RECORDS || g == AKUA_GATHER_PACKED_RECORDS) {
+            AK_CUDA(s, dalloc(&s->pv, cap));
+            AK_CUDA(s, cudaMemsetAsync(s->pv, 0, cap * sizeof(PosVel), s->stream));
+        }
+    }
+    AK_CUDA(s, dalloc(&s->dMassRange, 2));
+    AK_CUDA(s, cudaMallocHost(reinterpret_cast<void**>(&s->hMassRange), 2 * sizeof(uint32_t)));
     AK_CUDA(s, dalloc(&s->keysUnsorted, cap));
     AK_CUDA(s, dalloc(&s->keyA, cap)); AK_CUDA(s, dalloc(&s->keyB, cap));
     AK_CUDA(s, dalloc(&s->valA, cap)); AK_CUDA(s, dalloc(&s->valB, cap));
@@ -731,7 +810,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
     void* ptrs[] = {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->id, s->idAlt, s->density, s->lambda,
                     s->omegaLen, s->omega, s->dpos, s->color, s->size, s->keysUnsorted, s->keyA, s->keyB, s->valA, s->valB,
                     s->bucketStart, s->cellRange, s->nbrList, s->nbrCount, s->sortWs.tileHist, s->sortWs.binTotal,
-                    s->aosStage, s->partSum, s->partMax};
+                    s->aosStage, s->partSum, s->partMax, s->xl, s->xw, s->pv, s->dMassRange};
+    if (s->hMassRange) cudaFreeHost(s->hMassRange);
     for (auto& g : s->graphs) if (g.used && g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : ptrs) if (p) cudaFree(p);
     {
@@ -814,7 +894,10 @@ int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     k_unpack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((const uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega,
         s->omegaLen, s->dpos, s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
     AK_LAUNCH_CHECK(s, "k_unpack_aos");
+    int rcm = massRangeAsync(s);
+    if (rcm) return rcm;
     AK_CUDA(s, cudaStreamSynchronize(s->stream));  // `src` may be reused by the caller as soon as we return
+    massRangeFinish(s);
     return AKUA_OK;
 }
 int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
@@ -850,8 +933,11 @@ int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* v
     // Host-side widening to float4, then two async copies. (Setup path; the per-step e2e path is AoS-108.)
     std::vector<float4> p4((size_t)n), v4((size_t)n);
     std::vector<uint32_t> ids((size_t)n);
+    bool uniform = true;
+    const float m0 = mass ? mass[0] : 1.0f;
     for (int64_t i = 0; i < n; i++) {
         float m = mass ? mass[i] : 1.0f;
+        uniform = uniform && std::memcmp(&m, &m0, 4) == 0;
         p4[i] = make_float4(pos_xyz[3 * i], pos_xyz[3 * i + 1], pos_xyz[3 * i + 2], m);
         v4[i] = vel_xyz ? make_float4(vel_xyz[3 * i], vel_xyz[3 * i + 1], vel_xyz[3 * i + 2], 0.f) : make_float4(0, 0, 0, 0);
         ids[i] = (uint32_t)i;
@@ -862,6 +948,7 @@ int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* v
     AK_CUDA(s, cudaMemcpyAsync(s->id, ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     s->ctr.h2d_bytes += n * 52;
+    s->massUniform = uniform; s->uniformMass = m0;
     return AKUA_OK;
 }
 int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t* id, int64_t n) {
@@ -953,6 +1040,9 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
         AK_CUDA(s, cudaMemcpy(s->size, size.data(), n * 4, cudaMemcpyHostToDevice));
     }
     s->n = h.n;
+    s->massUniform = n > 0;
+    s->uniformMass = n ? pos[0].w : 0.0f;
+    for (size_t i = 1; i < n && s->massUniform; i++) s->massUniform = std::memcmp(&pos[i].w, &pos[0].w, 4) == 0;
     s->cfg.gravity[0] = h.cfg.gravity[0]; s->cfg.gravity[1] = h.cfg.gravity[1]; s->cfg.gravity[2] = h.cfg.gravity[2];
     s->accumulator = h.accumulator;
     s->ctr.steps = h.steps;

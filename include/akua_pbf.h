@@ -68,6 +68,24 @@ typedef enum akua_key_mode {
 } akua_key_mode;
 
 /* Knobs that exist only on the B200 side (no reference counterpart). Zero-initialise, then akua_pbf_default_options. */
+/* How the neighbour sweeps fetch a neighbour's data (single-GPU path; x-slab mode always uses the plain layout).
+ * The sweeps are bound by L1 gather wavefronts (profiles/), so each sweep wants ONE gather per neighbour:
+ *   packed  : pass A also writes (x*, lambda) as one float4 and K11 writes (x, |omega|), so that pass B and K12 gather
+ *             16 bytes from one array instead of 16 + 4 bytes from two (-11 % on both kernels, measured). Needs every
+ *             particle to have the same mass (checked at each upload; the reference's scenes use mass 1,
+ *             Application.cpp:186) — otherwise those two sweeps silently keep the plain layout.
+ *   records : the committing pass B also writes 32-byte (position, velocity) records; K11 and K13 fetch a neighbour with
+ *             one 256-bit load (LDG.E.256) instead of two 128-bit loads. Measured -3 % on those kernels, cancelled by the
+ *             record writes: kept as an opt-in, not part of the default.
+ * Results are bit-identical in every layout (tests/test_parity_gpu.py::test_gather_layouts_are_bit_identical). */
+typedef enum akua_gather_layout {
+    AKUA_GATHER_AUTO = 0,            /* = packed */
+    AKUA_GATHER_PLAIN = 1,
+    AKUA_GATHER_PACKED = 2,
+    AKUA_GATHER_RECORDS = 3,
+    AKUA_GATHER_PACKED_RECORDS = 4
+} akua_gather_layout;
+
 typedef struct akua_pbf_options {
     int32_t key_mode;        /* akua_key_mode; default AKUA_KEY_LINEAR_CELL */
     int32_t device;          /* CUDA device ordinal; default 0 */
@@ -75,7 +93,8 @@ typedef struct akua_pbf_options {
     int32_t fast_math;       /* 1 (default) = r and 1/r of the spiky gradient from one MUFU rsqrt (max 2 ulp, the same error
                                 class as the reference's own powf calls); 0 = IEEE sqrtf and division */
     float capacity_factor;   /* device arrays are sized for capacity_factor * n particles (ghosts, migration); default 1 */
-    int32_t reserved[8];
+    int32_t gather_layout;   /* akua_gather_layout; default AKUA_GATHER_AUTO. Results are bit-identical in every layout. */
+    int32_t reserved[7];
 } akua_pbf_options;
 
 void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */

@@ -16,7 +16,8 @@ import numpy as np
 import pytest
 
 import parity_lib as pl
-from akuaengine_b200 import DBG, KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PARTICLE_DTYPE, PBFSolver, scenes
+from akuaengine_b200 import (DBG, GATHER_AUTO, GATHER_PACKED, GATHER_PACKED_RECORDS, GATHER_PLAIN, GATHER_RECORDS,
+                             KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PARTICLE_DTYPE, PBFSolver, scenes)
 
 pytestmark = pytest.mark.gpu
 
@@ -240,6 +241,55 @@ def test_graph_replay_is_bit_identical_to_eager_launches(mode):
         assert c["kernel_launches"] > 7 * 15
         s.close()
     assert outs[0].tobytes() == outs[1].tobytes()
+
+
+@pytest.mark.parametrize("masses", ["uniform", "random"])
+@pytest.mark.parametrize("fast", [True, False], ids=["rsqrt", "ieee"])
+def test_gather_layouts_are_bit_identical(masses, fast):
+    """options.gather_layout only changes WHERE a sweep fetches a neighbour's data from (packed (x*, lambda) / (x, |omega|)
+    arrays, 32-byte position+velocity records read with one 256-bit load); every layout must leave exactly the state the
+    plain per-array layout leaves. With non-uniform masses the packed layout must switch itself off."""
+    if masses == "uniform":
+        init, bmin, bmax = scenes.dam_break(16)
+    else:
+        g = dict(np.load(GOLDEN / "jitter.npz"))
+        init, bmin, bmax = g["init"], g["box_min"], g["box_max"]
+        assert len(np.unique(init["mass"])) > 1
+    outs = {}
+    for layout in (GATHER_PLAIN, GATHER_AUTO, GATHER_PACKED, GATHER_RECORDS, GATHER_PACKED_RECORDS):
+        for use_graph in (False, True):
+            s = PBFSolver(len(init), gather_layout=layout, use_graph=use_graph, fast_math=fast)
+            s.upload_particles(init)
+            for _ in range(6):
+                s.step(0.0083, bmin, bmax)
+            s.step(0.0083, bmin, bmax, solverIterations=0)   # commit outside the fused pass B: records rebuilt by k_build_posvel
+            s.step(0.0083, bmin, bmax)
+            outs[(layout, use_graph)] = s.download_particles().tobytes()
+            s.close()
+    ref = outs[(GATHER_PLAIN, False)]
+    for k, v in outs.items():
+        assert v == ref, k
+
+
+def test_gather_layout_follows_the_uploaded_masses():
+    """Uniform-mass detection happens at every upload: a solver that first saw uniform masses must fall back to the plain
+    pass-B / K12 gathers when re-uploaded with mixed masses (and back)."""
+    init, bmin, bmax = scenes.dam_break(12)
+    mixed = init.copy()
+    mixed["mass"][::3] = 1.25
+    res = []
+    for layout in (GATHER_PLAIN, GATHER_AUTO):
+        s = PBFSolver(len(init), gather_layout=layout)
+        out = []
+        for p in (init, mixed, init):
+            s.upload_particles(p)
+            for _ in range(3):
+                s.step(0.0083, bmin, bmax)
+            out.append(s.download_particles().tobytes())
+        res.append(out)
+        s.close()
+    assert res[0] == res[1]
+    assert res[0][0] == res[0][2] and res[0][0] != res[0][1]
 
 
 def test_graph_cache_backs_off_when_parameters_change_every_step():

@@ -1,4 +1,5 @@
-"""Times alternative builds of libakua_pbf.so (tuning experiments): python tools/time_variants.py build/*.so"""
+"""Times alternative builds of libakua_pbf.so and the gather layouts (tuning experiments):
+python tools/time_variants.py [build/*.so]   — every library x fast_math {0,1} x AKUA_GATHER_LAYOUT {plain, packed, records, packed+records}"""
 import json, os, subprocess, sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parents[1]
@@ -18,10 +19,13 @@ s.enable_timing(True); s.step(0.0083, bmin, bmax); ph = s.last_step_timing()
 print(json.dumps({"ms": round(wall*1e3, 4), "A": round(ph["pass_a_sum"]/4*1e3), "B": round(ph["pass_b_sum"]/4*1e3), "lists": round(ph["neighbour_lists"]*1e3), "post": round(ph["post"]*1e3), "sort": round(ph["sort"]*1e3)}))
 ''' % str(REPO)
 libs = sys.argv[1:] or [""]
+LAYOUTS = {1: "plain", 2: "packed", 3: "records", 4: "packed+records"}
 for n_side in (100,):
-    for fast in (0, 1):
+    for fast in (1,):
         for lib in libs:
-            env = dict(os.environ)
-            if lib: env["AKUA_PBF_LIB"] = str(Path(lib).resolve())
-            r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
-            print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s}", r.stdout.strip() or r.stderr[-300:], flush=True)
+            for layout, lname in LAYOUTS.items():
+                env = dict(os.environ)
+                if lib: env["AKUA_PBF_LIB"] = str(Path(lib).resolve())
+                env["AKUA_GATHER_LAYOUT"] = str(layout)
+                r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
+                print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s} {lname:8s}", r.stdout.strip() or r.stderr[-300:], flush=True)

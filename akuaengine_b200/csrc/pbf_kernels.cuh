@@ -56,19 +56,26 @@ __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 __device__ __forceinline__ float poly6(float d2, const SphParams& P) {  // SmoothingKernelsCUDA.h:16-21
-    float t = P.h2 - d2;
-    return d2 > P.h2 ? 0.0f : P.poly6Coef * (t * t * t);
+    // d2 > h2 ? 0 : coef * (h2 - d2)^3, with the cut-off as a clamp (one FMNMX instead of FSETP + FSEL): for d2 <= h2 the
+    // clamp is the identity, beyond it the cube is exactly 0.
+    float t = fmaxf(P.h2 - d2, 0.0f);
+    return P.poly6Coef * (t * t * t);
 }
 // Spiky gradient, SmoothingKernelsCUDA.h:23-28. Returns the scalar s such that grad = s * r_vector
-// (s = coef*(h-r)^2 / r, 0 outside (1e-5, h]).
+// (s = coef*(h-r)^2 / r, 0 outside (1e-5, h]; the r > h cut-off is a clamp of h - r, see poly6).
 template <bool FAST>
 __device__ __forceinline__ float spiky_scale(float d2, const SphParams& P) {
     float r, invr;
-    if (FAST) { invr = rsqrtf(fmaxf(d2, 1e-30f)); r = d2 * invr; }  // d2 == 0 (coincident / masked self slot) -> r = 0 -> s = 0
-    else      { r = sqrtf(d2); invr = 1.0f / r; }
-    float t = P.h - r;
+    if (FAST) {
+        // one MUFU.RSQ: the operand is clamped to a normal float, so the denormal pre/post-scaling of rsqrtf() (three more
+        // instructions per neighbour) can never trigger. d2 == 0 (coincident / masked self slot) -> r = 0 -> s = 0.
+        float d = fmaxf(d2, 1e-30f);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(invr) : "f"(d));
+        r = d2 * invr;
+    } else { r = sqrtf(d2); invr = 1.0f / r; }
+    float t = fmaxf(P.h - r, 0.0f);
     float s = P.spikyCoef * (t * t) * invr;
-    return (r > P.h || r < 1e-5f) ? 0.0f : s;
+    return r < 1e-5f ? 0.0f : s;
 }
 __device__ __forceinline__ int3 cell_of(float x, float y, float z, float cellSize) {
     // NeighbourSearchCUDA.cu:15-21: floorf of a true IEEE division
@@ -363,8 +370,13 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
             float ax = s * dx, ay = s * dy, az = s * dz;        // grad W_spiky
             gx = fmaf(m, ax, gx); gy = fmaf(m, ay, gy); gz = fmaf(m, az, gz);
             float q = -P.invRestDensity * m;                     // grad_pj C_i = q * gradW
-            float bx = q * ax, by = q * ay, bz = q * az;
-            sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
+            if (FAST) {                                          // |q * s * r_vec|^2 = (q s)^2 d2: 3 instructions, not 8
+                float qs = q * s;
+                sum = fmaf(qs * qs, d2, sum);
+            } else {
+                float bx = q * ax, by = q * ay, bz = q * az;
+                sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
+            }
         });
     gx *= P.invRestDensity; gy *= P.invRestDensity; gz *= P.invRestDensity;
     float C = rho * P.invRestDensity - 1.0f;
@@ -419,7 +431,9 @@ __device__ __forceinline__ void damp_velocity(float px, float py, float pz, floa
 // (IntegrationCUDA.cu:38-49) and kernel_apply_boundary_velocity_damping (:75-102), both per-particle.
 // PACK (every particle has the mass P.uniformMass): x* and lambda of a neighbour come from ONE gather of pass A's packed
 // (x*, lambda) array `xl` instead of a 16-byte and a 4-byte gather; the arithmetic is the same expression on the same values.
-template <bool FAST, bool FINAL, bool PACK>
+// CORR4: the artificial-pressure exponent n is 4 (the reference's default, PBFConfig.h:14): two multiplies instead of powf,
+// and no per-neighbour branch on it.
+template <bool FAST, bool FINAL, bool PACK, bool CORR4>
 __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
                                                      const float* __restrict__ lambda, const float4* __restrict__ xl,
                                                      const uint32_t* __restrict__ list,
@@ -451,7 +465,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
             float d2 = dist2(dx, dy, dz);
             float ratio = poly6(d2, P) * P.invPoly6Dq;
             float pw;
-            if (P.corrNIsFour) { float r2 = ratio * ratio; pw = r2 * r2; }
+            if (CORR4) { float r2 = ratio * ratio; pw = r2 * r2; }
             else pw = powf(ratio, P.corrN);
             float corr = -P.corrK * pw;
             float coef = (li + nb.l + corr) * nb.x.w * spiky_scale<FAST>(d2, P);

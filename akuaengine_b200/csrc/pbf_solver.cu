@@ -371,15 +371,14 @@ int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams
     const PeerPush px = push ? slabPush(s, s->xsAlt) : PeerPush{};
     const PeerPush pv = (push && fin) ? slabPush(s, s->vel) : PeerPush{};
     PosVel* rec = (fin && useRec(s)) ? s->pv : nullptr;
-#define AK_DELTA(F, L, K) k_delta_apply<F, L, K><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->xl, \
+#define AK_DELTA(F, L, K, C) k_delta_apply<F, L, K, C><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->xl, \
             s->nbrList, s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, rec, dt, px, pv, hs)
-    if (usePack(s)) {
-        if (s->opt.fast_math) { if (fin) AK_DELTA(true, true, true); else AK_DELTA(true, false, true); }
-        else                  { if (fin) AK_DELTA(false, true, true); else AK_DELTA(false, false, true); }
-    } else {
-        if (s->opt.fast_math) { if (fin) AK_DELTA(true, true, false); else AK_DELTA(true, false, false); }
-        else                  { if (fin) AK_DELTA(false, true, false); else AK_DELTA(false, false, false); }
-    }
+#define AK_DELTA_C(F, L, K) do { if (P.corrNIsFour) AK_DELTA(F, L, K, true); else AK_DELTA(F, L, K, false); } while (0)
+#define AK_DELTA_L(F, K) do { if (fin) AK_DELTA_C(F, true, K); else AK_DELTA_C(F, false, K); } while (0)
+    if (usePack(s)) { if (s->opt.fast_math) AK_DELTA_L(true, true); else AK_DELTA_L(false, true); }
+    else            { if (s->opt.fast_math) AK_DELTA_L(true, false); else AK_DELTA_L(false, false); }
+#undef AK_DELTA_L
+#undef AK_DELTA_C
 #undef AK_DELTA
     AK_LAUNCH_CHECK(s, "k_delta_apply");
     if (rec) s->pvFresh = true;

@@ -20,6 +20,8 @@ print(json.dumps({"ms": round(wall*1e3, 4), "A": round(ph["pass_a_sum"]/4*1e3), 
 ''' % str(REPO)
 libs = sys.argv[1:] or [""]
 LAYOUTS = {1: "plain", 2: "packed", 3: "records", 4: "packed+records"}
+if os.environ.get("AKUA_TV_LAYOUTS"):
+    LAYOUTS = {int(k): LAYOUTS[int(k)] for k in os.environ["AKUA_TV_LAYOUTS"].split(",")}
 for n_side in (100,):
     for fast in (1,):
         for lib in libs:

@@ -80,7 +80,7 @@ class PBFConfig(C.Structure):
 
 class PBFOptions(C.Structure):
     _fields_ = [("key_mode", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("fast_math", C.c_int32),
-                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Counters(C.Structure):
@@ -229,7 +229,7 @@ class PBFSolver:
 
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
-                 capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO):
+                 capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None):
         self._lib = load_library()
         self.config = config or PBFConfig()
         self.corrParams = corrParams or LambdaCorrParams()
@@ -239,6 +239,8 @@ class PBFSolver:
         opt.key_mode, opt.device, opt.fast_math, opt.use_graph = int(key_mode), int(device), int(fast_math), int(use_graph)
         opt.capacity_factor = float(capacity_factor)
         opt.gather_layout = int(gather_layout)
+        if use_pdl is not None:
+            opt.use_pdl = int(use_pdl)
         self.options = opt
         self._h = C.c_void_p()
         rc = self._lib.akua_pbf_create(C.byref(self._h), self.numParticles, C.byref(self.config),

@@ -50,6 +50,15 @@ struct BoxParams {
     float dampingMinDist, restitution, oneMinusFriction;  // 0.025 (IntegrationCUDA.cu:88), 0, 1-0.95 (PBFSolver.cpp:64)
 };
 
+// ------------------------------------------------------------------------------------------------ programmatic dependent launch
+// The step is ~23 short kernels in a row; with programmatic dependent launch (options.use_pdl) kernel N+1 is scheduled while
+// kernel N drains instead of after it, which hides the launch latency between them. Every kernel of the step calls
+// pdl_wait() before it touches global memory (it returns once ALL grids it depends on have completed and flushed — so the
+// data dependencies are exactly those of plain stream order) and pdl_trigger() once its main loop is done (the next grid may
+// start occupying SM slots from then on). Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------ device math
 __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
     // exactly the reference's contraction (kernel_find_neighbours SASS): fma(dz,dz, fma(dx,dx, dy*dy))
@@ -218,6 +227,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                      float4* __restrict__ xs, uint32_t* __restrict__ keys, uint32_t n,
                                                      float dt, float3 g, GridParams G, int doPredict) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 x;
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(256) k_reorder_ranges(const uint32_t* __restri
                                                         float4* __restrict__ posOut, float4* __restrict__ velOut,
                                                         float4* __restrict__ xsOut, uint32_t* __restrict__ idOut,
                                                         uint32_t* __restrict__ bucketStart, uint2* __restrict__ cellRange) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t src = perm[i];
@@ -267,6 +278,7 @@ __global__ void __launch_bounds__(256) k_reorder_ranges(const uint32_t* __restri
 // it with UINT32_MAX every step: NeighbourSearchCUDA.cu:157 — 512 B per particle per step).
 __global__ void __launch_bounds__(256) k_clear_buckets(const uint32_t* __restrict__ keysSorted, uint32_t n,
                                                        uint32_t* __restrict__ bucketStart) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k = keysSorted[i];
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
                                                           const uint2* __restrict__ cellRange, uint32_t n,
                                                           uint32_t stride, uint32_t maxN, uint32_t* __restrict__ list,
                                                           uint32_t* __restrict__ cnt, GridParams G, float h) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 xi = xs[i];
@@ -338,6 +351,7 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
             }
         }
     }
+    pdl_trigger();
     cnt[i] = count;
     for (uint32_t k = count; k < ((count + 3u) & ~3u); k++) list[list_slot(i, k, stride)] = i;
 }
@@ -351,6 +365,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
                                                         float* __restrict__ density, float* __restrict__ lambda,
                                                         float4* __restrict__ xl, SphParams P, PeerPush pushLambda,
                                                         HaloSync hs) {
+    pdl_wait();
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
@@ -378,13 +393,19 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
                 sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
             }
         });
+    pdl_trigger();
     gx *= P.invRestDensity; gy *= P.invRestDensity; gz *= P.invRestDensity;
     float C = rho * P.invRestDensity - 1.0f;
     float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
     density[i] = rho;
     lambda[i] = lam;
-    if (xl) xl[i] = make_float4(xi.x, xi.y, xi.z, lam);   // packed-gather layout: pass B fetches x* and lambda in one gather
-    peer_push(pushLambda, i, lam);
+    if (xl) {   // packed-gather layout: pass B fetches x* and lambda in one gather (the halo push then carries the pair too)
+        const float4 v = make_float4(xi.x, xi.y, xi.z, lam);
+        xl[i] = v;
+        peer_push(pushLambda, i, v);
+    } else {
+        peer_push(pushLambda, i, lam);
+    }
     }
     halo_signal(hs);
 }
@@ -442,6 +463,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
                                                      float4* __restrict__ pos, float4* __restrict__ vel,
                                                      const float* __restrict__ density, PosVel* __restrict__ pvOut,
                                                      float dt, PeerPush pushX, PeerPush pushV, HaloSync hs) {
+    pdl_wait();
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
@@ -472,6 +494,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
             coef = valid ? coef : 0.0f;
             px = fmaf(coef, dx, px); py = fmaf(coef, dy, py); pz = fmaf(coef, dz, pz);
         });
+    pdl_trigger();
     px *= P.invRestDensity; py *= P.invRestDensity; pz *= P.invRestDensity;
     if (dposOut) dposOut[i] = make_float4(px, py, pz, 0.f);
     float x = collide_axis(xi.x + px, B.bmin.x, B.bmax.x, B);
@@ -497,6 +520,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
 // API, solverIterations == 0).
 __global__ void __launch_bounds__(256) k_build_posvel(const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                       uint32_t n, PosVel* __restrict__ pv) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PosVel r; r.x = pos[i]; r.v = vel[i];
@@ -507,6 +531,7 @@ __global__ void __launch_bounds__(256) k_build_posvel(const float4* __restrict__
 __global__ void __launch_bounds__(256) k_update(const float4* __restrict__ xs, float4* __restrict__ pos,
                                                 float4* __restrict__ vel, const float* __restrict__ density, uint32_t n,
                                                 float dt) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 x = xs[i], p = pos[i];
@@ -515,6 +540,7 @@ __global__ void __launch_bounds__(256) k_update(const float4* __restrict__ xs, f
 }
 __global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos, float4* __restrict__ vel, uint32_t n,
                                                  BoxParams B) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pos[i], v = vel[i];
@@ -533,6 +559,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
                                                    uint32_t stride, Span sp, float4* __restrict__ omega,
                                                    float* __restrict__ omegaLen, float4* __restrict__ xw, SphParams P,
                                                    PeerPush pushLen, HaloSync hs) {
+    pdl_wait();
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
@@ -556,11 +583,17 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
             float m = valid ? -nb.x.w : 0.0f;
             wx = fmaf(m, cx, wx); wy = fmaf(m, cy, wy); wz = fmaf(m, cz, wz);
         });
+    pdl_trigger();
     float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
     omega[i] = make_float4(wx, wy, wz, len);
     omegaLen[i] = len;
-    if (xw) xw[i] = make_float4(xi.x, xi.y, xi.z, len);
-    peer_push(pushLen, i, len);
+    if (xw) {
+        const float4 v = make_float4(xi.x, xi.y, xi.z, len);
+        xw[i] = v;
+        peer_push(pushLen, i, v);
+    } else {
+        peer_push(pushLen, i, len);
+    }
     }
     halo_signal(hs);
 }
@@ -577,6 +610,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
                                                      uint32_t stride, Span sp, float4* __restrict__ vel,
                                                      PosVel* __restrict__ pvOut, SphParams P,
                                                      float dt, float eps, PeerPush pushV, HaloSync hs) {
+    pdl_wait();
     halo_wait(hs);
     uint32_t i;
     const bool live = span_index(sp, i);
@@ -600,6 +634,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
             coef = valid ? coef : 0.0f;
             ex = fmaf(coef, dx, ex); ey = fmaf(coef, dy, ey); ez = fmaf(coef, dz, ez);
         });
+    pdl_trigger();
     ex *= invDensity; ey *= invDensity; ez *= invDensity;
     float len = sqrtf(fmaf(ez, ez, fmaf(ex, ex, ey * ey)));
     if (len >= 1e-5f) {
@@ -625,6 +660,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const fl
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                               uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
                                               float cvisc, HaloSync hs) {
+    pdl_wait();
     halo_wait(hs);
     uint32_t i;
     if (!span_index(sp, i)) return;
@@ -645,6 +681,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const fl
             w = valid ? w : 0.0f;
             ax = fmaf(mr * (nb.v.x - vi.x), w, ax); ay = fmaf(mr * (nb.v.y - vi.y), w, ay); az = fmaf(mr * (nb.v.z - vi.z), w, az);
         });
+    pdl_trigger();
     velOut[i] = make_float4(fmaf(cvisc, ax, vi.x), fmaf(cvisc, ay, vi.y), fmaf(cvisc, az, vi.z), vi.w);
 }
 

@@ -83,6 +83,8 @@ template <typename T> T* peerOf(const akua_pbf_solver* s, const SlabPeer& peer, 
     if (m == sl.velBuf[1]) return reinterpret_cast<T*>(peer.velBuf[1]);
     if (m == s->lambda) return reinterpret_cast<T*>(peer.lambda);
     if (m == s->omegaLen) return reinterpret_cast<T*>(peer.omegaLen);
+    if (m == s->xl) return reinterpret_cast<T*>(peer.xl);
+    if (m == s->xw) return reinterpret_cast<T*>(peer.xw);
     return nullptr;
 }
 template <typename T>
@@ -218,6 +220,33 @@ int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
     if (rc) return rc;
     return slabWait(s, t);
 }
+// Packed gather layout in x-slab mode: pass B / K12 read ghosts through the packed (x*, lambda) / (x, |omega|) arrays and the
+// sweeps multiply by ONE mass, so the layout is only used when every particle of every rank has the same mass and every
+// rank holds the packed arrays. Global uniformity cannot change through migration, only through uploads, so the verdict is
+// taken where the masses enter: in akua_pbf_set_slab and, once slab mode is on, in every upload — which makes those calls
+// COLLECTIVE in slab mode (every rank calls them, like akua_pbf_rebalance). One MIN all-reduce of (lo, ~hi, has-arrays).
+int slabAgreeMass(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.enabled || !sl.comm || sl.nranks < 2) return AKUA_OK;
+    uint32_t lo = 0xffffffffu, hi = 0u;                       // neutral: a rank without particles
+    if (s->n > 0) {
+        if (s->massUniform) { uint32_t b; std::memcpy(&b, &s->uniformMass, 4); lo = hi = (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+        else { lo = 0u; hi = 0xffffffffu; }
+    }
+    uint32_t msg[4] = {lo, ~hi, (s->xl && s->xw) ? 1u : 0u, 0u};
+    uint32_t* d = sl.dCounts + 8;                             // words 8..11 are not used by the step
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    AK_CUDA(s, cudaMemcpy(d, msg, sizeof(msg), cudaMemcpyHostToDevice));
+    AK_NCCL(s, g_nccl.AllReduce(d, d, 4, ncclUint32, ncclMin, (ncclComm_t)sl.comm, sl.commStream));
+    AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
+    AK_CUDA(s, cudaMemcpy(msg, d, sizeof(msg), cudaMemcpyDeviceToHost));
+    const uint32_t glo = msg[0], ghi = ~msg[1];
+    s->massUniform = msg[2] != 0 && glo == ghi && glo != 0xffffffffu;
+    const uint32_t bits = (glo & 0x80000000u) ? (glo ^ 0x80000000u) : ~glo;
+    std::memcpy(&s->uniformMass, &bits, 4);
+    return AKUA_OK;
+}
+
 // Interior / boundary index spans of the owned range for the current step's plane sizes.
 SweepSpans sweepSpans(const akua_pbf_solver* s) {
     const SlabState& sl = s->slab;
@@ -239,6 +268,21 @@ SweepSpans sweepSpans(const akua_pbf_solver* s) {
 int slabSwapCounts(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    if (sl.p2p) {
+        // CUDA-IPC transport: counters (and, through k_mig_pack, the migration records) are stored straight into the
+        // neighbours' memory; everything stays on the main stream — no NCCL kernel, no stream hop.
+        const uint32_t epoch = ++sl.countEpoch;
+        slab::k_publish_counts<<<1, 32, 0, s->stream>>>(sl.dCounts, hasL ? sl.peerL.dCounts : nullptr, hasR ? sl.peerR.dCounts : nullptr,
+                                                        hasL ? sl.peerL.flags + 5 : nullptr, hasR ? sl.peerR.flags + 4 : nullptr, epoch);
+        AK_LAUNCH_CHECK(s, "k_publish_counts");
+        slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, epoch, sl.dCounts + 31, 4000000000LL);
+        AK_LAUNCH_CHECK(s, "k_wait_flags");
+        AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        AK_CUDA(s, cudaStreamSynchronize(s->stream));
+        if (!hasL) sl.hCounts[24] = sl.hCounts[25] = sl.hCounts[26] = 0;
+        if (!hasR) sl.hCounts[28] = sl.hCounts[29] = sl.hCounts[30] = 0;
+        return AKUA_OK;
+    }
     ncclComm_t comm = (ncclComm_t)sl.comm;
     cudaStream_t st = sl.commStream;
     int rc;
@@ -285,8 +329,16 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     AK_LAUNCH_CHECK(s, "k_mig_count");
     slab::k_mig_scan<<<1, 1024, 0, s->stream>>>(sl.blockCnt, blocks, sl.dCounts);
     AK_LAUNCH_CHECK(s, "k_mig_scan");
+    // p2p transport: leavers are packed straight into the neighbours' inboxes (my left neighbour receives them "from its
+    // right"); otherwise into local send buffers that NCCL ships after the count exchange
+    const bool hasLn = sl.rank > 0, hasRn = sl.rank + 1 < sl.nranks;
+    slab::MigRecord* outBufL = (sl.p2p && hasLn) ? sl.peerL.recvR : sl.sendL;
+    slab::MigRecord* outBufR = (sl.p2p && hasRn) ? sl.peerR.recvL : sl.sendR;
+    uint32_t packCap = sl.migCap;
+    if (sl.p2p && hasLn) packCap = std::min(packCap, sl.peerL.migCap);
+    if (sl.p2p && hasRn) packCap = std::min(packCap, sl.peerR.migCap);
     slab::k_mig_pack<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sentinel, s->pos,
-                                                       s->vel, s->xs, s->id, sl.sendL, sl.sendR, sl.migCap);
+                                                       s->vel, s->xs, s->id, outBufL, outBufR, packCap);
     AK_LAUNCH_CHECK(s, "k_mig_pack");
     if ((rc = slabSwapCounts(s))) return rc;
     const uint32_t* hc = sl.hCounts;
@@ -296,15 +348,17 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     // Post-migration plane sizes, known before the sort: my boundary planes = stayers + arrivals that land in them;
     // a neighbour's facing plane (= my ghosts) = its stayers there + my leavers that land there. (Arrivals from the far
     // side cannot reach the near plane: slabs are >= 2 planes wide and the stepper moves particles by << one slab.)
-    const bool hasLn = sl.rank > 0, hasRn = sl.rank + 1 < sl.nranks;
     sl.nPlaneL = hasLn ? hc[2] + hc[25] : 0;
     sl.nPlaneR = hasRn ? hc[3] + hc[29] : 0;
     sl.nGhostL = hasLn ? hc[26] + hc[4] : 0;
     sl.nGhostR = hasRn ? hc[30] + hc[5] : 0;
     if (sl.rank == 0 && outL) { s->err = "slab: internal error (leavers beyond the first rank)"; return AKUA_ERR_INVALID; }
-    if (outL > sl.migCap || outR > sl.migCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
+    if (outL > packCap || outR > packCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
     if ((uint64_t)n + inL + inR > (uint64_t)sl.ghostBaseL) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
-    {
+    if (sl.p2p) {   // the records arrived with the count message
+        sl.exchanges++;
+        sl.bytesSent += ((size_t)outL + outR) * sizeof(slab::MigRecord);
+    } else {
         const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
         ncclComm_t comm = (ncclComm_t)sl.comm;
         cudaStream_t st = sl.commStream;   // already ordered after the pack kernel by the count swap's host sync
@@ -332,7 +386,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
     if (nPre) {
         int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, nPre, sortBits, s->sortWs, s->stream,
-                                         &s->keysSorted, &s->perm);
+                                         &s->keysSorted, &s->perm, usePdl(s));
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
         s->ctr.kernel_launches += launches;
@@ -341,7 +395,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     mark(s, PH_REORDER);
     s->n = nOwn;
     if (nOwn) {
-        k_reorder_ranges<KEY_LINEAR><<<gridFor(nOwn), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, nOwn, s->pos, s->vel, s->xs, s->id,
+        launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(nOwn), kBlock, s->keysSorted, s->perm, nOwn, s->pos, s->vel, s->xs, s->id,
             s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
         AK_LAUNCH_CHECK(s, "k_reorder_ranges");
     }
@@ -359,7 +413,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         const uint32_t cntG = side == 0 ? sl.nGhostL : sl.nGhostR, base = side == 0 ? sl.ghostBaseL : sl.ghostBaseR;
         if (!cntG) continue;
         float3 g0 = make_float3(0, 0, 0);
-        k_predict_key<KEY_LINEAR><<<gridFor(cntG), kBlock, 0, s->stream>>>(nullptr, nullptr, s->xs + base, s->keysSorted + base, cntG, 0.0f, g0, G, 0);
+        launchK(s, k_predict_key<KEY_LINEAR>, gridFor(cntG), kBlock, nullptr, nullptr, s->xs + base, s->keysSorted + base, cntG, 0.0f, g0, G, 0);
         AK_LAUNCH_CHECK(s, "k_predict_key(ghosts)");
         slab::k_ranges<<<gridFor(cntG), kBlock, 0, s->stream>>>(s->keysSorted, base, base + cntG, s->cellRange);
         AK_LAUNCH_CHECK(s, "k_ranges(ghosts)");
@@ -368,7 +422,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     // ---- 5. neighbour lists of the owned particles (candidates include the ghost planes) ----
     mark(s, PH_LISTS);
     if (nOwn) {
-        k_build_neighbours<KEY_LINEAR><<<gridFor(nOwn), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, nOwn,
+        launchK(s, k_build_neighbours<KEY_LINEAR>, gridFor(nOwn), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, nOwn,
             s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
         AK_LAUNCH_CHECK(s, "k_build_neighbours");
     }

@@ -46,7 +46,11 @@ struct SlabPeer {            // a neighbour's allocations, opened through CUDA I
     float4* velBuf[2] = {nullptr, nullptr};
     float* lambda = nullptr;
     float* omegaLen = nullptr;
+    float4 *xl = nullptr, *xw = nullptr;                        // packed gather arrays (null when a rank has none)
     uint32_t* flags = nullptr;
+    uint32_t* dCounts = nullptr;                               // the neighbour's counter block (count exchange by P2P stores)
+    slab::MigRecord *recvL = nullptr, *recvR = nullptr;       // the neighbour's migration inboxes
+    uint32_t migCap = 0;
     uint32_t ghostBaseL = 0, ghostBaseR = 0;
 };
 struct SlabTicket { bool valid = false; cudaEvent_t ev = nullptr; uint32_t epoch = 0; };
@@ -82,6 +86,7 @@ struct SlabState {
     void* velBuf[2] = {nullptr, nullptr};
     uint32_t* flags = nullptr;             // [0] epoch published by the left rank, [1] by the right rank
     uint32_t epoch = 0;
+    uint32_t countEpoch = 0;               // p2p: epoch of the per-step count + migration message (flags[4] / flags[5])
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
     int64_t rebalances = 0;
@@ -183,6 +188,23 @@ namespace {
         (s)->ctr.kernel_launches++;                                                                    \
     } while (0)
 
+// Kernel launch on the solver's current stream. With options.use_pdl the launch carries the programmatic
+// stream serialization attribute: the kernel may be scheduled while its predecessor drains (pdl_wait() in every kernel keeps
+// the data dependencies those of plain stream order); captured into the step's CUDA graph as programmatic edges.
+inline bool usePdl(const akua_pbf_solver* s) { return s->opt.use_pdl != 0; }
+template <typename... KArgs, typename... Args>
+inline void launchK(const akua_pbf_solver* s, void (*kernel)(KArgs...), uint32_t grid, uint32_t block, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = s->stream;
+    cudaLaunchAttribute at{};
+    if (usePdl(s)) {
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T>
 cudaError_t dalloc(T** p, size_t count) {
     *p = nullptr;
@@ -281,9 +303,9 @@ int phasePredictKey(akua_pbf_solver* s, float dt, bool doPredict, bool doKeys) {
     float3 g = make_float3(s->cfg.gravity[0], s->cfg.gravity[1], s->cfg.gravity[2]);
     uint32_t* keys = doKeys ? s->keysUnsorted : nullptr;
     if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH)
-        k_predict_key<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+        launchK(s, k_predict_key<KEY_HASH>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
     else
-        k_predict_key<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+        launchK(s, k_predict_key<KEY_LINEAR>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
     AK_LAUNCH_CHECK(s, "k_predict_key");
     return AKUA_OK;
 }
@@ -294,14 +316,14 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     const bool hash = s->opt.key_mode == AKUA_KEY_REFERENCE_HASH;
     if (hash) {
         if (s->bucketsDirty) {
-            k_clear_buckets<<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, n, s->bucketStart);
+            launchK(s, k_clear_buckets, gridFor(n), kBlock, s->keysSorted, n, s->bucketStart);
             AK_LAUNCH_CHECK(s, "k_clear_buckets");
         }
     } else {
         AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
     }
     int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, n, s->keyBits, s->sortWs,
-                                     s->stream, &s->keysSorted, &s->perm);
+                                     s->stream, &s->keysSorted, &s->perm, usePdl(s));
     {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
@@ -310,10 +332,10 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     s->ctr.sort_passes_last = launches / 3;
     mark(s, PH_REORDER);
     if (hash)
-        k_reorder_ranges<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
+        launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
             s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
     else
-        k_reorder_ranges<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
+        launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(n), kBlock, s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
             s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
     AK_LAUNCH_CHECK(s, "k_reorder_ranges");
     std::swap(s->pos, s->posAlt);
@@ -323,10 +345,10 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     s->bucketsDirty = hash;
     mark(s, PH_LISTS);
     if (hash)
-        k_build_neighbours<KEY_HASH><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
+        launchK(s, k_build_neighbours<KEY_HASH>, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
             s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
     else
-        k_build_neighbours<KEY_LINEAR><<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
+        launchK(s, k_build_neighbours<KEY_LINEAR>, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
             s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
     AK_LAUNCH_CHECK(s, "k_build_neighbours");
     return AKUA_OK;
@@ -337,6 +359,7 @@ template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);       
 template <typename T> int slabExchangeAsync(akua_pbf_solver* s, T* arr, SlabTicket* t);  // on the comm stream
 template <typename T, typename U> int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, SlabTicket* t);
 int slabWait(akua_pbf_solver* s, const SlabTicket& t);
+int slabAgreeMass(akua_pbf_solver* s);
 template <typename T> PeerPush slabPush(const akua_pbf_solver* s, T* arr);        // null pushes unless the p2p transport is on
 int slabSignalAfterKernel(akua_pbf_solver* s, SlabTicket* t);                   // publish "boundary results pushed" to both peers
 // Fused path: builds the in-kernel wait (on `waitFor`) / signal (new ticket in *out when non-null) block of a boundary launch.
@@ -345,11 +368,12 @@ struct SweepSpans { Span interior, boundary; };
 SweepSpans sweepSpans(const akua_pbf_solver* s);
 
 // ---- sweep launchers over an index span ----
-// Gather layouts (akua_pbf_options::gather_layout). Slab mode keeps the plain per-array layout: its halo exchanges move
-// ghost planes array by array.
+// Gather layouts (akua_pbf_options::gather_layout). The 32-byte records are single-GPU only.
 inline bool usePack(const akua_pbf_solver* s) {
     const int g = s->opt.gather_layout;
-    return s->massUniform && !s->slab.enabled && (g == AKUA_GATHER_AUTO || g == AKUA_GATHER_PACKED || g == AKUA_GATHER_PACKED_RECORDS);
+    // x-slab mode: massUniform is then the verdict ALL ranks agreed on (slabAgreeMass), because the packed arrays are
+    // what the halo exchanges carry
+    return s->massUniform && s->xl && (g == AKUA_GATHER_AUTO || g == AKUA_GATHER_PACKED || g == AKUA_GATHER_PACKED_RECORDS);
 }
 inline bool useRec(const akua_pbf_solver* s) {
     const int g = s->opt.gather_layout;
@@ -358,10 +382,10 @@ inline bool useRec(const akua_pbf_solver* s) {
 
 int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    const PeerPush pl = push ? slabPush(s, s->lambda) : PeerPush{};
     float4* xl = usePack(s) ? s->xl : nullptr;
-    if (s->opt.fast_math) k_density_lambda<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
-    else                  k_density_lambda<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
+    const PeerPush pl = !push ? PeerPush{} : (xl ? slabPush(s, xl) : slabPush(s, s->lambda));
+    if (s->opt.fast_math) launchK(s, k_density_lambda<true>, sweepGrid(sp.count), kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
+    else                  launchK(s, k_density_lambda<false>, sweepGrid(sp.count), kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
     AK_LAUNCH_CHECK(s, "k_density_lambda");
     return AKUA_OK;
 }
@@ -371,7 +395,7 @@ int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams
     const PeerPush px = push ? slabPush(s, s->xsAlt) : PeerPush{};
     const PeerPush pv = (push && fin) ? slabPush(s, s->vel) : PeerPush{};
     PosVel* rec = (fin && useRec(s)) ? s->pv : nullptr;
-#define AK_DELTA(F, L, K, C) k_delta_apply<F, L, K, C><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->xsAlt, s->lambda, s->xl, \
+#define AK_DELTA(F, L, K, C) launchK(s, k_delta_apply<F, L, K, C>, sweepGrid(sp.count), kSweepBlock, s->xs, s->xsAlt, s->lambda, s->xl, \
             s->nbrList, s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, rec, dt, px, pv, hs)
 #define AK_DELTA_C(F, L, K) do { if (P.corrNIsFour) AK_DELTA(F, L, K, true); else AK_DELTA(F, L, K, false); } while (0)
 #define AK_DELTA_L(F, K) do { if (fin) AK_DELTA_C(F, true, K); else AK_DELTA_C(F, false, K); } while (0)
@@ -386,9 +410,9 @@ int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams
 }
 int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    const PeerPush pw = push ? slabPush(s, s->omegaLen) : PeerPush{};
     float4* xw = usePack(s) ? s->xw : nullptr;
-#define AK_VORT(F, R) k_vorticity<F, R><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, \
+    const PeerPush pw = !push ? PeerPush{} : (xw ? slabPush(s, xw) : slabPush(s, s->omegaLen));
+#define AK_VORT(F, R) launchK(s, k_vorticity<F, R>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, \
             s->nbrStride, sp, s->omega, s->omegaLen, xw, P, pw, hs)
     if (useRec(s)) { if (s->opt.fast_math) AK_VORT(true, true); else AK_VORT(false, true); }
     else           { if (s->opt.fast_math) AK_VORT(true, false); else AK_VORT(false, false); }
@@ -400,7 +424,7 @@ int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt,
     if (!sp.count) return AKUA_OK;
     const PeerPush pv = push ? slabPush(s, s->vel) : PeerPush{};
     PosVel* rec = useRec(s) ? s->pv : nullptr;
-#define AK_CONF(F, K) k_confinement<F, K><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->omega, s->omegaLen, s->xw, s->density, \
+#define AK_CONF(F, K) launchK(s, k_confinement<F, K>, sweepGrid(sp.count), kSweepBlock, s->xs, s->omega, s->omegaLen, s->xw, s->density, \
             s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, rec, P, dt, s->cfg.vorticityEpsilon, pv, hs)
     if (usePack(s)) { if (s->opt.fast_math) AK_CONF(true, true); else AK_CONF(false, true); }
     else            { if (s->opt.fast_math) AK_CONF(true, false); else AK_CONF(false, false); }
@@ -410,8 +434,8 @@ int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt,
 }
 int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P, const HaloSync& hs = HaloSync{}) {
     if (!sp.count) return AKUA_OK;
-    if (useRec(s)) k_xsph<true><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
-    else           k_xsph<false><<<sweepGrid(sp.count), kSweepBlock, 0, s->stream>>>(s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
+    if (useRec(s)) launchK(s, k_xsph<true>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
+    else           launchK(s, k_xsph<false>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
     AK_LAUNCH_CHECK(s, "k_xsph");
     return AKUA_OK;
 }
@@ -471,7 +495,7 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
                 else if ((rc = slabWait(s, s->slab.pending))) return rc;                       // ghosts' x*
                 s->slab.pending = SlabTicket{};
                 if ((rc = launchPassA(s, sp.boundary, P, p2p && fused, hs))) return rc;
-                if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->lambda, &tkL))) return rc;
+                if (!(p2p && fused) && (rc = usePack(s) ? slabExchangeAsync(s, s->xl, &tkL) : slabExchangeAsync(s, s->lambda, &tkL))) return rc;
             }
             if ((rc = slabJoin(s))) return rc;   // pass B reads lambda across the interior / boundary split
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
@@ -503,14 +527,14 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
 int phaseUpdate(akua_pbf_solver* s, float dt) {
     const uint32_t n = (uint32_t)s->n;
     if (n == 0) return AKUA_OK;
-    k_update<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->pos, s->vel, s->density, n, dt);
+    launchK(s, k_update, gridFor(n), kBlock, s->xs, s->pos, s->vel, s->density, n, dt);
     AK_LAUNCH_CHECK(s, "k_update");
     return AKUA_OK;
 }
 int phaseDamping(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     const uint32_t n = (uint32_t)s->n;
     if (n == 0) return AKUA_OK;
-    k_damping<<<gridFor(n), kBlock, 0, s->stream>>>(s->pos, s->vel, n, makeBox(bmin, bmax));
+    launchK(s, k_damping, gridFor(n), kBlock, s->pos, s->vel, n, makeBox(bmin, bmax));
     AK_LAUNCH_CHECK(s, "k_damping");
     return AKUA_OK;
 }
@@ -523,7 +547,7 @@ int phasePost(akua_pbf_solver* s, float dt) {
     if (!slabMode) {
         const Span all = fullSpan(n);
         if (useRec(s) && !s->pvFresh) {   // committed outside the fused final pass B (phase-level API, 0 iterations)
-            k_build_posvel<<<gridFor(n), kBlock, 0, s->stream>>>(s->xs, s->vel, n, s->pv);
+            launchK(s, k_build_posvel, gridFor(n), kBlock, s->xs, s->vel, n, s->pv);
             AK_LAUNCH_CHECK(s, "k_build_posvel");
         }
         s->pvFresh = false;               // K12 / K13 leave the records behind the committed state
@@ -545,7 +569,7 @@ int phasePost(akua_pbf_solver* s, float dt) {
         else if ((rc = slabWait(s, s->slab.pending))) return rc;                              // ghosts' final x*, v
         s->slab.pending = SlabTicket{};
         if ((rc = launchVorticity(s, sp.boundary, P, p2p && fused, hs))) return rc;
-        if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->omegaLen, &evW))) return rc;      // ghosts' |omega| for K12
+        if (!(p2p && fused) && (rc = usePack(s) ? slabExchangeAsync(s, s->xw, &evW) : slabExchangeAsync(s, s->omegaLen, &evW))) return rc;  // ghosts' |omega| for K12
     }
     if ((rc = slabJoin(s))) return rc;
     if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
@@ -583,7 +607,7 @@ void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* b
     key[9] = f2(bmin[0], bmin[1]); key[10] = f2(bmin[2], bmax[0]); key[11] = f2(bmax[1], bmax[2]);
     key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math;
     uint32_t mbits; std::memcpy(&mbits, &s->uniformMass, 4);
-    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u);
+    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u);
 }
 
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
@@ -709,6 +733,7 @@ void akua_pbf_default_options(akua_pbf_options* o) {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));
     o->key_mode = AKUA_KEY_LINEAR_CELL; o->device = 0; o->use_graph = 1; o->fast_math = 1; o->capacity_factor = 1.0f;
+    o->use_pdl = 1;
 }
 
 int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_config* cfg, const akua_corr_params* corr,
@@ -747,6 +772,7 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     AK_CUDA(s, dalloc(&s->density, cap)); AK_CUDA(s, dalloc(&s->lambda, cap)); AK_CUDA(s, dalloc(&s->omegaLen, cap));
     AK_CUDA(s, dalloc(&s->omega, cap)); AK_CUDA(s, dalloc(&s->dpos, cap));
     AK_CUDA(s, dalloc(&s->color, cap)); AK_CUDA(s, dalloc(&s->size, cap));
+    if (const char* e = std::getenv("AKUA_PDL")) s->opt.use_pdl = std::atoi(e) != 0;   // tuning experiments
     if (const char* e = std::getenv("AKUA_GATHER_LAYOUT")) s->opt.gather_layout = std::atoi(e);   // tuning experiments
     if (s->opt.gather_layout < AKUA_GATHER_AUTO || s->opt.gather_layout > AKUA_GATHER_PACKED_RECORDS) { s->err = "unknown gather_layout"; return AKUA_ERR_INVALID; }
     {
@@ -819,7 +845,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         for (void* p : sp) if (p) cudaFree(p);
         for (SlabPeer* p : {&sl.peerL, &sl.peerR})
             if (p->open) for (void* q : {(void*)p->xsBuf[0], (void*)p->xsBuf[1], (void*)p->velBuf[0], (void*)p->velBuf[1],
-                                         (void*)p->lambda, (void*)p->omegaLen, (void*)p->flags}) cudaIpcCloseMemHandle(q);
+                                         (void*)p->lambda, (void*)p->omegaLen, (void*)p->flags, (void*)p->dCounts,
+                                         (void*)p->recvL, (void*)p->recvR, (void*)p->xl, (void*)p->xw}) if (q) cudaIpcCloseMemHandle(q);
         if (sl.flags) cudaFree(sl.flags);
         if (sl.hCounts) cudaFreeHost(sl.hCounts);
         if (sl.dHist) cudaFree(sl.dHist);
@@ -897,7 +924,7 @@ int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     if (rcm) return rcm;
     AK_CUDA(s, cudaStreamSynchronize(s->stream));  // `src` may be reused by the caller as soon as we return
     massRangeFinish(s);
-    return AKUA_OK;
+    return slabAgreeMass(s);
 }
 int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
     if (!s || !dst || n != s->n) { if (s) s->err = "download_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
@@ -948,7 +975,7 @@ int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* v
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     s->ctr.h2d_bytes += n * 52;
     s->massUniform = uniform; s->uniformMass = m0;
-    return AKUA_OK;
+    return slabAgreeMass(s);
 }
 int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t* id, int64_t n) {
     if (!s || n != s->n) { if (s) s->err = "download_soa: bad arguments"; return AKUA_ERR_INVALID; }
@@ -1045,7 +1072,7 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
     s->cfg.gravity[0] = h.cfg.gravity[0]; s->cfg.gravity[1] = h.cfg.gravity[1]; s->cfg.gravity[2] = h.cfg.gravity[2];
     s->accumulator = h.accumulator;
     s->ctr.steps = h.steps;
-    return AKUA_OK;
+    return slabAgreeMass(s);
 }
 
 // ---- multi-GPU (x-slab) ----
@@ -1099,18 +1126,23 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     sl.ghostBaseR = (uint32_t)s->capacity - sl.ghostCap;
     if (s->n > (int64_t)sl.ghostBaseL) { s->err = "comm_init: capacity_factor too small for the ghost regions (use >= 1.4)"; return AKUA_ERR_INVALID; }
     sl.xsBuf[0] = s->xs; sl.xsBuf[1] = s->xsAlt; sl.velBuf[0] = s->vel; sl.velBuf[1] = s->velAlt;
-    AK_CUDA(s, dalloc(&sl.flags, 4));
-    AK_CUDA(s, cudaMemsetAsync(sl.flags, 0, 4 * sizeof(uint32_t), s->stream));
+    // flag words: [0] / [1] ghost-exchange epoch published by the left / right rank, [3] CTA completion counter of the fused
+    // pushes, [4] / [5] epoch of the left / right rank's per-step count + migration message
+    AK_CUDA(s, dalloc(&sl.flags, 8));
+    AK_CUDA(s, cudaMemsetAsync(sl.flags, 0, 8 * sizeof(uint32_t), s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     // ---- CUDA IPC: open the neighbours' arrays so that ghost planes can be copied straight into them ----
     const char* env = std::getenv("AKUA_SLAB_P2P");
     const bool wantP2p = !(env && env[0] == '0') && nranks > 1;
-    struct PeerMsg { cudaIpcMemHandle_t h[7]; uint32_t ghostBaseL, ghostBaseR, ok, pad; };
+    constexpr int kIpc = 12;   // the last two (packed gather arrays) may be absent
+    struct PeerMsg { cudaIpcMemHandle_t h[kIpc]; uint32_t ghostBaseL, ghostBaseR, ok, migCap, hasPack, pad[3]; };
     PeerMsg mine{};
-    mine.ghostBaseL = sl.ghostBaseL; mine.ghostBaseR = sl.ghostBaseR; mine.ok = wantP2p ? 1u : 0u;
+    mine.ghostBaseL = sl.ghostBaseL; mine.ghostBaseR = sl.ghostBaseR; mine.ok = wantP2p ? 1u : 0u; mine.migCap = sl.migCap;
     if (wantP2p) {
-        void* arrs[7] = {sl.xsBuf[0], sl.xsBuf[1], sl.velBuf[0], sl.velBuf[1], s->lambda, s->omegaLen, sl.flags};
-        for (int k = 0; k < 7; k++)
+        void* arrs[kIpc] = {sl.xsBuf[0], sl.xsBuf[1], sl.velBuf[0], sl.velBuf[1], s->lambda, s->omegaLen, sl.flags,
+                            sl.dCounts, sl.recvL, sl.recvR, s->xl, s->xw};
+        mine.hasPack = (s->xl && s->xw) ? 1u : 0u;
+        for (int k = 0; k < (mine.hasPack ? kIpc : kIpc - 2); k++)
             if (cudaIpcGetMemHandle(&mine.h[k], arrs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); break; }
     }
     if (nranks > 1) {
@@ -1130,11 +1162,13 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         cudaFree(dmsg);
         bool ok = mine.ok != 0 && (!hasL || got[0].ok) && (!hasR || got[1].ok);
         auto openPeer = [&](const PeerMsg& m, SlabPeer& p) {
-            void* ptr[7] = {};
-            for (int k = 0; k < 7; k++)
+            void* ptr[kIpc] = {};
+            for (int k = 0; k < (m.hasPack ? kIpc : kIpc - 2); k++)
                 if (cudaIpcOpenMemHandle(&ptr[k], m.h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
             p.xsBuf[0] = (float4*)ptr[0]; p.xsBuf[1] = (float4*)ptr[1]; p.velBuf[0] = (float4*)ptr[2]; p.velBuf[1] = (float4*)ptr[3];
             p.lambda = (float*)ptr[4]; p.omegaLen = (float*)ptr[5]; p.flags = (uint32_t*)ptr[6];
+            p.dCounts = (uint32_t*)ptr[7]; p.recvL = (slab::MigRecord*)ptr[8]; p.recvR = (slab::MigRecord*)ptr[9];
+            p.migCap = m.migCap; p.xl = (float4*)ptr[10]; p.xw = (float4*)ptr[11];
             p.ghostBaseL = m.ghostBaseL; p.ghostBaseR = m.ghostBaseR; p.open = true;
             return true;
         };
@@ -1159,8 +1193,10 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi) {
     if (!s || !s->slab.comm) { if (s) s->err = "set_slab: call akua_pbf_comm_init first"; return AKUA_ERR_INVALID; }
     if (xCellHi <= xCellLo) { s->err = "set_slab: empty interval"; return AKUA_ERR_INVALID; }
-    s->slab.xLoAbs = xCellLo; s->slab.xHiAbs = xCellHi; s->slab.enabled = true;
-    return AKUA_OK;
+    s->slab.xLoAbs = xCellLo; s->slab.xHiAbs = xCellHi;
+    const bool first = !s->slab.enabled;
+    s->slab.enabled = true;
+    return first ? slabAgreeMass(s) : AKUA_OK;   // collective, like the call itself
 }
 int akua_pbf_rebalance(akua_pbf_solver* s) {
     if (!s) return AKUA_ERR_INVALID;

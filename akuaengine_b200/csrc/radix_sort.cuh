@@ -26,6 +26,8 @@ constexpr int kWarps = kThreads / 32;
 // that the count / scatter grids still fill 148 SMs several times over (at 1 M keys a 4096-key tiling is only 245 CTAs).
 constexpr int kItemsLarge = 16, kItemsSmall = 4;
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }   // see pbf_kernels.cuh
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -35,6 +37,7 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 template <int kItems>
 __global__ void __launch_bounds__(kThreads) k_count(const uint32_t* __restrict__ keys, uint32_t n, int shift,
                                                     uint32_t* __restrict__ tileHist, uint32_t numTiles) {
+    pdl_wait();
     constexpr int kTile = kThreads * kItems;
     __shared__ uint32_t hist[256];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -78,6 +81,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* sm
 
 __global__ void __launch_bounds__(kThreads) k_scan(uint32_t* __restrict__ tileHist, uint32_t numTiles,
                                                    uint32_t* __restrict__ binTotal) {
+    pdl_wait();
     __shared__ uint32_t s8[kWarps];
     uint32_t* row = tileHist + (size_t)blockIdx.x * numTiles;
     uint32_t carry = 0;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict
                                                       uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                       uint32_t n, int shift, const uint32_t* __restrict__ tileHist,
                                                       uint32_t numTiles, const uint32_t* __restrict__ binTotal) {
+    pdl_wait();
     constexpr int kTile = kThreads * kItems;
     constexpr int kWarpSpan = 32 * kItems;  // keys handled by one warp (contiguous -> stability)
     __shared__ uint32_t warpCnt[kWarps][256];  // per-warp running digit counts, then exclusive warp prefixes
@@ -196,9 +201,23 @@ inline int passes_for_bits(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
 
 // Sorts n (key, index) pairs. keysIn is preserved. Results land in (*keysOut, *valsOut), which point into bufA or bufB.
 // Returns the number of kernel launches issued.
+// `pdl`: launch with programmatic stream serialization (every kernel here starts with pdl_wait()).
+template <typename... KArgs, typename... Args>
+inline void launch(bool pdl, void (*kernel)(KArgs...), uint32_t grid, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.stream = st;
+    cudaLaunchAttribute at{};
+    if (pdl) {
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
-                      uint32_t** valsOut) {
+                      uint32_t** valsOut, bool pdl = false) {
     const uint32_t numTiles = tiles_for(n);
     const bool small = items_for(n) == kItemsSmall;
     const int passes = passes_for_bits(keyBits);
@@ -209,10 +228,10 @@ inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, ui
     int launches = 0;
     for (int p = 0; p < passes; p++) {
         int shift = 8 * p;
-        if (small) k_count<kItemsSmall><<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
-        else       k_count<kItemsLarge><<<numTiles, kThreads, 0, st>>>(kin, n, shift, ws.tileHist, numTiles);
-        k_scan<<<256, kThreads, 0, st>>>(ws.tileHist, numTiles, ws.binTotal);
-#define AK_SCATTER(F, I) k_scatter<F, I><<<numTiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal)
+        if (small) launch(pdl, k_count<kItemsSmall>, numTiles, st, kin, n, shift, ws.tileHist, numTiles);
+        else       launch(pdl, k_count<kItemsLarge>, numTiles, st, kin, n, shift, ws.tileHist, numTiles);
+        launch(pdl, k_scan, 256u, st, ws.tileHist, numTiles, ws.binTotal);
+#define AK_SCATTER(F, I) launch(pdl, k_scatter<F, I>, numTiles, st, kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal)
         if (p == 0) { if (small) AK_SCATTER(true, kItemsSmall); else AK_SCATTER(true, kItemsLarge); }
         else        { if (small) AK_SCATTER(false, kItemsSmall); else AK_SCATTER(false, kItemsLarge); }
 #undef AK_SCATTER

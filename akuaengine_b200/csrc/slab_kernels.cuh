@@ -182,6 +182,23 @@ __global__ void k_signal_flag(uint32_t* __restrict__ peerFlag, uint32_t epoch) {
     *(volatile uint32_t*)peerFlag = epoch;
     __threadfence_system();
 }
+// CUDA-IPC transport of the per-step count message: the three counters for each neighbour (assembled by k_mig_scan at
+// counts[16..18] / [20..22]) are stored straight into the neighbour's counter block (the slots it reads them from:
+// [28..30] of the left rank = "from my right", [24..26] of the right rank = "from my left"), then the message epoch is
+// published in the neighbour's flag word. The migration records were stored into the neighbour's inbox by k_mig_pack
+// earlier in the same stream, so one flag covers both. One thread.
+__global__ void k_publish_counts(const uint32_t* __restrict__ counts, uint32_t* __restrict__ peerCountsL,
+                                 uint32_t* __restrict__ peerCountsR, uint32_t* __restrict__ peerFlagL,
+                                 uint32_t* __restrict__ peerFlagR, uint32_t epoch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence_system();
+    if (peerCountsL) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerCountsL)[28 + k] = counts[16 + k];
+    if (peerCountsR) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerCountsR)[24 + k] = counts[20 + k];
+    __threadfence_system();
+    if (peerFlagL) *(volatile uint32_t*)peerFlagL = epoch;
+    if (peerFlagR) *(volatile uint32_t*)peerFlagR = epoch;
+    __threadfence_system();
+}
 __global__ void k_wait_flags(const uint32_t* __restrict__ flags, int waitL, int waitR, uint32_t epoch,
                              uint32_t* __restrict__ errWord, long long timeoutCycles) {
     const long long t0 = clock64();

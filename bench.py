@@ -29,6 +29,17 @@ from pathlib import Path
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout. Libraries loaded below (NCCL prints its version banner to stdout on some boxes)
+# must not add to it: file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved
+# descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
@@ -300,7 +311,7 @@ def run_ours(args):
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(out))
+        emit(out)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
@@ -377,7 +388,7 @@ def run_reference(args):
                       "requested_steps": args.steps, "requested_warmup": args.warmup},
            "cpu_baseline": {"value": value, "unit": "particle-iterations/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "particle-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
     o.close()
 
 

@@ -94,7 +94,9 @@ typedef struct akua_pbf_options {
                                 class as the reference's own powf calls); 0 = IEEE sqrtf and division */
     float capacity_factor;   /* device arrays are sized for capacity_factor * n particles (ghosts, migration); default 1 */
     int32_t gather_layout;   /* akua_gather_layout; default AKUA_GATHER_AUTO. Results are bit-identical in every layout. */
-    int32_t reserved[7];
+    int32_t use_pdl;         /* 1 (default) = the step's kernels are launched with programmatic dependent launch: each is
+                                scheduled while its predecessor drains (also between the eagerly launched kernels of the x-slab path); 0 = plain stream order */
+    int32_t reserved[6];
 } akua_pbf_options;
 
 void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */

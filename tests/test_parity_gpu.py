@@ -271,6 +271,27 @@ def test_gather_layouts_are_bit_identical(masses, fast):
         assert v == ref, k
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_programmatic_dependent_launch_is_bit_identical(mode):
+    """options.use_pdl only lets kernel N+1 be scheduled while kernel N drains (every kernel starts with
+    griddepcontrol.wait): the state after a run must not depend on it, eager or graph-replayed."""
+    init, bmin, bmax = scenes.dam_break(16)
+    outs = {}
+    for use_pdl in (False, True):
+        for use_graph in (False, True):
+            s = PBFSolver(len(init), key_mode=mode, use_pdl=use_pdl, use_graph=use_graph)
+            s.upload_particles(init)
+            for _ in range(8):
+                s.step(0.0083, bmin, bmax)
+            outs[(use_pdl, use_graph)] = s.download_particles().tobytes()
+            if use_graph:
+                assert s.counters()["graph_replays"] == 8
+            s.close()
+    ref = outs[(False, False)]
+    for k, v in outs.items():
+        assert v == ref, k
+
+
 def test_gather_layout_follows_the_uploaded_masses():
     """Uniform-mass detection happens at every upload: a solver that first saw uniform masses must fall back to the plain
     pass-B / K12 gathers when re-uploaded with mixed masses (and back)."""

@@ -22,12 +22,14 @@ libs = sys.argv[1:] or [""]
 LAYOUTS = {1: "plain", 2: "packed", 3: "records", 4: "packed+records"}
 if os.environ.get("AKUA_TV_LAYOUTS"):
     LAYOUTS = {int(k): LAYOUTS[int(k)] for k in os.environ["AKUA_TV_LAYOUTS"].split(",")}
-for n_side in (100,):
+for n_side in [int(v) for v in os.environ.get("AKUA_TV_NSIDE", "100").split(",")]:
     for fast in (1,):
         for lib in libs:
             for layout, lname in LAYOUTS.items():
                 env = dict(os.environ)
                 if lib: env["AKUA_PBF_LIB"] = str(Path(lib).resolve())
                 env["AKUA_GATHER_LAYOUT"] = str(layout)
-                r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
-                print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s} {lname:8s}", r.stdout.strip() or r.stderr[-300:], flush=True)
+                for pdl in os.environ.get("AKUA_TV_PDL", "1").split(","):
+                    env["AKUA_PDL"] = pdl
+                    r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
+                    print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s} {lname:8s} pdl={pdl}", r.stdout.strip() or r.stderr[-300:], flush=True)

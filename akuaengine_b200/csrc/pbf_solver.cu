@@ -912,7 +912,7 @@ int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     if (!s || !src || n < 0 || n > s->capacity) { if (s) s->err = "upload_aos108: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     s->n = n;  // the live particle count follows the upload (slab ranks upload their own share)
-    if (n == 0) return AKUA_OK;
+    if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }   // still takes part in the slab-mode verdict
     int rc = ensureStage(s);
     if (rc) return rc;
     AK_CUDA(s, cudaMemcpyAsync(s->aosStage, src, (size_t)n * 108, cudaMemcpyHostToDevice, s->stream));
@@ -955,7 +955,7 @@ int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* v
     if (!s || !pos_xyz || n < 0 || n > s->capacity) { if (s) s->err = "upload_soa: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     s->n = n;
-    if (n == 0) return AKUA_OK;
+    if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }
     // Host-side widening to float4, then two async copies. (Setup path; the per-step e2e path is AoS-108.)
     std::vector<float4> p4((size_t)n), v4((size_t)n);
     std::vector<uint32_t> ids((size_t)n);

@@ -278,8 +278,8 @@ def run_ours(args):
                    "l2": "no explicit flush: per-step working set (neighbour lists ~100 B/particle + 7 float4 arrays) "
                          f"= ~{(100 + 7 * 16 + 24) * n / 1e6:.0f} MB vs 126 MB L2",
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} x-slabs (one per GPU), 1-cell ghost planes + per-step migration over NCCL send/recv inside "
-                   "akua_pbf_step"},
+                   f"{world} x-slabs (one per GPU), 1-cell ghost planes + per-step migration over NVLink inside akua_pbf_step "
+                   "(CUDA-IPC P2P stores / copy-engine pushes; NCCL send/recv as fallback)"},
         "e2e": {"value": e2e_value, "unit": "particle-iterations/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": 108 * n_total, "d2h_bytes_per_step": 108 * n_total,
                 "what": "akua_pbf_upload_aos108(pinned host) + akua_pbf_step + akua_pbf_download_aos108(pinned host) per step"},

@@ -175,6 +175,10 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path);
  *           The render payload (color, size) is not migrated between ranks: AoS downloads in slab mode carry the
  *           reference scene's defaults (blue, 50 — Application.cpp:186-187); ids are what identifies a particle. */
 int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
+/* COLLECTIVE CALLS in slab mode: akua_pbf_set_slab, akua_pbf_rebalance and — once akua_pbf_set_slab has been called — every
+ * upload (akua_pbf_upload_aos108 / _soa, akua_pbf_checkpoint_load): each contains one small all-reduce in which the ranks
+ * agree whether all particles of all ranks share one mass (the packed gather layout, akua_gather_layout, is what the halo
+ * exchanges then carry). Every rank must make these calls the same number of times, a rank without particles with n = 0. */
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);

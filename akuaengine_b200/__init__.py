@@ -19,12 +19,15 @@ __all__ = [
     "PBFConfig", "LambdaCorrParams", "PBFOptions", "PBFSolver", "PARTICLE_DTYPE", "AkuaError", "load_library",
     "KEY_REFERENCE_HASH", "KEY_LINEAR_CELL", "DBG", "PinnedBuffer",
     "GATHER_AUTO", "GATHER_PLAIN", "GATHER_PACKED", "GATHER_RECORDS", "GATHER_PACKED_RECORDS",
+    "LIST_BUILD_SCAN", "LIST_BUILD_MASK4", "LIST_BUILD_MASK8",
 ]
 
 KEY_REFERENCE_HASH = 0
 KEY_LINEAR_CELL = 1
 # akua_gather_layout (include/akua_pbf.h): how the sweeps fetch a neighbour; results are bit-identical in every layout
 GATHER_AUTO, GATHER_PLAIN, GATHER_PACKED, GATHER_RECORDS, GATHER_PACKED_RECORDS = 0, 1, 2, 3, 4
+# akua_list_build (include/akua_pbf.h): how LINEAR_CELL neighbour lists are built; lists are bit-identical in every variant
+LIST_BUILD_SCAN, LIST_BUILD_MASK4, LIST_BUILD_MASK8 = 0, 1, 2
 
 # include/AkuaEngine/Simulation/Particle.h:8-31 — packed, 108 bytes
 PARTICLE_DTYPE = np.dtype([
@@ -80,7 +83,7 @@ class PBFConfig(C.Structure):
 
 class PBFOptions(C.Structure):
     _fields_ = [("key_mode", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("fast_math", C.c_int32),
-                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("list_build", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Counters(C.Structure):
@@ -229,7 +232,8 @@ class PBFSolver:
 
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
-                 capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None):
+                 capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None,
+                 list_build: int | None = None):
         self._lib = load_library()
         self.config = config or PBFConfig()
         self.corrParams = corrParams or LambdaCorrParams()
@@ -241,6 +245,8 @@ class PBFSolver:
         opt.gather_layout = int(gather_layout)
         if use_pdl is not None:
             opt.use_pdl = int(use_pdl)
+        if list_build is not None:
+            opt.list_build = int(list_build)
         self.options = opt
         self._h = C.c_void_p()
         rc = self._lib.akua_pbf_create(C.byref(self._h), self.numParticles, C.byref(self.config),

@@ -60,9 +60,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ device math
-__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+// dist2 / cell_of / clampi / linear_key are __host__ __device__ so that tests/cpp/list_build_host.cu can run the per-particle
+// list-build functions of list_build.cuh on the CPU (same source, IEEE-identical float expressions); the device code is unchanged.
+__host__ __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
     // exactly the reference's contraction (kernel_find_neighbours SASS): fma(dz,dz, fma(dx,dx, dy*dy))
+#ifdef __CUDA_ARCH__
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+#else
+    const volatile float yy = dy * dy;   // volatile: the product is rounded before it enters the fma, whatever -ffp-contract says
+    return fmaf(dz, dz, fmaf(dx, dx, yy));
+#endif
 }
 __device__ __forceinline__ float poly6(float d2, const SphParams& P) {  // SmoothingKernelsCUDA.h:16-21
     // d2 > h2 ? 0 : coef * (h2 - d2)^3, with the cut-off as a clamp (one FMNMX instead of FSETP + FSEL): for d2 <= h2 the
@@ -86,17 +93,21 @@ __device__ __forceinline__ float spiky_scale(float d2, const SphParams& P) {
     float s = P.spikyCoef * (t * t) * invr;
     return r < 1e-5f ? 0.0f : s;
 }
-__device__ __forceinline__ int3 cell_of(float x, float y, float z, float cellSize) {
+__host__ __device__ __forceinline__ int3 cell_of(float x, float y, float z, float cellSize) {
     // NeighbourSearchCUDA.cu:15-21: floorf of a true IEEE division
+#ifdef __CUDA_ARCH__
     return make_int3((int)floorf(__fdiv_rn(x, cellSize)), (int)floorf(__fdiv_rn(y, cellSize)),
                      (int)floorf(__fdiv_rn(z, cellSize)));
+#else
+    return make_int3((int)floorf(x / cellSize), (int)floorf(y / cellSize), (int)floorf(z / cellSize));
+#endif
 }
 __device__ __forceinline__ uint32_t ref_hash(int cx, int cy, int cz, uint32_t tableSize) {
     // NeighbourSearchCUDA.cu:23-27
     return (((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u) ^ ((uint32_t)cz * 83492791u)) % tableSize;
 }
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-__device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams& G) {
+__host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams& G) {
     int x = clampi(c.x - G.gridMin.x, 0, G.gridDim.x - 1);
     int y = clampi(c.y - G.gridMin.y, 0, G.gridDim.y - 1);
     int z = clampi(c.z - G.gridMin.z, 0, G.gridDim.z - 1);
@@ -174,7 +185,7 @@ __device__ __forceinline__ void halo_signal(const HaloSync& hs) {
 }
 
 // ------------------------------------------------------------------------------------------------ neighbour list access
-__device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
+__host__ __device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
     return ((size_t)(k >> 2) * stride + i) * 4 + (k & 3);
 }
 // Streaming 16-byte load of four neighbour indices: read once per sweep, so keep it out of L1 (the gathers want L1).

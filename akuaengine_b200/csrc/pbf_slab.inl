@@ -421,11 +421,7 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
 
     // ---- 5. neighbour lists of the owned particles (candidates include the ghost planes) ----
     mark(s, PH_LISTS);
-    if (nOwn) {
-        launchK(s, k_build_neighbours<KEY_LINEAR>, gridFor(nOwn), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, nOwn,
-            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
-        AK_LAUNCH_CHECK(s, "k_build_neighbours");
-    }
+    if ((rc = launchBuildNeighbours(s, nOwn))) return rc;
 
     sl.pending = SlabTicket{};
     // ---- 6. constraint solve and post-solve on the owned range, with the per-pass ghost exchanges inside ----

@@ -7,6 +7,7 @@
 // state on the device, and issues the whole step asynchronously on one stream.
 #include "../../include/akua_pbf.h"
 #include "pbf_kernels.cuh"
+#include "list_build.cuh"
 #include "radix_sort.cuh"
 #include "slab_kernels.cuh"
 
@@ -310,6 +311,21 @@ int phasePredictKey(akua_pbf_solver* s, float dt, bool doPredict, bool doKeys) {
     return AKUA_OK;
 }
 
+// K4 launch over the first n (owned) particles: REFERENCE_HASH scans its buckets; LINEAR_CELL scans row ranges one candidate
+// at a time (default) or with the two-phase mask variants of list_build.cuh (options.list_build). Same lists either way.
+int launchBuildNeighbours(akua_pbf_solver* s, uint32_t n) {
+    if (n == 0) return AKUA_OK;
+#define AK_BUILD(K) launchK(s, K, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n, s->nbrStride, \
+            (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius)
+    if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) AK_BUILD(k_build_neighbours<KEY_HASH>);
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) AK_BUILD(k_build_neighbours_mask<4>);
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) AK_BUILD(k_build_neighbours_mask<8>);
+    else AK_BUILD(k_build_neighbours<KEY_LINEAR>);
+#undef AK_BUILD
+    AK_LAUNCH_CHECK(s, "k_build_neighbours");
+    return AKUA_OK;
+}
+
 int phaseSortReorderLists(akua_pbf_solver* s) {
     const uint32_t n = (uint32_t)s->n;
     if (n == 0) return AKUA_OK;
@@ -344,14 +360,7 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     std::swap(s->id, s->idAlt);
     s->bucketsDirty = hash;
     mark(s, PH_LISTS);
-    if (hash)
-        launchK(s, k_build_neighbours<KEY_HASH>, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
-            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
-    else
-        launchK(s, k_build_neighbours<KEY_LINEAR>, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n,
-            s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius);
-    AK_LAUNCH_CHECK(s, "k_build_neighbours");
-    return AKUA_OK;
+    return launchBuildNeighbours(s, n);
 }
 
 // ---- slab-mode plumbing used by the sweeps below (definitions in pbf_slab.inl) ----
@@ -775,6 +784,8 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     if (const char* e = std::getenv("AKUA_PDL")) s->opt.use_pdl = std::atoi(e) != 0;   // tuning experiments
     if (const char* e = std::getenv("AKUA_GATHER_LAYOUT")) s->opt.gather_layout = std::atoi(e);   // tuning experiments
     if (s->opt.gather_layout < AKUA_GATHER_AUTO || s->opt.gather_layout > AKUA_GATHER_PACKED_RECORDS) { s->err = "unknown gather_layout"; return AKUA_ERR_INVALID; }
+    if (const char* e = std::getenv("AKUA_LIST_BUILD")) s->opt.list_build = std::atoi(e);   // tuning experiments
+    if (s->opt.list_build < AKUA_LIST_BUILD_SCAN || s->opt.list_build > AKUA_LIST_BUILD_MASK8) { s->err = "unknown list_build"; return AKUA_ERR_INVALID; }
     {
         const int g = s->opt.gather_layout;
         if (g != AKUA_GATHER_PLAIN && g != AKUA_GATHER_RECORDS) {

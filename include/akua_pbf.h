@@ -86,6 +86,17 @@ typedef enum akua_gather_layout {
     AKUA_GATHER_PACKED_RECORDS = 4
 } akua_gather_layout;
 
+/* How the neighbour lists are built in LINEAR_CELL mode (REFERENCE_HASH always scans its buckets). Lists are bit-identical
+ * in every variant (tests/test_list_build_host.py on the CPU, test_list_build_variants_identical on the GPU).
+ *   scan  : one candidate at a time, test and append in the same loop (k_build_neighbours) — the measured default.
+ *   mask4 / mask8 : two phases per row chunk of <= 32 candidates — a hit bitmask from 4 / 8 independent loads in flight, then
+ *           the set bits are appended (akuaengine_b200/csrc/list_build.cuh). Opt-in until timed on a B200. */
+typedef enum akua_list_build {
+    AKUA_LIST_BUILD_SCAN = 0,
+    AKUA_LIST_BUILD_MASK4 = 1,
+    AKUA_LIST_BUILD_MASK8 = 2
+} akua_list_build;
+
 typedef struct akua_pbf_options {
     int32_t key_mode;        /* akua_key_mode; default AKUA_KEY_LINEAR_CELL */
     int32_t device;          /* CUDA device ordinal; default 0 */
@@ -96,7 +107,9 @@ typedef struct akua_pbf_options {
     int32_t gather_layout;   /* akua_gather_layout; default AKUA_GATHER_AUTO. Results are bit-identical in every layout. */
     int32_t use_pdl;         /* 1 (default) = the step's kernels are launched with programmatic dependent launch: each is
                                 scheduled while its predecessor drains (also between the eagerly launched kernels of the x-slab path); 0 = plain stream order */
-    int32_t reserved[6];
+    int32_t list_build;      /* akua_list_build; default AKUA_LIST_BUILD_SCAN (takes the first of the formerly reserved words:
+                                a zero-initialised struct from an older caller selects the default) */
+    int32_t reserved[5];
 } akua_pbf_options;
 
 void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */

@@ -104,7 +104,7 @@ ABI_SYMBOLS = [
     "akua_pbf_create", "akua_pbf_destroy", "akua_pbf_step", "akua_pbf_step_iters", "akua_pbf_set_gravity",
     "akua_pbf_advance", "akua_pbf_run_steps", "akua_pbf_checkpoint_save", "akua_pbf_checkpoint_load",
     "akua_pbf_sync", "akua_pbf_last_error", "akua_pbf_num_particles", "akua_pbf_upload_aos108",
-    "akua_pbf_download_aos108", "akua_pbf_export_aos108_device", "akua_pbf_upload_soa", "akua_pbf_download_soa", "akua_pbf_positions_device",
+    "akua_pbf_download_aos108", "akua_pbf_export_aos108_device", "akua_pbf_export_to_graphics_resource", "akua_pbf_upload_soa", "akua_pbf_download_soa", "akua_pbf_positions_device",
     "akua_pbf_velocities_device", "akua_pbf_host_alloc", "akua_pbf_host_free", "akua_pbf_phase_predict",
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
@@ -156,6 +156,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_upload_aos108.argtypes = [vp, vp, C.c_int64]
     lib.akua_pbf_download_aos108.argtypes = [vp, vp, C.c_int64]
     lib.akua_pbf_export_aos108_device.argtypes = [vp, vp, C.c_int64]
+    lib.akua_pbf_export_to_graphics_resource.argtypes = [vp, vp]
     lib.akua_pbf_upload_soa.argtypes = [vp, vp, vp, vp, C.c_int64]
     lib.akua_pbf_download_soa.argtypes = [vp, vp, vp, vp, C.c_int64]
     lib.akua_pbf_positions_device.argtypes = [vp]

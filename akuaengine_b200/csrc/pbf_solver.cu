@@ -962,6 +962,23 @@ int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t 
     return AKUA_OK;
 }
 
+int akua_pbf_export_to_graphics_resource(akua_pbf_solver* s, void* graphicsResource) {
+    if (!s || !graphicsResource) { if (s) s->err = "export_to_graphics_resource: null resource"; return AKUA_ERR_INVALID; }
+    AK_CUDA(s, cudaSetDevice(s->device));
+    cudaGraphicsResource_t res = reinterpret_cast<cudaGraphicsResource_t>(graphicsResource);
+    AK_CUDA(s, cudaGraphicsMapResources(1, &res, s->stream));
+    void* dst = nullptr;
+    size_t bytes = 0;
+    int rc = AKUA_OK;
+    cudaError_t e = cudaGraphicsResourceGetMappedPointer(&dst, &bytes, res);
+    if (e != cudaSuccess) { s->err = std::string("cudaGraphicsResourceGetMappedPointer: ") + cudaGetErrorString(e); rc = AKUA_ERR_CUDA; }
+    else if (bytes < (size_t)s->n * 108) { s->err = "export_to_graphics_resource: the buffer is smaller than 108 * numParticles bytes"; rc = AKUA_ERR_INVALID; }
+    else rc = akua_pbf_export_aos108_device(s, dst, s->n);
+    e = cudaGraphicsUnmapResources(1, &res, s->stream);   // stream-ordered behind the pack kernel
+    if (rc == AKUA_OK && e != cudaSuccess) { s->err = std::string("cudaGraphicsUnmapResources: ") + cudaGetErrorString(e); rc = AKUA_ERR_CUDA; }
+    return rc;
+}
+
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n) {
     if (!s || !pos_xyz || n < 0 || n > s->capacity) { if (s) s->err = "upload_soa: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));

@@ -159,6 +159,12 @@ int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n);
  * e.g. the pointer obtained from cudaGraphicsResourceGetMappedPointer on the renderer's VBO (layout the reference's
  * renderer binds: position@0, color@88, size@104, stride 108 — src/Rendering/Renderer.cpp:201-213). Asynchronous. */
 int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t n);
+/* The same, through a registered graphics resource: `graphicsResource` is the cudaGraphicsResource* of the particle VBO
+ * (the handle the reference keeps in InteropResource, src/Interop/InteropResource.cpp:9-35, and passes to every wrapper,
+ * e.g. src/CUDA/IntegrationCUDA.cu:199-214). Maps it on the solver's stream, checks its size (>= 108 * numParticles bytes),
+ * writes the AoS-108 buffer and unmaps — the map / get-pointer / unmap triple each reference wrapper performs, once per
+ * frame instead of six times per step. Asynchronous (stream-ordered); no GL headers are needed on either side. */
+int akua_pbf_export_to_graphics_resource(akua_pbf_solver* s, void* graphicsResource);
 /* Lean interchange: xyz triples + mass (mass may be NULL => 1.0). Host pointers. */
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n);
 /* pos4/vel4 are n float4 (xyz + mass / xyz + density); id is the upload index of each returned particle. Any may be NULL. */

@@ -81,6 +81,8 @@ public:
     void downloadParticles(void* particles, int64_t n) { check(akua_pbf_download_aos108(h_, particles, n), "download"); }
     // GL consumer: `deviceDst` is device memory, e.g. the mapped particle VBO (stride 108, Renderer.cpp:201-213)
     void downloadParticlesDevice(void* deviceDst) { check(akua_pbf_export_aos108_device(h_, deviceDst, numParticles()), "export"); }
+    // the same through the registered VBO handle the reference keeps in InteropResource (map, write, unmap on the solver's stream)
+    void exportToGraphicsResource(void* cudaGraphicsResource) { check(akua_pbf_export_to_graphics_resource(h_, cudaGraphicsResource), "export"); }
     const float* positionsDevice() { return akua_pbf_positions_device(h_); }   // float4 per particle, device memory
     const float* velocitiesDevice() { return akua_pbf_velocities_device(h_); }
     int64_t numParticles() const { return akua_pbf_num_particles(h_); }

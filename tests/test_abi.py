@@ -75,3 +75,14 @@ def test_missing_library_is_loud(tmp_path):
     from akuaengine_b200 import AkuaError, load_library
     with pytest.raises(AkuaError):
         load_library(tmp_path / "nope.so")
+
+
+@pytest.mark.gpu
+def test_graphics_resource_export_rejects_a_null_handle(akua_lib):
+    """akua_pbf_export_to_graphics_resource needs a registered cudaGraphicsResource (a GL context, not available headless):
+    only its argument checking can run here."""
+    from akuaengine_b200 import PBFSolver
+    s = PBFSolver(64)
+    assert akua_lib.akua_pbf_export_to_graphics_resource(s._h, None) == 1
+    assert b"null resource" in akua_lib.akua_pbf_last_error(s._h)
+    s.close()

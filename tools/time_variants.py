@@ -1,5 +1,7 @@
 """Times alternative builds of libakua_pbf.so and the gather layouts (tuning experiments):
-python tools/time_variants.py [build/*.so]   — every library x fast_math {0,1} x AKUA_GATHER_LAYOUT {plain, packed, records, packed+records}"""
+python tools/time_variants.py [build/*.so]   — every library x fast_math {0,1} x AKUA_GATHER_LAYOUT {plain, packed, records, packed+records}
+Environment: AKUA_TV_LAYOUTS=2 (layouts to run), AKUA_TV_NSIDE=100,160, AKUA_TV_PDL=0,1, AKUA_TV_LIST_BUILD=0,1,2 (akua_list_build:
+scan / mask4 / mask8)."""
 import json, os, subprocess, sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parents[1]
@@ -31,5 +33,7 @@ for n_side in [int(v) for v in os.environ.get("AKUA_TV_NSIDE", "100").split(",")
                 env["AKUA_GATHER_LAYOUT"] = str(layout)
                 for pdl in os.environ.get("AKUA_TV_PDL", "1").split(","):
                     env["AKUA_PDL"] = pdl
-                    r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
-                    print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s} {lname:8s} pdl={pdl}", r.stdout.strip() or r.stderr[-300:], flush=True)
+                    for lb in os.environ.get("AKUA_TV_LIST_BUILD", "0").split(","):
+                        env["AKUA_LIST_BUILD"] = lb
+                        r = subprocess.run([sys.executable, "-c", CODE, str(n_side), str(fast)], env=env, capture_output=True, text=True)
+                        print(f"n_side={n_side} fast={fast} {Path(lib).name or 'default':20s} {lname:8s} pdl={pdl} list_build={lb}", r.stdout.strip() or r.stderr[-300:], flush=True)

@@ -6,6 +6,12 @@ set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 | tee gpurun_out/r02_pytest_gpu.log
 AKUA_TV_LAYOUTS=2 AKUA_TV_NSIDE=100,160 AKUA_TV_LIST_BUILD=0,1,2 timeout 400 python tools/time_variants.py 2>&1 | tee gpurun_out/r02_list_build_variants.txt
+# L1 gather cost model (lines vs sectors vs slot collisions): feeds tests/gather_locality_study.py
+mkdir -p tools/_build
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/_build/l1_gather_probe tools/l1_gather_probe.cu \
+  && timeout 120 tools/_build/l1_gather_probe | tee gpurun_out/r02_l1_gather_probe.jsonl
+timeout 200 ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,gpu__time_duration.sum \
+  --clock-control none --csv --log-file gpurun_out/r02_l1_gather_probe_ncu.csv tools/_build/l1_gather_probe > /dev/null 2>&1
 for lb in 0 1 2; do
   AKUA_LIST_BUILD=$lb timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_build_neighbours -s 3 -c 1 \
     -o gpurun_out/r02_list_build_$lb python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ncu_lb$lb.log 2>&1

@@ -476,20 +476,10 @@ int slabRebalance(akua_pbf_solver* s) {
     std::vector<int64_t> hist(gx);
     for (int x = 0; x < gx; x++) hist[x] = (int64_t)sl.hHist[x];
     std::vector<int32_t> bounds(R + 1), old(R + 1);
-    if (akua_slab_partition(hist.data(), gx, R, bounds.data()) != AKUA_OK) { s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID; }
     for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[gx + r];
     old[0] = 0; old[R] = gx;
-    // clamp: boundary r (between ranks r-1 and r) stays strictly inside (old[r-1], old[r+1]) and moves at most
-    // migCap/2 particles
-    const int64_t maxMove = (int64_t)sl.migCap / 2;
-    for (int r = 1; r < R; r++) {
-        // stay inside the two old slabs and keep every slab at least two planes wide
-        int b = std::min(std::max(bounds[r], std::max(old[r - 1] + 1, bounds[r - 1] + 2)), old[r + 1] - 2);
-        int64_t moved = 0;
-        if (b > old[r]) { int x = old[r]; while (x < b && moved + hist[x] <= maxMove) { moved += hist[x]; x++; } b = x; }
-        else if (b < old[r]) { int x = old[r]; while (x > b && moved + hist[x - 1] <= maxMove) { moved += hist[x - 1]; x--; } b = x; }
-        if (b < bounds[r - 1] + 2) b = std::min(bounds[r - 1] + 2, old[r + 1] - 2);
-        bounds[r] = b;
+    if (akua_slab_rebalance_bounds(hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, bounds.data()) != AKUA_OK) {
+        s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
     sl.xLoAbs = G.gridMin.x + bounds[sl.rank];

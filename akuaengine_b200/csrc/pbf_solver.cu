@@ -1261,6 +1261,30 @@ int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int3
     return AKUA_OK;
 }
 
+// New slab boundaries for a re-balancing step (pure host code, no CUDA; used by akua_pbf_rebalance on every rank with the
+// all-reduced histogram, so all ranks compute the same result). Starts from the balanced partition of `hist` and clamps
+// every boundary r (between ranks r-1 and r) so that the ORDINARY per-step migration of the next step can carry the
+// transfer: it stays strictly inside the two old slabs it separates (particles only ever move to an adjacent rank, and
+// arrivals never reach a slab's far boundary plane), every slab stays at least two planes wide, and at most maxMove
+// particles cross it.
+int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
+                               int32_t* bounds) {
+    if (!hist || !oldBounds || !bounds) return AKUA_ERR_INVALID;
+    const int R = nranks;
+    const int32_t* old = oldBounds;
+    if (akua_slab_partition(hist, ncols, nranks, bounds) != AKUA_OK) return AKUA_ERR_INVALID;
+    for (int r = 1; r < R; r++) {
+        // stay inside the two old slabs and keep every slab at least two planes wide
+        int b = std::min(std::max(bounds[r], std::max(old[r - 1] + 1, bounds[r - 1] + 2)), old[r + 1] - 2);
+        int64_t moved = 0;
+        if (b > old[r]) { int x = old[r]; while (x < b && moved + hist[x] <= maxMove) { moved += hist[x]; x++; } b = x; }
+        else if (b < old[r]) { int x = old[r]; while (x > b && moved + hist[x - 1] <= maxMove) { moved += hist[x - 1]; x--; } b = x; }
+        if (b < bounds[r - 1] + 2) b = std::min(bounds[r - 1] + 2, old[r + 1] - 2);
+        bounds[r] = b;
+    }
+    return AKUA_OK;
+}
+
 // ---- phase-level operators ----
 int akua_pbf_phase_predict(akua_pbf_solver* s, float dt) {
     if (!s) return AKUA_ERR_INVALID;

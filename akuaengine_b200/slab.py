@@ -31,6 +31,20 @@ def partition_columns(hist: np.ndarray, nranks: int) -> np.ndarray:
     return bounds
 
 
+def rebalance_bounds(hist: np.ndarray, old_bounds: np.ndarray, max_move: int) -> np.ndarray:
+    """Boundaries akua_pbf_rebalance would adopt for the global histogram `hist` and the current `old_bounds` when at most
+    `max_move` particles may cross a boundary in one step (library host code, no GPU needed)."""
+    hist = np.ascontiguousarray(hist, dtype=np.int64)
+    old = np.ascontiguousarray(old_bounds, dtype=np.int32)
+    bounds = np.zeros(len(old), np.int32)
+    rc = load_library().akua_slab_rebalance_bounds(hist.ctypes.data_as(C.POINTER(C.c_int64)), len(hist), len(old) - 1,
+                                                   old.ctypes.data_as(C.POINTER(C.c_int32)), int(max_move),
+                                                   bounds.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise ValueError(f"akua_slab_rebalance_bounds failed (status {rc})")
+    return bounds
+
+
 def global_histogram(cols_local: np.ndarray, dist=None):
     """(col_min, histogram over [col_min, col_max]) of all ranks' particles. `dist` = torch.distributed or None."""
     lo = int(cols_local.min()) if len(cols_local) else INT_MAX

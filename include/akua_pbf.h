@@ -212,6 +212,12 @@ int akua_pbf_rebalance(akua_pbf_solver* s);
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]);
 /* Balanced slab boundaries from a per-x-column particle histogram. Pure host code (callable without a GPU). */
 int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds /* nranks + 1 */);
+/* Boundaries for a re-balancing step from the global per-column histogram and the current boundaries (pure host code; what
+ * akua_pbf_rebalance evaluates on every rank): the balanced partition, clamped so that the next step's ordinary migration
+ * can carry the transfer — boundary r stays strictly inside the two old slabs it separates, slabs stay >= 2 columns wide,
+ * and at most maxMove particles cross a boundary. oldBounds / bounds hold nranks + 1 entries (first 0, last ncols). */
+int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
+                               int32_t* bounds);
 
 /* Page-locked host memory for the interchange buffers (so uploads/downloads run at full PCIe rate). */
 void* akua_pbf_host_alloc(int64_t bytes);

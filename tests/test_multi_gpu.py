@@ -29,6 +29,49 @@ def test_partition_is_balanced_and_contiguous(akua_lib):
         partition_columns(np.ones(2, np.int64), 4)
 
 
+def test_rebalance_bounds_keep_the_migration_contract(akua_lib):
+    """What the next step's ordinary migration relies on after akua_pbf_rebalance moved the boundaries: every boundary lies
+    strictly inside the two OLD slabs it separates (so particles only move to an adjacent rank and arrivals never reach a
+    slab's far boundary plane), slabs stay at least two planes wide, at most max_move particles cross a boundary (unless the
+    two-plane minimum forces more), and repeated calls converge to the balanced partition."""
+    from akuaengine_b200.slab import partition_columns, rebalance_bounds
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        R = int(rng.integers(2, 9))
+        gx = int(rng.integers(4 * R, 12 * R))
+        hist = rng.integers(0, 2000, gx).astype(np.int64)
+        if trial % 3 == 0:                       # dam-break like: most columns empty
+            hist[rng.integers(0, gx, gx // 2)] = 0
+        # a valid current state: slabs at least two planes wide
+        cuts = np.sort(rng.choice(np.arange(1, gx // 2), R - 1, replace=False)) * 2
+        old = np.concatenate([[0], cuts, [gx]]).astype(np.int32)
+        assert np.all(np.diff(old) >= 2)
+        max_move = int(rng.integers(500, 20000))
+        target = partition_columns(hist, R)
+        cur = old
+        for it in range(200):
+            new = rebalance_bounds(hist, cur, max_move)
+            assert new[0] == 0 and new[-1] == gx
+            assert np.all(np.diff(new) >= 2), (cur, new)
+            for r in range(1, R):
+                assert cur[r - 1] < new[r] <= cur[r + 1] - 2, (r, cur, new)      # strictly inside the two old slabs
+                lo, hi = sorted((int(cur[r]), int(new[r])))
+                moved = int(hist[lo:hi].sum())
+                forced = new[r] == new[r - 1] + 2 and new[r] > cur[r]            # pushed up by the two-plane minimum
+                assert moved <= max_move or forced, (r, cur, new, moved, max_move)
+            if np.array_equal(new, cur):
+                break
+            cur = new
+        # fixed point: either the balanced partition, or every remaining difference is blocked by one over-full plane
+        for r in range(1, R):
+            if cur[r] != target[r]:
+                step = 1 if target[r] > cur[r] else -1
+                plane = int(cur[r]) if step > 0 else int(cur[r]) - 1
+                blocked_by_size = hist[plane] > max_move
+                blocked_by_width = (step > 0 and cur[r] + 1 > cur[r + 1] - 2) or (step < 0 and cur[r] - 1 < cur[r - 1] + 2)
+                assert blocked_by_size or blocked_by_width, (r, cur, target, hist[plane], max_move)
+
+
 def _gloo_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch

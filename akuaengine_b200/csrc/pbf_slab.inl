@@ -50,6 +50,11 @@ const char* loadNccl() {
         }                                                                                         \
     } while (0)
 
+// Bound of the k_wait_flags spins in SM clock cycles (~20 s at 1.97 GHz): long enough for any host-side skew between the
+// ranks' launch loops (the count exchange at the top of a step is where a late rank is waited for), short enough that a
+// lost neighbour ends in an error instead of a hung GPU.
+constexpr long long kFlagWaitCycles = 40000000000LL;
+
 cudaEvent_t slabNextEvent(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     cudaEvent_t e = sl.evPool[sl.evNext];
@@ -159,7 +164,7 @@ int slabWait(akua_pbf_solver* s, const SlabTicket& t) {
     if (sl.p2p) {
         const int hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
         if (hasL || hasR) {
-            slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags, hasL, hasR, t.epoch, sl.dCounts + 31, 4000000000LL);
+            slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags, hasL, hasR, t.epoch, sl.dCounts + 31, kFlagWaitCycles);
             AK_LAUNCH_CHECK(s, "k_wait_flags");
         }
     }
@@ -275,7 +280,7 @@ int slabSwapCounts(akua_pbf_solver* s) {
         slab::k_publish_counts<<<1, 32, 0, s->stream>>>(sl.dCounts, hasL ? sl.peerL.dCounts : nullptr, hasR ? sl.peerR.dCounts : nullptr,
                                                         hasL ? sl.peerL.flags + 5 : nullptr, hasR ? sl.peerR.flags + 4 : nullptr, epoch);
         AK_LAUNCH_CHECK(s, "k_publish_counts");
-        slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, epoch, sl.dCounts + 31, 4000000000LL);
+        slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, epoch, sl.dCounts + 31, kFlagWaitCycles);
         AK_LAUNCH_CHECK(s, "k_wait_flags");
         AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
         AK_CUDA(s, cudaStreamSynchronize(s->stream));

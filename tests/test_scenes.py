@@ -40,3 +40,28 @@ def test_clouds_are_deterministic_and_bounded():
     # density: ~8 particles per h-cell on average
     side = bmax[0]
     assert abs(5000 / (side / 0.1) ** 3 - 8.0) < 0.01
+
+
+def test_scene_descriptions_build_the_baseline_configs():
+    """scenes_json/*.json name real scenes of the sizes BASELINE.json quotes; building one needs no GPU."""
+    import json
+    from pathlib import Path
+    from akuaengine_b200.run import build_scene, gravity_at
+    want = {"config1_dambreak_27k.json": 27_000, "config2_dambreak_1m.json": 1_000_000}
+    root = Path(__file__).resolve().parents[1] / "scenes_json"
+    names = sorted(p.name for p in root.glob("*.json"))
+    assert set(want) <= set(names) and len(names) >= 4
+    for name in names:
+        desc = json.loads((root / name).read_text())
+        assert desc["scene"] in ("dam_break", "tank", "uniform_cloud", "clustered_cloud")
+        if name in want:
+            particles, bmin, bmax = build_scene(desc)
+            assert len(particles) == want[name]
+            p = particles["position"]
+            assert np.all(p >= bmin) and np.all(p <= bmax)
+    # piecewise-constant gravity schedule: the last entry whose time has been reached wins
+    sched = [[0.0, 0, -9.8, 0], [0.5, 2.5, -9.5, 0], [1.0, -2.5, -9.5, 0]]
+    assert gravity_at(sched, 0.25, [0, -1, 0]) == [0, -9.8, 0]
+    assert gravity_at(sched, 0.5, [0, -1, 0]) == [2.5, -9.5, 0]
+    assert gravity_at(sched, 7.0, [0, -1, 0]) == [-2.5, -9.5, 0]
+    assert gravity_at([], 1.0, [0, -1, 0]) == [0, -1, 0]

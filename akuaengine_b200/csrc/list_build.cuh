@@ -116,9 +116,11 @@ __host__ __device__ __forceinline__ void finish_list(uint32_t i, uint32_t count,
 }
 
 #ifdef __CUDACC__
-// Same parameter list as k_build_neighbours<KEY_LINEAR> so that the host code can launch either.
-template <int UNROLL>
-__global__ void __launch_bounds__(256) k_build_neighbours_mask(const float4* __restrict__ xs,
+// Same parameter list as k_build_neighbours<KEY_LINEAR> so that the host code can launch either. MINB (resident CTAs per SM)
+// fixes the register budget explicitly: <4, 5> compiles to 48 registers, <8, 4> to 64, both without spills (ptxas -v); left to
+// its own heuristics ptxas squeezes the 8-deep variant into 48 registers and spills.
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_build_neighbours_mask(const float4* __restrict__ xs,
                                                                const uint32_t* __restrict__ /*keysSorted*/,
                                                                const uint32_t* __restrict__ /*bucketStart*/,
                                                                const uint2* __restrict__ cellRange, uint32_t n,

@@ -318,8 +318,8 @@ int launchBuildNeighbours(akua_pbf_solver* s, uint32_t n) {
 #define AK_BUILD(K) launchK(s, K, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n, s->nbrStride, \
             (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius)
     if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) AK_BUILD(k_build_neighbours<KEY_HASH>);
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) AK_BUILD(k_build_neighbours_mask<4>);
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) AK_BUILD(k_build_neighbours_mask<8>);
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) AK_BUILD((k_build_neighbours_mask<4, 5>));
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) AK_BUILD((k_build_neighbours_mask<8, 4>));
     else AK_BUILD(k_build_neighbours<KEY_LINEAR>);
 #undef AK_BUILD
     AK_LAUNCH_CHECK(s, "k_build_neighbours");

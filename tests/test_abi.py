@@ -86,3 +86,29 @@ def test_graphics_resource_export_rejects_a_null_handle(akua_lib):
     assert akua_lib.akua_pbf_export_to_graphics_resource(s._h, None) == 1
     assert b"null resource" in akua_lib.akua_pbf_last_error(s._h)
     s.close()
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The Python binding re-declares the header's structs by hand; a C program compiled against include/akua_pbf.h prints
+    sizeof / offsetof of every field and the ctypes mirrors must agree (catches drift when an option is added)."""
+    import subprocess
+    from akuaengine_b200 import Counters, LambdaCorrParams, PBFConfig, PBFOptions
+    mirrors = {"akua_pbf_config": PBFConfig, "akua_corr_params": LambdaCorrParams, "akua_pbf_options": PBFOptions,
+               "akua_pbf_counters": Counters}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "akua_pbf.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    res = subprocess.run(["gcc", "-std=c11", "-I", str(REPO / "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr       # also proves the header is plain C and every mirrored field exists in it
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l}
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)

@@ -56,8 +56,15 @@ struct BoxParams {
 // pdl_wait() before it touches global memory (it returns once ALL grids it depends on have completed and flushed — so the
 // data dependencies are exactly those of plain stream order) and pdl_trigger() once its main loop is done (the next grid may
 // start occupying SM slots from then on). Both are no-ops for a kernel launched without the attribute.
+// (AKUA_HOST_EMU: the kernels compiled for the CPU by tests/emu — test infrastructure only, see tests/emu/cuda_runtime.h; the
+// inline PTX of this file has a plain C++ equivalent under that macro and nowhere else.)
+#ifdef AKUA_HOST_EMU
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------------------------------------ device math
 // dist2 / cell_of / clampi / linear_key are __host__ __device__ so that tests/cpp/list_build_host.cu can run the per-particle
@@ -86,7 +93,11 @@ __device__ __forceinline__ float spiky_scale(float d2, const SphParams& P) {
         // one MUFU.RSQ: the operand is clamped to a normal float, so the denormal pre/post-scaling of rsqrtf() (three more
         // instructions per neighbour) can never trigger. d2 == 0 (coincident / masked self slot) -> r = 0 -> s = 0.
         float d = fmaxf(d2, 1e-30f);
+#ifdef AKUA_HOST_EMU
+        invr = 1.0f / sqrtf(d);
+#else
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(invr) : "f"(d));
+#endif
         r = d2 * invr;
     } else { r = sqrtf(d2); invr = 1.0f / r; }
     float t = fmaxf(P.h - r, 0.0f);
@@ -191,8 +202,12 @@ __host__ __device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uin
 // Streaming 16-byte load of four neighbour indices: read once per sweep, so keep it out of L1 (the gathers want L1).
 __device__ __forceinline__ uint4 ld_list4(const uint4* p) {
     uint4 v;
+#ifdef AKUA_HOST_EMU
+    v = *p;
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
     return v;
 }
 // Post-solve gather record: committed position (w = mass) and velocity (w = density) of one particle side by side, so that
@@ -202,9 +217,13 @@ __device__ __forceinline__ uint4 ld_list4(const uint4* p) {
 struct __align__(32) PosVel { float4 x, v; };
 __device__ __forceinline__ PosVel ld_posvel(const PosVel* p) {
     PosVel r;
+#ifdef AKUA_HOST_EMU
+    r = *p;
+#else
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.x.x), "=f"(r.x.y), "=f"(r.x.z), "=f"(r.x.w), "=f"(r.v.x), "=f"(r.v.y), "=f"(r.v.z), "=f"(r.v.w)
                  : "l"(p));
+#endif
     return r;
 }
 // Drives one neighbour sweep for particle i: `load(j)` gathers whatever the sweep needs of neighbour j, `acc(payload,

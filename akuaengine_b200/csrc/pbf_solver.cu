@@ -7,6 +7,7 @@
 // state on the device, and issues the whole step asynchronously on one stream.
 #include "../../include/akua_pbf.h"
 #include "pbf_kernels.cuh"
+#include "pbf_params.h"
 #include "list_build.cuh"
 #include "radix_sort.cuh"
 #include "slab_kernels.cuh"
@@ -213,46 +214,10 @@ cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
-SphParams makeSph(const akua_pbf_solver* s) {
-    SphParams P{};
-    const float h = s->cfg.smoothRadius;
-    P.h = h;
-    P.h2 = h * h;
-    // Same float expressions as include/AkuaEngine/CUDA/SmoothingKernelsCUDA.h:20,27, evaluated once on the host.
-    P.poly6Coef = 315.0f / (64.0f * 3.14f * powf(h, 9.0f));
-    P.spikyCoef = -45.0f / (3.14f * powf(h, 6.0f));
-    float t0 = P.h2 - 0.0f;
-    P.selfW = P.poly6Coef * (t0 * t0 * t0);
-    P.invRestDensity = 1.0f / s->cfg.restDensity;  // ConstraintSolverCUDA.cu:201
-    P.relaxation = s->cfg.relaxation;
-    P.corrK = s->corr.k;
-    P.corrN = s->corr.n;
-    float dq2 = s->corr.delta_q * s->corr.delta_q;
-    float tq = P.h2 - dq2;
-    float wdq = dq2 > P.h2 ? 0.0f : P.poly6Coef * (tq * tq * tq);
-    P.invPoly6Dq = 1.0f / wdq;
-    P.corrNIsFour = (s->corr.n == 4.0f) ? 1 : 0;
-    P.uniformMass = s->uniformMass;
-    return P;
-}
+SphParams makeSph(const akua_pbf_solver* s) { return make_sph_params(s->cfg, s->corr, s->uniformMass); }
+BoxParams makeBox(const float* bmin, const float* bmax) { return make_box_params(bmin, bmax); }
 
-BoxParams makeBox(const float* bmin, const float* bmax) {
-    BoxParams B{};
-    B.bmin = make_float3(bmin[0], bmin[1], bmin[2]);
-    B.bmax = make_float3(bmax[0], bmax[1], bmax[2]);
-    B.collisionMinDist = 0.025f;   // ConstraintSolverCUDA.cu:137
-    B.collisionStiffness = 0.5f;   // ConstraintSolverCUDA.cu:138
-    B.dampingMinDist = 0.025f;     // IntegrationCUDA.cu:88
-    B.restitution = 0.0f;          // PBFSolver.cpp:64
-    B.oneMinusFriction = 1.0f - 0.95f;
-    return B;
-}
-
-int bitsFor(uint64_t maxKey) {
-    int b = 1;
-    while (b < 32 && (maxKey >> b) != 0) b++;
-    return b;
-}
+int bitsFor(uint64_t maxKey) { return bits_for_key(maxKey); }
 
 void rememberBox(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     for (int a = 0; a < 3; a++) { s->lastBoxMin[a] = bmin[a]; s->lastBoxMax[a] = bmax[a]; }
@@ -264,16 +229,9 @@ void rememberBox(akua_pbf_solver* s, const float* bmin, const float* bmax) {
 // test decides), only slower.
 int layoutGrid(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) return AKUA_OK;
-    const float cs = s->cfg.smoothRadius;
-    int lo[3], dim[3];
-    int64_t cells = 1;
-    for (int a = 0; a < 3; a++) {
-        if (!(bmax[a] > bmin[a])) { s->err = "box max must exceed box min"; return AKUA_ERR_INVALID; }
-        lo[a] = (int)std::floor(bmin[a] / cs) - 2;
-        int hi = (int)std::floor(bmax[a] / cs) + 2;
-        dim[a] = hi - lo[a] + 1;
-        cells *= dim[a];
-    }
+    int3 gmin, gdim;
+    const int64_t cells = layout_linear_grid(s->cfg.smoothRadius, bmin, bmax, &gmin, &gdim);
+    if (cells < 0) { s->err = "box max must exceed box min"; return AKUA_ERR_INVALID; }
     if (cells >= (int64_t)1 << 31) { s->err = "LINEAR_CELL grid too large (>= 2^31 cells)"; return AKUA_ERR_INVALID; }
     if (cells > s->cellCapacity) {  // only when the box grows beyond anything seen so far
         if (s->cellRange) { AK_CUDA(s, cudaStreamSynchronize(s->stream)); AK_CUDA(s, cudaFree(s->cellRange)); }
@@ -281,8 +239,8 @@ int layoutGrid(akua_pbf_solver* s, const float* bmin, const float* bmax) {
         AK_CUDA(s, dalloc(&s->cellRange, (size_t)cells));
         s->cellCapacity = cells;
     }
-    s->grid.gridMin = make_int3(lo[0], lo[1], lo[2]);
-    s->grid.gridDim = make_int3(dim[0], dim[1], dim[2]);
+    s->grid.gridMin = gmin;
+    s->grid.gridDim = gdim;
     s->keyBits = bitsFor((uint64_t)cells - 1);
     s->ctr.num_cells = cells;
     return AKUA_OK;

@@ -26,11 +26,19 @@ constexpr int kWarps = kThreads / 32;
 // that the count / scatter grids still fill 148 SMs several times over (at 1 M keys a 4096-key tiling is only 245 CTAs).
 constexpr int kItemsLarge = 16, kItemsSmall = 4;
 
+#ifdef AKUA_HOST_EMU   // tests/emu (CPU emulation of the kernels, test infrastructure only)
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }   // see pbf_kernels.cuh
+#endif
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
+#ifdef AKUA_HOST_EMU
+    m = (1u << (threadIdx.x & 31u)) - 1u;
+#else
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+#endif
     return m;
 }
 

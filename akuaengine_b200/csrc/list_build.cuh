@@ -115,7 +115,7 @@ __host__ __device__ __forceinline__ void finish_list(uint32_t i, uint32_t count,
     for (uint32_t k = count; k < ((count + 3u) & ~3u); k++) list[list_slot(i, k, stride)] = i;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(AKUA_HOST_EMU)
 // Same parameter list as k_build_neighbours<KEY_LINEAR> so that the host code can launch either. MINB (resident CTAs per SM)
 // fixes the register budget explicitly: <4, 5> compiles to 48 registers, <8, 4> to 64, both without spills (ptxas -v); left to
 // its own heuristics ptxas squeezes the 8-deep variant into 48 registers and spills.

@@ -7,6 +7,7 @@
 // port of the reference and with the golden fixtures without a GPU.
 #include "../../akuaengine_b200/csrc/pbf_kernels.cuh"
 #include "../../akuaengine_b200/csrc/list_build.cuh"
+#include "../../akuaengine_b200/csrc/pbf_params.h"
 #include "../../akuaengine_b200/csrc/radix_sort.cuh"
 #include "../../akuaengine_b200/csrc/slab_kernels.cuh"
 
@@ -43,6 +44,220 @@ int emu_sort_pairs(const uint32_t* keysIn, uint32_t n, int keyBits, uint32_t* ke
     std::copy(ko, ko + n, keysOut);
     std::copy(vo, vo + n, valsOut);
     return launches;
+}
+
+
+// ---- a whole solver on host arrays: the sequence of stepEager() / phaseSolve() / phasePost() in pbf_solver.cu ----
+struct EmuSolver {
+    uint32_t n = 0;
+    akua_pbf_config cfg{};
+    akua_corr_params corr{};
+    int keyMode = AKUA_KEY_LINEAR_CELL, fastMath = 1, pack = 1, listBuild = 0;
+    std::vector<float4> pos, posAlt, vel, velAlt, xs, xsAlt, omega, dpos, color, xl, xw;
+    std::vector<float> density, lambda, omegaLen, size;
+    std::vector<uint32_t> id, idAlt, keysUnsorted, keyA, keyB, valA, valB, bucketStart, nbrList, nbrCount, tileHist, binTotal;
+    std::vector<uint2> cellRange;
+    uint32_t *keysSorted = nullptr, *perm = nullptr;
+    float4 *pPos, *pPosAlt, *pVel, *pVelAlt, *pXs, *pXsAlt;
+    uint32_t *pId, *pIdAlt;
+    GridParams grid{};
+    int keyBits = 1;
+    uint32_t nbrStride = 0;
+    bool bucketsDirty = false, massUniform = false;
+    float uniformMass = 0.f;
+    rsort::Workspace ws;
+    long launches = 0;
+};
+
+void* emu_create(uint32_t n, const akua_pbf_config* cfg, const akua_corr_params* corr, int keyMode, int fastMath, int pack,
+                 int listBuild) {
+    EmuSolver* s = new EmuSolver();
+    s->n = n; s->cfg = *cfg; s->corr = *corr; s->keyMode = keyMode; s->fastMath = fastMath; s->pack = pack; s->listBuild = listBuild;
+    const size_t cap = n ? n : 1;
+    for (auto* v : {&s->pos, &s->posAlt, &s->vel, &s->velAlt, &s->xs, &s->xsAlt, &s->omega, &s->dpos, &s->color, &s->xl, &s->xw})
+        v->assign(cap, make_float4(0, 0, 0, 0));
+    for (auto* v : {&s->density, &s->lambda, &s->omegaLen, &s->size}) v->assign(cap, 0.f);
+    for (auto* v : {&s->id, &s->idAlt, &s->keysUnsorted, &s->keyA, &s->keyB, &s->valA, &s->valB, &s->nbrCount}) v->assign(cap, 0u);
+    s->pPos = s->pos.data(); s->pPosAlt = s->posAlt.data(); s->pVel = s->vel.data(); s->pVelAlt = s->velAlt.data();
+    s->pXs = s->xs.data(); s->pXsAlt = s->xsAlt.data(); s->pId = s->id.data(); s->pIdAlt = s->idAlt.data();
+    s->keysSorted = s->keyA.data(); s->perm = s->valA.data();
+    s->nbrStride = (uint32_t)((cap + 31) / 32 * 32);
+    s->nbrList.assign((size_t)s->nbrStride * (size_t)((cfg->maxNeighbours + 3) / 4 * 4), 0u);
+    s->ws.maxTiles = rsort::max_tiles_for_capacity(cap);
+    s->tileHist.assign((size_t)256 * s->ws.maxTiles, 0u); s->binTotal.assign(256, 0u);
+    s->ws.tileHist = s->tileHist.data(); s->ws.binTotal = s->binTotal.data();
+    s->grid.cellSize = cfg->smoothRadius;
+    s->grid.lookupCellSize = cfg->spatialHashCellSize;
+    if (keyMode == AKUA_KEY_REFERENCE_HASH) {
+        const int64_t ts = n ? (int64_t)cfg->maxNeighbours * n : 1;   // PBFSolver.cpp:15
+        s->grid.tableSize = (uint32_t)ts;
+        s->keyBits = bits_for_key((uint64_t)ts - 1);
+        s->bucketStart.assign((size_t)ts, 0xffffffffu);
+    }
+    return s;
+}
+void emu_destroy(void* h) { delete static_cast<EmuSolver*>(h); }
+
+int emu_upload_aos108(void* h, const void* src) {
+    EmuSolver* s = static_cast<EmuSolver*>(h);
+    const uint32_t n = s->n;
+    if (!n) return 0;
+    run(k_unpack_aos, gridFor(n), 256u, (const uint32_t*)src, n, s->pPos, s->pVel, s->pXs, s->omega.data(), s->omegaLen.data(),
+        s->dpos.data(), s->density.data(), s->lambda.data(), s->keysSorted, s->color.data(), s->size.data(), s->pId);
+    uint32_t range[2] = {0xffffffffu, 0u};   // massRangeAsync / massRangeFinish
+    run(k_mass_range, std::min<uint32_t>(gridFor(n), 148 * 8), 256u, (const float4*)s->pPos, n, range);
+    s->massUniform = range[0] == range[1];
+    const uint32_t bits = (range[0] & 0x80000000u) ? (range[0] ^ 0x80000000u) : ~range[0];
+    std::memcpy(&s->uniformMass, &bits, 4);
+    return 0;
+}
+int emu_download_aos108(void* h, void* dst) {
+    EmuSolver* s = static_cast<EmuSolver*>(h);
+    const uint32_t n = s->n;
+    if (!n) return 0;
+    run(k_pack_aos, gridFor(n), 256u, (uint32_t*)dst, n, (const float4*)s->pPos, (const float4*)s->pVel, (const float4*)s->pXs,
+        (const float4*)s->omega.data(), (const float4*)s->dpos.data(), (const float*)s->density.data(), (const float*)s->lambda.data(),
+        (const uint32_t*)s->keysSorted, (const float4*)s->color.data(), (const float*)s->size.data(), (const uint32_t*)s->pId, 1);
+    return 0;
+}
+
+int emu_step(void* h, float dt, int iterations, const float* bmin, const float* bmax) {
+    EmuSolver* s = static_cast<EmuSolver*>(h);
+    const uint32_t n = s->n;
+    if (!n) return 0;
+    const bool hash = s->keyMode == AKUA_KEY_REFERENCE_HASH;
+    const bool pack = s->pack && s->massUniform;
+    if (!hash) {   // layoutGrid
+        int3 gmin, gdim;
+        const int64_t cells = layout_linear_grid(s->cfg.smoothRadius, bmin, bmax, &gmin, &gdim);
+        if (cells < 0 || cells >= (int64_t)1 << 31) return 1;
+        s->cellRange.assign((size_t)cells, make_uint2(0, 0));   // = the per-step memset
+        s->grid.gridMin = gmin; s->grid.gridDim = gdim;
+        s->keyBits = bits_for_key((uint64_t)cells - 1);
+    }
+    const float3 g = make_float3(s->cfg.gravity[0], s->cfg.gravity[1], s->cfg.gravity[2]);
+    // phasePredictKey
+    if (hash) run(k_predict_key<KEY_HASH>, gridFor(n), 256u, (const float4*)s->pPos, (const float4*)s->pVel, s->pXs, s->keysUnsorted.data(), n, dt, g, s->grid, 1);
+    else      run(k_predict_key<KEY_LINEAR>, gridFor(n), 256u, (const float4*)s->pPos, (const float4*)s->pVel, s->pXs, s->keysUnsorted.data(), n, dt, g, s->grid, 1);
+    // phaseSortReorderLists
+    if (hash && s->bucketsDirty) run(k_clear_buckets, gridFor(n), 256u, (const uint32_t*)s->keysSorted, n, s->bucketStart.data());
+    s->launches += rsort::sort_pairs(s->keysUnsorted.data(), s->keyA.data(), s->valA.data(), s->keyB.data(), s->valB.data(), n, s->keyBits,
+                                     s->ws, nullptr, &s->keysSorted, &s->perm, true);
+    if (hash) run(k_reorder_ranges<KEY_HASH>, gridFor(n), 256u, (const uint32_t*)s->keysSorted, (const uint32_t*)s->perm, n, (const float4*)s->pPos,
+                  (const float4*)s->pVel, (const float4*)s->pXs, (const uint32_t*)s->pId, s->pPosAlt, s->pVelAlt, s->pXsAlt, s->pIdAlt,
+                  s->bucketStart.data(), s->cellRange.data());
+    else      run(k_reorder_ranges<KEY_LINEAR>, gridFor(n), 256u, (const uint32_t*)s->keysSorted, (const uint32_t*)s->perm, n, (const float4*)s->pPos,
+                  (const float4*)s->pVel, (const float4*)s->pXs, (const uint32_t*)s->pId, s->pPosAlt, s->pVelAlt, s->pXsAlt, s->pIdAlt,
+                  s->bucketStart.data(), s->cellRange.data());
+    std::swap(s->pPos, s->pPosAlt); std::swap(s->pVel, s->pVelAlt); std::swap(s->pXs, s->pXsAlt); std::swap(s->pId, s->pIdAlt);
+    s->bucketsDirty = hash;
+#define EMU_BUILD(K) run(K, gridFor(n), 256u, (const float4*)s->pXs, (const uint32_t*)s->keysSorted, (const uint32_t*)s->bucketStart.data(), \
+                         (const uint2*)s->cellRange.data(), n, s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList.data(), s->nbrCount.data(), \
+                         s->grid, s->cfg.smoothRadius)
+    if (hash) EMU_BUILD(k_build_neighbours<KEY_HASH>);
+    else if (s->listBuild == 1) EMU_BUILD((k_build_neighbours_mask<4, 5>));
+    else if (s->listBuild == 2) EMU_BUILD((k_build_neighbours_mask<8, 4>));
+    else EMU_BUILD(k_build_neighbours<KEY_LINEAR>);
+#undef EMU_BUILD
+    // phaseSolve (single GPU: one span over all particles; the last pass B commits)
+    const SphParams P = make_sph_params(s->cfg, s->corr, s->uniformMass);
+    const BoxParams B = make_box_params(bmin, bmax);
+    const Span all{n, 0u, 0xffffffffu, 0u};
+    const uint32_t sg = gridFor(n, AKUA_SWEEP_BLOCK), sb = AKUA_SWEEP_BLOCK;
+    float4* xl = pack ? s->xl.data() : nullptr;
+    float4* xw = pack ? s->xw.data() : nullptr;
+    const PeerPush nop{};
+    const HaloSync nohs{};
+    bool committed = false;
+    for (int it = 0; it < iterations; it++) {
+        const bool fin = it == iterations - 1;
+#define EMU_A(F) run(k_density_lambda<F>, sg, sb, (const float4*)s->pXs, (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(), \
+                     s->nbrStride, all, s->density.data(), s->lambda.data(), xl, P, nop, nohs)
+        if (s->fastMath) EMU_A(true); else EMU_A(false);
+#undef EMU_A
+#define EMU_B(F, L, K, C) run(k_delta_apply<F, L, K, C>, sg, sb, (const float4*)s->pXs, s->pXsAlt, (const float*)s->lambda.data(), (const float4*)s->xl.data(), \
+                     (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, P, B, s->dpos.data(), s->pPos, s->pVel, \
+                     (const float*)s->density.data(), (PosVel*)nullptr, dt, nop, nop, nohs)
+#define EMU_B_C(F, L, K) do { if (P.corrNIsFour) EMU_B(F, L, K, true); else EMU_B(F, L, K, false); } while (0)
+#define EMU_B_L(F, K) do { if (fin) EMU_B_C(F, true, K); else EMU_B_C(F, false, K); } while (0)
+        if (pack) { if (s->fastMath) EMU_B_L(true, true); else EMU_B_L(false, true); }
+        else      { if (s->fastMath) EMU_B_L(true, false); else EMU_B_L(false, false); }
+#undef EMU_B_L
+#undef EMU_B_C
+#undef EMU_B
+        std::swap(s->pXs, s->pXsAlt);
+        if (fin) committed = true;
+    }
+    if (!committed) {   // solverIterations == 0
+        run(k_update, gridFor(n), 256u, (const float4*)s->pXs, s->pPos, s->pVel, (const float*)s->density.data(), n, dt);
+        run(k_damping, gridFor(n), 256u, (const float4*)s->pPos, s->pVel, n, B);
+    }
+    // phasePost
+#define EMU_V(F) run(k_vorticity<F, false>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)nullptr, (const uint32_t*)s->nbrList.data(), \
+                     (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->omega.data(), s->omegaLen.data(), xw, P, nop, nohs)
+    if (s->fastMath) EMU_V(true); else EMU_V(false);
+#undef EMU_V
+#define EMU_C(F, K) run(k_confinement<F, K>, sg, sb, (const float4*)s->pXs, (const float4*)s->omega.data(), (const float*)s->omegaLen.data(), \
+                     (const float4*)s->xw.data(), (const float*)s->density.data(), (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(), \
+                     s->nbrStride, all, s->pVel, (PosVel*)nullptr, P, dt, s->cfg.vorticityEpsilon, nop, nohs)
+    if (pack) { if (s->fastMath) EMU_C(true, true); else EMU_C(false, true); }
+    else      { if (s->fastMath) EMU_C(true, false); else EMU_C(false, false); }
+#undef EMU_C
+    run(k_xsph<false>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)nullptr, (const uint32_t*)s->nbrList.data(),
+        (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->pVelAlt, P, s->cfg.viscosity, nohs);
+    std::swap(s->pVel, s->pVelAlt);
+    return 0;
+}
+
+// debug taps (which: 0 unsorted keys, 1 sorted keys, 2 permutation, 3 ids, 6 neighbour counts, 7 neighbour lists row-major)
+int emu_debug_get(void* h, int which, uint32_t* dst) {
+    EmuSolver* s = static_cast<EmuSolver*>(h);
+    const uint32_t n = s->n;
+    switch (which) {
+        case 0: std::copy(s->keysUnsorted.begin(), s->keysUnsorted.begin() + n, dst); return 0;
+        case 1: std::copy(s->keysSorted, s->keysSorted + n, dst); return 0;
+        case 2: std::copy(s->perm, s->perm + n, dst); return 0;
+        case 3: std::copy(s->pId, s->pId + n, dst); return 0;
+        case 6: std::copy(s->nbrCount.begin(), s->nbrCount.begin() + n, dst); return 0;
+        case 7: {
+            const uint32_t maxN = (uint32_t)s->cfg.maxNeighbours;
+            run(k_list_to_rowmajor, gridFor((uint64_t)n * maxN), 256u, (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(),
+                s->nbrStride, n, maxN, dst);
+            return 0;
+        }
+    }
+    return 1;
+}
+
+
+// ---- x-slab migration compaction: k_mig_count -> k_mig_scan -> k_mig_pack on host arrays (slab_kernels.cuh) ----
+// keys: n unsorted LINEAR_CELL keys (modified: leavers get `sentinel`). ids: particle ids carried in MigRecord::meta.x.
+// counts[32] = the device counter block; idsL / idsR receive the ids of the records packed for the left / right rank in order.
+int emu_migration(uint32_t* keys, uint32_t n, uint32_t planeCells, int xLo, int xHi, uint32_t sentinel, const uint32_t* ids,
+                  uint32_t cap, uint32_t* counts, uint32_t* idsL, uint32_t* idsR) {
+    const uint32_t blocks = std::max(1u, gridFor(n));
+    std::vector<uint32_t> blockCnt((size_t)2 * (blocks + 1), 0u);
+    std::vector<float4> pos(n ? n : 1, make_float4(1, 2, 3, 4)), vel(pos), xs(pos);
+    std::vector<slab::MigRecord> sendL(cap), sendR(cap);
+    std::fill(counts, counts + 32, 0u);
+    run(slab::k_mig_count, blocks, 256u, (const uint32_t*)keys, n, planeCells, xLo, xHi, blockCnt.data(), counts + 2);
+    run(slab::k_mig_scan, 1u, 1024u, blockCnt.data(), blocks, counts);
+    run(slab::k_mig_pack, blocks, 256u, keys, n, planeCells, xLo, xHi, (const uint32_t*)blockCnt.data(), sentinel, (const float4*)pos.data(),
+        (const float4*)vel.data(), (const float4*)xs.data(), ids, sendL.data(), sendR.data(), cap);
+    for (uint32_t k = 0; k < std::min(counts[0], cap); k++) idsL[k] = sendL[k].meta.x;
+    for (uint32_t k = 0; k < std::min(counts[1], cap); k++) idsR[k] = sendR[k].meta.x;
+    return 0;
+}
+
+// Per-x-plane histogram of sorted keys (k_plane_hist, used by akua_pbf_rebalance) and the plane-size check (k_plane_verify).
+int emu_plane_hist(const uint32_t* keysSorted, uint32_t n, uint32_t planeCells, int gx, unsigned long long* hist) {
+    run(slab::k_plane_hist, gridFor((uint64_t)gx), 256u, keysSorted, n, planeCells, gx, hist);
+    return 0;
+}
+int emu_plane_verify(const uint32_t* keysSorted, uint32_t n, uint32_t planeCells, int xLo, int xHi, uint32_t predictFirst,
+                     uint32_t predictLast, uint32_t* counts32) {
+    run(slab::k_plane_verify, 1u, 32u, keysSorted, n, planeCells, xLo, xHi, predictFirst, predictLast, 1, 1, counts32);
+    return 0;
 }
 
 }  // extern "C"

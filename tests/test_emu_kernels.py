@@ -217,3 +217,52 @@ def test_plane_histogram_and_plane_verify(emu):
     assert c[31] == 0
     emu.emu_plane_verify(keys.ctypes.data, n, plane, x_lo, x_hi, first + 1, last, c.ctypes.data)
     assert c[31] == 1      # a wrong prediction raises the sticky error word
+
+
+def test_fuzz_against_the_cpu_port(emu):
+    """Differential fuzz of the emulated kernel source (REFERENCE_HASH mode) against the CPU port of the reference on small
+    random scenes chosen to hit the edges: 1-3 particles, mixed masses, neighbour caps of 5 / 16 that bite, dense blobs,
+    particles outside the box and around the origin (where the reference's hash collides). Integer
+    structures must agree bit for bit after every step; floats within 2e-4 (two free-running steps) except in the dense
+    blobs, whose violent first steps amplify last-ulp differences."""
+    from oracle import PortOracle, param_block
+    rng = np.random.default_rng(0)
+    bmin, bmax = np.array([1.5, 0, 1.5], np.float32), np.array([4.5, 4, 4.5], np.float32)
+    dt = 0.0083
+    for trial in range(14):
+        n = int(rng.choice([1, 2, 3, 7, 33, 100, 257, 600]))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            pos = rng.uniform([1.6, 0.1, 1.6], [2.2, 0.6, 2.2], (n, 3))
+        elif kind == 1:
+            pos = np.array([3, 2, 3]) + rng.normal(0, 0.05, (n, 3))
+        elif kind == 2:
+            pos = rng.uniform([1.0, -0.5, 1.0], [5.0, 4.5, 5.0], (n, 3))
+        else:
+            pos = np.array([-0.02, 0.03, 0.01]) + rng.uniform(-0.15, 0.15, (n, 3))
+        p = np.zeros(n, PARTICLE_DTYPE)
+        p["position"] = pos.astype(np.float32)
+        p["velocity"] = rng.normal(0, 0.5, (n, 3)).astype(np.float32)
+        p["mass"] = 1.0 if rng.random() < 0.5 else rng.uniform(0.5, 1.5, n).astype(np.float32)
+        p["color"][:, 0] = np.arange(n)
+        max_n = int(rng.choice([128, 128, 16, 5]))
+        params = param_block(maxNeighbours=max_n)
+        o = PortOracle(p.copy(), params)
+        s = EmuSolver(emu, n, params, KEY_REFERENCE_HASH)
+        s.upload(p)
+        for step in range(2):
+            o.step(dt, bmin, bmax)
+            s.step(dt, bmin, bmax)
+            got, want = s.download(), o.particles
+            arr, cnt = o.neighbours()
+            where = (trial, n, kind, max_n, step)
+            assert np.array_equal(got["hash"], want["hash"]), where
+            assert np.array_equal(pl.ids_of(got), pl.ids_of(want)), where
+            assert np.array_equal(s.debug(6), cnt), where
+            lst = s.debug(7, (n, max_n))
+            mask = np.arange(max_n)[None, :] < cnt[:, None]
+            assert np.array_equal(lst[mask], arr[:, :max_n][mask]), where
+            if kind != 1 and np.isfinite(want["position"]).all():
+                assert np.abs(got["position"] - want["position"]).max() / pl.H < 2e-4, where
+                assert np.abs(got["velocity"] - want["velocity"]).max() / (pl.H / dt) < 2e-4, where
+        s.close(); o.close()

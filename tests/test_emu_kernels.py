@@ -223,8 +223,8 @@ def test_fuzz_against_the_cpu_port(emu):
     """Differential fuzz of the emulated kernel source (REFERENCE_HASH mode) against the CPU port of the reference on small
     random scenes chosen to hit the edges: 1-3 particles, mixed masses, neighbour caps of 5 / 16 that bite, dense blobs,
     particles outside the box and around the origin (where the reference's hash collides). Integer
-    structures must agree bit for bit after every step; floats within 2e-4 (two free-running steps) except in the dense
-    blobs, whose violent first steps amplify last-ulp differences."""
+    structures must agree bit for bit after every step (each step teacher-forced from the port's state); floats within 2e-4
+    except in the dense blobs, whose violent steps amplify last-ulp differences."""
     from oracle import PortOracle, param_block
     rng = np.random.default_rng(0)
     bmin, bmax = np.array([1.5, 0, 1.5], np.float32), np.array([4.5, 4, 4.5], np.float32)
@@ -265,4 +265,37 @@ def test_fuzz_against_the_cpu_port(emu):
             if kind != 1 and np.isfinite(want["position"]).all():
                 assert np.abs(got["position"] - want["position"]).max() / pl.H < 2e-4, where
                 assert np.abs(got["velocity"] - want["velocity"]).max() / (pl.H / dt) < 2e-4, where
+            # teacher forcing: the next step starts from the port's state, so that integer structures stay comparable (free
+            # running, last-ulp differences flip a neighbour at d == h or move a particle across a cell face)
+            s.upload(want.copy())
         s.close(); o.close()
+
+
+def test_linear_cell_mode_finds_the_same_neighbour_sets(emu):
+    """LINEAR_CELL keys change the order of particles and of list entries, never the neighbour SETS (away from the
+    reference's origin hash collisions and while the cap does not bite): compare as sets of particle ids with the CPU port."""
+    from oracle import PortOracle, param_block
+    rng = np.random.default_rng(21)
+    bmin, bmax = np.array([1.5, 0, 1.5], np.float32), np.array([4.5, 4, 4.5], np.float32)
+    for n, lo, hi in [(400, [1.6, 0.1, 1.6], [2.3, 0.7, 2.3]), (700, [1.0, -0.5, 1.0], [3.0, 1.5, 3.0])]:
+        p = np.zeros(n, PARTICLE_DTYPE)
+        p["position"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+        p["mass"] = 1.0
+        p["color"][:, 0] = np.arange(n)
+        params = param_block()
+        o = PortOracle(p.copy(), params)
+        o.step(0.0083, bmin, bmax)
+        arr, cnt = o.neighbours()
+        assert cnt.max() < 128
+        want = pl.neighbour_sets_by_id(arr, cnt, pl.ids_of(o.particles))
+        for lb in (0, 1):
+            s = EmuSolver(emu, n, params, KEY_LINEAR_CELL, list_build=lb)
+            s.upload(p)
+            s.step(0.0083, bmin, bmax)
+            got_p = s.download()
+            got = pl.neighbour_sets_by_id(s.debug(7, (n, 128)), s.debug(6), pl.ids_of(got_p))
+            assert got == want, (n, lb)
+            a, b = np.argsort(pl.ids_of(got_p)), np.argsort(pl.ids_of(o.particles))
+            assert np.abs(got_p["position"][a] - o.particles["position"][b]).max() / pl.H < 2e-5
+            s.close()
+        o.close()

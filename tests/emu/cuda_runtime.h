@@ -16,6 +16,7 @@
 #error "tests/emu/cuda_runtime.h is the host emulation shim; compile with -DAKUA_HOST_EMU (tests only)"
 #endif
 #include <stdint.h>
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <cmath>
@@ -66,7 +67,9 @@ struct Warp {
     uint64_t bufGen[2] = {~0ull, ~0ull};
 };
 struct Thread {
-    ucontext_t ctx;
+    ucontext_t ctx;            // entry point only: switches after the first go through _setjmp / _longjmp (no signal-mask syscalls)
+    jmp_buf jb;
+    bool started = false;
     bool done = false;
     uint64_t gen = 0;          // warp collectives this lane has completed
     uint64_t barrierGen = 0;   // __syncthreads this thread has passed
@@ -77,6 +80,7 @@ struct Cta {
     std::vector<Warp> warps;
     std::vector<char> stacks;
     ucontext_t sched;
+    jmp_buf schedJb;
     int current = -1;
     uint64_t barrierGen = 0;
     std::function<void()> body;

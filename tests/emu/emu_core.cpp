@@ -15,10 +15,16 @@ std::vector<char> g_stacks;
 uint64_t g_progress = 0;
 int g_live = 0, g_atBarrier = 0;
 
+// One fiber per thread slot, created once per launch and re-used for every CTA of the grid: after the kernel body returns
+// the fiber parks in the scheduler and runs the body again when it is resumed for the next CTA.
 void fiber_main() {
     Cta* c = g_cta;
-    c->body();
-    c->threads[c->current].done = true;   // uc_link returns to the scheduler
+    for (;;) {
+        c->body();
+        Thread& th = c->threads[c->current];
+        th.done = true;
+        yield();
+    }
 }
 
 void try_release_barrier(Cta& c) {
@@ -33,7 +39,7 @@ void try_release_barrier(Cta& c) {
 
 void yield() {
     Cta& c = *g_cta;
-    swapcontext(&c.threads[c.current].ctx, &c.sched);
+    if (_setjmp(c.threads[c.current].jb) == 0) _longjmp(c.schedJb, 1);
 }
 
 uint32_t live_mask(int warp) {
@@ -82,17 +88,18 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
     g_cta = &c;
     ::gridDim = grid;
     ::blockDim = block;
+    for (int t = 0; t < n; t++) {
+        Thread& th = c.threads[t];
+        th.started = false;
+        getcontext(&th.ctx);
+        th.ctx.uc_stack.ss_sp = g_stacks.data() + (size_t)t * kStackBytes;
+        th.ctx.uc_stack.ss_size = kStackBytes;
+        th.ctx.uc_link = &c.sched;
+        makecontext(&th.ctx, fiber_main, 0);
+    }
     for (uint32_t bx = 0; bx < grid.x; bx++) {
         ::blockIdx = uint3{bx, 0, 0};
-        for (int t = 0; t < n; t++) {
-            Thread& th = c.threads[t];
-            th = Thread{};
-            getcontext(&th.ctx);
-            th.ctx.uc_stack.ss_sp = g_stacks.data() + (size_t)t * kStackBytes;
-            th.ctx.uc_stack.ss_size = kStackBytes;
-            th.ctx.uc_link = &c.sched;
-            makecontext(&th.ctx, fiber_main, 0);
-        }
+        for (Thread& th : c.threads) { th.done = false; th.gen = 0; th.barrierGen = 0; th.atBarrier = false; }
         for (Warp& w : c.warps) w = Warp{};
         c.barrierGen = 0;
         g_live = n;
@@ -105,7 +112,10 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
                 if (th.done) continue;
                 c.current = t;
                 ::threadIdx = uint3{(uint32_t)t, 0, 0};
-                swapcontext(&c.sched, &th.ctx);
+                if (_setjmp(c.schedJb) == 0) {
+                    if (!th.started) { th.started = true; setcontext(&th.ctx); }
+                    else _longjmp(th.jb, 1);
+                }
                 if (th.done) {
                     remaining--;
                     g_live--;

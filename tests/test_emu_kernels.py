@@ -32,7 +32,7 @@ DEPS = [EMU / "emu_harness.cpp", EMU / "emu_core.cpp", EMU / "cuda_runtime.h", *
 def emu():
     if not OUT.exists() or any(p.stat().st_mtime > OUT.stat().st_mtime for p in DEPS):
         OUT.parent.mkdir(parents=True, exist_ok=True)
-        cmd = ["g++", "-O2", "-std=c++17", "-DAKUA_HOST_EMU", "-ffp-contract=off", "-fPIC", "-shared", "-I", str(EMU),
+        cmd = ["g++", "-O2", "-std=c++17", "-DAKUA_HOST_EMU", "-U_FORTIFY_SOURCE", "-ffp-contract=off", "-fPIC", "-shared", "-I", str(EMU),
                "-o", str(OUT), str(EMU / "emu_harness.cpp"), str(EMU / "emu_core.cpp")]
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-4000:]

@@ -299,3 +299,25 @@ def test_linear_cell_mode_finds_the_same_neighbour_sets(emu):
             assert np.abs(got_p["position"][a] - o.particles["position"][b]).max() / pl.H < 2e-5
             s.close()
         o.close()
+
+
+def test_readme_dam_break_27k_ten_steps(emu):
+    """BASELINE config 1 (the README scene: 30^3 particles, dt 0.0083, 4 iterations) through the emulated kernel source,
+    against the fixture recorded from the unmodified reference kernels: same tolerances as the GPU test."""
+    from akuaengine_b200 import scenes
+    g = dict(np.load(GOLDEN / "dambreak27k.npz"))
+    init, _, _ = scenes.dam_break(30)
+    init["color"][:, 0] = np.arange(len(init), dtype=np.float32)
+    dt = float(g["dt"])
+    s = EmuSolver(emu, len(init), g["params"], KEY_LINEAR_CELL)
+    s.upload(init)
+    for k in range(1, 11):
+        s.step(dt, g["box_min"], g["box_max"])
+        if k in (1, 10):
+            p = s.download()
+            a = np.argsort(pl.ids_of(p)); b = np.argsort(g[f"step{k}_id"])
+            dp = np.abs(p["position"][a].astype(np.float64) - g[f"step{k}_position"][b]).max() / pl.H
+            dv = np.abs(p["velocity"][a].astype(np.float64) - g[f"step{k}_velocity"][b]).max() / (pl.H / dt)
+            tol = 2e-5 if k == 1 else 1e-3
+            assert dp < tol and dv < tol, (k, dp, dv)
+    s.close()

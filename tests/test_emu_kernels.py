@@ -175,13 +175,13 @@ def test_ieee_math_path_and_zero_iterations(emu):
     s.close()
 
 
-def test_migration_compaction_is_deterministic_and_ordered(emu):
+@pytest.mark.parametrize("n", [3000, 262149])     # the larger case makes k_mig_scan carry across 1024-block chunks
+def test_migration_compaction_is_deterministic_and_ordered(emu, n):
     """k_mig_count / k_mig_scan / k_mig_pack: leavers are packed in index order per direction, get the sentinel key, and the
     count message carries the plane populations the single count exchange of a slab step relies on."""
     rng = np.random.default_rng(3)
     gy, gz, gx = 7, 5, 12
     plane = gy * gz
-    n = 3000
     cx = rng.integers(0, gx, n)
     keys = (cx * plane + rng.integers(0, plane, n)).astype(np.uint32)
     ids = rng.permutation(n).astype(np.uint32)

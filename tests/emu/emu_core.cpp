@@ -37,9 +37,15 @@ void try_release_barrier(Cta& c) {
 }
 }  // namespace
 
+// EMU_USE_SWAPCONTEXT: every switch through swapcontext (slower: two signal-mask syscalls each) — what AddressSanitizer's
+// interceptors understand; used by the sanitizer run of tests/test_emu_kernels.py.
 void yield() {
     Cta& c = *g_cta;
+#ifdef EMU_USE_SWAPCONTEXT
+    swapcontext(&c.threads[c.current].ctx, &c.sched);
+#else
     if (_setjmp(c.threads[c.current].jb) == 0) _longjmp(c.schedJb, 1);
+#endif
 }
 
 uint32_t live_mask(int warp) {
@@ -112,10 +118,14 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
                 if (th.done) continue;
                 c.current = t;
                 ::threadIdx = uint3{(uint32_t)t, 0, 0};
+#ifdef EMU_USE_SWAPCONTEXT
+                swapcontext(&c.sched, &th.ctx);
+#else
                 if (_setjmp(c.schedJb) == 0) {
                     if (!th.started) { th.started = true; setcontext(&th.ctx); }
                     else _longjmp(th.jb, 1);
                 }
+#endif
                 if (th.done) {
                     remaining--;
                     g_live--;

@@ -230,6 +230,41 @@ int emu_debug_get(void* h, int which, uint32_t* dst) {
 }
 
 
+// ---- interior / boundary split of a sweep and the fused halo push (multi-GPU overlap, pbf_solver.cu: sweepSpans, slabPush) ----
+// After at least one emu_step (lists exist): runs pass A once over the whole range and once as interior + boundary launches
+// with the boundary launch pushing (x*, lambda) / lambda of the first planeL and last planeR particles into "peer" buffers.
+// Returns 0 when density, lambda and the packed array are bit-identical and the pushed planes equal the corresponding slices.
+int emu_span_push_check(void* h, uint32_t planeL, uint32_t planeR) {
+    EmuSolver* s = static_cast<EmuSolver*>(h);
+    const uint32_t n = s->n;
+    if ((uint64_t)planeL + planeR >= n) return -1;
+    const SphParams P = make_sph_params(s->cfg, s->corr, s->uniformMass);
+    const bool pack = s->pack && s->massUniform;
+    const uint32_t sb = AKUA_SWEEP_BLOCK;
+    const HaloSync nohs{};
+    auto passA = [&](Span sp, float* density, float* lambda, float4* xl, PeerPush pp) {
+        run(k_density_lambda<true>, gridFor(sp.count, sb), sb, (const float4*)s->pXs, (const uint32_t*)s->nbrList.data(),
+            (const uint32_t*)s->nbrCount.data(), s->nbrStride, sp, density, lambda, xl, P, pp, nohs);
+    };
+    std::vector<float> d0(n, -1.f), l0(n, -1.f), d1(n, -2.f), l1(n, -2.f);
+    std::vector<float4> x0(n, make_float4(0, 0, 0, 0)), x1(n, make_float4(9, 9, 9, 9));
+    passA(Span{n, 0u, 0xffffffffu, 0u}, d0.data(), l0.data(), pack ? x0.data() : nullptr, PeerPush{});
+    std::vector<float4> peerL4(planeL + 1), peerR4(planeR + 1);
+    std::vector<float> peerL1(planeL + 1), peerR1(planeR + 1);
+    PeerPush pp;
+    pp.dstL = pack ? (void*)peerL4.data() : (void*)peerL1.data(); pp.nL = planeL;
+    pp.dstR = pack ? (void*)peerR4.data() : (void*)peerR1.data(); pp.startR = n - planeR;
+    passA(Span{n - planeL - planeR, planeL, 0xffffffffu, 0u}, d1.data(), l1.data(), pack ? x1.data() : nullptr, PeerPush{});   // interior
+    passA(Span{planeL + planeR, 0u, planeL, n - planeR - planeL}, d1.data(), l1.data(), pack ? x1.data() : nullptr, pp);      // boundary
+    if (std::memcmp(d0.data(), d1.data(), n * 4) || std::memcmp(l0.data(), l1.data(), n * 4)) return 1;
+    if (pack && std::memcmp(x0.data(), x1.data(), (size_t)n * 16)) return 2;
+    for (uint32_t k = 0; k < planeL; k++)
+        if (pack ? std::memcmp(&peerL4[k], &x0[k], 16) != 0 : std::memcmp(&peerL1[k], &l0[k], 4) != 0) return 3;
+    for (uint32_t k = 0; k < planeR; k++)
+        if (pack ? std::memcmp(&peerR4[k], &x0[n - planeR + k], 16) != 0 : std::memcmp(&peerR1[k], &l0[n - planeR + k], 4) != 0) return 4;
+    return 0;
+}
+
 // ---- x-slab migration compaction: k_mig_count -> k_mig_scan -> k_mig_pack on host arrays (slab_kernels.cuh) ----
 // keys: n unsorted LINEAR_CELL keys (modified: leavers get `sentinel`). ids: particle ids carried in MigRecord::meta.x.
 // counts[32] = the device counter block; idsL / idsR receive the ids of the records packed for the left / right rank in order.

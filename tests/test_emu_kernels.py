@@ -47,6 +47,7 @@ def emu():
     lib.emu_step.argtypes = [vp, C.c_float, C.c_int, vp, vp]
     lib.emu_debug_get.argtypes = [vp, C.c_int, vp]
     lib.emu_migration.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
+    lib.emu_span_push_check.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.emu_plane_hist.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp]
     lib.emu_plane_verify.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]
     return lib
@@ -320,4 +321,18 @@ def test_readme_dam_break_27k_ten_steps(emu):
             dv = np.abs(p["velocity"][a].astype(np.float64) - g[f"step{k}_velocity"][b]).max() / (pl.H / dt)
             tol = 2e-5 if k == 1 else 1e-3
             assert dp < tol and dv < tol, (k, dp, dv)
+    s.close()
+
+
+@pytest.mark.parametrize("pack", [1, 0], ids=["packed", "plain"])
+def test_interior_boundary_split_and_fused_push(emu, pack):
+    """Multi-GPU overlap splits every sweep into the slab interior and its two boundary planes (Span) and lets the boundary
+    launch store its results straight into the neighbours' ghost regions (PeerPush): the split must compute exactly what one
+    launch over the whole range computes, and the pushed planes must be the first / last stretch of the result."""
+    g = dict(np.load(GOLDEN / "lattice12.npz"))
+    s = EmuSolver(emu, len(g["init"]), g["params"], KEY_LINEAR_CELL, pack=pack)
+    s.upload(g["init"])
+    s.step(float(g["dt"]), g["box_min"], g["box_max"])
+    for plane_l, plane_r in [(0, 0), (100, 250), (1, 1726), (300, 0), (0, 17), (127, 129)]:
+        assert emu.emu_span_push_check(s.h, plane_l, plane_r) == 0, (plane_l, plane_r)
     s.close()

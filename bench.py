@@ -275,6 +275,7 @@ def run_ours(args):
         "config": {"workload": f"{scene_name}: {n_total} particles, dt={DT}, {ITERS} solver iterations, artificial pressure + "
                                "vorticity confinement + XSPH, box " + str([float(x) for x in bmin]) + "-" + str([float(x) for x in bmax]),
                    "particles_total": n_total, "particles_rank0": n, "key_mode": args.key_mode, "fast_math": bool(args.fast_math),
+                   "list_build": {"0": "scan", "1": "mask4", "2": "mask8"}.get(os.environ.get("AKUA_LIST_BUILD", "0"), "scan"),
                    "l2": "no explicit flush: per-step working set (neighbour lists ~100 B/particle + 7 float4 arrays) "
                          f"= ~{(100 + 7 * 16 + 24) * n / 1e6:.0f} MB vs 126 MB L2",
                    "parallelism": "single GPU" if world == 1 else

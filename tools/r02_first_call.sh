@@ -20,3 +20,9 @@ for lb in 0 1 2; do
   AKUA_LIST_BUILD=$lb timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_lb$lb.json 2> gpurun_out/r02_bench_lb$lb.err
   tail -c 400 gpurun_out/r02_bench_lb$lb.json
 done
+# BASELINE config 5 at its largest size (round 1 stopped at 64 M), and the clustered scenes where the list build dominates,
+# with the scan and the mask list build
+for lb in 0 1; do
+  AKUA_LIST_BUILD=$lb timeout 900 python tools/bench_neighbour_search.py --sizes 16,128 --reps 3 > gpurun_out/r02_neighbour_search_lb$lb.jsonl 2> gpurun_out/r02_neighbour_search_lb$lb.err
+  tail -n 2 gpurun_out/r02_neighbour_search_lb$lb.jsonl | cut -c1-300
+done

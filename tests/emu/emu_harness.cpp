@@ -52,7 +52,8 @@ struct EmuSolver {
     uint32_t n = 0;
     akua_pbf_config cfg{};
     akua_corr_params corr{};
-    int keyMode = AKUA_KEY_LINEAR_CELL, fastMath = 1, pack = 1, listBuild = 0;
+    int keyMode = AKUA_KEY_LINEAR_CELL, fastMath = 1, pack = 1, listBuild = 0;   // pack: bit 0 packed arrays, bit 1 32-byte records
+    std::vector<PosVel> pv;
     std::vector<float4> pos, posAlt, vel, velAlt, xs, xsAlt, omega, dpos, color, xl, xw;
     std::vector<float> density, lambda, omegaLen, size;
     std::vector<uint32_t> id, idAlt, keysUnsorted, keyA, keyB, valA, valB, bucketStart, nbrList, nbrCount, tileHist, binTotal;
@@ -126,7 +127,10 @@ int emu_step(void* h, float dt, int iterations, const float* bmin, const float* 
     const uint32_t n = s->n;
     if (!n) return 0;
     const bool hash = s->keyMode == AKUA_KEY_REFERENCE_HASH;
-    const bool pack = s->pack && s->massUniform;
+    const bool pack = (s->pack & 1) && s->massUniform;
+    const bool rec = (s->pack & 2) != 0;
+    if (rec && s->pv.size() < n) s->pv.assign(n, PosVel{});
+    PosVel* pvp = rec ? s->pv.data() : nullptr;
     if (!hash) {   // layoutGrid
         int3 gmin, gdim;
         const int64_t cells = layout_linear_grid(s->cfg.smoothRadius, bmin, bmax, &gmin, &gdim);
@@ -177,7 +181,7 @@ int emu_step(void* h, float dt, int iterations, const float* bmin, const float* 
 #undef EMU_A
 #define EMU_B(F, L, K, C) run(k_delta_apply<F, L, K, C>, sg, sb, (const float4*)s->pXs, s->pXsAlt, (const float*)s->lambda.data(), (const float4*)s->xl.data(), \
                      (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, P, B, s->dpos.data(), s->pPos, s->pVel, \
-                     (const float*)s->density.data(), (PosVel*)nullptr, dt, nop, nop, nohs)
+                     (const float*)s->density.data(), (fin ? pvp : (PosVel*)nullptr), dt, nop, nop, nohs)
 #define EMU_B_C(F, L, K) do { if (P.corrNIsFour) EMU_B(F, L, K, true); else EMU_B(F, L, K, false); } while (0)
 #define EMU_B_L(F, K) do { if (fin) EMU_B_C(F, true, K); else EMU_B_C(F, false, K); } while (0)
         if (pack) { if (s->fastMath) EMU_B_L(true, true); else EMU_B_L(false, true); }
@@ -193,18 +197,22 @@ int emu_step(void* h, float dt, int iterations, const float* bmin, const float* 
         run(k_damping, gridFor(n), 256u, (const float4*)s->pPos, s->pVel, n, B);
     }
     // phasePost
-#define EMU_V(F) run(k_vorticity<F, false>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)nullptr, (const uint32_t*)s->nbrList.data(), \
+    if (rec && !committed) run(k_build_posvel, gridFor(n), 256u, (const float4*)s->pXs, (const float4*)s->pVel, n, pvp);   // as pbf_solver.cu does
+#define EMU_V(F, R) run(k_vorticity<F, R>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)pvp, (const uint32_t*)s->nbrList.data(), \
                      (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->omega.data(), s->omegaLen.data(), xw, P, nop, nohs)
-    if (s->fastMath) EMU_V(true); else EMU_V(false);
+    if (rec) { if (s->fastMath) EMU_V(true, true); else EMU_V(false, true); }
+    else     { if (s->fastMath) EMU_V(true, false); else EMU_V(false, false); }
 #undef EMU_V
 #define EMU_C(F, K) run(k_confinement<F, K>, sg, sb, (const float4*)s->pXs, (const float4*)s->omega.data(), (const float*)s->omegaLen.data(), \
                      (const float4*)s->xw.data(), (const float*)s->density.data(), (const uint32_t*)s->nbrList.data(), (const uint32_t*)s->nbrCount.data(), \
-                     s->nbrStride, all, s->pVel, (PosVel*)nullptr, P, dt, s->cfg.vorticityEpsilon, nop, nohs)
+                     s->nbrStride, all, s->pVel, pvp, P, dt, s->cfg.vorticityEpsilon, nop, nohs)
     if (pack) { if (s->fastMath) EMU_C(true, true); else EMU_C(false, true); }
     else      { if (s->fastMath) EMU_C(true, false); else EMU_C(false, false); }
 #undef EMU_C
-    run(k_xsph<false>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)nullptr, (const uint32_t*)s->nbrList.data(),
-        (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->pVelAlt, P, s->cfg.viscosity, nohs);
+    if (rec) run(k_xsph<true>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)pvp, (const uint32_t*)s->nbrList.data(),
+                 (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->pVelAlt, P, s->cfg.viscosity, nohs);
+    else     run(k_xsph<false>, sg, sb, (const float4*)s->pXs, (const float4*)s->pVel, (const PosVel*)nullptr, (const uint32_t*)s->nbrList.data(),
+                 (const uint32_t*)s->nbrCount.data(), s->nbrStride, all, s->pVelAlt, P, s->cfg.viscosity, nohs);
     std::swap(s->pVel, s->pVelAlt);
     return 0;
 }

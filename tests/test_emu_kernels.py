@@ -135,17 +135,21 @@ def test_kernel_source_reproduces_the_reference_golden(emu, name, mode):
 
 
 def test_variants_leave_identical_state(emu):
-    """Gather layout (packed / plain) and list build (scan / mask4 / mask8) must not change a single bit of the state — the
+    """Gather layout (plain / packed / records / both) and list build (scan / mask4 / mask8) must not change a single bit of the state — the
     emulated counterpart of test_gather_layouts_are_bit_identical / test_list_build_variants_identical."""
     g = dict(np.load(GOLDEN / "lattice12.npz"))     # uniform masses: the packed layout is really taken
     init, dt, bmin, bmax = g["init"], float(g["dt"]), g["box_min"], g["box_max"]
     outs = {}
-    for pack in (0, 1):
+    for pack in (0, 1, 2, 3):           # bit 0: packed (x*, lambda) / (x, |omega|) arrays; bit 1: 32-byte (position, velocity) records
         for lb in (0, 1, 2):
+            if pack >= 2 and lb:
+                continue
             s = EmuSolver(emu, len(init), g["params"], KEY_LINEAR_CELL, pack=pack, list_build=lb)
             s.upload(init)
             for _ in range(3):
                 s.step(dt, bmin, bmax)
+            s.step(dt, bmin, bmax, iters=0)     # commit outside the fused pass B: records rebuilt by k_build_posvel
+            s.step(dt, bmin, bmax)
             outs[(pack, lb)] = (s.download().tobytes(), s.debug(6).tobytes(), s.debug(7, (len(init), s.cfg.maxNeighbours)).tobytes())
             s.close()
     ref = outs[(0, 0)]

@@ -102,3 +102,77 @@ def setup_slab_solver(particles: np.ndarray, ids: np.ndarray, dist, rank: int, n
     solver.upload_particles(own)
     solver.upload_ids(np.ascontiguousarray(ids[mine], dtype=np.uint32))
     return solver
+
+
+def slab_selfcheck(dist, rank: int, nranks: int, device: int, steps: int = 24, dt: float = 0.0083, h: float = 0.1,
+                   vx: float = 1.0) -> dict:
+    """Runs a small tank scene (32*nranks x 24 x 32 lattice, tilted gravity, initial x velocity so that particles migrate)
+    on all ranks through the x-slab path and on rank 0 through the single-GPU path, and compares them particle by particle
+    (matched by id). Collective. Returns the same verdict dict on every rank: ids conserved, max position / velocity
+    difference in units of h and h/dt, and the mean density-constraint error of both runs."""
+    import torch
+    from . import scenes
+    particles, bmin, bmax = scenes.tank(32 * nranks, 24, 32)
+    particles["velocity"][:, 0] = np.float32(vx)
+    # payload that must follow its particle through sorts and migrations (reference: the struct is sorted as a whole)
+    n = len(particles)
+    particles["color"][:, 0] = (np.arange(n) % 251).astype(np.float32)
+    particles["size"] = (np.arange(n) % 17 + 1).astype(np.float32)
+    ids = np.arange(n, dtype=np.uint32)
+    g = scenes.tank_gravity(15.0)
+    solver = setup_slab_solver(particles, ids, dist, rank, nranks, device, h, capacity_factor=2.0)
+    solver.setGravity(g)
+    for _ in range(steps):
+        solver.step(dt, bmin, bmax)
+    pos4, vel4, pid = solver.download()
+    aos = solver.download_particles()
+    st = solver.slab_stats()
+    merr, _ = solver.density_error()
+    m = solver.n
+    solver.close()
+    owned = torch.tensor([m, st["migrated_in"]], device="cuda", dtype=torch.int64)
+    all_owned = [torch.zeros_like(owned) for _ in range(nranks)]
+    dist.all_gather(all_owned, owned)
+    counts = [int(t[0]) for t in all_owned]
+    migrated = sum(int(t[1]) for t in all_owned)
+    mx = max(counts)
+    pack = torch.zeros((mx, 12), dtype=torch.float64, device="cuda")
+    pack[:m, 0:3] = torch.from_numpy(pos4[:, :3].astype(np.float64)).cuda()
+    pack[:m, 3:7] = torch.from_numpy(vel4.astype(np.float64)).cuda()
+    pack[:m, 7] = torch.from_numpy(pid.astype(np.float64)).cuda()
+    pack[:m, 8] = torch.from_numpy(aos["color"][:, 0].astype(np.float64)).cuda()
+    pack[:m, 9] = torch.from_numpy(aos["size"].astype(np.float64)).cuda()
+    gathered = [torch.zeros_like(pack) for _ in range(nranks)]
+    dist.all_gather(gathered, pack)
+    verdict = torch.zeros(8, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        allp = np.concatenate([t[:c].cpu().numpy() for t, c in zip(gathered, counts)])
+        got_ids = allp[:, 7].astype(np.int64)
+        conserved = len(got_ids) == n and np.array_equal(np.sort(got_ids), np.arange(n))
+        ref = PBFSolver(n, device=device)
+        ref.upload_particles(particles)
+        ref.setGravity(g)
+        for _ in range(steps):
+            ref.step(dt, bmin, bmax)
+        rp, rv, rid = ref.download()
+        rerr, _ = ref.density_error()
+        ref.close()
+        dp = dv = payload_ok = float("nan")
+        if conserved:
+            o1, o2 = np.argsort(got_ids), np.argsort(rid)
+            dp = float(np.abs(allp[o1, 0:3] - rp[o2, :3]).max() / h)
+            dv = float(np.abs(allp[o1, 3:6] - rv[o2, :3]).max() / (h / dt))
+            payload_ok = float(np.array_equal(allp[o1, 8], particles["color"][:, 0].astype(np.float64))
+                               and np.array_equal(allp[o1, 9], particles["size"].astype(np.float64)))
+        verdict = torch.tensor([float(conserved), dp, dv, rerr, float(migrated), payload_ok, 0.0, 0.0], dtype=torch.float64, device="cuda")
+    dist.broadcast(verdict, src=0)
+    errs = torch.tensor([merr * m, float(m)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(errs)
+    v = verdict.cpu().numpy()
+    slab_err = float(errs[0] / max(float(errs[1]), 1.0))
+    tol = 1e-3   # same class as the free-running trajectory tests (summation order differs between 1 and N GPUs)
+    return {"particles": n, "steps": steps, "ranks": nranks, "ids_conserved": bool(v[0]), "payload_follows_particles": bool(v[5] == 1.0),
+            "max_dpos_over_h": float(v[1]), "max_dvel_over_h_dt": float(v[2]), "tolerance": tol,
+            "density_error_mean_slab": slab_err, "density_error_mean_single_gpu": float(v[3]),
+            "migrated": int(v[4]), "owned_per_rank": counts, "transport": st["transport"],
+            "ok": bool(v[0]) and bool(v[1] < tol) and bool(v[2] < tol) and bool(v[5] == 1.0)}

@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the PBF simulation step (BASELINE.json metric: particle-iterations / second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-side S] [--key-mode linear|hash]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Default workload = BASELINE.json config 4, weak scaling: tank slosh, a 200^3 lattice (8 M particles) PER GPU, x-slab
+partitioned: 8 M on 1 GPU ... 64 M on 8 GPUs. (`--workload dam --n-side 100|252` = configs 2 / 3; the default run reports
+them in an `extra` block at N = 1.)
 
 A "step" is one call of the hot path (PBFSolver::step: predict, neighbour search, `solverIterations` constraint
-iterations, commit, damping, vorticity confinement, XSPH) over the whole particle set of the named scene.
+iterations, commit, damping, vorticity confinement, XSPH) over the whole particle set.
 metric = N_particles * solverIterations * K / seconds, whole steps (all phases), aggregate over all ranks.
 
-  value     : state resident in HBM when the timed region starts; K steps, CUDA events on the solver's stream.
-  e2e       : the same K steps through the reference-facing C-ABI calls with HOST buffers: every step uploads the
+Protocol (BASELINE.md §3 / SURVEY.md §8d): `--settle` steps (default 300) so that the fluid is disordered, W warm-up steps,
+then `--windows` (default 5) timed windows of EXACTLY K steps each, every window bracketed by a barrier +
+synchronize, CUDA events on the solver's stream, max over ranks; the MEDIAN window is the value, all windows are listed.
+
+  value     : state resident in HBM when the timed region starts.
+  e2e       : the same steps through the reference-facing C-ABI calls with HOST buffers: every step uploads the
               AoS-108 particle buffer from pinned host memory, steps, and downloads the AoS-108 buffer back.
-  roofline  : dominant kernel (constraint pass B: delta-p + apply + collision): algorithmic bytes per launch (36 B per
-              particle) / average launch duration measured live with CUDA events on the solver's stream.
+  roofline  : constraint pass B (delta-p + apply + collision): algorithmic bytes per launch (36 B per particle,
+              SURVEY.md §8d) / average launch duration measured live with CUDA events on the solver's stream.
   cpu_baseline : the host-C++ restatement (oracle/, kind "port") timed on this box's cores on a bounded sample.
-  --impl reference : the UNMODIFIED reference kernels rebuilt headless (oracle/_ref, the reference has no CPU path);
-              if that library is not present, the CPU port on a reduced sample.
+  --impl reference : the UNMODIFIED reference kernels rebuilt headless (oracle/_ref; the reference has no CPU path) on
+              the same workload as our N = 1 arm; if that library is not present, the CPU port on a reduced sample.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -40,6 +49,7 @@ def emit(obj) -> None:
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
+
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
@@ -48,6 +58,11 @@ ITERS = 4
 PASS_B_BYTES = 36   # R x* 16 + lambda 4 -> W x* 16 (phase D pass 2)
 PASS_A_BYTES = 20   # R x* 16 -> W lambda 4
 STEP_BYTES = 460 + 56 * ITERS
+KERNEL_SOURCES = ["akuaengine_b200/csrc/pbf_kernels.cuh"]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
 
 
 def measured_peaks():
@@ -58,6 +73,35 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash() -> str:
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        h.update((REPO / rel).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(n_rank: int):
+    """DRAM bytes per pass-B launch from the committed `ncu --set full` capture (profiles/r02_ncu_traffic.json), looked up
+    by the per-rank particle count; only trusted while the kernel source it was captured from is unchanged."""
+    f = REPO / "profiles" / "r02_ncu_traffic.json"
+    if not f.exists():
+        return None, None, "no committed ncu capture"
+    try:
+        d = json.loads(f.read_text())
+    except Exception:
+        return None, None, "unreadable profiles/r02_ncu_traffic.json"
+    if d.get("kernel_source_sha") != kernel_source_hash():
+        return None, None, "kernel source changed since the committed ncu capture (profiles/r02_ncu_traffic.json)"
+    best = None
+    for key, row in d.get("pass_b", {}).items():
+        if abs(int(key) - n_rank) <= 0.02 * n_rank and (best is None or abs(int(key) - n_rank) < abs(int(best[0]) - n_rank)):
+            best = (key, row)
+    if best is None:
+        return None, None, f"no capture at ~{n_rank} particles per GPU"
+    row = best[1]
+    return int(row["dram_bytes"]), row.get("dram_pct_of_peak"), f"ncu --set full at {best[0]} particles ({d.get('source', '')})"
 
 
 class ClockSampler:
@@ -93,7 +137,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -102,11 +146,15 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def dist_env():
@@ -116,24 +164,40 @@ def dist_env():
     return rank, world, local
 
 
-def run_ours(args):
-    import torch
-    from akuaengine_b200 import KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PARTICLE_DTYPE, PBFSolver, PinnedBuffer, scenes
+def bind_to_gpu_numa_node(local: int):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated, so
+    that the e2e staging buffers of N ranks are spread over the host's memory controllers instead of all landing on node 0.
+    Pure /sys reads; a no-op where the topology is not exposed."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+        node = int(path.read_text().strip())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return {"numa_node": node, "cpus": len(ids)}
+        return {"numa_node": node, "cpus": 0}
+    except Exception as e:  # no sysfs, no permission: run unbound
+        return {"numa_node": None, "why": str(e)[:80]}
 
-    rank, world, local = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU/oracle arm)")
-    torch.cuda.set_device(local)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    key_mode = KEY_LINEAR_CELL if args.key_mode == "linear" else KEY_REFERENCE_HASH
+# ---------------------------------------------------------------------------------------------------------------- workload
+def workload(args, world: int):
+    """(lattice dims, origin, boxMin, boxMax, gravity, scaling, config dict). The config dict is the same object for our
+    arm and for the reference arm (which always runs the world = 1 instance)."""
+    from akuaengine_b200 import scenes
     gravity = None
     if args.workload == "tank":
-        # config 4: tank slosh; --tank-per-gpu => weak scaling (nx grows with the GPU count), --tank-total => strong
         if args.tank_total:
             dims = [int(v) for v in args.tank_total.split(",")]
             scaling = "strong"
@@ -143,13 +207,30 @@ def run_ours(args):
             scaling = "weak"
         (nx, ny, nz), origin, bmin, bmax = scenes.tank_layout(*dims)
         gravity = scenes.tank_gravity(15.0)
-        scene_name = f"tank slosh {nx}x{ny}x{nz} lattice, gravity tilted 15 deg (SURVEY.md §8d config 4)"
+        name = f"tank slosh {nx}x{ny}x{nz} lattice, gravity tilted 15 deg (BASELINE.json config 4, SURVEY.md §8d)"
     else:
         (nx, ny, nz), origin, bmin, bmax = scenes.dam_break_wide_layout(args.n_side, world)
         scaling = "weak"
-        scene_name = (f"dam break {args.n_side}^3 lattice (SURVEY.md §8d config {'2' if args.n_side == 100 else 'n/a'})"
-                      + (f", {world}x as long in x for {world} GPUs" if world > 1 else ""))
+        cfgno = {30: "1", 100: "2", 252: "3"}.get(args.n_side, "n/a")
+        name = (f"dam break {args.n_side}^3 lattice (BASELINE.json config {cfgno})"
+                + (f", {world}x as long in x for {world} GPUs" if world > 1 else ""))
     n_total = nx * ny * nz
+    config = {
+        "workload": f"{name}: {n_total} particles, dt={DT}, {ITERS} solver iterations, artificial pressure + vorticity "
+                    f"confinement + XSPH, box {[round(float(x), 4) for x in bmin]}-{[round(float(x), 4) for x in bmax]}",
+        "particles_total": n_total, "dt": DT, "solver_iterations": ITERS,
+        "l2": "no explicit flush: the per-step working set (neighbour lists ~100 B/particle + 7 float4 arrays = "
+              f"~{(100 + 7 * 16 + 24) * (n_total // world) / 1e6:.0f} MB per GPU) exceeds the 126 MB L2",
+        "parallelism": "single GPU" if world == 1 else f"{world} x-slabs, one per GPU",
+    }
+    return (nx, ny, nz), origin, bmin, bmax, gravity, scaling, config
+
+
+def make_solver(args, world, rank, local, dist, dims, origin, gravity, capacity_factor=1.6):
+    """Creates the solver with this rank's share of the lattice uploaded. Returns (solver, n_local)."""
+    from akuaengine_b200 import KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PBFSolver, scenes
+    nx, ny, nz = dims
+    key_mode = KEY_LINEAR_CELL if args.key_mode == "linear" else KEY_REFERENCE_HASH
     if world == 1:
         pos, ids = scenes.lattice_slab(nx, ny, nz, origin, 0, nx)
         particles = scenes.particles_from_positions(pos)
@@ -158,9 +239,9 @@ def run_ours(args):
         solver = PBFSolver(n, key_mode=key_mode, device=local, fast_math=bool(args.fast_math))
         solver.upload_particles(particles)
     else:
-        # x-slab partition (one slab per GPU); ghost planes + migration go over NCCL/NVLink inside akua_pbf_step
+        # x-slab partition (one slab per GPU); ghost planes + migration go over NVLink inside akua_pbf_step
         # (csrc/pbf_slab.inl). Each rank generates only its own slab of the lattice.
-        from akuaengine_b200.slab import partition_columns, broadcast_unique_id
+        from akuaengine_b200.slab import broadcast_unique_id, partition_columns
         cols1d = scenes.lattice_x_columns(nx, origin[0])
         col_min = int(cols1d.min())
         hist = np.bincount(cols1d - col_min).astype(np.int64) * (ny * nz)
@@ -171,8 +252,8 @@ def run_ours(args):
         particles = scenes.particles_from_positions(pos)
         del pos
         n = len(particles)
-        solver = PBFSolver(max(n, n_total // world), key_mode=key_mode, device=local, fast_math=bool(args.fast_math),
-                           capacity_factor=1.6)
+        solver = PBFSolver(max(n, (nx * ny * nz) // world), key_mode=key_mode, device=local, fast_math=bool(args.fast_math),
+                           capacity_factor=capacity_factor)
         solver.comm_init(rank, world, broadcast_unique_id(dist, rank))
         solver.set_slab(lo, hi)
         solver.upload_particles(particles)
@@ -180,6 +261,58 @@ def run_ours(args):
     del particles
     if gravity is not None:
         solver.setGravity(gravity)
+    return solver, n
+
+
+def id_checksums(ids: np.ndarray):
+    """Order-independent fingerprint of a multiset of particle ids: count, sum, sum of squares (mod 2^64), xor."""
+    a = ids.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return np.array([len(a), int(a.sum(dtype=np.uint64)), int((a * a).sum(dtype=np.uint64)),
+                         int(np.bitwise_xor.reduce(a)) if len(a) else 0], dtype=np.uint64)
+
+
+def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows):
+    import torch
+    out = []
+    for _ in range(windows):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            solver.step(DT, bmin, bmax)
+        e1.record(stream)
+        barrier()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+def run_ours(args):
+    import torch
+    from akuaengine_b200 import PARTICLE_DTYPE, PinnedBuffer
+
+    rank, world, local = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU/oracle arm)")
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    dims, origin, bmin, bmax, gravity, scaling, config = workload(args, world)
+    n_total = dims[0] * dims[1] * dims[2]
+
+    # ---- multi-GPU self-check on a small instance of the same scene: N-slab result against a 1-GPU replica ----------
+    mgpu_check = None
+    if world > 1 and not args.no_selfcheck:
+        from akuaengine_b200.slab import slab_selfcheck
+        mgpu_check = slab_selfcheck(dist, rank, world, local, steps=24)
+        log(f"[rank {rank}] slab self-check: {mgpu_check}")
+
+    solver, n = make_solver(args, world, rank, local, dist, dims, origin, gravity)
     stream = torch.cuda.ExternalStream(solver.stream_ptr(), device=local)
 
     def barrier():
@@ -189,23 +322,23 @@ def run_ours(args):
             dist.barrier()
 
     # ---- device-resident timing -------------------------------------------------------------------------------
+    t_settle = time.perf_counter()
+    for k in range(args.settle):
+        solver.step(DT, bmin, bmax)
+        if world > 1 and args.rebalance_every and (k + 1) % args.rebalance_every == 0:
+            solver.rebalance()
+    barrier()
+    t_settle = time.perf_counter() - t_settle
     for _ in range(args.warmup):
         solver.step(DT, bmin, bmax)
     barrier()
     c0 = solver.counters()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        solver.step(DT, bmin, bmax)
-    e1.record(stream)
-    barrier()
+    win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows)
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
     c1 = solver.counters()
-    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    launches = (c1["kernel_launches"] - c0["kernel_launches"]) // args.windows
 
     # ---- dominant-kernel timing, live, CUDA events around every pass-A / pass-B launch on the solver's stream ----
     solver.enable_timing(True)
@@ -218,9 +351,36 @@ def run_ours(args):
     solver.enable_timing(False)
     pass_a_ms, pass_b_ms = float(np.mean(pa)), float(np.mean(pb))
     mean_err, max_err = solver.density_error()
+    n_rank = solver.n
+
+    # ---- particle conservation across ranks (ids are a permutation of 0..n_total-1) ------------------------------
+    conservation = None
+    if world > 1:
+        ids_now = solver.debug(3)
+        fp = torch.from_numpy(id_checksums(ids_now).view(np.int64)).cuda()
+        allfp = [torch.zeros_like(fp) for _ in range(world)]
+        dist.all_gather(allfp, fp)
+        got = np.stack([t.cpu().numpy().view(np.uint64) for t in allfp])
+        with np.errstate(over="ignore"):
+            tot = np.array([got[:, 0].sum(dtype=np.uint64), got[:, 1].sum(dtype=np.uint64), got[:, 2].sum(dtype=np.uint64),
+                            np.bitwise_xor.reduce(got[:, 3])], dtype=np.uint64)
+        # expected fingerprint of 0..n_total-1, in chunks to bound memory
+        exp = np.zeros(4, np.uint64)
+        with np.errstate(over="ignore"):
+            for a in range(0, n_total, 1 << 24):
+                c = id_checksums(np.arange(a, min(n_total, a + (1 << 24)), dtype=np.uint64))
+                exp[0] += c[0]; exp[1] += c[1]; exp[2] += c[2]; exp[3] ^= c[3]
+        errs = torch.tensor([mean_err * n_rank, max_err, float(n_rank)], device="cuda", dtype=torch.float64)
+        allerr = [torch.zeros_like(errs) for _ in range(world)]
+        dist.all_gather(allerr, errs)
+        allerr = np.stack([t.cpu().numpy() for t in allerr])
+        conservation = {"ids_are_a_permutation": bool(np.array_equal(tot, exp)), "owned_per_rank": [int(x) for x in got[:, 0]],
+                        "density_error_mean_global": float(allerr[:, 0].sum() / max(allerr[:, 2].sum(), 1.0)),
+                        "density_error_max_global": float(allerr[:, 1].max()),
+                        "check": "count, sum, sum of squares and xor of all ranks' particle ids equal those of 0..n-1"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------------
-    cap = int(max(n, solver.n) * 1.6) + 1024
+    cap = int(max(n, n_rank) * 1.6) + 1024
     pin = PinnedBuffer((cap,), PARTICLE_DTYPE)
     pin_ids = np.empty(cap, np.uint32)
 
@@ -243,11 +403,11 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_steps = max(3, min(args.steps, 20))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
-    moved = 0
     for _ in range(e2e_steps):
-        moved += e2e_step()
+        e2e_step()
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
@@ -255,76 +415,117 @@ def run_ours(args):
     pin.free()
 
     # ---- max over ranks -----------------------------------------------------------------------------------------
-    ms_step = ms_total / args.steps
+    win = np.array(win_ms, dtype=np.float64) / args.steps
     if world > 1:
-        t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor(list(win) + [e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms = float(t[0]), float(t[1])
-    total_particles = n_total
-    n_owned_end = solver.n
+        win, e2e_ms = t[:-1].cpu().numpy(), float(t[-1])
+        fin = torch.tensor([1 if finite else 0], device="cuda")
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        finite = bool(int(fin))
+    ms_step = float(np.median(win))
     slab_stats = solver.slab_stats() if world > 1 else None
-    value = total_particles * ITERS / (ms_step * 1e-3)
-    e2e_value = total_particles * ITERS / (e2e_ms * 1e-3)
+    value = n_total * ITERS / (ms_step * 1e-3)
+    e2e_value = n_total * ITERS / (e2e_ms * 1e-3)
 
     peak, peak_src = measured_peaks()
-    achieved = PASS_B_BYTES * n / (pass_b_ms * 1e-3) / 1e9
+    achieved = PASS_B_BYTES * n_rank / (pass_b_ms * 1e-3) / 1e9
+    traffic, dram_pct, traffic_src = ncu_traffic(n_rank)
     out = {
         "metric": "particle-iterations/sec", "value": value, "unit": "particle-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{scene_name}: {n_total} particles, dt={DT}, {ITERS} solver iterations, artificial pressure + "
-                               "vorticity confinement + XSPH, box " + str([float(x) for x in bmin]) + "-" + str([float(x) for x in bmax]),
-                   "particles_total": n_total, "particles_rank0": n, "key_mode": args.key_mode, "fast_math": bool(args.fast_math),
-                   "list_build": {"0": "scan", "1": "mask4", "2": "mask8"}.get(os.environ.get("AKUA_LIST_BUILD", "0"), "scan"),
-                   "l2": "no explicit flush: per-step working set (neighbour lists ~100 B/particle + 7 float4 arrays) "
-                         f"= ~{(100 + 7 * 16 + 24) * n / 1e6:.0f} MB vs 126 MB L2",
-                   "parallelism": "single GPU" if world == 1 else
-                   f"{world} x-slabs (one per GPU), 1-cell ghost planes + per-step migration over NVLink inside akua_pbf_step "
-                   "(CUDA-IPC P2P stores / copy-engine pushes; NCCL send/recv as fallback)"},
+        "config": config,
+        "protocol": {"settle_steps": args.settle, "settle_wall_s": round(t_settle, 2), "windows": args.windows,
+                     "window_ms_per_step": [round(float(x), 5) for x in win], "value_is": "median window",
+                     "simulated_time_at_start_s": round((args.settle + args.warmup) * DT, 3)},
+        "impl_config": {"key_mode": args.key_mode, "fast_math": bool(args.fast_math), "particles_rank0": int(n_rank),
+                        "list_build": os.environ.get("AKUA_LIST_BUILD", "default"),
+                        "transport": (slab_stats or {}).get("transport", "none (single GPU)"), "numa": numa},
         "e2e": {"value": e2e_value, "unit": "particle-iterations/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": 108 * n_total, "d2h_bytes_per_step": 108 * n_total,
                 "what": "akua_pbf_upload_aos108(pinned host) + akua_pbf_step + akua_pbf_download_aos108(pinned host) per step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_delta_apply (constraint pass B)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "dram_frac_ncu": (dram_pct / 100.0) if dram_pct is not None else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": PASS_B_BYTES, "launch_ms": pass_b_ms,
                      "launch_ms_source": "CUDA events recorded on the solver's stream around every pass-A / pass-B launch of "
                                          "10 further steps run right after the timed region (event pairs per launch "
                                          "would perturb the graph-replayed timed region itself)",
                      "pass_a": {"kernel": "k_density_lambda", "launch_ms": pass_a_ms,
-                                "achieved": PASS_A_BYTES * n / (pass_a_ms * 1e-3) / 1e9},
+                                "achieved": PASS_A_BYTES * n_rank / (pass_a_ms * 1e-3) / 1e9},
                      "whole_step": {"algorithmic_bytes_per_particle": STEP_BYTES,
-                                    "achieved": STEP_BYTES * n / (ms_step * 1e-3) / 1e9,
-                                    "frac": STEP_BYTES * n / (ms_step * 1e-3) / 1e9 / peak}},
+                                    "achieved": STEP_BYTES * n_total / world / (ms_step * 1e-3) / 1e9,
+                                    "frac": STEP_BYTES * n_total / world / (ms_step * 1e-3) / 1e9 / peak}},
         "phases_ms": ph,
         "density_error": {"mean": mean_err, "max": max_err},
         "finite": finite,
     }
     if world > 1:
-        out["slab_rank0"] = {"owned_start": n, "owned_end": n_owned_end, **slab_stats}
-    prof = REPO / "profiles" / "r01_ncu_pass_b_traffic.json"
-    if prof.exists():
-        try:
-            out["roofline"]["traffic"] = json.loads(prof.read_text()).get(str(n))
-        except Exception:
-            pass
+        out["slab_rank0"] = {"owned_start": n, "owned_end": int(n_rank), **slab_stats}
+        out["mgpu_check"] = {"small_scene_vs_single_gpu": mgpu_check, "conservation": conservation}
+    solver.close()
     if rank == 0:
+        if world == 1 and not args.no_extra:
+            out["extra"] = extra_configs(args, local)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args)
         emit(out)
-    solver.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, n_side=None, steps=8):
-    """The CPU port (oracle/pbf_oracle.cpp, OpenMP) on a bounded sample of the same workload."""
+def extra_configs(args, local):
+    """BASELINE.json configs 2 and 3 (dam break 1 M / 16 M on one GPU), device-resident, one window each."""
+    import torch
+    from akuaengine_b200 import PBFSolver, scenes
+    res = {}
+    for name, side, settle, steps in (("config2_dam_break_1m", 100, 300, 50), ("config3_dam_break_16m", 252, 60, 10)):
+        try:
+            p, bmin, bmax = scenes.dam_break(side)
+            s = PBFSolver(len(p), device=local, fast_math=bool(args.fast_math))
+            s.upload_particles(p)
+            n = len(p)
+            del p
+            stream = torch.cuda.ExternalStream(s.stream_ptr(), device=local)
+            for _ in range(settle):
+                s.step(DT, bmin, bmax)
+            s.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                s.step(DT, bmin, bmax)
+            e1.record(stream)
+            s.sync()
+            ms = e0.elapsed_time(e1) / steps
+            me, mx = s.density_error()
+            res[name] = {"particles": n, "ms_per_step": ms, "value": n * ITERS / (ms * 1e-3), "unit": "particle-iterations/s",
+                         "settle_steps": settle, "steps": steps, "density_error_mean": me}
+            s.close()
+        except Exception as e:  # never lose the headline line to an extra
+            res[name] = {"error": str(e)[:200]}
+    return res
+
+
+def cpu_baseline(args, steps=6):
+    """The CPU port (oracle/pbf_oracle.cpp, OpenMP) on a bounded sample of the same workload family."""
     from akuaengine_b200 import scenes
     from oracle import PortOracle, param_block
-    n_side = n_side or args.n_side
-    particles, bmin, bmax = scenes.dam_break(n_side)
+    if args.workload == "tank":
+        particles, bmin, bmax = scenes.tank(100, 100, 100)
+        g = scenes.tank_gravity(15.0)
+        what = "100x100x100 tank (1/8 of the per-GPU workload)"
+    else:
+        particles, bmin, bmax = scenes.dam_break(min(args.n_side, 100))
+        g = None
+        what = f"{min(args.n_side, 100)}^3 dam break"
     o = PortOracle(particles, param_block())
+    if g is not None:
+        o.setGravity(g)
     o.step(DT, bmin, bmax)  # warm (first touch of the 128*N table)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -334,24 +535,28 @@ def cpu_baseline(args, n_side=None, steps=8):
     cores = o.threads
     o.close()
     return {"value": val, "unit": "particle-iterations/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steps (after 1 warm-up step from rest) of the {len(particles)}-particle dam break, "
+            "sample": f"{steps} steps (after 1 warm-up step from rest) of a {len(particles)}-particle {what}, "
                       f"oracle/pbf_oracle.cpp with OpenMP on {cores} threads", "ms_per_step": dt / steps * 1e3}
 
 
 def run_reference(args):
     """Reference arm: the reference's own implementation of the path. Its solver is CUDA-only (no CPU path exists), so
     this runs the UNMODIFIED reference kernels rebuilt headless (oracle/_ref/libakua_ref.so) through PBFSolver::step on
-    cuda:0, driven by one host thread. Falls back to the CPU port when that library did not travel."""
+    cuda:0, driven by one host thread, on the SAME workload as our N = 1 arm (the reference is single-GPU and its
+    `int tableSize = 128 * N` caps it at 16.7 M particles). Falls back to the CPU port when that library did not travel."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     from akuaengine_b200 import scenes
     from oracle import REF_LIB, PortOracle, RefOracle, param_block
-    n_side = args.n_side
+    dims, origin, bmin, bmax, gravity, scaling, config = workload(args, 1)
     use_ref = REF_LIB.exists()
+    why = ""
     if use_ref:
         try:
-            particles, bmin, bmax = scenes.dam_break(n_side)
+            pos, _ = scenes.lattice_slab(*dims, origin, 0, dims[0])
+            particles = scenes.particles_from_positions(pos)
+            del pos
             o = RefOracle(particles, param_block())
             kind, cores = "reference", 1
             where = "unmodified reference kernels (oracle/_ref) on cuda:0, 1 host thread; the reference has no CPU path"
@@ -359,18 +564,28 @@ def run_reference(args):
             use_ref = False
             why = str(e)
     if not use_ref:
-        n_side = min(n_side, 50)  # bounded sample so K steps finish within minutes on CPU
-        particles, bmin, bmax = scenes.dam_break(n_side)
+        # bounded sample so K steps finish within minutes on CPU: 1/64 (tank) of the workload
+        if args.workload == "tank":
+            sdims = [max(8, d // 4) for d in dims]
+            (nx, ny, nz), origin, bmin, bmax = scenes.tank_layout(*sdims)
+            pos, _ = scenes.lattice_slab(nx, ny, nz, origin, 0, nx)
+            particles = scenes.particles_from_positions(pos)
+        else:
+            particles, bmin, bmax = scenes.dam_break(min(args.n_side, 50))
         o = PortOracle(particles, param_block())
         kind, cores = "port", o.threads
-        where = f"CPU port (oracle/pbf_oracle.cpp, OpenMP {cores} threads) on a reduced {n_side}^3 sample"
+        where = (f"CPU port (oracle/pbf_oracle.cpp, OpenMP {cores} threads) on a reduced {len(particles)}-particle sample"
+                 + (f" [{why[:80]}]" if why else ""))
+    if gravity is not None:
+        o.setGravity(gravity)
     n = len(particles)
+    del particles
     steps, warm = args.steps, args.warmup
     if use_ref:
         # the reference round-trips 2 KB/particle/step over PCIe: keep the whole run within a few minutes
         o.step(DT, bmin, bmax)
         t0 = time.perf_counter(); o.step(DT, bmin, bmax); one = time.perf_counter() - t0
-        budget = 150.0
+        budget = 170.0
         if one * (steps + warm) > budget:
             warm = max(1, min(warm, int(0.2 * budget / one)))
             steps = max(2, min(steps, int(0.8 * budget / one)))
@@ -381,12 +596,14 @@ def run_reference(args):
         o.step(DT, bmin, bmax)
     dt = time.perf_counter() - t0
     value = n * ITERS * steps / dt
-    sample = f"{steps} timed steps after {warm} warm-up steps of the {n}-particle dam break; {where}"
+    sample = f"{steps} timed steps after {warm + (2 if use_ref else 0)} warm-up steps from rest, {n} particles; {where}"
     out = {"impl": "reference", "metric": "particle-iterations/sec", "value": value, "unit": "particle-iterations/s",
            "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"dam break {n} particles ({n_side}^3 lattice), dt={DT}, {ITERS} solver iterations",
-                      "requested_steps": args.steps, "requested_warmup": args.warmup},
+           "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config if n == config["particles_total"] else dict(config, workload=config["workload"] + f" [REDUCED SAMPLE: {n} particles]", particles_total=n),
+           "protocol": {"requested_steps": args.steps, "requested_warmup": args.warmup,
+                        "note": "starts from the lattice at rest (the reference cannot afford our arm's settle steps: "
+                                f"{dt / steps:.2f} s per step)"},
            "cpu_baseline": {"value": value, "unit": "particle-iterations/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "particle-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -396,16 +613,21 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-side", type=int, default=100, help="lattice side: 30 -> 27 K (config 1), 100 -> 1 M (config 2), 252 -> 16 M (config 3)")
-    ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
-    ap.add_argument("--workload", default="dam", choices=["dam", "tank"])
+    ap.add_argument("--workload", default="tank", choices=["dam", "tank"])
     ap.add_argument("--tank-per-gpu", default="200,200,200", help="tank lattice per GPU (weak scaling): nx,ny,nz")
     ap.add_argument("--tank-total", default="", help="tank lattice in total (strong scaling), e.g. 400,400,400 = 64 M")
+    ap.add_argument("--n-side", type=int, default=100, help="--workload dam: 30 -> 27 K (config 1), 100 -> 1 M (config 2), 252 -> 16 M (config 3)")
+    ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
+    ap.add_argument("--settle", type=int, default=300, help="untimed steps before the warm-up, so that the fluid is disordered")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps each; the median is reported")
+    ap.add_argument("--rebalance-every", type=int, default=0, help="multi-GPU: akua_pbf_rebalance every k settle steps")
     ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs 2 / 3 extra block")
+    ap.add_argument("--no-selfcheck", action="store_true", help="multi-GPU: skip the small-scene check against one GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

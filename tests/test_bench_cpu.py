@@ -15,7 +15,7 @@ REPO = Path(__file__).resolve().parents[1]
 @pytest.mark.skipif(HAS_GPU, reason="GPU present: the reference arm would run the reference kernels instead")
 def test_reference_arm_falls_back_to_cpu_port():
     res = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
-                          "--n-side", "24"], capture_output=True, text=True, timeout=600)
+                          "--workload", "dam", "--n-side", "24"], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)

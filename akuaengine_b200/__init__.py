@@ -236,8 +236,9 @@ class PBFSolver:
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
                  capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None,
-                 list_build: int | None = None):
-        self._lib = load_library()
+                 list_build: int | None = None, lib=None):
+        # `lib`: an alternative build of the same C ABI (load_library(path)), e.g. the host-emulated build of tests/emu
+        self._lib = lib if lib is not None else load_library()
         self.config = config or PBFConfig()
         self.corrParams = corrParams or LambdaCorrParams()
         self.numParticles = int(numParticles)
@@ -407,9 +408,9 @@ class PBFSolver:
 
     # -- multi-GPU (x-slab) plumbing; see akuaengine_b200/slab.py for the torch.distributed driver
     @staticmethod
-    def comm_unique_id() -> np.ndarray:
+    def comm_unique_id(lib=None) -> np.ndarray:
         buf = np.zeros(128, np.uint8)
-        rc = load_library().akua_pbf_comm_unique_id(buf.ctypes.data, 128)
+        rc = (lib if lib is not None else load_library()).akua_pbf_comm_unique_id(buf.ctypes.data, 128)
         if rc != 0:
             raise AkuaError(f"akua_pbf_comm_unique_id failed (status {rc}): is libnccl.so.2 loadable?")
         return buf

@@ -119,19 +119,23 @@ __host__ __device__ __forceinline__ void finish_list(uint32_t i, uint32_t count,
 // Same parameter list as k_build_neighbours<KEY_LINEAR> so that the host code can launch either. MINB (resident CTAs per SM)
 // fixes the register budget explicitly: <4, 5> compiles to 48 registers, <8, 4> to 64, both without spills (ptxas -v); left to
 // its own heuristics ptxas squeezes the 8-deep variant into 48 registers and spills.
-template <int UNROLL, int MINB>
+template <int UNROLL, int MINB, bool STRIDED>
 __global__ void __launch_bounds__(256, MINB) k_build_neighbours_mask(const float4* __restrict__ xs,
                                                                const uint32_t* __restrict__ /*keysSorted*/,
                                                                const uint32_t* __restrict__ /*bucketStart*/,
                                                                const uint2* __restrict__ cellRange, uint32_t n,
                                                                uint32_t stride, uint32_t maxN, uint32_t* __restrict__ list,
-                                                               uint32_t* __restrict__ cnt, GridParams G, float h) {
+                                                               uint32_t* __restrict__ cnt, GridParams G, float h,
+                                                               const uint32_t* __restrict__ nPtr) {
     pdl_wait();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t count = build_list_mask<UNROLL>(i, xs, cellRange, stride, maxN, list, G, h);
-    pdl_trigger();
-    finish_list(i, count, stride, list, cnt);
+    if (STRIDED) n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t count = build_list_mask<UNROLL>(i, xs, cellRange, stride, maxN, list, G, h);
+        if (!STRIDED) pdl_trigger();
+        finish_list(i, count, stride, list, cnt);
+        if (!STRIDED) break;
+    }
+    if (STRIDED) pdl_trigger();
 }
 #endif
 

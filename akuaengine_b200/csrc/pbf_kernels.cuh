@@ -18,7 +18,9 @@
 #ifndef AKUA_SWEEP_MINBLOCKS
 #define AKUA_SWEEP_MINBLOCKS 8
 #endif
-#define AKUA_SWEEP_BOUNDS __launch_bounds__(AKUA_SWEEP_BLOCK, AKUA_SWEEP_MINBLOCKS)
+// SLAB instantiations (x-slab mode: grid-stride loop, halo wait / signal, peer pushes) carry a few more live values: one
+// resident CTA fewer per SM keeps them spill-free
+#define AKUA_SWEEP_BOUNDS __launch_bounds__(AKUA_SWEEP_BLOCK, SLAB ? AKUA_SWEEP_MINBLOCKS - 1 : AKUA_SWEEP_MINBLOCKS)
 
 namespace akua {
 
@@ -125,54 +127,104 @@ __host__ __device__ __forceinline__ uint32_t linear_key(int3 c, const GridParams
     return (uint32_t)((x * G.gridDim.y + y) * G.gridDim.z + z);
 }
 
+// ------------------------------------------------------------------------------------------------ x-slab step dimensions
+// In x-slab (multi-GPU) mode every per-step size lives in a device-resident block of 64 u32 words ("dims"), written by the
+// migration kernels and by slab::k_slab_plan and read by every kernel of the step: the host never learns this step's sizes,
+// so the step needs no host synchronisation and can be replayed as a CUDA graph. Launch grids come from a host ESTIMATE
+// (the sizes of an earlier step, read back asynchronously); kernels loop (grid-stride) so any estimate is correct.
+enum : int {
+    D_OUT_L = 0, D_OUT_R = 1,                                       // leavers of this step (k_mig_scan)
+    D_STAY_FIRST = 2, D_STAY_LAST = 3, D_LAND_L = 4, D_LAND_R = 5,  // plane populations (k_mig_count)
+    D_MASS = 8,                                                     // 8..11: scratch of the uniform-mass agreement
+    D_MSG_TO_L = 16, D_MSG_TO_R = 20, D_MSG_FROM_L = 24, D_MSG_FROM_R = 28,   // the per-step count messages (3 words each)
+    D_ERROR = 31,                                                   // sticky error word (akua_slab_error bits)
+    D_N = 32,                                                       // owned particles between steps
+    D_IN_L = 33, D_IN_R = 34, D_NPRE = 35, D_NOWN = 36,             // arrivals; resident before the sort; owned after it
+    D_PLANE_L = 37, D_PLANE_R = 38, D_GHOST_L = 39, D_GHOST_R = 40, // boundary planes sent / ghost planes received
+    D_EPOCH = 41,                                                   // epoch base of this step: exchange e carries D_EPOCH + e + 1
+    D_STAT_MIG_IN = 42, D_STAT_MIG_OUT = 44, D_STAT_BYTES = 46,     // u64 accumulators (two words each)
+    D_STEPS = 48,                                                   // steps completed on the device
+    D_WORDS = 64
+};
+enum : uint32_t {   // bits of dims[D_ERROR]
+    SLAB_ERR_PLANE_PREDICTION = 1u, SLAB_ERR_TIMEOUT = 2u, SLAB_ERR_MIG_OVERFLOW = 4u, SLAB_ERR_CAPACITY = 8u,
+    SLAB_ERR_GHOST_OVERFLOW = 16u
+};
+
 // Index span of a sweep launch: thread t handles particle base + t (+ skip once t >= split). One launch can thus cover
 // the whole owned range (single GPU), the interior of a slab, or its two boundary planes (multi-GPU overlap).
-struct Span { uint32_t count, base, split, skip; };
-__device__ __forceinline__ bool span_index(const Span& sp, uint32_t& i) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= sp.count) return false;
-    i = sp.base + t + (t >= sp.split ? sp.skip : 0u);
-    return true;
+// mode 0: the host filled count/base/split/skip. Slab mode: resolved on the device from `dims` —
+// mode 1 = all owned particles, 2 = slab interior (needs no ghost data), 3 = the two boundary planes.
+enum : int { SPAN_FIXED = 0, SPAN_OWNED = 1, SPAN_INTERIOR = 2, SPAN_BOUNDARY = 3 };
+struct Span { uint32_t count, base, split, skip; const uint32_t* dims; int mode; };
+__device__ __forceinline__ Span resolve_span(Span sp) {
+    if (sp.mode == SPAN_FIXED) return sp;
+    const uint32_t n = sp.dims[D_NOWN], pl = sp.dims[D_PLANE_L], pr = sp.dims[D_PLANE_R];
+    const bool allBoundary = (uint64_t)pl + pr >= n;   // slab only one or two planes wide: everything is boundary
+    sp.split = 0xffffffffu; sp.skip = 0u; sp.base = 0u;
+    if (sp.mode == SPAN_OWNED) sp.count = n;
+    else if (sp.mode == SPAN_INTERIOR) { sp.count = allBoundary ? 0u : n - pl - pr; sp.base = pl; }
+    else if (allBoundary) sp.count = n;
+    else { sp.count = pl + pr; sp.split = pl; sp.skip = n - pr - pl; }
+    return sp;
 }
+__device__ __forceinline__ uint32_t span_particle(const Span& sp, uint32_t t) { return sp.base + t + (t >= sp.split ? sp.skip : 0u); }
 
 // Fused compute + halo push (multi-GPU, CUDA-IPC transport): a boundary particle's result is also stored straight into the
 // neighbouring rank's ghost region through the peer-mapped pointer (NVLink P2P store), so no separate copy or
 // collective follows the sweep. dstL / dstR already point at the ghost region's first element; null = nothing to push.
+// The plane sizes come from `dims` (resolve_push).
 struct PeerPush {
     void* dstL = nullptr;   // left rank: particles [0, nL) of this rank's owned range
     void* dstR = nullptr;   // right rank: particles [startR, nOwn)
     uint32_t nL = 0, startR = 0xffffffffu;
+    const uint32_t* dims = nullptr;
 };
+__device__ __forceinline__ void resolve_push(PeerPush& pp) {
+    if (!pp.dims) return;
+    pp.nL = pp.dims[D_PLANE_L];
+    pp.startR = pp.dims[D_NOWN] - pp.dims[D_PLANE_R];
+}
 template <typename T>
 __device__ __forceinline__ void peer_push(const PeerPush& pp, uint32_t i, const T& v) {
     if (pp.dstL && i < pp.nL) static_cast<T*>(pp.dstL)[i] = v;
     if (pp.dstR && i >= pp.startR) static_cast<T*>(pp.dstR)[i - pp.startR] = v;
 }
 
-// In-kernel halo synchronisation for the fused path: a boundary sweep first waits (one thread per CTA, bounded spin) until
-// both neighbours have published the epoch of the ghost data it is about to read, and, when it has pushed its own
-// results, the LAST CTA to finish publishes this exchange's epoch in the neighbours' flag words. No extra kernels, no
-// copy engine, no collective: compute, communication and synchronisation are one launch.
+// In-kernel halo synchronisation: a boundary sweep first waits (one thread per CTA, bounded spin) until both neighbours
+// have published the epoch of the ghost data it is about to read, and, when it has pushed its own results, the LAST CTA
+// to finish publishes this exchange's epoch in the neighbours' flag words. No extra kernels, no copy engine, no
+// collective: compute, communication and synchronisation are one launch. Epochs are dims[D_EPOCH] + index + 1, so the
+// kernel arguments are the same every step (CUDA-graph replay).
 struct HaloSync {
     const uint32_t* waitFlags = nullptr;   // this rank's flag words: [0] written by the left rank, [1] by the right rank
     int waitL = 0, waitR = 0;
-    uint32_t waitEpoch = 0;
+    int waitIdx = -1;                      // exchange index to wait for (-1: none)
     uint32_t* signalL = nullptr;           // neighbours' flag words to publish into (null: no neighbour / nothing pushed)
     uint32_t* signalR = nullptr;
-    uint32_t signalEpoch = 0;
+    int signalIdx = -1;
     uint32_t* doneCounter = nullptr;       // CTA completion counter for this launch (zero before and after)
-    uint32_t* errWord = nullptr;
+    uint32_t* dims = nullptr;              // D_EPOCH, D_ERROR
+    long long timeoutCycles = 0;
 };
+// Bounded spin of ONE thread on a flag word until it reaches `epoch` (wrap-safe); false on time-out.
+__device__ __forceinline__ bool spin_until(const volatile uint32_t* f, uint32_t epoch, long long timeoutCycles) {
+    const long long t0 = clock64();
+    unsigned ns = 32;
+    while ((int32_t)(*f - epoch) < 0) {
+        if (clock64() - t0 > timeoutCycles) return false;
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+    }
+    return true;
+}
 __device__ __forceinline__ void halo_wait(const HaloSync& hs) {
-    if (!hs.waitFlags) return;
+    if (!hs.waitFlags || hs.waitIdx < 0) return;
     if (threadIdx.x == 0) {
-        const long long t0 = clock64();
+        const uint32_t epoch = hs.dims[D_EPOCH] + (uint32_t)hs.waitIdx + 1u;
         for (int side = 0; side < 2; side++) {
             if (!(side == 0 ? hs.waitL : hs.waitR)) continue;
-            const volatile uint32_t* f = hs.waitFlags + side;
-            while ((int32_t)(*f - hs.waitEpoch) < 0) {
-                if (clock64() - t0 > 4000000000LL) { *hs.errWord = 2; break; }
-            }
+            if (!spin_until(hs.waitFlags + side, epoch, hs.timeoutCycles)) { atomicOr(hs.dims + D_ERROR, (uint32_t)SLAB_ERR_TIMEOUT); break; }
         }
         __threadfence_system();
     }
@@ -180,20 +232,23 @@ __device__ __forceinline__ void halo_wait(const HaloSync& hs) {
 }
 // Call with ALL threads of the CTA (no early returns before it) once the CTA's pushes are issued.
 __device__ __forceinline__ void halo_signal(const HaloSync& hs) {
-    if (!hs.doneCounter) return;
+    if (!hs.doneCounter || hs.signalIdx < 0) return;
     __syncthreads();   // every thread's pushes happen-before thread 0's fence below (fences are cumulative)
     if (threadIdx.x == 0) {
         __threadfence_system();
         const uint32_t done = atomicAdd(hs.doneCounter, 1u);
         if (done == gridDim.x - 1) {
             __threadfence_system();
-            if (hs.signalL) *(volatile uint32_t*)hs.signalL = hs.signalEpoch;
-            if (hs.signalR) *(volatile uint32_t*)hs.signalR = hs.signalEpoch;
+            const uint32_t epoch = hs.dims[D_EPOCH] + (uint32_t)hs.signalIdx + 1u;
+            if (hs.signalL) *(volatile uint32_t*)hs.signalL = epoch;
+            if (hs.signalR) *(volatile uint32_t*)hs.signalR = epoch;
             *hs.doneCounter = 0;
             __threadfence_system();
         }
     }
 }
+// particle count of a kernel launch: the host's value, or (slab mode) a word of `dims`
+__device__ __forceinline__ uint32_t live_count(uint32_t n, const uint32_t* nPtr) { return nPtr ? *nPtr : n; }
 
 // ------------------------------------------------------------------------------------------------ neighbour list access
 __host__ __device__ __forceinline__ size_t list_slot(uint32_t i, uint32_t k, uint32_t stride) {
@@ -256,22 +311,24 @@ __device__ __forceinline__ void neighbour_sweep(const uint32_t* __restrict__ lis
 template <int MODE>
 __global__ void __launch_bounds__(256) k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                      float4* __restrict__ xs, uint32_t* __restrict__ keys, uint32_t n,
-                                                     float dt, float3 g, GridParams G, int doPredict) {
+                                                     const uint32_t* __restrict__ nPtr, float dt, float3 g, GridParams G,
+                                                     int doPredict) {
     pdl_wait();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 x;
-    if (doPredict) {
-        float4 p = pos[i], v = vel[i];
-        float vx = __fmaf_rn(g.x, dt, v.x), vy = __fmaf_rn(g.y, dt, v.y), vz = __fmaf_rn(g.z, dt, v.z);
-        x = make_float4(__fmaf_rn(vx, dt, p.x), __fmaf_rn(vy, dt, p.y), __fmaf_rn(vz, dt, p.z), p.w);
-        xs[i] = x;
-    } else {
-        x = xs[i];
-    }
-    if (keys) {
-        int3 c = cell_of(x.x, x.y, x.z, G.cellSize);
-        keys[i] = MODE == KEY_HASH ? ref_hash(c.x, c.y, c.z, G.tableSize) : linear_key(c, G);
+    n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 x;
+        if (doPredict) {
+            float4 p = pos[i], v = vel[i];
+            float vx = __fmaf_rn(g.x, dt, v.x), vy = __fmaf_rn(g.y, dt, v.y), vz = __fmaf_rn(g.z, dt, v.z);
+            x = make_float4(__fmaf_rn(vx, dt, p.x), __fmaf_rn(vy, dt, p.y), __fmaf_rn(vz, dt, p.z), p.w);
+            xs[i] = x;
+        } else {
+            x = xs[i];
+        }
+        if (keys) {
+            int3 c = cell_of(x.x, x.y, x.z, G.cellSize);
+            keys[i] = MODE == KEY_HASH ? ref_hash(c.x, c.y, c.z, G.tableSize) : linear_key(c, G);
+        }
     }
 }
 
@@ -281,27 +338,31 @@ __global__ void __launch_bounds__(256) k_predict_key(const float4* __restrict__ 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_reorder_ranges(const uint32_t* __restrict__ keysSorted,
                                                         const uint32_t* __restrict__ perm, uint32_t n,
+                                                        const uint32_t* __restrict__ nPtr,
                                                         const float4* __restrict__ posIn, const float4* __restrict__ velIn,
                                                         const float4* __restrict__ xsIn, const uint32_t* __restrict__ idIn,
                                                         float4* __restrict__ posOut, float4* __restrict__ velOut,
                                                         float4* __restrict__ xsOut, uint32_t* __restrict__ idOut,
-                                                        uint32_t* __restrict__ bucketStart, uint2* __restrict__ cellRange) {
+                                                        uint32_t* __restrict__ bucketStart, uint2* __restrict__ cellRange,
+                                                        const uint32_t* __restrict__ slotIn, uint32_t* __restrict__ slotOut) {
     pdl_wait();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t src = perm[i];
-    posOut[i] = posIn[src];
-    velOut[i] = velIn[src];
-    xsOut[i] = xsIn[src];
-    idOut[i] = idIn[src];
-    uint32_t k = keysSorted[i];
-    bool first = (i == 0) || (keysSorted[i - 1] != k);
-    if (MODE == KEY_HASH) {
-        if (first) bucketStart[k] = i;
-    } else {
-        bool last = (i == n - 1) || (keysSorted[i + 1] != k);
-        if (first) cellRange[k].x = i;
-        if (last) cellRange[k].y = i + 1;
+    n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t src = perm[i];
+        posOut[i] = posIn[src];
+        velOut[i] = velIn[src];
+        xsOut[i] = xsIn[src];
+        idOut[i] = idIn[src];
+        if (slotIn) slotOut[i] = slotIn[src];   // x-slab mode: where the particle's render payload lives (see k_pack_aos)
+        uint32_t k = keysSorted[i];
+        bool first = (i == 0) || (keysSorted[i - 1] != k);
+        if (MODE == KEY_HASH) {
+            if (first) bucketStart[k] = i;
+        } else {
+            bool last = (i == n - 1) || (keysSorted[i + 1] != k);
+            if (first) cellRange[k].x = i;
+            if (last) cellRange[k].y = i + 1;
+        }
     }
 }
 // Undo last step's bucket-start writes instead of refilling the 128*N-entry table (the reference allocates and fills
@@ -320,20 +381,27 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ p, uint
     for (; i < count; i += stride) p[i] = v;
 }
 
+__global__ void __launch_bounds__(256) k_fill_payload(float4* __restrict__ color, float* __restrict__ size, uint32_t n, float4 c,
+                                                      float sz) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { color[i] = c; size[i] = sz; }
+}
+
 // ------------------------------------------------------------------------------------------------ K4
 // kernel_find_neighbours (NeighbourSearchCUDA.cu:72-130): 27-cell scan in the reference's order (dx outer, dz inner,
 // bucket order = sorted order), strict d2 < h*h, self skipped, capped at maxNeighbours. The list is written
 // column-major in groups of four (list_slot); the unused tail of the last group is padded with the particle's own index.
-template <int MODE>
+// STRIDED (x-slab mode): the particle count lives on the device and the kernel loops; otherwise one particle per thread.
+template <int MODE, bool STRIDED>
 __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restrict__ xs,
                                                           const uint32_t* __restrict__ keysSorted,
                                                           const uint32_t* __restrict__ bucketStart,
                                                           const uint2* __restrict__ cellRange, uint32_t n,
                                                           uint32_t stride, uint32_t maxN, uint32_t* __restrict__ list,
-                                                          uint32_t* __restrict__ cnt, GridParams G, float h) {
+                                                          uint32_t* __restrict__ cnt, GridParams G, float h,
+                                                          const uint32_t* __restrict__ nPtr) {
     pdl_wait();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (STRIDED) n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 xi = xs[i];
     const float h2 = __fmul_rn(h, h);
     const int3 c = cell_of(xi.x, xi.y, xi.z, G.lookupCellSize);
@@ -381,25 +449,28 @@ __global__ void __launch_bounds__(256) k_build_neighbours(const float4* __restri
             }
         }
     }
-    pdl_trigger();
+    if (!STRIDED) pdl_trigger();
     cnt[i] = count;
     for (uint32_t k = count; k < ((count + 3u) & ~3u); k++) list[list_slot(i, k, stride)] = i;
+    if (!STRIDED) break;
+    }
+    if (STRIDED) pdl_trigger();
 }
 
 // ------------------------------------------------------------------------------------------------ pass A = K5 + K6
 // kernel_calculate_densities (ConstraintSolverCUDA.cu:16-42) + kernel_calculate_lambdas (:51-97), one neighbour loop.
 // Each accumulator sees its terms in the reference's order, so fusing the loops does not change the sums.
-template <bool FAST>
+template <bool FAST, bool SLAB>
 __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs, const uint32_t* __restrict__ list,
                                                         const uint32_t* __restrict__ cnt, uint32_t stride, Span sp,
                                                         float* __restrict__ density, float* __restrict__ lambda,
                                                         float4* __restrict__ xl, SphParams P, PeerPush pushLambda,
                                                         HaloSync hs) {
     pdl_wait();
-    halo_wait(hs);
-    uint32_t i;
-    const bool live = span_index(sp, i);
-    if (live) {
+    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushLambda); }
+    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    const uint32_t i = span_particle(sp, t);
     const float4 xi = xs[i];
     const uint32_t c = cnt[i];
     float rho = xi.w * P.selfW;
@@ -423,7 +494,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
                 sum += fmaf(bz, bz, fmaf(bx, bx, by * by));
             }
         });
-    pdl_trigger();
+    if (!SLAB) pdl_trigger();
     gx *= P.invRestDensity; gy *= P.invRestDensity; gz *= P.invRestDensity;
     float C = rho * P.invRestDensity - 1.0f;
     float lam = -C / (sum + fmaf(gz, gz, fmaf(gx, gx, gy * gy)) + P.relaxation);
@@ -432,12 +503,13 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
     if (xl) {   // packed-gather layout: pass B fetches x* and lambda in one gather (the halo push then carries the pair too)
         const float4 v = make_float4(xi.x, xi.y, xi.z, lam);
         xl[i] = v;
-        peer_push(pushLambda, i, v);
+        if (SLAB) peer_push(pushLambda, i, v);
     } else {
-        peer_push(pushLambda, i, lam);
+        if (SLAB) peer_push(pushLambda, i, lam);
     }
+    if (!SLAB) break;
     }
-    halo_signal(hs);
+    if (SLAB) { pdl_trigger(); halo_signal(hs); }
 }
 
 // ------------------------------------------------------------------------------------------------ K8 / K9 / K10 pieces
@@ -484,7 +556,7 @@ __device__ __forceinline__ void damp_velocity(float px, float py, float pz, floa
 // (x*, lambda) array `xl` instead of a 16-byte and a 4-byte gather; the arithmetic is the same expression on the same values.
 // CORR4: the artificial-pressure exponent n is 4 (the reference's default, PBFConfig.h:14): two multiplies instead of powf,
 // and no per-neighbour branch on it.
-template <bool FAST, bool FINAL, bool PACK, bool CORR4>
+template <bool FAST, bool FINAL, bool PACK, bool CORR4, bool SLAB>
 __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn, float4* __restrict__ xsOut,
                                                      const float* __restrict__ lambda, const float4* __restrict__ xl,
                                                      const uint32_t* __restrict__ list,
@@ -494,10 +566,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
                                                      const float* __restrict__ density, PosVel* __restrict__ pvOut,
                                                      float dt, PeerPush pushX, PeerPush pushV, HaloSync hs) {
     pdl_wait();
-    halo_wait(hs);
-    uint32_t i;
-    const bool live = span_index(sp, i);
-    if (live) {
+    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushX); resolve_push(pushV); }
+    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    const uint32_t i = span_particle(sp, t);
     float4 xi;
     float li;
     if (PACK) { const float4 t = xl[i]; li = t.w; xi = make_float4(t.x, t.y, t.z, P.uniformMass); }
@@ -524,14 +596,14 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
             coef = valid ? coef : 0.0f;
             px = fmaf(coef, dx, px); py = fmaf(coef, dy, py); pz = fmaf(coef, dz, pz);
         });
-    pdl_trigger();
+    if (!SLAB) pdl_trigger();
     px *= P.invRestDensity; py *= P.invRestDensity; pz *= P.invRestDensity;
     if (dposOut) dposOut[i] = make_float4(px, py, pz, 0.f);
     float x = collide_axis(xi.x + px, B.bmin.x, B.bmax.x, B);
     float y = collide_axis(xi.y + py, B.bmin.y, B.bmax.y, B);
     float z = collide_axis(xi.z + pz, B.bmin.z, B.bmax.z, B);
     xsOut[i] = make_float4(x, y, z, xi.w);
-    peer_push(pushX, i, make_float4(x, y, z, xi.w));
+    if (SLAB) peer_push(pushX, i, make_float4(x, y, z, xi.w));
     if (FINAL) {
         float4 p = pos[i];
         float vx = (x - p.x) / dt, vy = (y - p.y) / dt, vz = (z - p.z) / dt;
@@ -540,10 +612,11 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
         const float4 vout = make_float4(vx, vy, vz, density[i]);
         vel[i] = vout;
         if (pvOut) { PosVel r; r.x = make_float4(x, y, z, xi.w); r.v = vout; pvOut[i] = r; }   // post-solve gather records
-        peer_push(pushV, i, vout);
+        if (SLAB) peer_push(pushV, i, vout);
     }
+    if (!SLAB) break;
     }
-    halo_signal(hs);
+    if (SLAB) { pdl_trigger(); halo_signal(hs); }
 }
 
 // (position, velocity) -> post-solve gather records, for callers that commit outside the fused final pass B (phase-level
@@ -560,29 +633,31 @@ __global__ void __launch_bounds__(256) k_build_posvel(const float4* __restrict__
 // Stand-alone K9 / K10 for the phase-level API (and solverIterations == 0).
 __global__ void __launch_bounds__(256) k_update(const float4* __restrict__ xs, float4* __restrict__ pos,
                                                 float4* __restrict__ vel, const float* __restrict__ density, uint32_t n,
-                                                float dt) {
+                                                float dt, const uint32_t* __restrict__ nPtr) {
     pdl_wait();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 x = xs[i], p = pos[i];
-    pos[i] = x;
-    vel[i] = make_float4((x.x - p.x) / dt, (x.y - p.y) / dt, (x.z - p.z) / dt, density[i]);
+    n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 x = xs[i], p = pos[i];
+        pos[i] = x;
+        vel[i] = make_float4((x.x - p.x) / dt, (x.y - p.y) / dt, (x.z - p.z) / dt, density[i]);
+    }
 }
 __global__ void __launch_bounds__(256) k_damping(const float4* __restrict__ pos, float4* __restrict__ vel, uint32_t n,
-                                                 BoxParams B) {
+                                                 BoxParams B, const uint32_t* __restrict__ nPtr) {
     pdl_wait();
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = pos[i], v = vel[i];
-    damp_velocity(p.x, p.y, p.z, v.x, v.y, v.z, B);
-    vel[i] = v;
+    n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pos[i], v = vel[i];
+        damp_velocity(p.x, p.y, p.z, v.x, v.y, v.z, B);
+        vel[i] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K11
 // kernel_compute_vorticities, IntegrationCUDA.cu:104-128. Also stores |omega| so K12 gathers 4 B per neighbour, not 12.
 // REC: neighbour position + velocity come from one 32-byte record gather (PosVel). `xw` (optional) receives the packed
 // (x, |omega|) array K12's PACK variant gathers from.
-template <bool FAST, bool REC>
+template <bool FAST, bool REC, bool SLAB>
 __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, const float4* __restrict__ vel,
                                                    const PosVel* __restrict__ pv,
                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
@@ -590,12 +665,12 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
                                                    float* __restrict__ omegaLen, float4* __restrict__ xw, SphParams P,
                                                    PeerPush pushLen, HaloSync hs) {
     pdl_wait();
-    halo_wait(hs);
-    uint32_t i;
-    const bool live = span_index(sp, i);
-    if (live) {
+    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushLen); }
+    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    const uint32_t i = span_particle(sp, t);
     float4 xi, vi;
-    if (REC) { const PosVel t = pv[i]; xi = t.x; vi = t.v; }
+    if (REC) { const PosVel r = pv[i]; xi = r.x; vi = r.v; }
     else     { xi = xs[i]; vi = vel[i]; }
     const uint32_t c = cnt[i];
     float wx = 0.f, wy = 0.f, wz = 0.f;
@@ -613,26 +688,27 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
             float m = valid ? -nb.x.w : 0.0f;
             wx = fmaf(m, cx, wx); wy = fmaf(m, cy, wy); wz = fmaf(m, cz, wz);
         });
-    pdl_trigger();
+    if (!SLAB) pdl_trigger();
     float len = sqrtf(fmaf(wz, wz, fmaf(wx, wx, wy * wy)));
     omega[i] = make_float4(wx, wy, wz, len);
     omegaLen[i] = len;
     if (xw) {
         const float4 v = make_float4(xi.x, xi.y, xi.z, len);
         xw[i] = v;
-        peer_push(pushLen, i, v);
+        if (SLAB) peer_push(pushLen, i, v);
     } else {
-        peer_push(pushLen, i, len);
+        if (SLAB) peer_push(pushLen, i, len);
     }
+    if (!SLAB) break;
     }
-    halo_signal(hs);
+    if (SLAB) { pdl_trigger(); halo_signal(hs); }
 }
 
 // ------------------------------------------------------------------------------------------------ K12
 // kernel_apply_vorticity_confinement, IntegrationCUDA.cu:130-165. Reads neighbours' |omega|, writes only its own
 // velocity: race-free in place. PACK (uniform mass): position and |omega| of a neighbour come from one gather of `xw`.
 // `pvOut` (optional): the updated velocity is mirrored into the post-solve gather records K13 reads.
-template <bool FAST, bool PACK>
+template <bool FAST, bool PACK, bool SLAB>
 __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, const float4* __restrict__ omega,
                                                      const float* __restrict__ omegaLen, const float4* __restrict__ xw,
                                                      const float* __restrict__ density,
@@ -641,10 +717,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
                                                      PosVel* __restrict__ pvOut, SphParams P,
                                                      float dt, float eps, PeerPush pushV, HaloSync hs) {
     pdl_wait();
-    halo_wait(hs);
-    uint32_t i;
-    const bool live = span_index(sp, i);
-    if (live) {
+    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushV); }
+    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    const uint32_t i = span_particle(sp, t);
     const float4 xi = PACK ? xw[i] : xs[i];
     const float4 oi = omega[i];
     const uint32_t c = cnt[i];
@@ -664,7 +740,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
             coef = valid ? coef : 0.0f;
             ex = fmaf(coef, dx, ex); ey = fmaf(coef, dy, ey); ez = fmaf(coef, dz, ez);
         });
-    pdl_trigger();
+    if (!SLAB) pdl_trigger();
     ex *= invDensity; ey *= invDensity; ez *= invDensity;
     float len = sqrtf(fmaf(ez, ez, fmaf(ex, ex, ey * ey)));
     if (len >= 1e-5f) {
@@ -674,28 +750,30 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
     v.x = fmaf(dt, fx, v.x); v.y = fmaf(dt, fy, v.y); v.z = fmaf(dt, fz, v.z);
     vel[i] = v;
     if (pvOut) pvOut[i].v = v;
-    peer_push(pushV, i, v);   // unchanged velocities were already pushed by the committing pass B
+    if (SLAB) peer_push(pushV, i, v);   // unchanged velocities were already pushed by the committing pass B
     }
+    if (!SLAB) break;
     }
-    halo_signal(hs);
+    if (SLAB) { pdl_trigger(); halo_signal(hs); }
 }
 
 // ------------------------------------------------------------------------------------------------ K13
 // kernel_apply_xsph_viscosity, IntegrationCUDA.cu:167-195 — as a Jacobi sweep (velIn -> velOut). The reference updates
 // velocity in place while neighbours read it (a data race, :187,:194); Jacobi is one of its legal outcomes and is
 // deterministic. REC: one 32-byte record gather per neighbour instead of two 16-byte gathers.
-template <bool REC>
+template <bool REC, bool SLAB>
 __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const float4* __restrict__ velIn,
                                               const PosVel* __restrict__ pv,
                                               const uint32_t* __restrict__ list, const uint32_t* __restrict__ cnt,
                                               uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
                                               float cvisc, HaloSync hs) {
     pdl_wait();
-    halo_wait(hs);
-    uint32_t i;
-    if (!span_index(sp, i)) return;
+    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); }
+    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    const uint32_t i = span_particle(sp, t);
     float4 xi, vi;
-    if (REC) { const PosVel t = pv[i]; xi = t.x; vi = t.v; }
+    if (REC) { const PosVel r = pv[i]; xi = r.x; vi = r.v; }
     else     { xi = xs[i]; vi = velIn[i]; }
     const uint32_t c = cnt[i];
     float ax = 0.f, ay = 0.f, az = 0.f;
@@ -711,8 +789,11 @@ __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const fl
             w = valid ? w : 0.0f;
             ax = fmaf(mr * (nb.v.x - vi.x), w, ax); ay = fmaf(mr * (nb.v.y - vi.y), w, ay); az = fmaf(mr * (nb.v.z - vi.z), w, az);
         });
-    pdl_trigger();
+    if (!SLAB) pdl_trigger();
     velOut[i] = make_float4(fmaf(cvisc, ax, vi.x), fmaf(cvisc, ay, vi.y), fmaf(cvisc, az, vi.z), vi.w);
+    if (!SLAB) break;
+    }
+    if (SLAB) pdl_trigger();
 }
 
 // ------------------------------------------------------------------------------------------------ AoS-108 interchange
@@ -756,7 +837,7 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
                                                   const float* __restrict__ density, const float* __restrict__ lambda,
                                                   const uint32_t* __restrict__ keys, const float4* __restrict__ color,
                                                   const float* __restrict__ size, const uint32_t* __restrict__ id,
-                                                  int payloadById) {
+                                                  const uint32_t* __restrict__ slot) {
     __shared__ uint32_t sm[256 * kAosWords];
     const uint32_t base = blockIdx.x * 256u;
     const uint32_t count = min(256u, n - base);
@@ -764,9 +845,11 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
         const uint32_t i = base + threadIdx.x;
         float* f = reinterpret_cast<float*>(sm + threadIdx.x * kAosWords);
         float4 p = pos[i], v = vel[i], x = xs[i], o = omega[i], d = dpos[i];
-        // slab mode: ids are global and the payload is not migrated -> the scene defaults of Application.cpp:186-187
-        uint32_t pid = id[i];
-        float4 c = payloadById ? color[pid] : make_float4(0.f, 0.f, 1.f, 1.f);
+        // The render payload (Particle::color / ::size) is never read by the solver, so it stays where the upload put it and
+        // only an index travels through the sorts: the upload index `id` on one GPU; in x-slab mode (ids are global there) a
+        // per-rank payload slot that migration re-assigns on the receiving rank (slab::k_mig_unpack).
+        const uint32_t pid = slot ? slot[i] : id[i];
+        float4 c = color[pid];
         f[0] = p.x; f[1] = p.y; f[2] = p.z;
         f[3] = v.x; f[4] = v.y; f[5] = v.z;
         f[6] = x.x; f[7] = x.y; f[8] = x.z;
@@ -776,7 +859,7 @@ __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, ui
         f[18] = p.w; f[19] = density[i]; f[20] = lambda[i];
         sm[threadIdx.x * kAosWords + 21] = keys[i];
         f[22] = c.x; f[23] = c.y; f[24] = c.z; f[25] = c.w;
-        f[26] = payloadById ? size[pid] : 50.0f;
+        f[26] = size[pid];
     }
     __syncthreads();
     uint32_t* dst = aos + (size_t)base * kAosWords;

@@ -27,6 +27,13 @@ NcclApi g_nccl;
 
 const char* loadNccl() {
     if (g_nccl.lib) return nullptr;
+#ifdef AKUA_HOST_EMU   // tests/emu: the in-process stand-in of tests/emu/nccl.h (test infrastructure only)
+    g_nccl.GetUniqueId = ncclGetUniqueId; g_nccl.CommInitRank = ncclCommInitRank; g_nccl.CommDestroy = ncclCommDestroy;
+    g_nccl.Send = ncclSend; g_nccl.Recv = ncclRecv; g_nccl.GroupStart = ncclGroupStart; g_nccl.GroupEnd = ncclGroupEnd;
+    g_nccl.AllReduce = ncclAllReduce; g_nccl.GetErrorString = ncclGetErrorString;
+    g_nccl.lib = &g_nccl;
+    return nullptr;
+#endif
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) return "cannot dlopen libnccl.so.2";
@@ -50,10 +57,15 @@ const char* loadNccl() {
         }                                                                                         \
     } while (0)
 
-// Bound of the k_wait_flags spins in SM clock cycles (~20 s at 1.97 GHz): long enough for any host-side skew between the
+// Bound of the in-kernel flag waits in SM clock cycles (~20 s at 1.97 GHz): long enough for any host-side skew between the
 // ranks' launch loops (the count exchange at the top of a step is where a late rank is waited for), short enough that a
-// lost neighbour ends in an error instead of a hung GPU.
-constexpr long long kFlagWaitCycles = 40000000000LL;
+// lost neighbour ends in an error instead of a hung GPU. One bound for every wait (count message and ghost planes).
+constexpr long long kFlagWaitCyclesDefault = 40000000000LL;
+long long flagWaitCycles() {   // AKUA_SLAB_WAIT_CYCLES: override for tests (a time-out must be reachable in a unit test)
+    static const long long v = [] { const char* e = std::getenv("AKUA_SLAB_WAIT_CYCLES"); return e ? std::atoll(e) : kFlagWaitCyclesDefault; }();
+    return v > 0 ? v : kFlagWaitCyclesDefault;
+}
+#define kFlagWaitCycles flagWaitCycles()
 
 cudaEvent_t slabNextEvent(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
@@ -68,17 +80,65 @@ int slabCommAfterMain(akua_pbf_solver* s) {
     AK_CUDA(s, cudaStreamWaitEvent(s->slab.commStream, e, 0));
     return AKUA_OK;
 }
+int slabMainAfterComm(akua_pbf_solver* s) {
+    cudaEvent_t e = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(e, s->slab.commStream));
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, e, 0));
+    return AKUA_OK;
+}
+
+const char* slabErrorText(uint32_t bits) {
+    if (bits & SLAB_ERR_TIMEOUT) return "slab: timed out waiting for a neighbour rank (count message or ghost planes)";
+    if (bits & SLAB_ERR_CAPACITY) return "slab: particle capacity exceeded by arrivals (raise capacity_factor)";
+    if (bits & SLAB_ERR_MIG_OVERFLOW) return "slab: migration buffer overflow (raise capacity_factor)";
+    if (bits & SLAB_ERR_GHOST_OVERFLOW) return "slab: boundary plane larger than the ghost region (raise capacity_factor)";
+    if (bits & SLAB_ERR_PLANE_PREDICTION) return "slab: boundary-plane size prediction failed (a particle crossed more than one slab in one step?)";
+    return "slab: unknown device-side error";
+}
+// Reports a sticky device-side error the pinned mirror already shows (no synchronisation: the mirror is refreshed at the end
+// of every step, so an error surfaces at the latest one call after the step that raised it, and at every synchronising call).
+int slabCheckError(akua_pbf_solver* s) {
+    const uint32_t e = s->slab.hDims ? s->slab.hDims[D_ERROR] : 0u;
+    if (!e) return AKUA_OK;
+    s->err = slabErrorText(e);
+    return (e & (SLAB_ERR_TIMEOUT | SLAB_ERR_PLANE_PREDICTION)) ? AKUA_ERR_COMM : AKUA_ERR_ALLOC;
+}
+// Synchronises the solver's stream and makes the host's view of the step sizes exact (s->n, plane / ghost sizes).
+int slabRefresh(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.enabled) return AKUA_OK;
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    AK_CUDA(s, cudaMemcpy((void*)sl.hDims, sl.dims, D_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    s->n = sl.hDims[D_N];
+    sl.nPlaneL = sl.hDims[D_PLANE_L]; sl.nPlaneR = sl.hDims[D_PLANE_R];
+    sl.nGhostL = sl.hDims[D_GHOST_L]; sl.nGhostR = sl.hDims[D_GHOST_R];
+    return slabCheckError(s);
+}
+// After an upload (or checkpoint load) of n particles: owned count, identity payload slots, full free-slot stack.
+int slabResetCounts(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.dims) return AKUA_OK;
+    const uint32_t n = (uint32_t)s->n, cap = (uint32_t)s->capacity;
+    launchPlain(s->stream, slab::k_slab_reset, std::min<uint32_t>(gridFor(cap), 148 * 8), kBlock, sl.dims, n, cap, sl.slot, sl.freeSlots);
+    AK_LAUNCH_CHECK(s, "k_slab_reset");
+    AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    sl.hDims[D_N] = n; sl.hDims[D_NOWN] = n;
+    sl.hDims[D_PLANE_L] = sl.hDims[D_PLANE_R] = sl.hDims[D_GHOST_L] = sl.hDims[D_GHOST_R] = 0;
+    sl.hDims[D_IN_L] = sl.hDims[D_IN_R] = 0;
+    sl.estN = sl.estBnd = sl.estGhost = sl.estIn = 0;   // re-derived at the next step
+    return AKUA_OK;
+}
 
 // ---- ghost-plane exchange --------------------------------------------------------------------------------------------
 // Ghost planes live at FIXED offsets at the top of every per-particle array (ghostBaseL for the plane received from the
 // left rank, ghostBaseR for the one from the right), so neither side needs the other's particle count.
 // Two transports:
-//   * CUDA IPC (default when the neighbours' allocations can be opened): the plane is copied straight from this rank's
-//     array into the neighbour's ghost region over NVLink by the copy engine (cudaMemcpyAsync to the peer-mapped pointer)
-//     and the exchange's epoch is published in the neighbour's flag word; the neighbour's main stream runs a bounded
-//     spin-wait kernel (k_wait_flags) before the kernel that reads the ghosts. No NCCL kernel, no SM time, no rendezvous.
-//   * NCCL send/recv (fallback; AKUA_SLAB_P2P=0): one grouped call per exchange.
-// A SlabTicket is what the main stream has to wait for before it touches the ghosts of an exchange.
+//   * CUDA IPC (default when the neighbours' allocations can be opened): the kernel that PRODUCES a boundary plane stores it
+//     straight into the neighbour's ghost region (P2P stores over NVLink, PeerPush) and its last CTA publishes the exchange's
+//     epoch in the neighbour's flag word; the kernel that CONSUMES ghosts waits in-kernel for the epoch (HaloSync). No copy
+//     engine, no NCCL kernel, no rendezvous, no host-side size: the step is one CUDA graph.
+//   * NCCL send/recv (fallback; AKUA_SLAB_P2P=0): one grouped call per exchange with host-known sizes, which costs one host
+//     synchronisation per step and rules out graph capture.
 template <typename T> T* peerOf(const akua_pbf_solver* s, const SlabPeer& peer, T* mine) {
     const SlabState& sl = s->slab;
     const void* m = mine;
@@ -93,138 +153,58 @@ template <typename T> T* peerOf(const akua_pbf_solver* s, const SlabPeer& peer, 
     return nullptr;
 }
 template <typename T>
-int slabPlanesOnComm(akua_pbf_solver* s, T* arr) {
-    SlabState& sl = s->slab;
-    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    const size_t nOwn = (size_t)s->n;
-    cudaStream_t st = sl.commStream;
-    if (sl.p2p) {
-        // my first plane -> the left rank's "from the right" ghost region; my last plane -> the right rank's "from the left"
-        if (hasL && sl.nPlaneL) {
-            T* dst = peerOf(s, sl.peerL, arr);
-            if (!dst) { s->err = "slab p2p: array has no peer mapping"; return AKUA_ERR_COMM; }
-            AK_CUDA(s, cudaMemcpyAsync(dst + sl.peerL.ghostBaseR, arr, (size_t)sl.nPlaneL * sizeof(T), cudaMemcpyDeviceToDevice, st));
-        }
-        if (hasR && sl.nPlaneR) {
-            T* dst = peerOf(s, sl.peerR, arr);
-            if (!dst) { s->err = "slab p2p: array has no peer mapping"; return AKUA_ERR_COMM; }
-            AK_CUDA(s, cudaMemcpyAsync(dst + sl.peerR.ghostBaseL, arr + (nOwn - sl.nPlaneR), (size_t)sl.nPlaneR * sizeof(T),
-                                       cudaMemcpyDeviceToDevice, st));
-        }
-    } else {
-        ncclComm_t comm = (ncclComm_t)sl.comm;
-        AK_NCCL(s, g_nccl.GroupStart());
-        if (hasL && sl.nPlaneL) AK_NCCL(s, g_nccl.Send(arr, (size_t)sl.nPlaneL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
-        if (hasR && sl.nPlaneR) AK_NCCL(s, g_nccl.Send(arr + (nOwn - sl.nPlaneR), (size_t)sl.nPlaneR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
-        if (hasL && sl.nGhostL) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseL, (size_t)sl.nGhostL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
-        if (hasR && sl.nGhostR) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseR, (size_t)sl.nGhostR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
-        AK_NCCL(s, g_nccl.GroupEnd());
-    }
-    sl.exchanges++;
-    sl.bytesSent += ((hasL ? sl.nPlaneL : 0) + (hasR ? sl.nPlaneR : 0)) * sizeof(T);
-    return AKUA_OK;
-}
-// Closes an exchange on the comm stream: publishes the epoch to the neighbours (p2p) and records the local event.
-int slabFinishExchange(akua_pbf_solver* s, SlabTicket* t) {
-    SlabState& sl = s->slab;
-    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    t->epoch = 0;
-    t->valid = true;
-    if (sl.p2p) {
-        t->epoch = ++sl.epoch;
-        if (hasL) { slab::k_signal_flag<<<1, 1, 0, sl.commStream>>>(sl.peerL.flags + 1, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
-        if (hasR) { slab::k_signal_flag<<<1, 1, 0, sl.commStream>>>(sl.peerR.flags + 0, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
-    }
-    t->ev = slabNextEvent(s);
-    AK_CUDA(s, cudaEventRecord(t->ev, sl.commStream));
-    return AKUA_OK;
-}
-// Asynchronous ghost-plane exchange: ordered after the main stream's work so far, runs on the comm stream.
-template <typename T>
-int slabExchangeAsync(akua_pbf_solver* s, T* arr, SlabTicket* t) {
-    int rc;
-    if ((rc = slabCommAfterMain(s))) return rc;
-    if ((rc = slabPlanesOnComm(s, arr))) return rc;
-    return slabFinishExchange(s, t);
-}
-template <typename T, typename U>
-int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, SlabTicket* t) {
-    int rc;
-    if ((rc = slabCommAfterMain(s))) return rc;
-    if ((rc = slabPlanesOnComm(s, a))) return rc;
-    if ((rc = slabPlanesOnComm(s, b))) return rc;
-    return slabFinishExchange(s, t);
-}
-// Main stream: do not run past this point before the exchange behind `t` has delivered this rank's ghosts (and has
-// finished reading this rank's planes).
-int slabWait(akua_pbf_solver* s, const SlabTicket& t) {
-    SlabState& sl = s->slab;
-    if (!t.valid) return AKUA_OK;
-    if (t.ev) AK_CUDA(s, cudaStreamWaitEvent(s->stream, t.ev, 0));
-    if (sl.p2p) {
-        const int hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-        if (hasL || hasR) {
-            slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags, hasL, hasR, t.epoch, sl.dCounts + 31, kFlagWaitCycles);
-            AK_LAUNCH_CHECK(s, "k_wait_flags");
-        }
-    }
-    return AKUA_OK;
-}
-// Fused path: the boundary kernel that just ran on the main stream already stored its planes into the neighbours' ghost
-// regions (PeerPush); all that is left is to publish the epoch, in stream order right behind that kernel.
-int slabSignalAfterKernel(akua_pbf_solver* s, SlabTicket* t) {
-    SlabState& sl = s->slab;
-    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    t->valid = true; t->ev = nullptr; t->epoch = ++sl.epoch;
-    if (hasL) { slab::k_signal_flag<<<1, 1, 0, s->stream>>>(sl.peerL.flags + 1, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
-    if (hasR) { slab::k_signal_flag<<<1, 1, 0, s->stream>>>(sl.peerR.flags + 0, t->epoch); AK_LAUNCH_CHECK(s, "k_signal_flag"); }
-    sl.exchanges++;
-    return AKUA_OK;
-}
-int slabHalo(akua_pbf_solver* s, const SlabTicket& waitFor, SlabTicket* out, bool launchHappens, HaloSync* hs) {
-    SlabState& sl = s->slab;
-    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    *hs = HaloSync{};
-    hs->errWord = sl.dCounts + 31;
-    if (!launchHappens) {
-        // no boundary particles on this rank: nothing reads ghosts, but the neighbours still expect the epoch
-        if (out) return slabSignalAfterKernel(s, out);
-        return AKUA_OK;
-    }
-    if (waitFor.valid) {
-        if (waitFor.ev) AK_CUDA(s, cudaStreamWaitEvent(s->stream, waitFor.ev, 0));
-        hs->waitFlags = sl.flags; hs->waitL = hasL ? 1 : 0; hs->waitR = hasR ? 1 : 0; hs->waitEpoch = waitFor.epoch;
-    }
-    if (out) {
-        out->valid = true; out->ev = nullptr; out->epoch = ++sl.epoch;
-        hs->signalL = hasL ? sl.peerL.flags + 1 : nullptr;
-        hs->signalR = hasR ? sl.peerR.flags + 0 : nullptr;
-        hs->signalEpoch = out->epoch;
-        hs->doneCounter = sl.flags + 3;
-        sl.exchanges++;
-    }
-    return AKUA_OK;
-}
-template <typename T>
 PeerPush slabPush(const akua_pbf_solver* s, T* arr) {
     const SlabState& sl = s->slab;
     PeerPush pp;
     if (!sl.p2p) return pp;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    const uint32_t nOwn = (uint32_t)s->n;
-    if (hasL && sl.nPlaneL) { T* d = peerOf(s, sl.peerL, arr); if (d) { pp.dstL = d + sl.peerL.ghostBaseR; pp.nL = sl.nPlaneL; } }
-    if (hasR && sl.nPlaneR) { T* d = peerOf(s, sl.peerR, arr); if (d) { pp.dstR = d + sl.peerR.ghostBaseL; pp.startR = nOwn - sl.nPlaneR; } }
+    // my first plane -> the left rank's "from the right" ghost region; my last plane -> the right rank's "from the left"
+    if (hasL) { T* d = peerOf(s, sl.peerL, arr); if (d) pp.dstL = d + sl.peerL.ghostBaseR; }
+    if (hasR) { T* d = peerOf(s, sl.peerR, arr); if (d) pp.dstR = d + sl.peerR.ghostBaseL; }
+    pp.dims = sl.dims;   // plane sizes are resolved on the device
     return pp;
 }
-// Blocking flavour: the main stream waits for the exchange.
-template <typename T>
-int slabExchangePlanes(akua_pbf_solver* s, T* arr) {
-    if (!s->slab.enabled) return AKUA_OK;
-    SlabTicket t;
-    int rc = slabExchangeAsync(s, arr, &t);
-    if (rc) return rc;
-    return slabWait(s, t);
+HaloSync slabHalo(const akua_pbf_solver* s, int waitIdx, int signalIdx) {
+    const SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    HaloSync hs;
+    hs.waitFlags = sl.flags; hs.waitL = hasL ? 1 : 0; hs.waitR = hasR ? 1 : 0; hs.waitIdx = waitIdx;
+    hs.signalL = hasL ? sl.peerL.flags + 1 : nullptr;
+    hs.signalR = hasR ? sl.peerR.flags + 0 : nullptr;
+    hs.signalIdx = signalIdx;
+    hs.doneCounter = sl.flags + 3;
+    hs.dims = sl.dims;
+    hs.timeoutCycles = kFlagWaitCycles;
+    return hs;
 }
+// NCCL fallback: blocking (in stream order on the main stream) exchange of the boundary planes of `arr`, host-known sizes.
+template <typename T>
+int slabNcclPlanes(akua_pbf_solver* s, T* arr) {
+    SlabState& sl = s->slab;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    const size_t nOwn = (size_t)s->n;
+    ncclComm_t comm = (ncclComm_t)sl.comm;
+    cudaStream_t st = s->stream;
+    AK_NCCL(s, g_nccl.GroupStart());
+    if (hasL && sl.nPlaneL) AK_NCCL(s, g_nccl.Send(arr, (size_t)sl.nPlaneL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
+    if (hasR && sl.nPlaneR) AK_NCCL(s, g_nccl.Send(arr + (nOwn - sl.nPlaneR), (size_t)sl.nPlaneR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
+    if (hasL && sl.nGhostL) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseL, (size_t)sl.nGhostL * sizeof(T), ncclUint8, sl.rank - 1, comm, st));
+    if (hasR && sl.nGhostR) AK_NCCL(s, g_nccl.Recv(arr + sl.ghostBaseR, (size_t)sl.nGhostR * sizeof(T), ncclUint8, sl.rank + 1, comm, st));
+    AK_NCCL(s, g_nccl.GroupEnd());
+    return AKUA_OK;
+}
+// p2p: pushes the boundary planes of `arr` with a small copy kernel (no sweep produces them) and publishes exchange `idx`.
+template <typename T>
+int slabPushPlanes(akua_pbf_solver* s, T* arr, int idx) {
+    SlabState& sl = s->slab;
+    if (!sl.p2p) return slabNcclPlanes(s, arr);
+    const PeerPush pp = slabPush(s, arr);
+    const HaloSync hs = slabHalo(s, -1, idx);
+    launchK(s, slab::k_push_planes<T>, std::max(1u, gridFor(sl.estBnd)), kBlock, (const T*)arr, pp, hs);
+    AK_LAUNCH_CHECK(s, "k_push_planes");
+    return AKUA_OK;
+}
+
 // Packed gather layout in x-slab mode: pass B / K12 read ghosts through the packed (x*, lambda) / (x, |omega|) arrays and the
 // sweeps multiply by ONE mass, so the layout is only used when every particle of every rank has the same mass and every
 // rank holds the packed arrays. Global uniformity cannot change through migration, only through uploads, so the verdict is
@@ -239,7 +219,7 @@ int slabAgreeMass(akua_pbf_solver* s) {
         else { lo = 0u; hi = 0xffffffffu; }
     }
     uint32_t msg[4] = {lo, ~hi, (s->xl && s->xw) ? 1u : 0u, 0u};
-    uint32_t* d = sl.dCounts + 8;                             // words 8..11 are not used by the step
+    uint32_t* d = sl.dims + D_MASS;                           // words 8..11 are not used by the step
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     AK_CUDA(s, cudaMemcpy(d, msg, sizeof(msg), cudaMemcpyHostToDevice));
     AK_NCCL(s, g_nccl.AllReduce(d, d, 4, ncclUint32, ncclMin, (ncclComm_t)sl.comm, sl.commStream));
@@ -252,73 +232,68 @@ int slabAgreeMass(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
-// Interior / boundary index spans of the owned range for the current step's plane sizes.
-SweepSpans sweepSpans(const akua_pbf_solver* s) {
-    const SlabState& sl = s->slab;
-    const uint32_t n = (uint32_t)s->n, pl = sl.nPlaneL, pr = sl.nPlaneR;
-    SweepSpans sp;
-    if ((uint64_t)pl + pr >= n) {  // slab only one or two planes wide: everything is boundary
-        sp.boundary = Span{n, 0u, 0xffffffffu, 0u};
-        sp.interior = Span{0u, 0u, 0xffffffffu, 0u};
-    } else {
-        sp.boundary = Span{pl + pr, 0u, pl, n - pr - pl};
-        sp.interior = Span{n - pl - pr, pl, 0xffffffffu, 0u};
-    }
-    return sp;
+// ---- the slab step ------------------------------------------------------------------------------------------------------
+// Launch-size estimates from the (asynchronously refreshed, possibly a step or two old) pinned mirror of dims. Bucketed with
+// hysteresis so that the CUDA graph of the step, whose grids they fix, is re-captured rarely.
+void slabEstimate(uint32_t actual, uint32_t bucket, uint32_t* est) {
+    if (actual > *est || (uint64_t)actual + 2ull * bucket < *est || *est == 0)
+        *est = (uint32_t)(((uint64_t)actual + bucket / 2 + bucket) / bucket * bucket);
+}
+void slabUpdateEstimates(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    const uint32_t cap = (uint32_t)s->capacity;
+    const uint32_t bN = std::max(8192u, cap / 128), bS = std::max(2048u, cap / 1024);
+    slabEstimate(sl.hDims[D_N], bN, &sl.estN);
+    slabEstimate(sl.hDims[D_PLANE_L] + sl.hDims[D_PLANE_R], bS, &sl.estBnd);
+    slabEstimate(sl.hDims[D_GHOST_L] + sl.hDims[D_GHOST_R], bS, &sl.estGhost);
+    slabEstimate(sl.hDims[D_IN_L] + sl.hDims[D_IN_R], bS, &sl.estIn);
+    sl.estN = std::min(sl.estN, cap);
 }
 
-// The one count exchange of a step: three u32 to each neighbour (assembled by k_mig_scan at dCounts[16..18] for the left
-// rank, [20..22] for the right rank), three from each (landing at [24..26] from the left, [28..30] from the right), then
-// all 32 counters go to the host — the only host synchronisation of the step.
-int slabSwapCounts(akua_pbf_solver* s) {
+// Slab-local cell grid: the global grid of the box (shared by all ranks: same y / z extent and origin) restricted in x to this
+// rank's planes plus, towards each neighbour, the ghost plane and one "far" plane into which everything beyond is clamped (a
+// leaver that lands deeper than the neighbour's boundary plane must not be counted into that plane). Keys are therefore
+// slab-relative: a 64 M-particle scene on 8 GPUs sorts 22-bit keys (3 digit passes) and clears an 8th of the cell table.
+int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     SlabState& sl = s->slab;
+    if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
+    int3 gmin, gdim;
+    const int64_t cellsGlobal = layout_linear_grid(s->cfg.smoothRadius, bmin, bmax, &gmin, &gdim);
+    if (cellsGlobal < 0) { s->err = "box max must exceed box min"; return AKUA_ERR_INVALID; }
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
-    if (sl.p2p) {
-        // CUDA-IPC transport: counters (and, through k_mig_pack, the migration records) are stored straight into the
-        // neighbours' memory; everything stays on the main stream — no NCCL kernel, no stream hop.
-        const uint32_t epoch = ++sl.countEpoch;
-        slab::k_publish_counts<<<1, 32, 0, s->stream>>>(sl.dCounts, hasL ? sl.peerL.dCounts : nullptr, hasR ? sl.peerR.dCounts : nullptr,
-                                                        hasL ? sl.peerL.flags + 5 : nullptr, hasR ? sl.peerR.flags + 4 : nullptr, epoch);
-        AK_LAUNCH_CHECK(s, "k_publish_counts");
-        slab::k_wait_flags<<<1, 1, 0, s->stream>>>(sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, epoch, sl.dCounts + 31, kFlagWaitCycles);
-        AK_LAUNCH_CHECK(s, "k_wait_flags");
-        AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-        AK_CUDA(s, cudaStreamSynchronize(s->stream));
-        if (!hasL) sl.hCounts[24] = sl.hCounts[25] = sl.hCounts[26] = 0;
-        if (!hasR) sl.hCounts[28] = sl.hCounts[29] = sl.hCounts[30] = 0;
-        return AKUA_OK;
+    // ownership in global grid planes; the end ranks own the clamped border planes too
+    const int xLoG = !hasL ? 0 : std::min(std::max(sl.xLoAbs - gmin.x, 0), gdim.x);
+    const int xHiG = !hasR ? gdim.x : std::min(std::max(sl.xHiAbs - gmin.x, 0), gdim.x);
+    if (xHiG <= xLoG) { s->err = "slab is empty in the current grid (box does not cover this rank's x range)"; return AKUA_ERR_INVALID; }
+    if (xHiG - xLoG < 2 && sl.nranks > 1) { s->err = "slab must be at least two x planes wide"; return AKUA_ERR_INVALID; }
+    const int x0 = hasL ? std::max(xLoG - 2, 0) : 0, x1 = hasR ? std::min(xHiG + 2, gdim.x) : gdim.x;
+    const int64_t cells = (int64_t)(x1 - x0) * gdim.y * gdim.z;
+    if (cells + 1 >= (int64_t)1 << 31) { s->err = "LINEAR_CELL grid too large (>= 2^31 cells)"; return AKUA_ERR_INVALID; }
+    if (cells > s->cellCapacity) {
+        if (s->cellRange) { AK_CUDA(s, cudaStreamSynchronize(s->stream)); AK_CUDA(s, cudaFree(s->cellRange)); }
+        s->cellRange = nullptr;
+        AK_CUDA(s, dalloc(&s->cellRange, (size_t)cells));
+        s->cellCapacity = cells;
     }
-    ncclComm_t comm = (ncclComm_t)sl.comm;
-    cudaStream_t st = sl.commStream;
-    int rc;
-    if ((rc = slabCommAfterMain(s))) return rc;
-    AK_NCCL(s, g_nccl.GroupStart());
-    if (hasL) AK_NCCL(s, g_nccl.Send(sl.dCounts + 16, 12, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR) AK_NCCL(s, g_nccl.Send(sl.dCounts + 20, 12, ncclUint8, sl.rank + 1, comm, st));
-    if (hasL) AK_NCCL(s, g_nccl.Recv(sl.dCounts + 24, 12, ncclUint8, sl.rank - 1, comm, st));
-    if (hasR) AK_NCCL(s, g_nccl.Recv(sl.dCounts + 28, 12, ncclUint8, sl.rank + 1, comm, st));
-    AK_NCCL(s, g_nccl.GroupEnd());
-    AK_CUDA(s, cudaMemcpyAsync(sl.hCounts, sl.dCounts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    AK_CUDA(s, cudaStreamSynchronize(st));
-    if (!hasL) sl.hCounts[24] = sl.hCounts[25] = sl.hCounts[26] = 0;
-    if (!hasR) sl.hCounts[28] = sl.hCounts[29] = sl.hCounts[30] = 0;
+    s->grid.gridMin = make_int3(gmin.x + x0, gmin.y, gmin.z);
+    s->grid.gridDim = make_int3(x1 - x0, gdim.y, gdim.z);
+    s->ctr.num_cells = cells;
+    sl.xLoL = xLoG - x0; sl.xHiL = xHiG - x0; sl.planeOffset = x0; sl.gxGlobal = gdim.x;
+    sl.sentinel = (uint32_t)cells;                 // one past the last valid key: leavers sort behind the owned range
+    sl.sortBits = bitsFor((uint64_t)cells);
+    s->keyBits = sl.sortBits;
     return AKUA_OK;
 }
 
-int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
+int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
     SlabState& sl = s->slab;
-    if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
-    int rc = layoutGrid(s, bmin, bmax);
-    if (rc) return rc;
+    int rc;
     const GridParams& G = s->grid;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
-    // ownership in grid-relative x planes; the end ranks own the clamped border planes too
-    int xLo = sl.rank == 0 ? 0 : std::min(std::max(sl.xLoAbs - G.gridMin.x, 0), G.gridDim.x);
-    int xHi = sl.rank + 1 == sl.nranks ? G.gridDim.x : std::min(std::max(sl.xHiAbs - G.gridMin.x, 0), G.gridDim.x);
-    if (xHi <= xLo) { s->err = "slab is empty in the current grid (box does not cover this rank's x range)"; return AKUA_ERR_INVALID; }
-    const uint32_t sentinel = (uint32_t)s->ctr.num_cells;  // one past the last valid key
-    const int sortBits = bitsFor((uint64_t)sentinel);
-    uint32_t n = (uint32_t)s->n;
+    const int xLo = sl.xLoL, xHi = sl.xHiL;
+    const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+    const bool p2p = sl.p2p;
+    uint32_t* dims = sl.dims;
 
     // ---- 1. predict + key (PBFSolver.cpp:30 + K2) ----
     mark(s, PH_PREDICT);
@@ -326,109 +301,101 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
 
     // ---- 2. migration: leavers out (sentinel key), arrivals appended ----
     mark(s, PH_SORT);
-    const uint32_t blocks = std::max(1u, gridFor(n));
-    if (blocks > sl.migBlocksCap) { s->err = "slab: migration scratch too small"; return AKUA_ERR_INVALID; }
-    if (xHi - xLo < 2 && sl.nranks > 1) { s->err = "slab must be at least two x planes wide"; return AKUA_ERR_INVALID; }
-    AK_CUDA(s, cudaMemsetAsync(sl.dCounts + 2, 0, 4 * sizeof(uint32_t), s->stream));   // the four plane populations
-    slab::k_mig_count<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sl.dCounts + 2);
+    const uint32_t migGrid = std::max(1u, std::min(gridFor(sl.estN), sl.migBlocksCap));
+    AK_CUDA(s, cudaMemsetAsync(dims + D_STAY_FIRST, 0, 4 * sizeof(uint32_t), s->stream));   // the four plane populations
+    launchPlain(s->stream, slab::k_mig_count, migGrid, kBlock, s->keysUnsorted, dims + D_N, planeCells, xLo, xHi, sl.blockCnt,
+                                                         sl.migBlocksCap, dims + D_STAY_FIRST);
     AK_LAUNCH_CHECK(s, "k_mig_count");
-    slab::k_mig_scan<<<1, 1024, 0, s->stream>>>(sl.blockCnt, blocks, sl.dCounts);
+    launchPlain(s->stream, slab::k_mig_scan, 1, 1024, sl.blockCnt, dims + D_N, sl.migBlocksCap, dims);
     AK_LAUNCH_CHECK(s, "k_mig_scan");
     // p2p transport: leavers are packed straight into the neighbours' inboxes (my left neighbour receives them "from its
     // right"); otherwise into local send buffers that NCCL ships after the count exchange
-    const bool hasLn = sl.rank > 0, hasRn = sl.rank + 1 < sl.nranks;
-    slab::MigRecord* outBufL = (sl.p2p && hasLn) ? sl.peerL.recvR : sl.sendL;
-    slab::MigRecord* outBufR = (sl.p2p && hasRn) ? sl.peerR.recvL : sl.sendR;
+    slab::MigRecord* outBufL = (p2p && hasL) ? sl.peerL.recvR : sl.sendL;
+    slab::MigRecord* outBufR = (p2p && hasR) ? sl.peerR.recvL : sl.sendR;
     uint32_t packCap = sl.migCap;
-    if (sl.p2p && hasLn) packCap = std::min(packCap, sl.peerL.migCap);
-    if (sl.p2p && hasRn) packCap = std::min(packCap, sl.peerR.migCap);
-    slab::k_mig_pack<<<blocks, kBlock, 0, s->stream>>>(s->keysUnsorted, n, planeCells, xLo, xHi, sl.blockCnt, sentinel, s->pos,
-                                                       s->vel, s->xs, s->id, outBufL, outBufR, packCap);
+    if (p2p && hasL) packCap = std::min(packCap, sl.peerL.migCap);
+    if (p2p && hasR) packCap = std::min(packCap, sl.peerR.migCap);
+    launchPlain(s->stream, slab::k_mig_pack, migGrid, kBlock, s->keysUnsorted, dims, planeCells, xLo, xHi, sl.blockCnt, sl.migBlocksCap,
+                                                        sl.sentinel, s->pos, s->vel, s->xs, s->id, sl.slot, s->color, s->size,
+                                                        sl.freeSlots, outBufL, outBufR, packCap);
     AK_LAUNCH_CHECK(s, "k_mig_pack");
-    if ((rc = slabSwapCounts(s))) return rc;
-    const uint32_t* hc = sl.hCounts;
-    if (hc[31] == 2) { s->err = "slab p2p: timed out waiting for a neighbour's ghost planes in the previous step"; return AKUA_ERR_COMM; }
-    if (hc[31]) { s->err = "slab: boundary-plane size prediction failed in the previous step (a particle crossed more than one slab?)"; return AKUA_ERR_INVALID; }
-    const uint32_t outL = hc[0], outR = hc[1], inL = hc[24], inR = hc[28];
-    // Post-migration plane sizes, known before the sort: my boundary planes = stayers + arrivals that land in them;
-    // a neighbour's facing plane (= my ghosts) = its stayers there + my leavers that land there. (Arrivals from the far
-    // side cannot reach the near plane: slabs are >= 2 planes wide and the stepper moves particles by << one slab.)
-    sl.nPlaneL = hasLn ? hc[2] + hc[25] : 0;
-    sl.nPlaneR = hasRn ? hc[3] + hc[29] : 0;
-    sl.nGhostL = hasLn ? hc[26] + hc[4] : 0;
-    sl.nGhostR = hasRn ? hc[30] + hc[5] : 0;
-    if (sl.rank == 0 && outL) { s->err = "slab: internal error (leavers beyond the first rank)"; return AKUA_ERR_INVALID; }
-    if (outL > packCap || outR > packCap || inL > sl.migCap || inR > sl.migCap) { s->err = "slab: migration buffer overflow (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
-    if ((uint64_t)n + inL + inR > (uint64_t)sl.ghostBaseL) { s->err = "slab: particle capacity exceeded by arrivals (raise capacity_factor)"; return AKUA_ERR_ALLOC; }
-    if (sl.p2p) {   // the records arrived with the count message
-        sl.exchanges++;
-        sl.bytesSent += ((size_t)outL + outR) * sizeof(slab::MigRecord);
+    slab::PlanCaps caps{};
+    caps.packCap = packCap; caps.migCap = sl.migCap; caps.ownedCap = sl.ghostBaseL; caps.ghostCap = sl.ghostCap;
+    caps.planeCapL = hasL ? (p2p ? std::min(sl.ghostCap, sl.peerL.ghostCap) : sl.ghostCap) : 0;
+    caps.planeCapR = hasR ? (p2p ? std::min(sl.ghostCap, sl.peerR.ghostCap) : sl.ghostCap) : 0;
+    caps.slotCap = (uint32_t)s->capacity;
+    if (p2p) {
+        // the count message and the records travel by P2P stores; the plan kernel waits for the neighbours' message in-kernel
+        launchPlain(s->stream, slab::k_publish_counts, 1, 32, dims, hasL ? sl.peerL.dims : nullptr, hasR ? sl.peerR.dims : nullptr,
+                                                        hasL ? sl.peerL.flags + 5 : nullptr, hasR ? sl.peerR.flags + 4 : nullptr);
+        AK_LAUNCH_CHECK(s, "k_publish_counts");
+        launchPlain(s->stream, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 1, caps, kFlagWaitCycles);
+        AK_LAUNCH_CHECK(s, "k_slab_plan");
     } else {
-        const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
+        // NCCL fallback: count messages, then ONE host synchronisation (the record sizes are needed on the host), then records
         ncclComm_t comm = (ncclComm_t)sl.comm;
-        cudaStream_t st = sl.commStream;   // already ordered after the pack kernel by the count swap's host sync
+        cudaStream_t st = s->stream;
+        AK_NCCL(s, g_nccl.GroupStart());
+        if (hasL) AK_NCCL(s, g_nccl.Send(dims + D_MSG_TO_L, 12, ncclUint8, sl.rank - 1, comm, st));
+        if (hasR) AK_NCCL(s, g_nccl.Send(dims + D_MSG_TO_R, 12, ncclUint8, sl.rank + 1, comm, st));
+        if (hasL) AK_NCCL(s, g_nccl.Recv(dims + D_MSG_FROM_L, 12, ncclUint8, sl.rank - 1, comm, st));
+        if (hasR) AK_NCCL(s, g_nccl.Recv(dims + D_MSG_FROM_R, 12, ncclUint8, sl.rank + 1, comm, st));
+        AK_NCCL(s, g_nccl.GroupEnd());
+        launchPlain(st, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 0, caps, kFlagWaitCycles);
+        AK_LAUNCH_CHECK(s, "k_slab_plan");
+        AK_CUDA(s, cudaMemcpyAsync((void*)sl.hDims, dims, D_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        AK_CUDA(s, cudaStreamSynchronize(st));
+        if ((rc = slabCheckError(s))) return rc;
+        const uint32_t outL = sl.hDims[D_OUT_L], outR = sl.hDims[D_OUT_R], inL = sl.hDims[D_IN_L], inR = sl.hDims[D_IN_R];
         AK_NCCL(s, g_nccl.GroupStart());
         if (hasL && outL) AK_NCCL(s, g_nccl.Send(sl.sendL, (size_t)outL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, st));
         if (hasR && outR) AK_NCCL(s, g_nccl.Send(sl.sendR, (size_t)outR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, st));
         if (hasL && inL) AK_NCCL(s, g_nccl.Recv(sl.recvL, (size_t)inL * sizeof(slab::MigRecord), ncclUint8, sl.rank - 1, comm, st));
         if (hasR && inR) AK_NCCL(s, g_nccl.Recv(sl.recvR, (size_t)inR * sizeof(slab::MigRecord), ncclUint8, sl.rank + 1, comm, st));
         AK_NCCL(s, g_nccl.GroupEnd());
-        {
-            cudaEvent_t e = slabNextEvent(s);
-            AK_CUDA(s, cudaEventRecord(e, st));
-            AK_CUDA(s, cudaStreamWaitEvent(s->stream, e, 0));
-        }
-        sl.exchanges++;
-        sl.bytesSent += ((size_t)outL + outR) * sizeof(slab::MigRecord);
+        // the host now knows this step's sizes exactly
+        s->n = sl.hDims[D_NOWN];
+        sl.nPlaneL = sl.hDims[D_PLANE_L]; sl.nPlaneR = sl.hDims[D_PLANE_R];
+        sl.nGhostL = sl.hDims[D_GHOST_L]; sl.nGhostR = sl.hDims[D_GHOST_R];
+        sl.estN = std::max<uint32_t>(sl.estN, (uint32_t)sl.hDims[D_NPRE]);
     }
-    if (inL) { slab::k_mig_unpack<<<gridFor(inL), kBlock, 0, s->stream>>>(sl.recvL, inL, n, s->pos, s->vel, s->xs, s->id, s->keysUnsorted, G); AK_LAUNCH_CHECK(s, "k_mig_unpack"); }
-    if (inR) { slab::k_mig_unpack<<<gridFor(inR), kBlock, 0, s->stream>>>(sl.recvR, inR, n + inL, s->pos, s->vel, s->xs, s->id, s->keysUnsorted, G); AK_LAUNCH_CHECK(s, "k_mig_unpack"); }
-    const uint32_t nPre = n + inL + inR;
-    const uint32_t nOwn = nPre - outL - outR;
-    sl.migratedIn += inL + inR; sl.migratedOut += outL + outR;
+    launchPlain(s->stream, slab::k_mig_unpack, std::max(1u, gridFor(sl.estIn)), kBlock, sl.recvL, sl.recvR, dims, s->pos, s->vel, s->xs, s->id,
+        sl.slot, s->color, s->size, sl.freeSlots, s->keysUnsorted, G, xLo, xHi);
+    AK_LAUNCH_CHECK(s, "k_mig_unpack");
 
     // ---- 3. sort everything resident (leavers end up past nOwn), reorder the owned range, owned cell ranges ----
     AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
-    if (nPre) {
-        int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, nPre, sortBits, s->sortWs, s->stream,
-                                         &s->keysSorted, &s->perm, usePdl(s));
+    {
+        const uint32_t nSort = std::min<uint32_t>(sl.estN + sl.estIn, (uint32_t)s->capacity);
+        int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, nSort, sl.sortBits, s->sortWs, s->stream,
+                                         &s->keysSorted, &s->perm, usePdl(s), dims + D_NPRE);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
         s->ctr.kernel_launches += launches;
         s->ctr.sort_passes_last = launches / 3;
     }
     mark(s, PH_REORDER);
-    s->n = nOwn;
-    if (nOwn) {
-        launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(nOwn), kBlock, s->keysSorted, s->perm, nOwn, s->pos, s->vel, s->xs, s->id,
-            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
-        AK_LAUNCH_CHECK(s, "k_reorder_ranges");
-    }
+    launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(sl.estN), kBlock, s->keysSorted, s->perm, sl.estN, dims + D_NOWN, s->pos, s->vel, s->xs,
+        s->id, s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange, sl.slot, sl.slotAlt);
+    AK_LAUNCH_CHECK(s, "k_reorder_ranges");
     std::swap(s->pos, s->posAlt); std::swap(s->vel, s->velAlt); std::swap(s->xs, s->xsAlt); std::swap(s->id, s->idAlt);
+    std::swap(sl.slot, sl.slotAlt);
 
-    // ---- 4. ghost planes: sizes, then x* of the neighbours' boundary planes, keyed and ranged in place ----
-    slab::k_plane_verify<<<1, 32, 0, s->stream>>>(s->keysSorted, nOwn, planeCells, xLo, xHi, sl.nPlaneL, sl.nPlaneR,
-                                                 hasLn ? 1 : 0, hasRn ? 1 : 0, sl.dCounts);
+    // ---- 4. ghost planes: x* of the neighbours' boundary planes (exchange 1), keyed and ranged in place ----
+    launchPlain(s->stream, slab::k_plane_verify, 1, 32, s->keysSorted, planeCells, xLo, xHi, hasL ? 1 : 0, hasR ? 1 : 0, dims);
     AK_LAUNCH_CHECK(s, "k_plane_verify");
-    if (sl.nGhostL > sl.ghostCap || sl.nGhostR > sl.ghostCap || sl.nPlaneL > sl.ghostCap || sl.nPlaneR > sl.ghostCap) {
-        s->err = "slab: boundary plane larger than the ghost region (raise capacity_factor)"; return AKUA_ERR_ALLOC;
-    }
-    if ((rc = slabExchangePlanes(s, s->xs))) return rc;
-    for (int side = 0; side < 2; side++) {   // ghost planes: keys from the received x*, then their cell ranges
-        const uint32_t cntG = side == 0 ? sl.nGhostL : sl.nGhostR, base = side == 0 ? sl.ghostBaseL : sl.ghostBaseR;
-        if (!cntG) continue;
-        float3 g0 = make_float3(0, 0, 0);
-        launchK(s, k_predict_key<KEY_LINEAR>, gridFor(cntG), kBlock, nullptr, nullptr, s->xs + base, s->keysSorted + base, cntG, 0.0f, g0, G, 0);
-        AK_LAUNCH_CHECK(s, "k_predict_key(ghosts)");
-        slab::k_ranges<<<gridFor(cntG), kBlock, 0, s->stream>>>(s->keysSorted, base, base + cntG, s->cellRange);
-        AK_LAUNCH_CHECK(s, "k_ranges(ghosts)");
+    if ((rc = slabPushPlanes(s, s->xs, 1))) return rc;
+    {
+        const HaloSync hs = p2p ? slabHalo(s, 1, -1) : HaloSync{};
+        launchK(s, slab::k_ghost_ranges, std::max(1u, gridFor(sl.estGhost)), kBlock, (const float4*)s->xs, s->keysSorted, (const uint32_t*)dims,
+                sl.ghostBaseL, sl.ghostBaseR, s->cellRange, G, hs);
+        AK_LAUNCH_CHECK(s, "k_ghost_ranges");
     }
 
     // ---- 5. neighbour lists of the owned particles (candidates include the ghost planes) ----
     mark(s, PH_LISTS);
-    if ((rc = launchBuildNeighbours(s, nOwn))) return rc;
+    if ((rc = launchBuildNeighbours(s))) return rc;
 
-    sl.pending = SlabTicket{};
     // ---- 6. constraint solve and post-solve on the owned range, with the per-pass ghost exchanges inside ----
     mark(s, PH_SOLVE);
     bool committed = false;
@@ -436,10 +403,20 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     if (!committed) {  // solverIterations == 0
         if ((rc = phaseUpdate(s, dt))) return rc;
         if ((rc = phaseDamping(s, bmin, bmax))) return rc;
-        if ((rc = slabExchangeAsync(s, s->vel, &sl.pending))) return rc;
+        if ((rc = slabPushPlanes(s, s->vel, 2))) return rc;
     }
     mark(s, PH_POST);
-    if ((rc = phasePost(s, dt))) return rc;
+    if ((rc = phasePost(s, dt, iterations))) return rc;
+    // ---- 7. close the step on the device and refresh the host's (asynchronous) view of its sizes ----
+    {
+        // bytes pushed per boundary-plane particle over the step: x* (16) once, per iteration (x*, lambda) 16 + x* 16,
+        // v 16 after the commit, (x, |omega|) 16, v 16
+        const uint32_t planeBytes = 16u + 32u * (uint32_t)iterations + 16u + 32u;
+        launchPlain(s->stream, slab::k_step_end, 1, 32, dims, (uint32_t)slabExchangesPerStep(iterations), planeBytes);
+        AK_LAUNCH_CHECK(s, "k_step_end");
+        AK_CUDA(s, cudaMemcpyAsync((void*)sl.hDims, dims, D_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    }
+    sl.exchanges += slabExchangesPerStep(iterations);
     mark(s, PH_END);
     s->timingValid = s->timing;
     s->ctr.steps++;
@@ -454,8 +431,12 @@ int stepSlab(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
 int slabRebalance(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     if (!sl.enabled || !s->haveBox) { s->err = "rebalance: slab mode with at least one completed step required"; return AKUA_ERR_INVALID; }
-    const GridParams& G = s->grid;
-    const int gx = G.gridDim.x, R = sl.nranks;
+    {
+        int rcr = slabRefresh(s);   // exact owned count; reports any pending device-side error
+        if (rcr) return rcr;
+    }
+    const GridParams& G = s->grid;   // slab-local grid of the last step; plane p of it is global plane planeOffset + p
+    const int gx = sl.gxGlobal, R = sl.nranks;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
     const size_t words = (size_t)gx + R;  // [0,gx): plane counts; [gx, gx+R): current lower bounds (grid-relative)
     if (words > sl.histCap) {
@@ -468,9 +449,9 @@ int slabRebalance(akua_pbf_solver* s) {
     }
     AK_CUDA(s, cudaMemsetAsync(sl.dHist, 0, words * sizeof(unsigned long long), s->stream));
     const uint32_t n = (uint32_t)s->n;
-    slab::k_plane_hist<<<(gx + 255) / 256, 256, 0, s->stream>>>(s->keysSorted, n, planeCells, gx, sl.dHist);
+    launchPlain(s->stream, slab::k_plane_hist, (G.gridDim.x + 255) / 256, 256, s->keysSorted, n, planeCells, G.gridDim.x, sl.planeOffset, sl.dHist);
     AK_LAUNCH_CHECK(s, "k_plane_hist");
-    const int curLo = sl.rank == 0 ? 0 : std::min(std::max(sl.xLoAbs - G.gridMin.x, 0), gx);
+    const int curLo = sl.rank == 0 ? 0 : sl.planeOffset + sl.xLoL;
     unsigned long long lo64 = (unsigned long long)curLo;
     AK_CUDA(s, cudaMemcpyAsync(sl.dHist + gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
     int rc;
@@ -487,8 +468,9 @@ int slabRebalance(akua_pbf_solver* s) {
         s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
-    sl.xLoAbs = G.gridMin.x + bounds[sl.rank];
-    sl.xHiAbs = G.gridMin.x + bounds[sl.rank + 1];
+    const int gminGlobalX = G.gridMin.x - sl.planeOffset;
+    sl.xLoAbs = gminGlobalX + bounds[sl.rank];
+    sl.xHiAbs = gminGlobalX + bounds[sl.rank + 1];
     sl.rebalances++;
     return AKUA_OK;
 }

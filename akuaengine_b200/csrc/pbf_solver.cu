@@ -33,7 +33,7 @@ namespace {
 #endif
 constexpr int kBlock = 256;
 constexpr int kSweepBlock = AKUA_SWEEP_BLOCK;
-inline Span fullSpan(uint32_t n) { return Span{n, 0u, 0xffffffffu, 0u}; }
+inline Span fullSpan(uint32_t n) { return Span{n, 0u, 0xffffffffu, 0u, nullptr, SPAN_FIXED}; }
 inline uint32_t sweepGrid(uint64_t n) { return (uint32_t)((n + kSweepBlock - 1) / kSweepBlock); }
 inline uint32_t gridFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
 
@@ -50,45 +50,50 @@ struct SlabPeer {            // a neighbour's allocations, opened through CUDA I
     float* omegaLen = nullptr;
     float4 *xl = nullptr, *xw = nullptr;                        // packed gather arrays (null when a rank has none)
     uint32_t* flags = nullptr;
-    uint32_t* dCounts = nullptr;                               // the neighbour's counter block (count exchange by P2P stores)
+    uint32_t* dims = nullptr;                                  // the neighbour's dims block (count exchange by P2P stores)
     slab::MigRecord *recvL = nullptr, *recvR = nullptr;       // the neighbour's migration inboxes
     uint32_t migCap = 0;
-    uint32_t ghostBaseL = 0, ghostBaseR = 0;
+    uint32_t ghostBaseL = 0, ghostBaseR = 0, ghostCap = 0;
 };
-struct SlabTicket { bool valid = false; cudaEvent_t ev = nullptr; uint32_t epoch = 0; };
 struct SlabState {
     bool enabled = false;
     int rank = 0, nranks = 1;
     void* comm = nullptr;                  // ncclComm_t
     int xLoAbs = 0, xHiAbs = 0;            // owned absolute x cells [lo, hi)
-    uint32_t* dCounts = nullptr;           // device u32[32]: 0,1 leavers L/R; 2..5 plane populations; 16..22 outgoing, 24..30
-                                           // incoming count messages; 31 sticky prediction-error flag
-    uint32_t* hCounts = nullptr;           // pinned mirror
+    uint32_t* dims = nullptr;              // device u32[D_WORDS]: every size of the current step (pbf_kernels.cuh D_*)
+    volatile uint32_t* hDims = nullptr;    // pinned mirror, refreshed asynchronously at the end of every step
     uint32_t* blockCnt = nullptr;          // [2][migBlocksCap]
     uint32_t migBlocksCap = 0;
     slab::MigRecord *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
     uint32_t migCap = 0;
+    uint32_t *slot = nullptr, *slotAlt = nullptr, *freeSlots = nullptr;   // render-payload slots (travel with the particles)
+    // host-side view of the sizes: exact after slabRefresh() (stream synchronised), otherwise an earlier step's
     uint32_t nPlaneL = 0, nPlaneR = 0, nGhostL = 0, nGhostR = 0;
-    int64_t exchanges = 0, bytesSent = 0, migratedIn = 0, migratedOut = 0;
-    cudaStream_t commStream = nullptr;     // high-priority stream all exchange traffic is issued on
+    // launch-size estimates (bucketed; kernels loop, so any estimate is correct) and the step's layout in the local grid
+    uint32_t estN = 1, estBnd = 1, estGhost = 1, estIn = 1;
+    int xLoL = 0, xHiL = 0;                // owned planes in slab-local grid coordinates
+    int planeOffset = 0;                   // local plane 0 in global grid planes
+    int gxGlobal = 0;
+    uint32_t sentinel = 0;
+    int sortBits = 1;
+    int64_t exchanges = 0;
+    cudaStream_t commStream = nullptr;     // set-up / re-balancing collectives and the NCCL fallback's traffic
     cudaStream_t bndStream = nullptr;      // boundary-plane sweeps run here, concurrently with the interior sweeps
     bool useBndStream = false;
     static constexpr int kEvents = 256;
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
-    SlabTicket pending;                    // the last asynchronous x* (/v) ghost exchange, not yet waited for
     // fixed ghost regions at the top of every per-particle array
     uint32_t ghostBaseL = 0, ghostBaseR = 0, ghostCap = 0;
-    // CUDA IPC transport
+    // CUDA IPC transport (default): pushes are P2P stores issued by the kernels that produce the data, waits are in-kernel;
+    // otherwise NCCL send/recv with one host synchronisation per step
     bool p2p = false;
-    bool fusedPush = false;                // p2p only: boundary kernels store straight into the neighbours' ghost regions
-                                           // (AKUA_SLAB_FUSED_PUSH=1); default: copy-engine pushes on the comm stream
+    bool graphBroken = false;              // a capture of the slab step failed once: stay eager
     SlabPeer peerL, peerR;
     void* xsBuf[2] = {nullptr, nullptr};   // this rank's two x* / velocity allocations (pointer identity across swaps)
     void* velBuf[2] = {nullptr, nullptr};
-    uint32_t* flags = nullptr;             // [0] epoch published by the left rank, [1] by the right rank
-    uint32_t epoch = 0;
-    uint32_t countEpoch = 0;               // p2p: epoch of the per-step count + migration message (flags[4] / flags[5])
+    uint32_t* flags = nullptr;             // [0]/[1] ghost-exchange epoch published by the left / right rank, [3] CTA
+                                           // completion counter, [4]/[5] epoch of the left / right rank's count message
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
     int64_t rebalances = 0;
@@ -128,6 +133,8 @@ struct akua_pbf_solver {
     uint32_t *keysSorted = nullptr, *perm = nullptr;  // alias keyA/B, valA/B after a sort
     uint32_t* bucketStart = nullptr;                  // REFERENCE_HASH: tableSize entries
     bool bucketsDirty = false;
+    uint32_t bucketsN = 0;                            // number of sorted keys the bucket table currently holds entries for
+    bool hashFromUpload = false;                      // Particle::hash of a download comes from the last upload until the next sort
     uint2* cellRange = nullptr;                       // LINEAR_CELL: numCells entries
     int64_t cellCapacity = 0;
     GridParams grid{};
@@ -153,13 +160,13 @@ struct akua_pbf_solver {
     // double buffer is current, so up to kGraphSlots graphs are cached, keyed by the pre-step state + parameters.
     struct GraphEntry {
         bool used = false;
-        uint64_t key[16] = {};
+        uint64_t key[20] = {};
         cudaGraphExec_t exec = nullptr;
         // host-side state after the step (the pointer swaps and flags the captured calls performed)
         float4 *pos, *posAlt, *vel, *velAlt, *xs, *xsAlt;
-        uint32_t *id, *idAlt, *keysSorted, *perm;
+        uint32_t *id, *idAlt, *keysSorted, *perm, *slot, *slotAlt;
         bool bucketsDirty;
-        int64_t launches, sortPasses;
+        int64_t launches, sortPasses, exchanges;
     };
     static constexpr int kGraphSlots = 4;
     GraphEntry graphs[kGraphSlots];
@@ -204,6 +211,17 @@ inline void launchK(const akua_pbf_solver* s, void (*kernel)(KArgs...), uint32_t
         at.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
     }
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Plain launch (no programmatic serialization) of a kernel that does not begin with pdl_wait(). Every launch of this file goes
+// through launchK / launchPlain / rsort::launch, i.e. cudaLaunchKernelEx: no <<<>>> syntax, so that the host code can also be
+// compiled by g++ against the SIMT emulator of tests/emu (test infrastructure: the whole C ABI, multi-rank step included, on
+// the CPU).
+template <typename... KArgs, typename... Args>
+inline void launchPlain(cudaStream_t st, void (*kernel)(KArgs...), uint32_t grid, uint32_t block, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = st;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -256,29 +274,37 @@ void mark(akua_pbf_solver* s, Phase p) {
 }
 
 // ---------------------------------------------------------------------------------------------------- phases
+// x-slab mode: the particle counts live on the device (dims); the host passes an ESTIMATE for the grid and a pointer to the
+// exact word. Single GPU: the host's count is exact and the pointer is null.
+inline bool slabOn(const akua_pbf_solver* s) { return s->slab.enabled; }
+inline uint32_t gridCount(const akua_pbf_solver* s) { return slabOn(s) ? s->slab.estN : (uint32_t)s->n; }
+inline const uint32_t* dimWord(const akua_pbf_solver* s, int w) { return slabOn(s) ? s->slab.dims + w : nullptr; }
+
 int phasePredictKey(akua_pbf_solver* s, float dt, bool doPredict, bool doKeys) {
-    const uint32_t n = (uint32_t)s->n;
+    const uint32_t n = gridCount(s);
     if (n == 0) return AKUA_OK;
     float3 g = make_float3(s->cfg.gravity[0], s->cfg.gravity[1], s->cfg.gravity[2]);
     uint32_t* keys = doKeys ? s->keysUnsorted : nullptr;
     if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH)
-        launchK(s, k_predict_key<KEY_HASH>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+        launchK(s, k_predict_key<KEY_HASH>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dimWord(s, D_N), dt, g, s->grid, doPredict ? 1 : 0);
     else
-        launchK(s, k_predict_key<KEY_LINEAR>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dt, g, s->grid, doPredict ? 1 : 0);
+        launchK(s, k_predict_key<KEY_LINEAR>, gridFor(n), kBlock, s->pos, s->vel, s->xs, keys, n, dimWord(s, D_N), dt, g, s->grid, doPredict ? 1 : 0);
     AK_LAUNCH_CHECK(s, "k_predict_key");
     return AKUA_OK;
 }
 
-// K4 launch over the first n (owned) particles: REFERENCE_HASH scans its buckets; LINEAR_CELL scans row ranges one candidate
-// at a time (default) or with the two-phase mask variants of list_build.cuh (options.list_build). Same lists either way.
-int launchBuildNeighbours(akua_pbf_solver* s, uint32_t n) {
+// K4 launch over the owned particles: REFERENCE_HASH scans its buckets; LINEAR_CELL scans row ranges one candidate
+// at a time or with the two-phase mask variants of list_build.cuh (options.list_build). Same lists either way.
+int launchBuildNeighbours(akua_pbf_solver* s) {
+    const uint32_t n = gridCount(s);
     if (n == 0) return AKUA_OK;
 #define AK_BUILD(K) launchK(s, K, gridFor(n), kBlock, s->xs, s->keysSorted, s->bucketStart, s->cellRange, n, s->nbrStride, \
-            (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius)
-    if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) AK_BUILD(k_build_neighbours<KEY_HASH>);
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) AK_BUILD((k_build_neighbours_mask<4, 5>));
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) AK_BUILD((k_build_neighbours_mask<8, 4>));
-    else AK_BUILD(k_build_neighbours<KEY_LINEAR>);
+            (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius, dimWord(s, D_NOWN))
+    const bool st = slabOn(s);
+    if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) AK_BUILD((k_build_neighbours<KEY_HASH, false>));
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) { if (st) AK_BUILD((k_build_neighbours_mask<4, 5, true>)); else AK_BUILD((k_build_neighbours_mask<4, 5, false>)); }
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) { if (st) AK_BUILD((k_build_neighbours_mask<8, 4, true>)); else AK_BUILD((k_build_neighbours_mask<8, 4, false>)); }
+    else { if (st) AK_BUILD((k_build_neighbours<KEY_LINEAR, true>)); else AK_BUILD((k_build_neighbours<KEY_LINEAR, false>)); }
 #undef AK_BUILD
     AK_LAUNCH_CHECK(s, "k_build_neighbours");
     return AKUA_OK;
@@ -289,8 +315,8 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     if (n == 0) return AKUA_OK;
     const bool hash = s->opt.key_mode == AKUA_KEY_REFERENCE_HASH;
     if (hash) {
-        if (s->bucketsDirty) {
-            launchK(s, k_clear_buckets, gridFor(n), kBlock, s->keysSorted, n, s->bucketStart);
+        if (s->bucketsDirty && s->bucketsN) {   // un-write the entries of the LAST sort (its count, not the current one)
+            launchK(s, k_clear_buckets, gridFor(s->bucketsN), kBlock, s->keysSorted, s->bucketsN, s->bucketStart);
             AK_LAUNCH_CHECK(s, "k_clear_buckets");
         }
     } else {
@@ -306,33 +332,30 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     s->ctr.sort_passes_last = launches / 3;
     mark(s, PH_REORDER);
     if (hash)
-        launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
-            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
+        launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, nullptr, s->pos, s->vel, s->xs, s->id,
+            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange, nullptr, nullptr);
     else
-        launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(n), kBlock, s->keysSorted, s->perm, n, s->pos, s->vel, s->xs, s->id,
-            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange);
+        launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(n), kBlock, s->keysSorted, s->perm, n, nullptr, s->pos, s->vel, s->xs, s->id,
+            s->posAlt, s->velAlt, s->xsAlt, s->idAlt, s->bucketStart, s->cellRange, nullptr, nullptr);
     AK_LAUNCH_CHECK(s, "k_reorder_ranges");
     std::swap(s->pos, s->posAlt);
     std::swap(s->vel, s->velAlt);
     std::swap(s->xs, s->xsAlt);
     std::swap(s->id, s->idAlt);
     s->bucketsDirty = hash;
+    s->bucketsN = hash ? n : 0;
+    s->hashFromUpload = false;
     mark(s, PH_LISTS);
-    return launchBuildNeighbours(s, n);
+    return launchBuildNeighbours(s);
 }
 
 // ---- slab-mode plumbing used by the sweeps below (definitions in pbf_slab.inl) ----
-template <typename T> int slabExchangePlanes(akua_pbf_solver* s, T* arr);           // blocking w.r.t. the main stream
-template <typename T> int slabExchangeAsync(akua_pbf_solver* s, T* arr, SlabTicket* t);  // on the comm stream
-template <typename T, typename U> int slabExchangeAsync2(akua_pbf_solver* s, T* a, U* b, SlabTicket* t);
-int slabWait(akua_pbf_solver* s, const SlabTicket& t);
 int slabAgreeMass(akua_pbf_solver* s);
 template <typename T> PeerPush slabPush(const akua_pbf_solver* s, T* arr);        // null pushes unless the p2p transport is on
-int slabSignalAfterKernel(akua_pbf_solver* s, SlabTicket* t);                   // publish "boundary results pushed" to both peers
-// Fused path: builds the in-kernel wait (on `waitFor`) / signal (new ticket in *out when non-null) block of a boundary launch.
-int slabHalo(akua_pbf_solver* s, const SlabTicket& waitFor, SlabTicket* out, bool launchHappens, HaloSync* hs);
-struct SweepSpans { Span interior, boundary; };
-SweepSpans sweepSpans(const akua_pbf_solver* s);
+// In-kernel wait (exchange index waitIdx, -1 none) / signal (signalIdx, -1 none) block of a boundary launch (p2p transport).
+HaloSync slabHalo(const akua_pbf_solver* s, int waitIdx, int signalIdx);
+template <typename T> int slabNcclPlanes(akua_pbf_solver* s, T* arr);             // NCCL fallback: blocking plane exchange
+struct SweepSpans { Span interior, boundary; uint32_t gridInterior, gridBoundary; };
 
 // ---- sweep launchers over an index span ----
 // Gather layouts (akua_pbf_options::gather_layout). The 32-byte records are single-GPU only.
@@ -346,63 +369,88 @@ inline bool useRec(const akua_pbf_solver* s) {
     const int g = s->opt.gather_layout;
     return !s->slab.enabled && (g == AKUA_GATHER_RECORDS || g == AKUA_GATHER_PACKED_RECORDS);
 }
+SweepSpans sweepSpans(const akua_pbf_solver* s) {
+    SweepSpans sp;
+    if (!slabOn(s)) {
+        sp.interior = fullSpan((uint32_t)s->n);
+        sp.boundary = Span{0, 0, 0, 0, nullptr, SPAN_FIXED};
+        sp.gridInterior = sweepGrid((uint64_t)s->n); sp.gridBoundary = 0;
+    } else {
+        sp.interior = Span{0, 0, 0, 0, s->slab.dims, SPAN_INTERIOR};
+        sp.boundary = Span{0, 0, 0, 0, s->slab.dims, SPAN_BOUNDARY};
+        sp.gridInterior = sweepGrid(s->slab.estN); sp.gridBoundary = sweepGrid(s->slab.estBnd);
+    }
+    return sp;
+}
 
-int launchPassA(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
-    if (!sp.count) return AKUA_OK;
+// Every sweep exists in two instantiations: SLAB = false is the single-GPU kernel (one particle per thread, no halo code at
+// all), SLAB = true loops over a device-resolved span, waits for / publishes halo epochs and pushes boundary results.
+int launchPassA(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
+    if (!grid) return AKUA_OK;
     float4* xl = usePack(s) ? s->xl : nullptr;
     const PeerPush pl = !push ? PeerPush{} : (xl ? slabPush(s, xl) : slabPush(s, s->lambda));
-    if (s->opt.fast_math) launchK(s, k_density_lambda<true>, sweepGrid(sp.count), kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
-    else                  launchK(s, k_density_lambda<false>, sweepGrid(sp.count), kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs);
+#define AK_A(F, S) launchK(s, k_density_lambda<F, S>, grid, kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, sp, s->density, s->lambda, xl, P, pl, hs)
+    if (slabOn(s)) { if (s->opt.fast_math) AK_A(true, true); else AK_A(false, true); }
+    else           { if (s->opt.fast_math) AK_A(true, false); else AK_A(false, false); }
+#undef AK_A
     AK_LAUNCH_CHECK(s, "k_density_lambda");
     return AKUA_OK;
 }
-int launchPassB(akua_pbf_solver* s, Span sp, const SphParams& P, const BoxParams& B, bool fin, float dt, bool push = false,
+int launchPassB(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, const BoxParams& B, bool fin, float dt, bool push = false,
                 const HaloSync& hs = HaloSync{}) {
-    if (!sp.count) return AKUA_OK;
+    if (!grid) return AKUA_OK;
     const PeerPush px = push ? slabPush(s, s->xsAlt) : PeerPush{};
     const PeerPush pv = (push && fin) ? slabPush(s, s->vel) : PeerPush{};
     PosVel* rec = (fin && useRec(s)) ? s->pv : nullptr;
-#define AK_DELTA(F, L, K, C) launchK(s, k_delta_apply<F, L, K, C>, sweepGrid(sp.count), kSweepBlock, s->xs, s->xsAlt, s->lambda, s->xl, \
+#define AK_DELTA(F, L, K, C, S) launchK(s, k_delta_apply<F, L, K, C, S>, grid, kSweepBlock, s->xs, s->xsAlt, s->lambda, s->xl, \
             s->nbrList, s->nbrCount, s->nbrStride, sp, P, B, s->dpos, s->pos, s->vel, s->density, rec, dt, px, pv, hs)
-#define AK_DELTA_C(F, L, K) do { if (P.corrNIsFour) AK_DELTA(F, L, K, true); else AK_DELTA(F, L, K, false); } while (0)
+#define AK_DELTA_S(F, L, K, C) do { if (slabOn(s)) AK_DELTA(F, L, K, C, true); else AK_DELTA(F, L, K, C, false); } while (0)
+#define AK_DELTA_C(F, L, K) do { if (P.corrNIsFour) AK_DELTA_S(F, L, K, true); else AK_DELTA_S(F, L, K, false); } while (0)
 #define AK_DELTA_L(F, K) do { if (fin) AK_DELTA_C(F, true, K); else AK_DELTA_C(F, false, K); } while (0)
     if (usePack(s)) { if (s->opt.fast_math) AK_DELTA_L(true, true); else AK_DELTA_L(false, true); }
     else            { if (s->opt.fast_math) AK_DELTA_L(true, false); else AK_DELTA_L(false, false); }
 #undef AK_DELTA_L
 #undef AK_DELTA_C
+#undef AK_DELTA_S
 #undef AK_DELTA
     AK_LAUNCH_CHECK(s, "k_delta_apply");
     if (rec) s->pvFresh = true;
     return AKUA_OK;
 }
-int launchVorticity(akua_pbf_solver* s, Span sp, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
-    if (!sp.count) return AKUA_OK;
+int launchVorticity(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, bool push = false, const HaloSync& hs = HaloSync{}) {
+    if (!grid) return AKUA_OK;
     float4* xw = usePack(s) ? s->xw : nullptr;
     const PeerPush pw = !push ? PeerPush{} : (xw ? slabPush(s, xw) : slabPush(s, s->omegaLen));
-#define AK_VORT(F, R) launchK(s, k_vorticity<F, R>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, \
+#define AK_VORT(F, R, S) launchK(s, k_vorticity<F, R, S>, grid, kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, \
             s->nbrStride, sp, s->omega, s->omegaLen, xw, P, pw, hs)
-    if (useRec(s)) { if (s->opt.fast_math) AK_VORT(true, true); else AK_VORT(false, true); }
-    else           { if (s->opt.fast_math) AK_VORT(true, false); else AK_VORT(false, false); }
+    if (slabOn(s)) { if (s->opt.fast_math) AK_VORT(true, false, true); else AK_VORT(false, false, true); }
+    else if (useRec(s)) { if (s->opt.fast_math) AK_VORT(true, true, false); else AK_VORT(false, true, false); }
+    else           { if (s->opt.fast_math) AK_VORT(true, false, false); else AK_VORT(false, false, false); }
 #undef AK_VORT
     AK_LAUNCH_CHECK(s, "k_vorticity");
     return AKUA_OK;
 }
-int launchConfinement(akua_pbf_solver* s, Span sp, const SphParams& P, float dt, bool push = false, const HaloSync& hs = HaloSync{}) {
-    if (!sp.count) return AKUA_OK;
+int launchConfinement(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, float dt, bool push = false, const HaloSync& hs = HaloSync{}) {
+    if (!grid) return AKUA_OK;
     const PeerPush pv = push ? slabPush(s, s->vel) : PeerPush{};
     PosVel* rec = useRec(s) ? s->pv : nullptr;
-#define AK_CONF(F, K) launchK(s, k_confinement<F, K>, sweepGrid(sp.count), kSweepBlock, s->xs, s->omega, s->omegaLen, s->xw, s->density, \
+#define AK_CONF(F, K, S) launchK(s, k_confinement<F, K, S>, grid, kSweepBlock, s->xs, s->omega, s->omegaLen, s->xw, s->density, \
             s->nbrList, s->nbrCount, s->nbrStride, sp, s->vel, rec, P, dt, s->cfg.vorticityEpsilon, pv, hs)
-    if (usePack(s)) { if (s->opt.fast_math) AK_CONF(true, true); else AK_CONF(false, true); }
-    else            { if (s->opt.fast_math) AK_CONF(true, false); else AK_CONF(false, false); }
+#define AK_CONF_S(F, K) do { if (slabOn(s)) AK_CONF(F, K, true); else AK_CONF(F, K, false); } while (0)
+    if (usePack(s)) { if (s->opt.fast_math) AK_CONF_S(true, true); else AK_CONF_S(false, true); }
+    else            { if (s->opt.fast_math) AK_CONF_S(true, false); else AK_CONF_S(false, false); }
+#undef AK_CONF_S
 #undef AK_CONF
     AK_LAUNCH_CHECK(s, "k_confinement");
     return AKUA_OK;
 }
-int launchXsph(akua_pbf_solver* s, Span sp, const SphParams& P, const HaloSync& hs = HaloSync{}) {
-    if (!sp.count) return AKUA_OK;
-    if (useRec(s)) launchK(s, k_xsph<true>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
-    else           launchK(s, k_xsph<false>, sweepGrid(sp.count), kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs);
+int launchXsph(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, const HaloSync& hs = HaloSync{}) {
+    if (!grid) return AKUA_OK;
+#define AK_X(R, S) launchK(s, k_xsph<R, S>, grid, kSweepBlock, s->xs, s->vel, s->pv, s->nbrList, s->nbrCount, s->nbrStride, sp, s->velAlt, P, s->cfg.viscosity, hs)
+    if (slabOn(s)) AK_X(false, true);
+    else if (useRec(s)) AK_X(true, false);
+    else AK_X(false, false);
+#undef AK_X
     AK_LAUNCH_CHECK(s, "k_xsph");
     return AKUA_OK;
 }
@@ -427,62 +475,60 @@ int slabJoin(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
+// Exchange indices of a slab step (the epoch of exchange e is dims[D_EPOCH] + e + 1; all ranks run the same sequence):
+//   0 count message + migration records      1 x* after the reorder (for the list build)
+//   2 + 2 it : (x*, lambda) after pass A of iteration it         3 + 2 it : x* (last iteration: + v, rho) after pass B
+//   solverIterations == 0: 2 = v after the stand-alone commit
+//   post-solve: pb = (x, |omega|) after K11, pb + 1 = v after K12, with pb = 2 + 2 I (3 when I == 0)
+inline int slabLastXIdx(int iterations) { return iterations > 0 ? 1 + 2 * iterations : 2; }
+inline int slabPostBaseIdx(int iterations) { return iterations > 0 ? 2 + 2 * iterations : 3; }
+inline int slabExchangesPerStep(int iterations) { return slabPostBaseIdx(iterations) + 2; }
+
 // `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
-// Slab mode: every sweep is split into the slab interior (needs no ghost data) and its two boundary planes. The
-// boundary planes run as soon as the ghost data they need has arrived and their results go out on the comm stream
-// while the interior of the NEXT sweep runs on the main stream — every exchange is hidden behind an interior launch.
+// Slab mode: every sweep is split into the slab interior (needs no ghost data) and its two boundary planes. The boundary
+// launch waits IN-KERNEL for the ghosts it reads, stores its own results straight into the neighbours' ghost regions
+// (P2P stores over NVLink) and its last CTA publishes the epoch; it runs on the boundary stream concurrently with the
+// interior launch, so no exchange sits on the critical path. (NCCL fallback: blocking send/recv after each boundary launch.)
 int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const float* bmax, bool commit, float dt,
                bool* committed) {
-    const uint32_t n = (uint32_t)s->n;
     *committed = false;
     const bool slabMode = s->slab.enabled;
-    if (n == 0 && !slabMode) return AKUA_OK;  // a slab rank without particles still takes part in the exchanges
+    if (s->n == 0 && !slabMode) return AKUA_OK;  // a slab rank without particles still takes part in the exchanges
     int rc;
     const SphParams P = makeSph(s);
     const BoxParams B = makeBox(bmin, bmax);
-    SweepSpans sp{fullSpan(n), Span{0, 0, 0, 0}};
-    if (slabMode) sp = sweepSpans(s);
+    const SweepSpans sp = sweepSpans(s);
+    const bool p2p = s->slab.p2p;
     s->timedIters = 0;
     for (int it = 0; it < iterations; it++) {
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
         const bool fin = commit && it == iterations - 1;
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
         if (it == 0 && (rc = slabJoin(s))) return rc;   // boundary stream catches up with the list build
-        if ((rc = launchPassA(s, sp.interior, P))) return rc;
+        if ((rc = launchPassA(s, sp.interior, sp.gridInterior, P))) return rc;
         if (slabMode) {
-            // CUDA-IPC transport: every boundary launch waits IN-KERNEL for the epoch of the ghosts it reads; its own planes
-            // reach the neighbours by copy-engine pushes on the comm stream (default) or, with fusedPush, by P2P stores from
-            // the boundary kernel itself whose last CTA publishes the epoch. NCCL transport: event waits + send/recv.
-            const bool p2p = s->slab.p2p, fused = s->slab.fusedPush, any = sp.boundary.count != 0;
-            SlabTicket tkL;
-            {   // ---- pass A on the boundary planes (boundary stream), lambda goes out
+            {   // ---- pass A on the boundary planes (boundary stream): needs the ghosts' x*, (x*, lambda) goes out
                 BndScope scope(s);
-                HaloSync hs;
-                if (p2p) { if ((rc = slabHalo(s, s->slab.pending, fused ? &tkL : nullptr, any, &hs))) return rc; }
-                else if ((rc = slabWait(s, s->slab.pending))) return rc;                       // ghosts' x*
-                s->slab.pending = SlabTicket{};
-                if ((rc = launchPassA(s, sp.boundary, P, p2p && fused, hs))) return rc;
-                if (!(p2p && fused) && (rc = usePack(s) ? slabExchangeAsync(s, s->xl, &tkL) : slabExchangeAsync(s, s->lambda, &tkL))) return rc;
+                const HaloSync hs = p2p ? slabHalo(s, 1 + 2 * it, 2 + 2 * it) : HaloSync{};
+                if ((rc = launchPassA(s, sp.boundary, sp.gridBoundary, P, p2p, hs))) return rc;
+                if (!p2p && (rc = usePack(s) ? slabNcclPlanes(s, s->xl) : slabNcclPlanes(s, s->lambda))) return rc;
             }
             if ((rc = slabJoin(s))) return rc;   // pass B reads lambda across the interior / boundary split
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
-            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;                 // hides the lambda exchange
+            if ((rc = launchPassB(s, sp.interior, sp.gridInterior, P, B, fin, dt))) return rc;
             {   // ---- pass B on the boundary planes, corrected x* (and after the commit v + rho) go out
                 BndScope scope(s);
-                HaloSync hs;
-                if (p2p) { if ((rc = slabHalo(s, tkL, fused ? &s->slab.pending : nullptr, any, &hs))) return rc; }
-                else if ((rc = slabWait(s, tkL))) return rc;
-                if ((rc = launchPassB(s, sp.boundary, P, B, fin, dt, p2p && fused, hs))) return rc;
-                if (!(p2p && fused)) {
-                    if (fin) rc = slabExchangeAsync2(s, s->xsAlt, s->vel, &s->slab.pending);
-                    else     rc = slabExchangeAsync(s, s->xsAlt, &s->slab.pending);
-                    if (rc) return rc;
+                const HaloSync hs = p2p ? slabHalo(s, 2 + 2 * it, 3 + 2 * it) : HaloSync{};
+                if ((rc = launchPassB(s, sp.boundary, sp.gridBoundary, P, B, fin, dt, p2p, hs))) return rc;
+                if (!p2p) {
+                    if ((rc = slabNcclPlanes(s, s->xsAlt))) return rc;
+                    if (fin && (rc = slabNcclPlanes(s, s->vel))) return rc;
                 }
             }
             if ((rc = slabJoin(s))) return rc;   // the next sweep reads x* across the split
         } else {
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
-            if ((rc = launchPassB(s, sp.interior, P, B, fin, dt))) return rc;
+            if ((rc = launchPassB(s, sp.interior, sp.gridInterior, P, B, fin, dt))) return rc;
         }
         if (timeIt) { cudaEventRecord(s->evPass[it][2], s->stream); s->timedIters = it + 1; }
         std::swap(s->xs, s->xsAlt);
@@ -492,70 +538,63 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
 }
 
 int phaseUpdate(akua_pbf_solver* s, float dt) {
-    const uint32_t n = (uint32_t)s->n;
+    const uint32_t n = gridCount(s);
     if (n == 0) return AKUA_OK;
-    launchK(s, k_update, gridFor(n), kBlock, s->xs, s->pos, s->vel, s->density, n, dt);
+    launchK(s, k_update, gridFor(n), kBlock, s->xs, s->pos, s->vel, s->density, n, dt, dimWord(s, D_NOWN));
     AK_LAUNCH_CHECK(s, "k_update");
     return AKUA_OK;
 }
 int phaseDamping(akua_pbf_solver* s, const float* bmin, const float* bmax) {
-    const uint32_t n = (uint32_t)s->n;
+    const uint32_t n = gridCount(s);
     if (n == 0) return AKUA_OK;
-    launchK(s, k_damping, gridFor(n), kBlock, s->pos, s->vel, n, makeBox(bmin, bmax));
+    launchK(s, k_damping, gridFor(n), kBlock, s->pos, s->vel, n, makeBox(bmin, bmax), dimWord(s, D_NOWN));
     AK_LAUNCH_CHECK(s, "k_damping");
     return AKUA_OK;
 }
-int phasePost(akua_pbf_solver* s, float dt) {
-    const uint32_t n = (uint32_t)s->n;
+// `iterations`: only read in slab mode (it fixes the exchange indices of the post-solve sweeps)
+int phasePost(akua_pbf_solver* s, float dt, int iterations) {
     const bool slabMode = s->slab.enabled;
-    if (n == 0 && !slabMode) return AKUA_OK;
+    if (s->n == 0 && !slabMode) return AKUA_OK;
     int rc;
     const SphParams P = makeSph(s);
+    const SweepSpans sp = sweepSpans(s);
     if (!slabMode) {
-        const Span all = fullSpan(n);
+        const uint32_t n = (uint32_t)s->n;
         if (useRec(s) && !s->pvFresh) {   // committed outside the fused final pass B (phase-level API, 0 iterations)
             launchK(s, k_build_posvel, gridFor(n), kBlock, s->xs, s->vel, n, s->pv);
             AK_LAUNCH_CHECK(s, "k_build_posvel");
         }
         s->pvFresh = false;               // K12 / K13 leave the records behind the committed state
-        if ((rc = launchVorticity(s, all, P))) return rc;
-        if ((rc = launchConfinement(s, all, P, dt))) return rc;
-        if ((rc = launchXsph(s, all, P))) return rc;
+        if ((rc = launchVorticity(s, sp.interior, sp.gridInterior, P))) return rc;
+        if ((rc = launchConfinement(s, sp.interior, sp.gridInterior, P, dt))) return rc;
+        if ((rc = launchXsph(s, sp.interior, sp.gridInterior, P))) return rc;
         std::swap(s->vel, s->velAlt);
         return AKUA_OK;
     }
-    const SweepSpans sp = sweepSpans(s);
-    SlabTicket evW, evV;
-    const bool p2p = s->slab.p2p, fused = s->slab.fusedPush, any = sp.boundary.count != 0;
+    const bool p2p = s->slab.p2p;
+    const int lastX = slabLastXIdx(iterations), pb = slabPostBaseIdx(iterations);
     if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchVorticity(s, sp.interior, P))) return rc;
-    {
+    if ((rc = launchVorticity(s, sp.interior, sp.gridInterior, P))) return rc;
+    {   // K11 on the boundary planes: needs the ghosts' final x*, v; (x, |omega|) goes out for K12
         BndScope scope(s);
-        HaloSync hs;
-        if (p2p) { if ((rc = slabHalo(s, s->slab.pending, fused ? &evW : nullptr, any, &hs))) return rc; }
-        else if ((rc = slabWait(s, s->slab.pending))) return rc;                              // ghosts' final x*, v
-        s->slab.pending = SlabTicket{};
-        if ((rc = launchVorticity(s, sp.boundary, P, p2p && fused, hs))) return rc;
-        if (!(p2p && fused) && (rc = usePack(s) ? slabExchangeAsync(s, s->xw, &evW) : slabExchangeAsync(s, s->omegaLen, &evW))) return rc;  // ghosts' |omega| for K12
+        const HaloSync hs = p2p ? slabHalo(s, lastX, pb) : HaloSync{};
+        if ((rc = launchVorticity(s, sp.boundary, sp.gridBoundary, P, p2p, hs))) return rc;
+        if (!p2p && (rc = usePack(s) ? slabNcclPlanes(s, s->xw) : slabNcclPlanes(s, s->omegaLen))) return rc;
     }
     if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchConfinement(s, sp.interior, P, dt))) return rc;
-    {
+    if ((rc = launchConfinement(s, sp.interior, sp.gridInterior, P, dt))) return rc;
+    {   // K12 on the boundary planes; the post-confinement v goes out for K13
         BndScope scope(s);
-        HaloSync hs;
-        if (p2p) { if ((rc = slabHalo(s, evW, fused ? &evV : nullptr, any, &hs))) return rc; }
-        else if ((rc = slabWait(s, evW))) return rc;
-        if ((rc = launchConfinement(s, sp.boundary, P, dt, p2p && fused, hs))) return rc;
-        if (!(p2p && fused) && (rc = slabExchangeAsync(s, s->vel, &evV))) return rc;           // ghosts' post-confinement v for K13
+        const HaloSync hs = p2p ? slabHalo(s, pb, pb + 1) : HaloSync{};
+        if ((rc = launchConfinement(s, sp.boundary, sp.gridBoundary, P, dt, p2p, hs))) return rc;
+        if (!p2p && (rc = slabNcclPlanes(s, s->vel))) return rc;
     }
     if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchXsph(s, sp.interior, P))) return rc;
+    if ((rc = launchXsph(s, sp.interior, sp.gridInterior, P))) return rc;
     {
         BndScope scope(s);
-        HaloSync hs;
-        if (p2p) { if ((rc = slabHalo(s, evV, nullptr, any, &hs))) return rc; }
-        else if ((rc = slabWait(s, evV))) return rc;
-        if ((rc = launchXsph(s, sp.boundary, P, hs))) return rc;
+        const HaloSync hs = p2p ? slabHalo(s, pb + 1, -1) : HaloSync{};
+        if ((rc = launchXsph(s, sp.boundary, sp.gridBoundary, P, hs))) return rc;
     }
     if ((rc = slabJoin(s))) return rc;   // the step ends on the main stream
     std::swap(s->vel, s->velAlt);
@@ -566,15 +605,21 @@ int phasePost(akua_pbf_solver* s, float dt) {
 
 int stepEager(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax);
 
-void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax, uint64_t key[16]) {
+void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax, uint64_t key[20]) {
     auto f2 = [](float a, float b) { uint32_t x, y; std::memcpy(&x, &a, 4); std::memcpy(&y, &b, 4); return ((uint64_t)x << 32) | y; };
     key[0] = (uint64_t)s->pos; key[1] = (uint64_t)s->vel; key[2] = (uint64_t)s->xs; key[3] = (uint64_t)s->id;
-    key[4] = (uint64_t)s->keysSorted; key[5] = (uint64_t)s->n; key[6] = ((uint64_t)iterations << 1) | (s->bucketsDirty ? 1 : 0);
+    key[4] = (uint64_t)s->keysSorted; key[5] = slabOn(s) ? 0 : (uint64_t)s->n; key[6] = ((uint64_t)iterations << 1) | (s->bucketsDirty ? 1 : 0);
     key[7] = f2(dt, s->cfg.gravity[0]); key[8] = f2(s->cfg.gravity[1], s->cfg.gravity[2]);
     key[9] = f2(bmin[0], bmin[1]); key[10] = f2(bmin[2], bmax[0]); key[11] = f2(bmax[1], bmax[2]);
     key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math;
     uint32_t mbits; std::memcpy(&mbits, &s->uniformMass, 4);
-    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u);
+    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u) | (slabOn(s) ? 8u : 0u);
+    // x-slab mode: the slab interval fixes the local grid, the (bucketed) size estimates fix the launch grids
+    const SlabState& sl = s->slab;
+    key[16] = slabOn(s) ? (((uint64_t)(uint32_t)sl.xLoAbs << 32) | (uint32_t)sl.xHiAbs) : 0;
+    key[17] = slabOn(s) ? (((uint64_t)sl.estN << 32) | sl.estBnd) : 0;
+    key[18] = slabOn(s) ? (((uint64_t)sl.estGhost << 32) | sl.estIn) : 0;
+    key[19] = slabOn(s) ? (uint64_t)sl.slot : (uint64_t)s->bucketsN;
 }
 
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
@@ -582,21 +627,30 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
     if (iterations < 0) { s->err = "solverIterations must be >= 0"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     rememberBox(s, bmin, bmax);
-    if (s->slab.enabled) return stepSlab(s, dt, iterations, bmin, bmax);
-    int rc = layoutGrid(s, bmin, bmax);  // may (re)allocate the cell table: stays outside any capture
-    if (rc) return rc;
-    if (!s->opt.use_graph || s->timing || s->n == 0) return stepEager(s, dt, iterations, bmin, bmax);
-    uint64_t key[16];
+    const bool slabMode = s->slab.enabled;
+    int rc;
+    if (slabMode) {
+        if ((rc = slabCheckError(s))) return rc;     // a device-side error of an earlier step (pinned mirror, no sync)
+        if ((rc = slabLayout(s, bmin, bmax))) return rc;
+        slabUpdateEstimates(s);
+    } else {
+        rc = layoutGrid(s, bmin, bmax);  // may (re)allocate the cell table: stays outside any capture
+        if (rc) return rc;
+    }
+    auto body = [&]() { return slabMode ? stepSlabBody(s, dt, iterations, bmin, bmax) : stepEager(s, dt, iterations, bmin, bmax); };
+    const bool graphable = s->opt.use_graph && !s->timing && (slabMode ? (s->slab.p2p && !s->slab.graphBroken) : s->n != 0);
+    if (!graphable) return body();
+    uint64_t key[20];
     graphKey(s, dt, iterations, bmin, bmax, key);
     akua_pbf_solver::GraphEntry* hit = nullptr;
     for (auto& g : s->graphs)
         if (g.used && std::memcmp(g.key, key, sizeof(key)) == 0) { hit = &g; break; }
     if (hit) s->graphMissStreak = 0;
-    else if (s->graphCooldown > 0) { s->graphCooldown--; return stepEager(s, dt, iterations, bmin, bmax); }
+    else if (s->graphCooldown > 0) { s->graphCooldown--; return body(); }
     else if (++s->graphMissStreak > 6) {
         // parameters keep changing (adaptive dt, moving box): capturing a graph per step costs more than it saves
         s->graphMissStreak = 0; s->graphCooldown = 64;
-        return stepEager(s, dt, iterations, bmin, bmax);
+        return body();
     }
     if (!hit) {
         // capture this step (the launches below are recorded, not executed), instantiate, then replay it
@@ -606,36 +660,58 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         g.used = false;
         // pre-state, restored before the replay so that capture + replay advance the state exactly once
         float4 *pos = s->pos, *posAlt = s->posAlt, *vel = s->vel, *velAlt = s->velAlt, *xs = s->xs, *xsAlt = s->xsAlt;
-        uint32_t *id = s->id, *idAlt = s->idAlt, *ks = s->keysSorted, *pm = s->perm;
-        const bool dirty = s->bucketsDirty;
-        const int64_t launches0 = s->ctr.kernel_launches, steps0 = s->ctr.steps;
-        AK_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-        rc = stepEager(s, dt, iterations, bmin, bmax);
+        uint32_t *id = s->id, *idAlt = s->idAlt, *ks = s->keysSorted, *pm = s->perm, *sl0 = s->slab.slot, *sl1 = s->slab.slotAlt;
+        const bool dirty = s->bucketsDirty, hfu0 = s->hashFromUpload;
+        const uint32_t bucketsN0 = s->bucketsN;
+        const int64_t launches0 = s->ctr.kernel_launches, steps0 = s->ctr.steps, exch0 = s->slab.exchanges;
+        auto restore = [&]() {
+            s->pos = pos; s->posAlt = posAlt; s->vel = vel; s->velAlt = velAlt; s->xs = xs; s->xsAlt = xsAlt;
+            s->id = id; s->idAlt = idAlt; s->keysSorted = ks; s->perm = pm; s->bucketsDirty = dirty;
+            s->slab.slot = sl0; s->slab.slotAlt = sl1; s->bucketsN = bucketsN0; s->hashFromUpload = hfu0;
+            s->ctr.kernel_launches = launches0; s->ctr.steps = steps0; s->slab.exchanges = exch0;
+        };
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            s->opt.use_graph = 0;     // a stream that cannot be captured (or a runtime without graphs): step eagerly from now on
+            return body();
+        }
+        rc = body();
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
-        if (rc != AKUA_OK || ce != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            if (rc == AKUA_OK) { s->err = std::string("graph capture: ") + cudaGetErrorString(ce); rc = AKUA_ERR_CUDA; }
-            cudaGetLastError();
-            return rc;
+        if (rc == AKUA_OK && ce == cudaSuccess && graph) {
+            ce = cudaGraphInstantiate(&g.exec, graph, 0);
+            if (ce != cudaSuccess) g.exec = nullptr;
         }
-        ce = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { s->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return AKUA_ERR_CUDA; }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != AKUA_OK || ce != cudaSuccess || !g.exec) {
+            // nothing was executed: put the host-side state back where it was before the capture
+            const std::string why = rc != AKUA_OK ? s->err : std::string("graph capture: ") + cudaGetErrorString(ce);
+            cudaGetLastError();
+            restore();
+            if (slabMode && rc == AKUA_OK) {   // e.g. a driver that cannot capture this multi-stream pattern: run eagerly from now on
+                s->slab.graphBroken = true;
+                return body();
+            }
+            s->err = why;
+            return rc != AKUA_OK ? rc : AKUA_ERR_CUDA;
+        }
         std::memcpy(g.key, key, sizeof(key));
         g.pos = s->pos; g.posAlt = s->posAlt; g.vel = s->vel; g.velAlt = s->velAlt; g.xs = s->xs; g.xsAlt = s->xsAlt;
         g.id = s->id; g.idAlt = s->idAlt; g.keysSorted = s->keysSorted; g.perm = s->perm; g.bucketsDirty = s->bucketsDirty;
+        g.slot = s->slab.slot; g.slotAlt = s->slab.slotAlt;
         g.launches = s->ctr.kernel_launches - launches0; g.sortPasses = s->ctr.sort_passes_last;
+        g.exchanges = s->slab.exchanges - exch0;
         g.used = true;
-        s->pos = pos; s->posAlt = posAlt; s->vel = vel; s->velAlt = velAlt; s->xs = xs; s->xsAlt = xsAlt;
-        s->id = id; s->idAlt = idAlt; s->keysSorted = ks; s->perm = pm; s->bucketsDirty = dirty;
-        s->ctr.kernel_launches = launches0; s->ctr.steps = steps0;
+        restore();
         hit = &g;
     }
     AK_CUDA(s, cudaGraphLaunch(hit->exec, s->stream));
     s->pos = hit->pos; s->posAlt = hit->posAlt; s->vel = hit->vel; s->velAlt = hit->velAlt; s->xs = hit->xs; s->xsAlt = hit->xsAlt;
     s->id = hit->id; s->idAlt = hit->idAlt; s->keysSorted = hit->keysSorted; s->perm = hit->perm; s->bucketsDirty = hit->bucketsDirty;
+    s->slab.slot = hit->slot; s->slab.slotAlt = hit->slotAlt;
+    s->bucketsN = hit->bucketsDirty ? (uint32_t)s->n : 0; s->hashFromUpload = false;
     s->ctr.kernel_launches += hit->launches; s->ctr.sort_passes_last = hit->sortPasses; s->ctr.steps++;
+    s->slab.exchanges += hit->exchanges;
     s->ctr.graph_replays++;
     return AKUA_OK;
 }
@@ -654,7 +730,7 @@ int stepEager(akua_pbf_solver* s, float dt, int iterations, const float* bmin, c
         if ((rc = phaseDamping(s, bmin, bmax))) return rc;                // PBFSolver.cpp:64
     }
     mark(s, PH_POST);
-    if ((rc = phasePost(s, dt))) return rc;                               // PBFSolver.cpp:67
+    if ((rc = phasePost(s, dt, iterations))) return rc;                   // PBFSolver.cpp:67
     mark(s, PH_END);
     s->timingValid = s->timing;
     s->ctr.steps++;
@@ -667,7 +743,7 @@ int massRangeAsync(akua_pbf_solver* s) {
     const uint32_t n = (uint32_t)s->n;
     AK_CUDA(s, cudaMemsetAsync(s->dMassRange, 0xff, sizeof(uint32_t), s->stream));
     AK_CUDA(s, cudaMemsetAsync(s->dMassRange + 1, 0, sizeof(uint32_t), s->stream));
-    k_mass_range<<<std::min<uint32_t>(gridFor(n), 148 * 8), kBlock, 0, s->stream>>>(s->pos, n, s->dMassRange);
+    launchPlain(s->stream, k_mass_range, std::min<uint32_t>(gridFor(n), 148 * 8), kBlock, s->pos, n, s->dMassRange);
     AK_LAUNCH_CHECK(s, "k_mass_range");
     AK_CUDA(s, cudaMemcpyAsync(s->hMassRange, s->dMassRange, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     return AKUA_OK;
@@ -678,6 +754,17 @@ void massRangeFinish(akua_pbf_solver* s) {   // after the stream synchronisation
     const uint32_t bits = (lo & 0x80000000u) ? (lo ^ 0x80000000u) : ~lo;   // decode
     std::memcpy(&s->uniformMass, &bits, 4);
 }
+
+// Every upload replaces the particle set: the live count follows it and, in x-slab mode, the device-side bookkeeping (owned
+// count, payload slots) is reset to match.
+int beforeUpload(akua_pbf_solver* s, int64_t n) {
+    s->n = n;
+    s->hashFromUpload = true;
+    return slabResetCounts(s);
+}
+// Particle::hash of an AoS export: the sorted keys of the current order (what the reference's struct holds after a step), or
+// the uploaded hash field while no sort has happened since the upload.
+const uint32_t* hashField(const akua_pbf_solver* s) { return s->hashFromUpload ? s->keysUnsorted : s->keysSorted; }
 
 }  // namespace
 
@@ -785,7 +872,7 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
         s->keyBits = bitsFor((uint64_t)ts - 1);
         s->ctr.num_cells = ts;
         AK_CUDA(s, dalloc(&s->bucketStart, (size_t)ts));
-        k_fill_u32<<<148 * 8, kBlock, 0, s->stream>>>(s->bucketStart, (uint64_t)ts, 0xffffffffu);
+        launchPlain(s->stream, k_fill_u32, 148 * 8, kBlock, s->bucketStart, (uint64_t)ts, 0xffffffffu);
         AK_LAUNCH_CHECK(s, "k_fill_u32");
     } else if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) {
         s->err = "unknown key_mode"; return AKUA_ERR_INVALID;
@@ -810,14 +897,14 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
     for (void* p : ptrs) if (p) cudaFree(p);
     {
         SlabState& sl = s->slab;
-        void* sp[] = {sl.dCounts, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR};
+        void* sp[] = {sl.dims, sl.blockCnt, sl.sendL, sl.sendR, sl.recvL, sl.recvR, sl.slot, sl.slotAlt, sl.freeSlots};
         for (void* p : sp) if (p) cudaFree(p);
         for (SlabPeer* p : {&sl.peerL, &sl.peerR})
             if (p->open) for (void* q : {(void*)p->xsBuf[0], (void*)p->xsBuf[1], (void*)p->velBuf[0], (void*)p->velBuf[1],
-                                         (void*)p->lambda, (void*)p->omegaLen, (void*)p->flags, (void*)p->dCounts,
+                                         (void*)p->lambda, (void*)p->omegaLen, (void*)p->flags, (void*)p->dims,
                                          (void*)p->recvL, (void*)p->recvR, (void*)p->xl, (void*)p->xw}) if (q) cudaIpcCloseMemHandle(q);
         if (sl.flags) cudaFree(sl.flags);
-        if (sl.hCounts) cudaFreeHost(sl.hCounts);
+        if (sl.hDims) cudaFreeHost((void*)sl.hDims);
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
         if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
@@ -848,7 +935,7 @@ int akua_pbf_advance(akua_pbf_solver* s, float frameTime, float deltaTime, int32
     int n = 0;
     while (s->accumulator >= deltaTime && n < maxStepsPerFrame) {   // Application.cpp:63-70
         int rc = stepImpl(s, deltaTime, s->cfg.solverIterations, boxMin, boxMax);
-        if (rc) return rc;
+        if (rc) { if (stepsDone) *stepsDone = n; return rc; }
         s->accumulator -= deltaTime;
         n++;
     }
@@ -871,23 +958,34 @@ int akua_pbf_set_gravity(akua_pbf_solver* s, const float g[3]) {
 int akua_pbf_sync(akua_pbf_solver* s) {
     if (!s) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    if (s->slab.enabled) return slabRefresh(s);   // synchronises, refreshes the live count, reports device-side errors
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
 }
 const char* akua_pbf_last_error(const akua_pbf_solver* s) { return s ? s->err.c_str() : "null solver"; }
-int64_t akua_pbf_num_particles(const akua_pbf_solver* s) { return s ? s->n : -1; }
+int64_t akua_pbf_num_particles(const akua_pbf_solver* s) {
+    if (!s) return -1;
+    if (s->slab.enabled) {   // the owned count changes on the device (migration): make the host's view exact
+        akua_pbf_solver* m = const_cast<akua_pbf_solver*>(s);
+        cudaSetDevice(m->device);
+        slabRefresh(m);
+    }
+    return s->n;
+}
 
 int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     if (!s || !src || n < 0 || n > s->capacity) { if (s) s->err = "upload_aos108: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
-    s->n = n;  // the live particle count follows the upload (slab ranks upload their own share)
-    if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }   // still takes part in the slab-mode verdict
-    int rc = ensureStage(s);
+    int rc = beforeUpload(s, n);   // the live particle count follows the upload (slab ranks upload their own share)
     if (rc) return rc;
+    if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }   // still takes part in the slab-mode verdict
+    if ((rc = ensureStage(s))) return rc;
     AK_CUDA(s, cudaMemcpyAsync(s->aosStage, src, (size_t)n * 108, cudaMemcpyHostToDevice, s->stream));
     s->ctr.h2d_bytes += n * 108;
-    k_unpack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((const uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega,
-        s->omegaLen, s->dpos, s->density, s->lambda, s->keysSorted, s->color, s->size, s->id);
+    // Particle::hash goes to the debug copy of the unsorted keys, NOT to keysSorted: in REFERENCE_HASH mode keysSorted must keep
+    // describing the bucket table's current entries (they are un-written from it at the next step)
+    launchPlain(s->stream, k_unpack_aos, gridFor(n), kBlock, (const uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega,
+        s->omegaLen, s->dpos, s->density, s->lambda, s->keysUnsorted, s->color, s->size, s->id);
     AK_LAUNCH_CHECK(s, "k_unpack_aos");
     int rcm = massRangeAsync(s);
     if (rcm) return rcm;
@@ -896,13 +994,15 @@ int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     return slabAgreeMass(s);
 }
 int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
-    if (!s || !dst || n != s->n) { if (s) s->err = "download_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    if (!s || !dst) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
-    if (n == 0) return AKUA_OK;
-    int rc = ensureStage(s);
+    int rc = slabRefresh(s);
     if (rc) return rc;
-    k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
-        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id, s->slab.enabled ? 0 : 1);
+    if (n != s->n) { s->err = "download_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    if (n == 0) return AKUA_OK;
+    if ((rc = ensureStage(s))) return rc;
+    launchPlain(s->stream, k_pack_aos, gridFor(n), kBlock, (uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
+        s->density, s->lambda, hashField(s), s->color, s->size, s->id, s->slab.enabled ? s->slab.slot : nullptr);
     AK_LAUNCH_CHECK(s, "k_pack_aos");
     AK_CUDA(s, cudaMemcpyAsync(dst, s->aosStage, (size_t)n * 108, cudaMemcpyDeviceToHost, s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -911,11 +1011,14 @@ int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
 }
 
 int akua_pbf_export_aos108_device(akua_pbf_solver* s, void* device_dst, int64_t n) {
-    if (!s || !device_dst || n != s->n) { if (s) s->err = "export_aos108_device: n must equal numParticles"; return AKUA_ERR_INVALID; }
+    if (!s || !device_dst) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    int rc = slabRefresh(s);
+    if (rc) return rc;
+    if (n != s->n) { s->err = "export_aos108_device: n must equal numParticles"; return AKUA_ERR_INVALID; }
     if (n == 0) return AKUA_OK;
-    k_pack_aos<<<gridFor(n), kBlock, 0, s->stream>>>((uint32_t*)device_dst, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
-        s->density, s->lambda, s->keysSorted, s->color, s->size, s->id, s->slab.enabled ? 0 : 1);
+    launchPlain(s->stream, k_pack_aos, gridFor(n), kBlock, (uint32_t*)device_dst, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
+        s->density, s->lambda, hashField(s), s->color, s->size, s->id, s->slab.enabled ? s->slab.slot : nullptr);
     AK_LAUNCH_CHECK(s, "k_pack_aos");
     return AKUA_OK;
 }
@@ -930,6 +1033,7 @@ int akua_pbf_export_to_graphics_resource(akua_pbf_solver* s, void* graphicsResou
     int rc = AKUA_OK;
     cudaError_t e = cudaGraphicsResourceGetMappedPointer(&dst, &bytes, res);
     if (e != cudaSuccess) { s->err = std::string("cudaGraphicsResourceGetMappedPointer: ") + cudaGetErrorString(e); rc = AKUA_ERR_CUDA; }
+    else if ((rc = slabRefresh(s)) != AKUA_OK) {}
     else if (bytes < (size_t)s->n * 108) { s->err = "export_to_graphics_resource: the buffer is smaller than 108 * numParticles bytes"; rc = AKUA_ERR_INVALID; }
     else rc = akua_pbf_export_aos108_device(s, dst, s->n);
     e = cudaGraphicsUnmapResources(1, &res, s->stream);   // stream-ordered behind the pack kernel
@@ -940,7 +1044,10 @@ int akua_pbf_export_to_graphics_resource(akua_pbf_solver* s, void* graphicsResou
 int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* vel_xyz, const float* mass, int64_t n) {
     if (!s || !pos_xyz || n < 0 || n > s->capacity) { if (s) s->err = "upload_soa: n must be in [0, capacity]"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
-    s->n = n;
+    {
+        int rc = beforeUpload(s, n);
+        if (rc) return rc;
+    }
     if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }
     // Host-side widening to float4, then two async copies. (Setup path; the per-step e2e path is AoS-108.)
     std::vector<float4> p4((size_t)n), v4((size_t)n);
@@ -958,14 +1065,26 @@ int akua_pbf_upload_soa(akua_pbf_solver* s, const float* pos_xyz, const float* v
     AK_CUDA(s, cudaMemcpyAsync(s->xs, p4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
     AK_CUDA(s, cudaMemcpyAsync(s->vel, v4.data(), (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
     AK_CUDA(s, cudaMemcpyAsync(s->id, ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    // the fields a lean upload does not carry get the scene defaults of Application.cpp:186-187 (blue, size 50) / zero
+    launchPlain(s->stream, k_fill_payload, std::min<uint32_t>(gridFor(n), 148 * 8), kBlock, s->color, s->size, (uint32_t)n,
+        make_float4(0.f, 0.f, 1.f, 1.f), 50.0f);
+    AK_LAUNCH_CHECK(s, "k_fill_payload");
+    for (float4* q : {s->omega, s->dpos}) AK_CUDA(s, cudaMemsetAsync(q, 0, (size_t)n * sizeof(float4), s->stream));
+    for (float* q : {s->density, s->lambda, s->omegaLen}) AK_CUDA(s, cudaMemsetAsync(q, 0, (size_t)n * sizeof(float), s->stream));
+    AK_CUDA(s, cudaMemsetAsync(s->keysUnsorted, 0, (size_t)n * sizeof(uint32_t), s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     s->ctr.h2d_bytes += n * 52;
     s->massUniform = uniform; s->uniformMass = m0;
     return slabAgreeMass(s);
 }
 int akua_pbf_download_soa(akua_pbf_solver* s, float* pos4, float* vel4, uint32_t* id, int64_t n) {
-    if (!s || n != s->n) { if (s) s->err = "download_soa: bad arguments"; return AKUA_ERR_INVALID; }
+    if (!s) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    {
+        int rc = slabRefresh(s);
+        if (rc) return rc;
+    }
+    if (n != s->n) { s->err = "download_soa: n must equal numParticles"; return AKUA_ERR_INVALID; }
     if (pos4) { AK_CUDA(s, cudaMemcpyAsync(pos4, s->pos, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 16; }
     if (vel4) { AK_CUDA(s, cudaMemcpyAsync(vel4, s->vel, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 16; }
     if (id)   { AK_CUDA(s, cudaMemcpyAsync(id, s->id, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream)); s->ctr.d2h_bytes += n * 4; }
@@ -985,7 +1104,9 @@ void akua_pbf_host_free(void* p) { if (p) cudaFreeHost(p); }
 // ---- checkpoint / resume (the reference keeps its state only in the GL VBO) ----
 namespace {
 struct CkptHeader {
-    char magic[8];          // "AKUAPBF1"
+    char magic[8];          // "AKUAPBF2"
+    uint32_t headerBytes;   // sizeof(CkptHeader): a file written by a different layout is rejected, not misread
+    uint32_t version;
     int64_t n;
     akua_pbf_config cfg;
     akua_corr_params corr;
@@ -993,26 +1114,35 @@ struct CkptHeader {
     float accumulator;
     int32_t key_mode;
 };
+constexpr uint32_t kCkptVersion = 2;
+bool sameBytes(const void* a, const void* b, size_t n) { return std::memcmp(a, b, n) == 0; }
 }
+// File: header, then per particle in the solver's CURRENT order: position (x,y,z,mass), velocity (vx,vy,vz,density), id,
+// color, size. The payload is stored per particle, so the file does not depend on where the solver keeps it.
 int akua_pbf_checkpoint_save(akua_pbf_solver* s, const char* path) {
     if (!s || !path) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    int rc = slabRefresh(s);
+    if (rc) return rc;
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
-    const size_t n = (size_t)s->n;
-    std::vector<float4> pos(n), vel(n), color(n);
-    std::vector<float> size(n);
-    std::vector<uint32_t> id(n);
+    const size_t n = (size_t)s->n, cap = (size_t)s->capacity;
+    std::vector<float4> pos(n), vel(n), colorAll(cap), color(n);
+    std::vector<float> sizeAll(cap), size(n);
+    std::vector<uint32_t> id(n), pidx(n);
     if (n) {
         AK_CUDA(s, cudaMemcpy(pos.data(), s->pos, n * 16, cudaMemcpyDeviceToHost));
         AK_CUDA(s, cudaMemcpy(vel.data(), s->vel, n * 16, cudaMemcpyDeviceToHost));
         AK_CUDA(s, cudaMemcpy(id.data(), s->id, n * 4, cudaMemcpyDeviceToHost));
-        AK_CUDA(s, cudaMemcpy(color.data(), s->color, n * 16, cudaMemcpyDeviceToHost));
-        AK_CUDA(s, cudaMemcpy(size.data(), s->size, n * 4, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(pidx.data(), s->slab.enabled ? s->slab.slot : s->id, n * 4, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(colorAll.data(), s->color, cap * 16, cudaMemcpyDeviceToHost));
+        AK_CUDA(s, cudaMemcpy(sizeAll.data(), s->size, cap * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) { const uint32_t q = pidx[i] < cap ? pidx[i] : 0u; color[i] = colorAll[q]; size[i] = sizeAll[q]; }
     }
     FILE* f = std::fopen(path, "wb");
     if (!f) { s->err = std::string("checkpoint_save: cannot open ") + path; return AKUA_ERR_INVALID; }
     CkptHeader h{};
-    std::memcpy(h.magic, "AKUAPBF1", 8);
+    std::memcpy(h.magic, "AKUAPBF2", 8);
+    h.headerBytes = (uint32_t)sizeof(CkptHeader); h.version = kCkptVersion;
     h.n = (int64_t)n; h.cfg = s->cfg; h.corr = s->corr; h.steps = s->ctr.steps; h.accumulator = s->accumulator;
     h.key_mode = s->opt.key_mode;
     bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
@@ -1023,16 +1153,30 @@ int akua_pbf_checkpoint_save(akua_pbf_solver* s, const char* path) {
     if (!ok) { s->err = "checkpoint_save: short write"; return AKUA_ERR_INVALID; }
     return AKUA_OK;
 }
+// A checkpoint continues bit-identically only under the parameters it was written with: the solver's config, correction
+// parameters and key mode must equal the file's (gravity excepted: it is runtime state and is restored from the file).
 int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
     if (!s || !path) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
     FILE* f = std::fopen(path, "rb");
     if (!f) { s->err = std::string("checkpoint_load: cannot open ") + path; return AKUA_ERR_INVALID; }
     CkptHeader h{};
-    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "AKUAPBF1", 8) != 0) {
-        std::fclose(f); s->err = "checkpoint_load: not an AKUAPBF1 file"; return AKUA_ERR_INVALID;
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "AKUAPBF2", 8) != 0 || h.headerBytes != sizeof(CkptHeader) ||
+        h.version != kCkptVersion) {
+        std::fclose(f); s->err = "checkpoint_load: not an AKUAPBF2 file of this library version"; return AKUA_ERR_INVALID;
     }
     if (h.n < 0 || h.n > s->capacity) { std::fclose(f); s->err = "checkpoint_load: particle count exceeds solver capacity"; return AKUA_ERR_INVALID; }
+    {
+        akua_pbf_config a = h.cfg, b = s->cfg;
+        for (int k = 0; k < 3; k++) a.gravity[k] = b.gravity[k] = 0.0f;
+        const char* why = nullptr;
+        if (!sameBytes(&a, &b, sizeof(a))) why = "checkpoint_load: the file was written with a different PBFConfig";
+        else if (!sameBytes(&h.corr, &s->corr, sizeof(h.corr))) why = "checkpoint_load: the file was written with different LambdaCorrParams";
+        else if (h.key_mode != s->opt.key_mode) why = "checkpoint_load: the file was written in a different key mode";
+        else if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH && (int64_t)s->cfg.maxNeighbours * h.n != (int64_t)s->grid.tableSize)
+            why = "checkpoint_load: REFERENCE_HASH needs the particle count the solver was created with (tableSize = 128 * n)";
+        if (why) { std::fclose(f); s->err = why; return AKUA_ERR_INVALID; }
+    }
     const size_t n = (size_t)h.n;
     std::vector<float4> pos(n), vel(n), color(n);
     std::vector<float> size(n);
@@ -1043,15 +1187,33 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
     std::fclose(f);
     if (!ok) { s->err = "checkpoint_load: truncated file"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
+    int rc = beforeUpload(s, h.n);
+    if (rc) return rc;
     if (n) {
+        // payload placement: slot i in x-slab mode (identity slots after the reset), index id[i] on one GPU
+        std::vector<float4> colorAt(n);
+        std::vector<float> sizeAt(n);
+        const bool byId = !s->slab.enabled;
+        for (size_t i = 0; i < n; i++) {
+            if (byId && id[i] >= (uint32_t)s->capacity) { s->err = "checkpoint_load: particle id outside the solver's capacity"; return AKUA_ERR_INVALID; }
+        }
+        if (byId) {
+            std::vector<float4> cfull((size_t)s->capacity, make_float4(0.f, 0.f, 1.f, 1.f));
+            std::vector<float> sfull((size_t)s->capacity, 50.0f);
+            for (size_t i = 0; i < n; i++) { cfull[id[i]] = color[i]; sfull[id[i]] = size[i]; }
+            AK_CUDA(s, cudaMemcpy(s->color, cfull.data(), cfull.size() * 16, cudaMemcpyHostToDevice));
+            AK_CUDA(s, cudaMemcpy(s->size, sfull.data(), sfull.size() * 4, cudaMemcpyHostToDevice));
+        } else {
+            AK_CUDA(s, cudaMemcpy(s->color, color.data(), n * 16, cudaMemcpyHostToDevice));
+            AK_CUDA(s, cudaMemcpy(s->size, size.data(), n * 4, cudaMemcpyHostToDevice));
+        }
         AK_CUDA(s, cudaMemcpy(s->pos, pos.data(), n * 16, cudaMemcpyHostToDevice));
         AK_CUDA(s, cudaMemcpy(s->xs, pos.data(), n * 16, cudaMemcpyHostToDevice));
         AK_CUDA(s, cudaMemcpy(s->vel, vel.data(), n * 16, cudaMemcpyHostToDevice));
         AK_CUDA(s, cudaMemcpy(s->id, id.data(), n * 4, cudaMemcpyHostToDevice));
-        AK_CUDA(s, cudaMemcpy(s->color, color.data(), n * 16, cudaMemcpyHostToDevice));
-        AK_CUDA(s, cudaMemcpy(s->size, size.data(), n * 4, cudaMemcpyHostToDevice));
+        AK_CUDA(s, cudaMemsetAsync(s->keysUnsorted, 0, n * sizeof(uint32_t), s->stream));
+        AK_CUDA(s, cudaStreamSynchronize(s->stream));
     }
-    s->n = h.n;
     s->massUniform = n > 0;
     s->uniformMass = n ? pos[0].w : 0.0f;
     for (size_t i = 1; i < n && s->massUniform; i++) s->massUniform = std::memcmp(&pos[i].w, &pos[0].w, 4) == 0;
@@ -1063,9 +1225,19 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path) {
 
 // ---- multi-GPU (x-slab) ----
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n) {
-    if (!s || !ids || n != s->n) { if (s) s->err = "upload_ids: n must equal the live particle count"; return AKUA_ERR_INVALID; }
+    if (!s || !ids) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    {
+        int rc = slabRefresh(s);
+        if (rc) return rc;
+    }
+    if (n != s->n) { s->err = "upload_ids: n must equal the live particle count"; return AKUA_ERR_INVALID; }
     if (n == 0) return AKUA_OK;
+    if (!s->slab.enabled) {
+        // on one GPU the id is also the index of the particle's render payload (k_pack_aos): it must stay inside the arrays
+        for (int64_t i = 0; i < n; i++)
+            if ((int64_t)ids[i] >= s->capacity) { s->err = "upload_ids: outside x-slab mode every id must be < capacity"; return AKUA_ERR_INVALID; }
+    }
     AK_CUDA(s, cudaMemcpyAsync(s->id, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
@@ -1090,19 +1262,21 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     AK_NCCL(s, g_nccl.CommInitRank(&comm, nranks, id, rank));
     sl.comm = comm; sl.rank = rank; sl.nranks = nranks;
     sl.migCap = (uint32_t)std::max<int64_t>(4096, s->capacity / 8);
-    sl.migBlocksCap = gridFor((uint64_t)s->capacity) + 1;
+    sl.migBlocksCap = (uint32_t)((s->capacity + slab::kMigTile - 1) / slab::kMigTile) + 1;
     {
         int lo = 0, hi = 0;
         AK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.bndStream, cudaStreamNonBlocking, hi));
-        const char* eb = std::getenv("AKUA_SLAB_BND_STREAM");
-        sl.useBndStream = !(eb && eb[0] == '0');
         for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
     }
-    AK_CUDA(s, dalloc(&sl.dCounts, 32));
-    AK_CUDA(s, cudaMemsetAsync(sl.dCounts, 0, 32 * sizeof(uint32_t), s->stream));
-    AK_CUDA(s, cudaMallocHost((void**)&sl.hCounts, 32 * sizeof(uint32_t)));
+    AK_CUDA(s, dalloc(&sl.dims, D_WORDS));
+    AK_CUDA(s, cudaMemsetAsync(sl.dims, 0, D_WORDS * sizeof(uint32_t), s->stream));
+    AK_CUDA(s, cudaMallocHost((void**)&sl.hDims, D_WORDS * sizeof(uint32_t)));
+    std::memset((void*)sl.hDims, 0, D_WORDS * sizeof(uint32_t));
+    AK_CUDA(s, dalloc(&sl.slot, (size_t)s->capacity)); AK_CUDA(s, dalloc(&sl.slotAlt, (size_t)s->capacity));
+    AK_CUDA(s, dalloc(&sl.freeSlots, (size_t)s->capacity));
+    AK_CUDA(s, cudaMemsetAsync(sl.slotAlt, 0, (size_t)s->capacity * sizeof(uint32_t), s->stream));
     AK_CUDA(s, dalloc(&sl.blockCnt, (size_t)2 * sl.migBlocksCap));
     AK_CUDA(s, dalloc(&sl.sendL, sl.migCap)); AK_CUDA(s, dalloc(&sl.sendR, sl.migCap));
     AK_CUDA(s, dalloc(&sl.recvL, sl.migCap)); AK_CUDA(s, dalloc(&sl.recvR, sl.migCap));
@@ -1121,12 +1295,13 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     const char* env = std::getenv("AKUA_SLAB_P2P");
     const bool wantP2p = !(env && env[0] == '0') && nranks > 1;
     constexpr int kIpc = 12;   // the last two (packed gather arrays) may be absent
-    struct PeerMsg { cudaIpcMemHandle_t h[kIpc]; uint32_t ghostBaseL, ghostBaseR, ok, migCap, hasPack, pad[3]; };
+    struct PeerMsg { cudaIpcMemHandle_t h[kIpc]; uint32_t ghostBaseL, ghostBaseR, ok, migCap, hasPack, ghostCap, pad[2]; };
     PeerMsg mine{};
     mine.ghostBaseL = sl.ghostBaseL; mine.ghostBaseR = sl.ghostBaseR; mine.ok = wantP2p ? 1u : 0u; mine.migCap = sl.migCap;
+    mine.ghostCap = sl.ghostCap;
     if (wantP2p) {
         void* arrs[kIpc] = {sl.xsBuf[0], sl.xsBuf[1], sl.velBuf[0], sl.velBuf[1], s->lambda, s->omegaLen, sl.flags,
-                            sl.dCounts, sl.recvL, sl.recvR, s->xl, s->xw};
+                            sl.dims, sl.recvL, sl.recvR, s->xl, s->xw};
         mine.hasPack = (s->xl && s->xw) ? 1u : 0u;
         for (int k = 0; k < (mine.hasPack ? kIpc : kIpc - 2); k++)
             if (cudaIpcGetMemHandle(&mine.h[k], arrs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); break; }
@@ -1153,9 +1328,9 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
                 if (cudaIpcOpenMemHandle(&ptr[k], m.h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
             p.xsBuf[0] = (float4*)ptr[0]; p.xsBuf[1] = (float4*)ptr[1]; p.velBuf[0] = (float4*)ptr[2]; p.velBuf[1] = (float4*)ptr[3];
             p.lambda = (float*)ptr[4]; p.omegaLen = (float*)ptr[5]; p.flags = (uint32_t*)ptr[6];
-            p.dCounts = (uint32_t*)ptr[7]; p.recvL = (slab::MigRecord*)ptr[8]; p.recvR = (slab::MigRecord*)ptr[9];
+            p.dims = (uint32_t*)ptr[7]; p.recvL = (slab::MigRecord*)ptr[8]; p.recvR = (slab::MigRecord*)ptr[9];
             p.migCap = m.migCap; p.xl = (float4*)ptr[10]; p.xw = (float4*)ptr[11];
-            p.ghostBaseL = m.ghostBaseL; p.ghostBaseR = m.ghostBaseR; p.open = true;
+            p.ghostBaseL = m.ghostBaseL; p.ghostBaseR = m.ghostBaseR; p.ghostCap = m.ghostCap; p.open = true;
             return true;
         };
         if (ok && hasL) ok = openPeer(got[0], sl.peerL);
@@ -1170,8 +1345,14 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         AK_CUDA(s, cudaMemcpy(&v, dflag, 4, cudaMemcpyDeviceToHost));
         cudaFree(dflag);
         sl.p2p = v != 0;
-        const char* fp = std::getenv("AKUA_SLAB_FUSED_PUSH");
-        sl.fusedPush = sl.p2p && fp && fp[0] == '1';
+    }
+    {
+        // boundary-plane launches get their own stream (overlap with the interior launches) under the p2p transport; the NCCL
+        // fallback issues everything in order on the main stream
+        const char* eb = std::getenv("AKUA_SLAB_BND_STREAM");
+        sl.useBndStream = sl.p2p && !(eb && eb[0] == '0');
+        const char* eg = std::getenv("AKUA_SLAB_GRAPH");
+        if (eg && eg[0] == '0') sl.graphBroken = true;
     }
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
@@ -1182,7 +1363,10 @@ int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi) {
     s->slab.xLoAbs = xCellLo; s->slab.xHiAbs = xCellHi;
     const bool first = !s->slab.enabled;
     s->slab.enabled = true;
-    return first ? slabAgreeMass(s) : AKUA_OK;   // collective, like the call itself
+    if (!first) return AKUA_OK;
+    int rc = slabResetCounts(s);                 // the particles uploaded so far are this rank's owned set
+    if (rc) return rc;
+    return slabAgreeMass(s);                     // collective, like the call itself
 }
 int akua_pbf_rebalance(akua_pbf_solver* s) {
     if (!s) return AKUA_ERR_INVALID;
@@ -1191,10 +1375,15 @@ int akua_pbf_rebalance(akua_pbf_solver* s) {
 }
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
     if (!s || !out) return AKUA_ERR_INVALID;
+    akua_pbf_solver* m = const_cast<akua_pbf_solver*>(s);
+    cudaSetDevice(m->device);
+    const int rc = slabRefresh(m);
     const SlabState& sl = s->slab;
+    unsigned long long st[3] = {0, 0, 0};
+    if (sl.hDims) std::memcpy(st, (const void*)(sl.hDims + D_STAT_MIG_IN), sizeof(st));
     out[0] = s->n; out[1] = sl.nGhostL; out[2] = sl.nGhostR; out[3] = sl.nPlaneL; out[4] = sl.nPlaneR;
-    out[5] = sl.exchanges; out[6] = sl.p2p ? -sl.bytesSent : sl.bytesSent; out[7] = sl.migratedIn;  // negative bytes: p2p transport
-    return AKUA_OK;
+    out[5] = sl.exchanges; out[6] = sl.p2p ? -(int64_t)st[2] : (int64_t)st[2]; out[7] = (int64_t)st[0];  // negative bytes: p2p transport
+    return rc;
 }
 // Balanced x-slab boundaries from a histogram of particles per absolute x cell column (pure host code, no CUDA):
 // bounds[r] .. bounds[r+1] is rank r's interval of columns (indices into hist); bounds[0] = 0, bounds[nranks] = ncols.
@@ -1244,13 +1433,19 @@ int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nrank
 }
 
 // ---- phase-level operators ----
-int akua_pbf_phase_predict(akua_pbf_solver* s, float dt) {
+static int phaseApiGuard(akua_pbf_solver* s) {
     if (!s) return AKUA_ERR_INVALID;
+    if (s->slab.enabled) { s->err = "phase-level operators are single-GPU only; use akua_pbf_step in slab mode"; return AKUA_ERR_INVALID; }
+    return AKUA_OK;
+}
+int akua_pbf_phase_predict(akua_pbf_solver* s, float dt) {
+    if (int g = phaseApiGuard(s)) return g;
     AK_CUDA(s, cudaSetDevice(s->device));
     return phasePredictKey(s, dt, true, false);
 }
 int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]) {
-    if (!s) return AKUA_ERR_INVALID;
+    if (int g = phaseApiGuard(s)) return g;
+    if ((boxMin == nullptr) != (boxMax == nullptr)) { s->err = "phase_neighbours: pass both box corners or neither"; return AKUA_ERR_INVALID; }
     AK_CUDA(s, cudaSetDevice(s->device));
     const float* bmin = boxMin ? boxMin : s->lastBoxMin;
     const float* bmax = boxMax ? boxMax : s->lastBoxMax;
@@ -1269,32 +1464,33 @@ int akua_pbf_phase_neighbours(akua_pbf_solver* s, const float boxMin[3], const f
 }
 int akua_pbf_phase_solve(akua_pbf_solver* s, int32_t iters, const float boxMin[3], const float boxMax[3]) {
     if (!s || !boxMin || !boxMax || iters < 0) return AKUA_ERR_INVALID;
-    if (s->slab.enabled) { s->err = "phase-level operators are single-GPU only; use akua_pbf_step in slab mode"; return AKUA_ERR_INVALID; }
+    if (int g = phaseApiGuard(s)) return g;
     AK_CUDA(s, cudaSetDevice(s->device));
     rememberBox(s, boxMin, boxMax);
     bool committed;
     return phaseSolve(s, iters, boxMin, boxMax, false, 0.0f, &committed);
 }
 int akua_pbf_phase_update(akua_pbf_solver* s, float dt) {
-    if (!s) return AKUA_ERR_INVALID;
+    if (int g = phaseApiGuard(s)) return g;
     AK_CUDA(s, cudaSetDevice(s->device));
     return phaseUpdate(s, dt);
 }
 int akua_pbf_phase_damping(akua_pbf_solver* s, const float boxMin[3], const float boxMax[3]) {
     if (!s || !boxMin || !boxMax) return AKUA_ERR_INVALID;
+    if (int g = phaseApiGuard(s)) return g;
     AK_CUDA(s, cudaSetDevice(s->device));
     return phaseDamping(s, boxMin, boxMax);
 }
 int akua_pbf_phase_vorticity_viscosity(akua_pbf_solver* s, float dt) {
-    if (!s) return AKUA_ERR_INVALID;
-    if (s->slab.enabled) { s->err = "phase-level operators are single-GPU only; use akua_pbf_step in slab mode"; return AKUA_ERR_INVALID; }
+    if (int g = phaseApiGuard(s)) return g;
     AK_CUDA(s, cudaSetDevice(s->device));
-    return phasePost(s, dt);
+    return phasePost(s, dt, 0);
 }
 
 // ---- debug taps ----
 int64_t akua_pbf_debug_size(akua_pbf_solver* s, int32_t which) {
     if (!s) return -1;
+    if (s->slab.enabled) { cudaSetDevice(s->device); slabRefresh(s); }
     const int64_t n = s->n;
     switch (which) {
         case AKUA_DBG_KEYS_UNSORTED: case AKUA_DBG_KEYS_SORTED: case AKUA_DBG_PERM: case AKUA_DBG_ID:
@@ -1333,7 +1529,7 @@ int akua_pbf_debug_get(akua_pbf_solver* s, int32_t which, void* dst, int64_t dst
             uint32_t* tmp = nullptr;
             AK_CUDA(s, cudaMalloc(&tmp, (size_t)need));
             uint64_t total = (uint64_t)s->n * s->cfg.maxNeighbours;
-            k_list_to_rowmajor<<<gridFor(total), kBlock, 0, s->stream>>>(s->nbrList, s->nbrCount, s->nbrStride, (uint32_t)s->n,
+            launchPlain(s->stream, k_list_to_rowmajor, gridFor(total), kBlock, s->nbrList, s->nbrCount, s->nbrStride, (uint32_t)s->n,
                 (uint32_t)s->cfg.maxNeighbours, tmp);
             AK_LAUNCH_CHECK(s, "k_list_to_rowmajor");
             cudaError_t e = cudaMemcpyAsync(dst, tmp, (size_t)need, cudaMemcpyDeviceToHost, s->stream);
@@ -1354,11 +1550,15 @@ int akua_pbf_debug_get(akua_pbf_solver* s, int32_t which, void* dst, int64_t dst
 int akua_pbf_density_error(akua_pbf_solver* s, float* mean, float* maxv) {
     if (!s) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
+    {
+        int rc = slabRefresh(s);
+        if (rc) return rc;
+    }
     const uint32_t n = (uint32_t)s->n;
     if (n == 0) { if (mean) *mean = 0; if (maxv) *maxv = 0; return AKUA_OK; }
     uint32_t blocks = gridFor(n);
     if (blocks > 1024) blocks = 1024;
-    k_density_error<<<blocks, kBlock, 0, s->stream>>>(s->density, n, 1.0f / s->cfg.restDensity, s->partSum, s->partMax);
+    launchPlain(s->stream, k_density_error, blocks, kBlock, s->density, n, 1.0f / s->cfg.restDensity, s->partSum, s->partMax);
     AK_LAUNCH_CHECK(s, "k_density_error");
     std::vector<float> hs(blocks), hm(blocks);
     AK_CUDA(s, cudaMemcpyAsync(hs.data(), s->partSum, blocks * 4, cudaMemcpyDeviceToHost, s->stream));

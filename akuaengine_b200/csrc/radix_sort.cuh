@@ -4,6 +4,8 @@
 // a CUB merge sort moving 216 B per particle per merge level) with a sort of 8-byte pairs followed by one gather.
 // Stable, so equal keys keep their input order — the same order the reference's (de-facto stable) merge sort leaves.
 //
+// The number of keys may live on the device (`nPtr`, x-slab mode: the host only knows an estimate): grids are sized from the
+// host's value and every kernel loops over the tiles of the actual count; tileHist rows have a fixed stride.
 // One pass per 8-bit digit, three launches per pass, no spin-waits between CTAs (nothing here can hang):
 //   count   : one CTA per 4096-key tile -> 256-bin histogram, written bin-major  tileHist[bin][tile]
 //   scan    : one CTA per bin           -> exclusive scan of that bin's row over tiles, row total -> binTotal[bin]
@@ -43,25 +45,30 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 template <int kItems>
-__global__ void __launch_bounds__(kThreads) k_count(const uint32_t* __restrict__ keys, uint32_t n, int shift,
-                                                    uint32_t* __restrict__ tileHist, uint32_t numTiles) {
+__global__ void __launch_bounds__(kThreads) k_count(const uint32_t* __restrict__ keys, uint32_t n,
+                                                    const uint32_t* __restrict__ nPtr, int shift,
+                                                    uint32_t* __restrict__ tileHist, uint32_t tileStride) {
     pdl_wait();
     constexpr int kTile = kThreads * kItems;
     __shared__ uint32_t hist[256];
     const int tid = threadIdx.x, lane = tid & 31;
-    hist[tid] = 0;
-    __syncthreads();
-    const uint32_t base = blockIdx.x * (uint32_t)kTile;
+    if (nPtr) n = *nPtr;
+    const uint32_t numTiles = (n + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t base = tile * (uint32_t)kTile;
 #pragma unroll 4
-    for (int r = 0; r < kItems; r++) {
-        uint32_t idx = base + r * kThreads + tid;
-        bool valid = idx < n;
-        uint32_t d = valid ? ((keys[idx] >> shift) & 255u) : 256u;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        for (int r = 0; r < kItems; r++) {
+            uint32_t idx = base + r * kThreads + tid;
+            bool valid = idx < n;
+            uint32_t d = valid ? ((keys[idx] >> shift) & 255u) : 256u;
+            uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        tileHist[(size_t)tid * tileStride + tile] = hist[tid];
     }
-    __syncthreads();
-    tileHist[(size_t)tid * numTiles + blockIdx.x] = hist[tid];
 }
 
 // Block-wide exclusive scan helper for 256 threads. Returns the exclusive prefix; *total gets the block sum.
@@ -87,11 +94,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* sm
     return incl - v + warpOff;
 }
 
-__global__ void __launch_bounds__(kThreads) k_scan(uint32_t* __restrict__ tileHist, uint32_t numTiles,
-                                                   uint32_t* __restrict__ binTotal) {
+__global__ void __launch_bounds__(kThreads) k_scan(uint32_t* __restrict__ tileHist, uint32_t n,
+                                                   const uint32_t* __restrict__ nPtr, uint32_t tileSize,
+                                                   uint32_t tileStride, uint32_t* __restrict__ binTotal) {
     pdl_wait();
     __shared__ uint32_t s8[kWarps];
-    uint32_t* row = tileHist + (size_t)blockIdx.x * numTiles;
+    if (nPtr) n = *nPtr;
+    const uint32_t numTiles = (n + tileSize - 1) / tileSize;
+    uint32_t* row = tileHist + (size_t)blockIdx.x * tileStride;
     uint32_t carry = 0;
     for (uint32_t base = 0; base < numTiles; base += kThreads) {
         uint32_t idx = base + threadIdx.x;
@@ -108,8 +118,9 @@ template <bool FIRST, int kItems>  // FIRST: input indices are implicit (idx its
 __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict__ keysIn,
                                                       const uint32_t* __restrict__ valsIn,
                                                       uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
-                                                      uint32_t n, int shift, const uint32_t* __restrict__ tileHist,
-                                                      uint32_t numTiles, const uint32_t* __restrict__ binTotal) {
+                                                      uint32_t n, const uint32_t* __restrict__ nPtr, int shift,
+                                                      const uint32_t* __restrict__ tileHist,
+                                                      uint32_t tileStride, const uint32_t* __restrict__ binTotal) {
     pdl_wait();
     constexpr int kTile = kThreads * kItems;
     constexpr int kWarpSpan = 32 * kItems;  // keys handled by one warp (contiguous -> stability)
@@ -120,17 +131,20 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict
     __shared__ uint32_t stageKey[kTile];
     __shared__ uint32_t stageVal[kTile];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (int i = tid; i < kWarps * 256; i += kThreads) (&warpCnt[0][0])[i] = 0;
+    if (nPtr) n = *nPtr;
+    const uint32_t numTiles = (n + kTile - 1) / kTile;
+    uint32_t binBase;
     {
         uint32_t tot;
-        uint32_t ex = block_excl_scan_256(binTotal[tid], s8, &tot);  // syncs inside
-        globalBase[tid] = ex + tileHist[(size_t)tid * numTiles + blockIdx.x];
+        binBase = block_excl_scan_256(binTotal[tid], s8, &tot);  // syncs inside
     }
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    for (int i = tid; i < kWarps * 256; i += kThreads) (&warpCnt[0][0])[i] = 0;
+    globalBase[tid] = binBase + tileHist[(size_t)tid * tileStride + tile];
     __syncthreads();
 
     uint32_t key[kItems], rank[kItems];
-    const uint32_t wbase = blockIdx.x * (uint32_t)kTile + warp * (uint32_t)kWarpSpan;
+    const uint32_t wbase = tile * (uint32_t)kTile + warp * (uint32_t)kWarpSpan;
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int r = 0; r < kItems; r++) {
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict
     }
     __syncthreads();
     // contiguous runs out: slot s holds digit d(s); its destination is globalBase[d] + (s - tileBase[d])
-    const uint32_t tileBeg = blockIdx.x * (uint32_t)kTile;
+    const uint32_t tileBeg = tile * (uint32_t)kTile;
     const uint32_t tileCount = min((uint32_t)kTile, n - tileBeg);
 #pragma unroll 4
     for (int r = 0; r < kItems; r++) {
@@ -186,6 +200,8 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const uint32_t* __restrict
             valsOut[dst] = stageVal[s];
         }
     }
+    __syncthreads();   // the staging arrays are reused by the next tile of this CTA
+    }
 }
 
 struct Workspace {
@@ -197,13 +213,11 @@ struct Workspace {
 constexpr uint64_t kSmallLimit = 8u << 20;
 inline int items_for(uint64_t n) { return n < kSmallLimit ? kItemsSmall : kItemsLarge; }
 inline uint32_t tiles_for(uint64_t n) { uint64_t t = (uint64_t)kThreads * items_for(n); return (uint32_t)((n + t - 1) / t); }
-// workspace must hold the tiling of any n <= capacity (the small tiling of a small n can need more tiles than the
-// large tiling of the capacity)
+// workspace must hold either tiling of any n <= capacity (with a device-side count the host picks the tiling from an
+// estimate, so the small tiling can meet a count up to the capacity)
 inline uint32_t max_tiles_for_capacity(uint64_t cap) {
-    uint64_t small = std::min<uint64_t>(cap, kSmallLimit - 1);
-    uint64_t a = (small + (uint64_t)kThreads * kItemsSmall - 1) / ((uint64_t)kThreads * kItemsSmall);
-    uint64_t b = (cap + (uint64_t)kThreads * kItemsLarge - 1) / ((uint64_t)kThreads * kItemsLarge);
-    return (uint32_t)std::max<uint64_t>(std::max(a, b), 1);
+    uint64_t a = (cap + (uint64_t)kThreads * kItemsSmall - 1) / ((uint64_t)kThreads * kItemsSmall);
+    return (uint32_t)std::max<uint64_t>(a, 1);
 }
 inline int passes_for_bits(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
 
@@ -223,11 +237,14 @@ inline void launch(bool pdl, void (*kernel)(KArgs...), uint32_t grid, cudaStream
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// `nPtr` (optional): the actual number of pairs lives on the device; `n` is then the host's estimate (grid sizing only).
 inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
-                      uint32_t** valsOut, bool pdl = false) {
-    const uint32_t numTiles = tiles_for(n);
+                      uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr) {
+    const uint32_t numTiles = std::max(1u, tiles_for(n));
     const bool small = items_for(n) == kItemsSmall;
+    const uint32_t tileSize = (uint32_t)kThreads * (small ? kItemsSmall : kItemsLarge);
+    const uint32_t tileStride = ws.maxTiles;
     const int passes = passes_for_bits(keyBits);
     const uint32_t* kin = keysIn;
     const uint32_t* vin = nullptr;
@@ -236,10 +253,10 @@ inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, ui
     int launches = 0;
     for (int p = 0; p < passes; p++) {
         int shift = 8 * p;
-        if (small) launch(pdl, k_count<kItemsSmall>, numTiles, st, kin, n, shift, ws.tileHist, numTiles);
-        else       launch(pdl, k_count<kItemsLarge>, numTiles, st, kin, n, shift, ws.tileHist, numTiles);
-        launch(pdl, k_scan, 256u, st, ws.tileHist, numTiles, ws.binTotal);
-#define AK_SCATTER(F, I) launch(pdl, k_scatter<F, I>, numTiles, st, kin, vin, kout, vout, n, shift, ws.tileHist, numTiles, ws.binTotal)
+        if (small) launch(pdl, k_count<kItemsSmall>, numTiles, st, kin, n, nPtr, shift, ws.tileHist, tileStride);
+        else       launch(pdl, k_count<kItemsLarge>, numTiles, st, kin, n, nPtr, shift, ws.tileHist, tileStride);
+        launch(pdl, k_scan, 256u, st, ws.tileHist, n, nPtr, tileSize, tileStride, ws.binTotal);
+#define AK_SCATTER(F, I) launch(pdl, k_scatter<F, I>, numTiles, st, kin, vin, kout, vout, n, nPtr, shift, ws.tileHist, tileStride, ws.binTotal)
         if (p == 0) { if (small) AK_SCATTER(true, kItemsSmall); else AK_SCATTER(true, kItemsLarge); }
         else        { if (small) AK_SCATTER(false, kItemsSmall); else AK_SCATTER(false, kItemsLarge); }
 #undef AK_SCATTER

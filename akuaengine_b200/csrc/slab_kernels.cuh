@@ -2,6 +2,10 @@
 // single-GPU). Keys are x-major, so after the sort a rank's particles are ordered by x-plane: the
 // boundary planes it must send as ghosts are contiguous ranges of every SoA array (no pack kernels on the per-iteration
 // path), and particles that left the slab carry a sentinel key that sorts them past the end of the owned range.
+//
+// Every size of a step (owned count, arrivals, leavers, boundary / ghost plane sizes) lives in the device-resident `dims`
+// block (pbf_kernels.cuh: D_*): the kernels below compute and consume them on the device, grids come from a host estimate
+// and every kernel loops, so the step needs no host synchronisation and is replayed as a CUDA graph.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,58 +16,72 @@
 namespace akua {
 namespace slab {
 
-struct MigRecord { float4 pos, vel, xs; uint4 meta; };  // meta.x = particle id
+// A migrating particle: solver state + the render payload (Particle::color / ::size follow the particle like they do in the
+// reference, which sorts whole structs: src/CUDA/NeighbourSearchCUDA.cu:167-170). meta = (global id, size bits, 0, 0).
+struct MigRecord { float4 pos, vel, xs, color; uint4 meta; };
 
-// Destination of a particle from its (grid-relative, clamped) x cell: 0 = left neighbour, 1 = stays, 2 = right neighbour.
+constexpr int kMigTile = 256;
+enum : int { D_FREE_TOP = 49, D_FREE_POP = 50 };   // payload-slot free stack: entries in use; pop base of this step's arrivals
+
+// Destination of a particle from its (slab-local, clamped) x cell: 0 = left neighbour, 1 = stays, 2 = right neighbour.
 __device__ __forceinline__ int dest_of(uint32_t key, uint32_t planeCells, int xLo, int xHi) {
     int cx = (int)(key / planeCells);
     return cx < xLo ? 0 : (cx >= xHi ? 2 : 1);
 }
 
-// Pass 1: per-CTA counts of leavers in each direction (deterministic compaction, no atomics on the compaction path),
+// Pass 1: per-tile counts of leavers in each direction (deterministic compaction, no atomics on the compaction path),
 // plus the four plane populations that let every rank PREDICT its post-migration boundary-plane and ghost-plane sizes
 // from one count exchange (extra[0] stayers in my first plane, [1] stayers in my last plane, [2] leavers to the left that
 // land in the left rank's last plane, [3] leavers to the right that land in the right rank's first plane).
-__global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, uint32_t n, uint32_t planeCells,
-                                                   int xLo, int xHi, uint32_t* __restrict__ blockCnt /*[2][blocks]*/,
+__global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nPtr,
+                                                   uint32_t planeCells, int xLo, int xHi,
+                                                   uint32_t* __restrict__ blockCnt /*[2][tileStride]*/, uint32_t tileStride,
                                                    uint32_t* __restrict__ extra /*[4], zeroed*/) {
     __shared__ uint32_t sL[8], sR[8], sE[4];
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x < 4) sE[threadIdx.x] = 0;
-    __syncthreads();
-    int cx = i < n ? (int)(keys[i] / planeCells) : xLo + 1;
-    int d = i < n ? (cx < xLo ? 0 : (cx >= xHi ? 2 : 1)) : 1;
-    uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
-    uint32_t b0 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xLo);
-    uint32_t b1 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xHi - 1);
-    uint32_t b2 = __ballot_sync(0xffffffffu, d == 0 && cx == xLo - 1);
-    uint32_t b3 = __ballot_sync(0xffffffffu, d == 2 && cx == xHi);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        sL[warp] = __popc(bl); sR[warp] = __popc(br);
-        if (b0) atomicAdd(&sE[0], (uint32_t)__popc(b0));
-        if (b1) atomicAdd(&sE[1], (uint32_t)__popc(b1));
-        if (b2) atomicAdd(&sE[2], (uint32_t)__popc(b2));
-        if (b3) atomicAdd(&sE[3], (uint32_t)__popc(b3));
+    const uint32_t n = *nPtr;
+    const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const uint32_t i = tile * kMigTile + threadIdx.x;
+        if (threadIdx.x < 4) sE[threadIdx.x] = 0;
+        __syncthreads();
+        int cx = i < n ? (int)(keys[i] / planeCells) : xLo + 1;
+        int d = i < n ? (cx < xLo ? 0 : (cx >= xHi ? 2 : 1)) : 1;
+        uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
+        uint32_t b0 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xLo);
+        uint32_t b1 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xHi - 1);
+        uint32_t b2 = __ballot_sync(0xffffffffu, d == 0 && cx == xLo - 1);
+        uint32_t b3 = __ballot_sync(0xffffffffu, d == 2 && cx == xHi);
+        if (lane == 0) {
+            sL[warp] = __popc(bl); sR[warp] = __popc(br);
+            if (b0) atomicAdd(&sE[0], (uint32_t)__popc(b0));
+            if (b1) atomicAdd(&sE[1], (uint32_t)__popc(b1));
+            if (b2) atomicAdd(&sE[2], (uint32_t)__popc(b2));
+            if (b3) atomicAdd(&sE[3], (uint32_t)__popc(b3));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t a = 0, b = 0;
+            for (int w = 0; w < 8; w++) { a += sL[w]; b += sR[w]; }
+            blockCnt[tile] = a;
+            blockCnt[tileStride + tile] = b;
+        }
+        if (threadIdx.x < 4 && sE[threadIdx.x]) atomicAdd(&extra[threadIdx.x], sE[threadIdx.x]);
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t a = 0, b = 0;
-        for (int w = 0; w < 8; w++) { a += sL[w]; b += sR[w]; }
-        blockCnt[blockIdx.x] = a;
-        blockCnt[gridDim.x + blockIdx.x] = b;
-    }
-    if (threadIdx.x < 4 && sE[threadIdx.x]) atomicAdd(&extra[threadIdx.x], sE[threadIdx.x]);
 }
-// Pass 2 (one CTA of 1024 threads): exclusive scan of the per-CTA counts in place, both directions at once; totals ->
-// counts[0] (left), counts[1] (right).
-__global__ void __launch_bounds__(1024) k_mig_scan(uint32_t* __restrict__ blockCnt, uint32_t blocks, uint32_t* __restrict__ counts) {
+// Pass 2 (one CTA of 1024 threads): exclusive scan of the per-tile counts in place, both directions at once; totals ->
+// dims[D_OUT_L], dims[D_OUT_R]; also assembles the two count messages.
+__global__ void __launch_bounds__(1024) k_mig_scan(uint32_t* __restrict__ blockCnt, const uint32_t* __restrict__ nPtr,
+                                                   uint32_t tileStride, uint32_t* __restrict__ counts) {
     __shared__ uint32_t wsum[2][32];
+    __shared__ uint32_t tot[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t blocks = (*nPtr + kMigTile - 1) / kMigTile;
     uint32_t carry0 = 0, carry1 = 0;
     for (uint32_t base = 0; base < blocks; base += 1024) {
         const uint32_t idx = base + tid;
-        const uint32_t v0 = idx < blocks ? blockCnt[idx] : 0u, v1 = idx < blocks ? blockCnt[blocks + idx] : 0u;
+        const uint32_t v0 = idx < blocks ? blockCnt[idx] : 0u, v1 = idx < blocks ? blockCnt[tileStride + idx] : 0u;
         uint32_t i0 = v0, i1 = v1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -83,68 +101,172 @@ __global__ void __launch_bounds__(1024) k_mig_scan(uint32_t* __restrict__ blockC
         }
         __syncthreads();
         const uint32_t off0 = wsum[0][warp], off1 = wsum[1][warp];
-        if (idx < blocks) { blockCnt[idx] = carry0 + off0 + i0 - v0; blockCnt[blocks + idx] = carry1 + off1 + i1 - v1; }
+        if (idx < blocks) { blockCnt[idx] = carry0 + off0 + i0 - v0; blockCnt[tileStride + idx] = carry1 + off1 + i1 - v1; }
         // chunk totals = exclusive offset of the last warp + its inclusive sum
-        __shared__ uint32_t tot[2];
         if (tid == 1023) { tot[0] = off0 + i0; tot[1] = off1 + i1; }
         __syncthreads();
         carry0 += tot[0]; carry1 += tot[1];
         __syncthreads();
     }
-    if (tid == 0) { counts[0] = carry0; counts[1] = carry1; }
     // messages for the single count exchange: to the left rank {leavers, leavers landing in its last plane, my
-    // first-plane stayers} at counts[16..18]; to the right rank the mirror image at counts[20..22]
-    if (threadIdx.x == 0) {
-        counts[16] = counts[0]; counts[17] = counts[4]; counts[18] = counts[2];
-        counts[20] = counts[1]; counts[21] = counts[5]; counts[22] = counts[3];
+    // first-plane stayers}; to the right rank the mirror image
+    if (tid == 0) {
+        counts[D_OUT_L] = carry0; counts[D_OUT_R] = carry1;
+        counts[D_MSG_TO_L] = carry0; counts[D_MSG_TO_L + 1] = counts[D_LAND_L]; counts[D_MSG_TO_L + 2] = counts[D_STAY_FIRST];
+        counts[D_MSG_TO_R] = carry1; counts[D_MSG_TO_R + 1] = counts[D_LAND_R]; counts[D_MSG_TO_R + 2] = counts[D_STAY_LAST];
     }
 }
-// Pass 3: leavers are copied (in index order) into the send buffers and get the sentinel key, which sorts them past the
-// owned range so the reorder drops them.
-__global__ void __launch_bounds__(256) k_mig_pack(uint32_t* __restrict__ keys, uint32_t n, uint32_t planeCells, int xLo,
-                                                  int xHi, const uint32_t* __restrict__ blockOff, uint32_t sentinel,
+// Pass 3: leavers are copied (in index order) into the send buffers — with the CUDA-IPC transport straight into the
+// neighbour's inbox over NVLink — and get the sentinel key, which sorts them past the owned range so the reorder drops
+// them. Their payload slots go back on the free stack (in send-buffer order: deterministic).
+__global__ void __launch_bounds__(256) k_mig_pack(uint32_t* __restrict__ keys, const uint32_t* __restrict__ dims,
+                                                  uint32_t planeCells, int xLo, int xHi, const uint32_t* __restrict__ blockOff,
+                                                  uint32_t tileStride, uint32_t sentinel,
                                                   const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                   const float4* __restrict__ xs, const uint32_t* __restrict__ id,
+                                                  const uint32_t* __restrict__ slot, const float4* __restrict__ color,
+                                                  const float* __restrict__ size, uint32_t* __restrict__ freeSlots,
                                                   MigRecord* __restrict__ sendL, MigRecord* __restrict__ sendR,
                                                   uint32_t cap) {
     __shared__ uint32_t sL[8], sR[8];
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    int d = i < n ? dest_of(keys[i], planeCells, xLo, xHi) : 1;
-    uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sL[warp] = __popc(bl); sR[warp] = __popc(br); }
-    __syncthreads();
-    if (d == 1) return;
-    uint32_t lt = (1u << lane) - 1;
-    uint32_t off = 0;
-    for (int w = 0; w < warp; w++) off += (d == 0 ? sL[w] : sR[w]);
-    off += __popc((d == 0 ? bl : br) & lt);
-    uint32_t slot = (d == 0 ? blockOff[blockIdx.x] : blockOff[gridDim.x + blockIdx.x]) + off;
-    if (slot < cap) {
-        MigRecord r;
-        r.pos = pos[i]; r.vel = vel[i]; r.xs = xs[i]; r.meta = make_uint4(id[i], 0, 0, 0);
-        (d == 0 ? sendL : sendR)[slot] = r;
+    const uint32_t n = dims[D_N];
+    const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
+    const uint32_t outL = min(dims[D_OUT_L], cap), freeTop = dims[D_FREE_TOP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const uint32_t i = tile * kMigTile + threadIdx.x;
+        int d = i < n ? dest_of(keys[i], planeCells, xLo, xHi) : 1;
+        uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
+        if (lane == 0) { sL[warp] = __popc(bl); sR[warp] = __popc(br); }
+        __syncthreads();
+        if (d != 1) {
+            uint32_t lt = (1u << lane) - 1;
+            uint32_t off = 0;
+            for (int w = 0; w < warp; w++) off += (d == 0 ? sL[w] : sR[w]);
+            off += __popc((d == 0 ? bl : br) & lt);
+            uint32_t dst = (d == 0 ? blockOff[tile] : blockOff[tileStride + tile]) + off;
+            if (dst < cap) {
+                const uint32_t ps = slot[i];
+                MigRecord r;
+                r.pos = pos[i]; r.vel = vel[i]; r.xs = xs[i]; r.color = color[ps];
+                r.meta = make_uint4(id[i], __float_as_uint(size[ps]), 0, 0);
+                (d == 0 ? sendL : sendR)[dst] = r;
+                freeSlots[freeTop + (d == 0 ? dst : outL + dst)] = ps;
+            }
+            keys[i] = sentinel;
+        }
+        __syncthreads();
     }
-    keys[i] = sentinel;
 }
-// Arrivals are appended after the resident particles (before the sort) and keyed like everyone else.
-__global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict__ recv, uint32_t count, uint32_t base,
+
+// CUDA-IPC transport of the per-step count message: the three counters for each neighbour (assembled by k_mig_scan) are
+// stored straight into the neighbour's dims block (the slots it reads them from: D_MSG_FROM_R of the left rank, D_MSG_FROM_L
+// of the right rank), then the message epoch is published in the neighbour's flag word. The migration records were stored
+// into the neighbour's inbox by k_mig_pack earlier in the same stream, so one flag covers both. One thread.
+__global__ void k_publish_counts(const uint32_t* __restrict__ dims, uint32_t* __restrict__ peerDimsL,
+                                 uint32_t* __restrict__ peerDimsR, uint32_t* __restrict__ peerFlagL,
+                                 uint32_t* __restrict__ peerFlagR) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t epoch = dims[D_EPOCH] + 1u;
+    __threadfence_system();
+    if (peerDimsL) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerDimsL)[D_MSG_FROM_R + k] = dims[D_MSG_TO_L + k];
+    if (peerDimsR) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerDimsR)[D_MSG_FROM_L + k] = dims[D_MSG_TO_R + k];
+    __threadfence_system();
+    if (peerFlagL) *(volatile uint32_t*)peerFlagL = epoch;
+    if (peerFlagR) *(volatile uint32_t*)peerFlagR = epoch;
+    __threadfence_system();
+}
+
+// The step's plan, computed on the device by one thread once both neighbours' count messages are in (CUDA-IPC transport:
+// bounded in-kernel wait on the message epochs; NCCL transport: the messages were received before the launch). Every later
+// kernel of the step reads its sizes from here. All sizes are clamped to the buffers they index (memory safety) and any
+// clamp raises a sticky error bit the host reports at its next look.
+struct PlanCaps {
+    uint32_t packCap;        // leavers per direction that fit the outboxes / the neighbours' inboxes
+    uint32_t migCap;         // arrivals per direction that fit this rank's inboxes
+    uint32_t ownedCap;       // owned + arriving particles that fit below the ghost regions
+    uint32_t planeCapL, planeCapR;   // boundary-plane particles that fit the left / right neighbour's ghost region
+    uint32_t ghostCap;       // ghost particles per side that fit this rank's ghost regions
+    uint32_t slotCap;        // payload slots
+};
+__global__ void k_slab_plan(uint32_t* __restrict__ dims, const uint32_t* __restrict__ countFlags /* [0] left, [1] right */,
+                            int hasL, int hasR, int waitFlags, PlanCaps caps, long long timeoutCycles) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t err = 0;
+    if (waitFlags) {
+        const uint32_t epoch = dims[D_EPOCH] + 1u;
+        if (hasL && !spin_until(countFlags + 0, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
+        if (hasR && !spin_until(countFlags + 1, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
+        __threadfence_system();
+    }
+    const volatile uint32_t* d = dims;
+    uint32_t outL = d[D_OUT_L], outR = d[D_OUT_R];
+    if (outL > caps.packCap) { outL = caps.packCap; err |= SLAB_ERR_MIG_OVERFLOW; }
+    if (outR > caps.packCap) { outR = caps.packCap; err |= SLAB_ERR_MIG_OVERFLOW; }
+    uint32_t inL = hasL ? d[D_MSG_FROM_L] : 0u, inR = hasR ? d[D_MSG_FROM_R] : 0u;
+    if (err & SLAB_ERR_TIMEOUT) inL = inR = 0;    // nothing trustworthy arrived
+    if (inL > caps.migCap) { inL = caps.migCap; err |= SLAB_ERR_MIG_OVERFLOW; }
+    if (inR > caps.migCap) { inR = caps.migCap; err |= SLAB_ERR_MIG_OVERFLOW; }
+    const uint32_t n = d[D_N];
+    uint32_t room = caps.ownedCap > n ? caps.ownedCap - n : 0u;
+    const uint32_t freeTop = min(d[D_FREE_TOP] + outL + outR, caps.slotCap);
+    room = min(room, freeTop);
+    if (inL > room) { inL = room; err |= SLAB_ERR_CAPACITY; }
+    if (inR > room - inL) { inR = room - inL; err |= SLAB_ERR_CAPACITY; }
+    const uint32_t nPre = n + inL + inR;
+    const uint32_t nOwn = nPre - outL - outR;
+    // Post-migration plane sizes, known before the sort: my boundary planes = stayers + arrivals that land in them; a
+    // neighbour's facing plane (= my ghosts) = its stayers there + my leavers that land there. (Arrivals from the far side
+    // cannot reach the near plane: slabs are >= 2 planes wide and the stepper moves particles by << one slab.)
+    uint32_t planeL = hasL ? d[D_STAY_FIRST] + d[D_MSG_FROM_L + 1] : 0u;
+    uint32_t planeR = hasR ? d[D_STAY_LAST] + d[D_MSG_FROM_R + 1] : 0u;
+    uint32_t ghostL = hasL ? d[D_MSG_FROM_L + 2] + d[D_LAND_L] : 0u;
+    uint32_t ghostR = hasR ? d[D_MSG_FROM_R + 2] + d[D_LAND_R] : 0u;
+    if (err & SLAB_ERR_TIMEOUT) ghostL = ghostR = 0;
+    if (planeL > caps.planeCapL) { planeL = caps.planeCapL; err |= SLAB_ERR_GHOST_OVERFLOW; }
+    if (planeR > caps.planeCapR) { planeR = caps.planeCapR; err |= SLAB_ERR_GHOST_OVERFLOW; }
+    if (ghostL > caps.ghostCap) { ghostL = caps.ghostCap; err |= SLAB_ERR_GHOST_OVERFLOW; }
+    if (ghostR > caps.ghostCap) { ghostR = caps.ghostCap; err |= SLAB_ERR_GHOST_OVERFLOW; }
+    if (planeL > nOwn) planeL = nOwn;
+    if (planeR > nOwn) planeR = nOwn;
+    dims[D_OUT_L] = outL; dims[D_OUT_R] = outR;
+    dims[D_IN_L] = inL; dims[D_IN_R] = inR; dims[D_NPRE] = nPre; dims[D_NOWN] = nOwn;
+    dims[D_PLANE_L] = planeL; dims[D_PLANE_R] = planeR; dims[D_GHOST_L] = ghostL; dims[D_GHOST_R] = ghostR;
+    dims[D_FREE_POP] = freeTop; dims[D_FREE_TOP] = freeTop - inL - inR;
+    if (err) atomicOr(dims + D_ERROR, err);
+}
+
+// Arrivals (left inbox first, then right) are appended after the resident particles (before the sort), keyed like everyone
+// else, and take a payload slot from the free stack. A record whose x* does not lie in this rank's planes (it crossed more
+// than a slab in one step) is filed under the nearest owned plane; the next step's migration moves it on.
+__global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict__ recvL, const MigRecord* __restrict__ recvR,
+                                                    const uint32_t* __restrict__ dims,
                                                     float4* __restrict__ pos, float4* __restrict__ vel,
                                                     float4* __restrict__ xs, uint32_t* __restrict__ id,
-                                                    uint32_t* __restrict__ keys, GridParams G) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    MigRecord r = recv[t];
-    uint32_t i = base + t;
-    pos[i] = r.pos; vel[i] = r.vel; xs[i] = r.xs; id[i] = r.meta.x;
-    keys[i] = linear_key(cell_of(r.xs.x, r.xs.y, r.xs.z, G.cellSize), G);
+                                                    uint32_t* __restrict__ slot, float4* __restrict__ color,
+                                                    float* __restrict__ size, const uint32_t* __restrict__ freeSlots,
+                                                    uint32_t* __restrict__ keys, GridParams G, int xLo, int xHi) {
+    const uint32_t inL = dims[D_IN_L], count = inL + dims[D_IN_R], base = dims[D_N], popBase = dims[D_FREE_POP];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const MigRecord r = t < inL ? recvL[t] : recvR[t - inL];
+        const uint32_t i = base + t;
+        const uint32_t ps = freeSlots[popBase - 1u - t];
+        pos[i] = r.pos; vel[i] = r.vel; xs[i] = r.xs; id[i] = r.meta.x;
+        slot[i] = ps; color[ps] = r.color; size[ps] = __uint_as_float(r.meta.y);
+        const int3 c = cell_of(r.xs.x, r.xs.y, r.xs.z, G.cellSize);
+        const int x = clampi(c.x - G.gridMin.x, xLo, xHi - 1);
+        const int y = clampi(c.y - G.gridMin.y, 0, G.gridDim.y - 1);
+        const int z = clampi(c.z - G.gridMin.z, 0, G.gridDim.z - 1);
+        keys[i] = (uint32_t)((x * G.gridDim.y + y) * G.gridDim.z + z);
+    }
 }
-// Verifies the predicted boundary-plane sizes against the sorted keys (binary searches; two threads): a mismatch sets
-// the sticky error word counts[31], which the host sees at the next step's count exchange.
-__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells, int xLo, int xHi,
-                               uint32_t predictFirst, uint32_t predictLast, int hasL, int hasR, uint32_t* __restrict__ counts) {
+// Verifies the predicted boundary-plane sizes against the sorted keys (binary searches; two threads): a mismatch raises the
+// sticky error word.
+__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
+                               int hasL, int hasR, uint32_t* __restrict__ dims) {
     int t = threadIdx.x;
     if (t > 1) return;
+    const uint32_t nOwn = dims[D_NOWN];
     uint64_t bound = (uint64_t)(t == 0 ? (xLo + 1) : (xHi - 1)) * planeCells;
     uint32_t lo = 0, hi = nOwn;
     while (lo < hi) {
@@ -152,13 +274,13 @@ __global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t
         if ((uint64_t)keysSorted[mid] < bound) lo = mid + 1; else hi = mid;
     }
     uint32_t actual = t == 0 ? lo : nOwn - lo;
-    if (t == 0 && hasL && actual != predictFirst) counts[31] = 1;
-    if (t == 1 && hasR && actual != predictLast) counts[31] = 1;
+    if (t == 0 && hasL && actual != dims[D_PLANE_L]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
+    if (t == 1 && hasR && actual != dims[D_PLANE_R]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
 }
-// Per-x-plane population of the owned (key-sorted) particles: hist[x] = #{ i : key_i / planeCells == x }, by two binary
-// searches per plane (one thread per plane). Used to re-balance the slab boundaries.
+// Per-x-plane population of the owned (key-sorted) particles: hist[planeOffset + x] = #{ i : key_i / planeCells == x }, by two
+// binary searches per plane (one thread per plane). Used to re-balance the slab boundaries.
 __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells,
-                                                    int gx, unsigned long long* __restrict__ hist) {
+                                                    int gx, int planeOffset, unsigned long long* __restrict__ hist) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= gx) return;
     auto lower = [&](uint64_t bound) {
@@ -169,58 +291,70 @@ __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__
         }
         return lo;
     };
-    hist[x] = (unsigned long long)(lower((uint64_t)(x + 1) * planeCells) - lower((uint64_t)x * planeCells));
+    hist[planeOffset + x] = (unsigned long long)(lower((uint64_t)(x + 1) * planeCells) - lower((uint64_t)x * planeCells));
 }
 
-// ---- peer-to-peer signalling (CUDA IPC path) ----
-// After a rank has copied its boundary plane straight into the neighbour's ghost region (peer-mapped memory over NVLink),
-// it publishes the exchange's epoch in the neighbour's flag word; the neighbour's stream runs k_wait_flags before the
-// kernel that reads the ghosts. Epochs only grow, so "flag >= epoch" (wrap-safe) is the wait condition. The wait is
-// bounded: on timeout it raises the sticky error word instead of hanging the GPU.
-__global__ void k_signal_flag(uint32_t* __restrict__ peerFlag, uint32_t epoch) {
-    __threadfence_system();
-    *(volatile uint32_t*)peerFlag = epoch;
-    __threadfence_system();
-}
-// CUDA-IPC transport of the per-step count message: the three counters for each neighbour (assembled by k_mig_scan at
-// counts[16..18] / [20..22]) are stored straight into the neighbour's counter block (the slots it reads them from:
-// [28..30] of the left rank = "from my right", [24..26] of the right rank = "from my left"), then the message epoch is
-// published in the neighbour's flag word. The migration records were stored into the neighbour's inbox by k_mig_pack
-// earlier in the same stream, so one flag covers both. One thread.
-__global__ void k_publish_counts(const uint32_t* __restrict__ counts, uint32_t* __restrict__ peerCountsL,
-                                 uint32_t* __restrict__ peerCountsR, uint32_t* __restrict__ peerFlagL,
-                                 uint32_t* __restrict__ peerFlagR, uint32_t epoch) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    __threadfence_system();
-    if (peerCountsL) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerCountsL)[28 + k] = counts[16 + k];
-    if (peerCountsR) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerCountsR)[24 + k] = counts[20 + k];
-    __threadfence_system();
-    if (peerFlagL) *(volatile uint32_t*)peerFlagL = epoch;
-    if (peerFlagR) *(volatile uint32_t*)peerFlagR = epoch;
-    __threadfence_system();
-}
-__global__ void k_wait_flags(const uint32_t* __restrict__ flags, int waitL, int waitR, uint32_t epoch,
-                             uint32_t* __restrict__ errWord, long long timeoutCycles) {
-    const long long t0 = clock64();
-    for (int side = 0; side < 2; side++) {
-        if (!(side == 0 ? waitL : waitR)) continue;
-        const volatile uint32_t* f = flags + side;
-        while ((int32_t)(*f - epoch) < 0) {
-            if (clock64() - t0 > timeoutCycles) { *errWord = 2; return; }
-            __nanosleep(200);
-        }
+// ---- fused halo push (CUDA IPC path) ----
+// Copies this rank's first / last boundary plane of `src` straight into the neighbours' ghost regions with P2P stores over
+// NVLink; the last CTA publishes the exchange's epoch (halo_signal). Used where no sweep produces the planes (x* after the
+// reorder; v when solverIterations == 0) — the sweeps push their own results (PeerPush in pbf_kernels.cuh).
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_planes(const T* __restrict__ src, PeerPush pp, HaloSync hs) {
+    pdl_wait();
+    resolve_push(pp);
+    const uint32_t n = pp.dims[D_NOWN];
+    const uint32_t nL = pp.dstL ? pp.nL : 0u, nR = (pp.dstR && pp.startR <= n) ? n - pp.startR : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nL + nR; t += gridDim.x * blockDim.x) {
+        if (t < nL) static_cast<T*>(pp.dstL)[t] = src[t];
+        else static_cast<T*>(pp.dstR)[t - nL] = src[pp.startR + (t - nL)];
     }
-    __threadfence_system();
+    halo_signal(hs);
 }
-
-// Cell ranges of a contiguous, already key-sorted block [begin, end) (ghost planes received from a neighbour).
-__global__ void __launch_bounds__(256) k_ranges(const uint32_t* __restrict__ keysSorted, uint32_t begin, uint32_t end,
-                                                uint2* __restrict__ cellRange) {
-    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
-    uint32_t k = keysSorted[i];
-    if (i == begin || keysSorted[i - 1] != k) cellRange[k].x = i;
-    if (i == end - 1 || keysSorted[i + 1] != k) cellRange[k].y = i + 1;
+// Ghost planes received from the neighbours (already key-sorted: one x plane each, ordered like this rank's cells): keys from
+// the received x*, and the (start, end) range of every ghost cell. Waits in-kernel for the x* exchange (CUDA IPC path).
+__global__ void __launch_bounds__(256) k_ghost_ranges(const float4* __restrict__ xs, uint32_t* __restrict__ keysSorted,
+                                                      const uint32_t* __restrict__ dims, uint32_t ghostBaseL,
+                                                      uint32_t ghostBaseR, uint2* __restrict__ cellRange, GridParams G,
+                                                      HaloSync hs) {
+    pdl_wait();
+    halo_wait(hs);
+    const uint32_t gL = dims[D_GHOST_L], gR = dims[D_GHOST_R];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < gL + gR; t += gridDim.x * blockDim.x) {
+        const bool left = t < gL;
+        const uint32_t local = left ? t : t - gL, cnt = left ? gL : gR;
+        const uint32_t j = (left ? ghostBaseL : ghostBaseR) + local;
+        const float4 x = xs[j];
+        const uint32_t k = linear_key(cell_of(x.x, x.y, x.z, G.cellSize), G);
+        keysSorted[j] = k;
+        bool first = local == 0, last = local + 1 == cnt;
+        if (!first) { const float4 a = xs[j - 1]; first = linear_key(cell_of(a.x, a.y, a.z, G.cellSize), G) != k; }
+        if (!last) { const float4 b = xs[j + 1]; last = linear_key(cell_of(b.x, b.y, b.z, G.cellSize), G) != k; }
+        if (first) cellRange[k].x = j;
+        if (last) cellRange[k].y = j + 1;
+    }
+}
+// Closes a step on the device: the owned count carries over, the epoch base advances past this step's exchanges, the
+// statistics accumulate. `planeBytes` = bytes pushed per boundary-plane particle over the whole step.
+__global__ void k_step_end(uint32_t* __restrict__ dims, uint32_t exchanges, uint32_t planeBytes) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    dims[D_N] = dims[D_NOWN];
+    dims[D_EPOCH] += exchanges;
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(dims + D_STAT_MIG_IN);
+    st[0] += dims[D_IN_L] + dims[D_IN_R];
+    st[1] += dims[D_OUT_L] + dims[D_OUT_R];
+    st[2] += (unsigned long long)(dims[D_PLANE_L] + dims[D_PLANE_R]) * planeBytes
+           + (unsigned long long)(dims[D_OUT_L] + dims[D_OUT_R]) * sizeof(MigRecord);
+    dims[D_STEPS] += 1;
+}
+// (Re)initialises the device-side bookkeeping after an upload: owned count, identity payload slots, full free stack.
+__global__ void __launch_bounds__(256) k_slab_reset(uint32_t* __restrict__ dims, uint32_t n, uint32_t cap,
+                                                    uint32_t* __restrict__ slot, uint32_t* __restrict__ freeSlots) {
+    const uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t t = t0; t < cap; t += gridDim.x * blockDim.x) {
+        if (t < n) slot[t] = t;
+        if (t < cap - n) freeSlots[t] = cap - 1u - t;   // popping yields n, n + 1, ...
+    }
+    if (t0 == 0) { dims[D_N] = n; dims[D_NOWN] = n; dims[D_NPRE] = n; dims[D_FREE_TOP] = cap - n; dims[D_FREE_POP] = cap - n; }
 }
 
 }  // namespace slab

@@ -10,7 +10,10 @@
 // intrinsic (__syncthreads, __syncwarp, warp shuffles / ballots / match / reduce), where they park until the other
 // participants have arrived — so warp-synchronous code (the radix sort's match-any ranking, the migration compaction) runs
 // with CUDA semantics. Exited threads count as arrived. Atomics are plain read-modify-writes (fibers are cooperative).
-// Not modelled: concurrency between CTAs or kernels (no inter-CTA spin waits), memory-model races, timing.
+// Not modelled: concurrency between CTAs or kernels of ONE device, memory-model races, timing.
+// All emulator state is thread_local (and __shared__ is `static thread_local`): one OS thread = one emulated device, so the
+// multi-rank x-slab step runs with one thread per rank, peer-to-peer stores being plain stores into the other thread's arrays
+// and the in-kernel flag waits real waits (tests/test_emu_slab.py). cuda_host_shim.h adds the host runtime API on top.
 #pragma once
 #ifndef AKUA_HOST_EMU
 #error "tests/emu/cuda_runtime.h is the host emulation shim; compile with -DAKUA_HOST_EMU (tests only)"
@@ -19,6 +22,7 @@
 #include <setjmp.h>
 #include <ucontext.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +35,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __shared__ static
+#define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 
@@ -85,8 +89,8 @@ struct Cta {
     uint64_t barrierGen = 0;
     std::function<void()> body;
 };
-extern Cta* g_cta;
-extern long long g_clock;
+extern thread_local Cta* g_cta;
+extern thread_local long long g_clock;
 void yield();
 uint32_t live_mask(int warp);
 // Gathers every participating lane's 64-bit payload; returns when all lanes named in `mask` (that are still alive) arrived.
@@ -95,8 +99,8 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body);
 
 }  // namespace emu
 
-extern uint3 threadIdx, blockIdx;
-extern dim3 blockDim, gridDim;
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(KArgs...), Args... args) {
@@ -107,9 +111,10 @@ inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern
 // ---- synchronisation ----
 void __syncthreads();
 inline void __syncwarp(uint32_t mask = 0xffffffffu) { uint64_t o[32]; uint32_t p; emu::warp_exchange(mask, 0, o, &p); }
-inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline void __nanosleep(unsigned) {}
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+void emu_pause();   // a spinning emulated thread lets the other ranks' OS threads run
+inline void __nanosleep(unsigned) { emu_pause(); }
 inline long long clock64() { return ++emu::g_clock; }
 
 // ---- warp collectives ----
@@ -166,6 +171,7 @@ inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
 template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <typename T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 
 // ---- math / bit intrinsics ----
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -177,7 +183,10 @@ inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+#include "cuda_host_shim.h"

@@ -1,19 +1,21 @@
 // tests/emu/emu_core.cpp — TEST INFRASTRUCTURE: the fiber scheduler behind tests/emu/cuda_runtime.h (see there).
 #include "cuda_runtime.h"
 
-uint3 threadIdx, blockIdx;
-dim3 blockDim, gridDim;
+#include <sched.h>
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+void emu_pause() { sched_yield(); }
 
 namespace emu {
 
-Cta* g_cta = nullptr;
-long long g_clock = 0;
+thread_local Cta* g_cta = nullptr;
+thread_local long long g_clock = 0;
 
 namespace {
 constexpr size_t kStackBytes = 64 * 1024;
-std::vector<char> g_stacks;
-uint64_t g_progress = 0;
-int g_live = 0, g_atBarrier = 0;
+thread_local std::vector<char> g_stacks;
+thread_local uint64_t g_progress = 0;
+thread_local int g_live = 0, g_atBarrier = 0;
 
 // One fiber per thread slot, created once per launch and re-used for every CTA of the grid: after the kernel body returns
 // the fiber parks in the scheduler and runs the body again when it is resumed for the next CTA.

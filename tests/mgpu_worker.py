@@ -38,6 +38,10 @@ def main():
         particles, bmin, bmax = scenes.tank(2 * args.side, args.side // 2, args.side)
     n = len(particles)
     particles["velocity"][:, 0] = np.float32(args.vx)
+    # a payload that must follow its particle through sorts and migrations (the reference sorts whole structs,
+    # src/CUDA/NeighbourSearchCUDA.cu:167-170; the renderer reads color@88 / size@104, src/Rendering/Renderer.cpp:201-213)
+    particles["color"][:, 0] = (np.arange(n) % 251).astype(np.float32)
+    particles["size"] = (np.arange(n) % 17 + 1).astype(np.float32)
     ids = np.arange(n, dtype=np.uint32)
     if args.scene == "tank":
         g = scenes.tank_gravity(15.0)
@@ -50,7 +54,9 @@ def main():
         if args.rebalance_every and (k + 1) % args.rebalance_every == 0:
             solver.rebalance()
     pos4, vel4, pid = solver.download()
+    aos = solver.download_particles()
     st = solver.slab_stats()
+    graph_replays = solver.counters()["graph_replays"]
     # gather everything on rank 0
     owned = torch.tensor([solver.n], device="cuda", dtype=torch.int64)
     all_owned = [torch.zeros_like(owned) for _ in range(world)]
@@ -60,17 +66,19 @@ def main():
     all_mig = [torch.zeros_like(migt) for _ in range(world)]
     dist.all_gather(all_mig, migt)
     mx = max(all_owned)
-    pack = torch.zeros((mx, 9), dtype=torch.float64, device="cuda")
+    pack = torch.zeros((mx, 11), dtype=torch.float64, device="cuda")
     pack[:solver.n, 0:4] = torch.from_numpy(pos4.astype(np.float64)).cuda()
     pack[:solver.n, 4:8] = torch.from_numpy(vel4.astype(np.float64)).cuda()
     pack[:solver.n, 8] = torch.from_numpy(pid.astype(np.float64)).cuda()
+    pack[:solver.n, 9] = torch.from_numpy(aos["color"][:, 0].astype(np.float64)).cuda()
+    pack[:solver.n, 10] = torch.from_numpy(aos["size"].astype(np.float64)).cuda()
     gathered = [torch.zeros_like(pack) for _ in range(world)]
     dist.all_gather(gathered, pack)
     ok = True
     if rank == 0:
         allp = np.concatenate([g[:c].cpu().numpy() for g, c in zip(gathered, all_owned)])
         got_ids = allp[:, 8].astype(np.int64)
-        print(f"ranks own {all_owned} (start {counts0} on rank 0), stats rank0 {st}")
+        print(f"ranks own {all_owned} (start {counts0} on rank 0), stats rank0 {st}, graph replays rank0 {graph_replays}")
         if sum(all_owned) != n or not np.array_equal(np.sort(got_ids), np.arange(n)):
             print("FAIL: particles not conserved / ids not a permutation"); ok = False
         ref = PBFSolver(n, device=local)
@@ -89,6 +97,9 @@ def main():
         print(f"slab({world}) vs single GPU after {args.steps} steps: dpos/h={dp:.3e} dvel/(h/dt)={dv:.3e} drho/rho0={drho:.3e} tol={tol}")
         if not (dp < tol and dv < tol):
             print("FAIL: slab result differs from the single-GPU result"); ok = False
+        if not (np.array_equal(allp[o1, 9], particles["color"][:, 0].astype(np.float64))
+                and np.array_equal(allp[o1, 10], particles["size"].astype(np.float64))):
+            print("FAIL: the render payload (color / size) did not follow its particle"); ok = False
         if args.rebalance_every and world > 1:
             imb = max(all_owned) / (sum(all_owned) / world)
             print(f"imbalance after rebalancing: {imb:.3f}")

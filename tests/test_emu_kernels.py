@@ -193,7 +193,7 @@ def test_migration_compaction_is_deterministic_and_ordered(emu, n):
     x_lo, x_hi = 4, 9
     sentinel = gx * plane
     k2 = keys.copy()
-    counts = np.zeros(32, np.uint32)
+    counts = np.zeros(64, np.uint32)
     ids_l, ids_r = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
     emu.emu_migration(k2.ctypes.data, n, plane, x_lo, x_hi, sentinel, ids.ctypes.data, n, counts.ctypes.data,
                       ids_l.ctypes.data, ids_r.ctypes.data)
@@ -217,11 +217,11 @@ def test_plane_histogram_and_plane_verify(emu):
     assert np.array_equal(hist, np.bincount(keys // plane, minlength=gx).astype(np.uint64))
     x_lo, x_hi = 2, 17
     first, last = int((keys // plane == x_lo).sum()), int((keys // plane == x_hi - 1).sum())
-    c = np.zeros(32, np.uint32)
+    c = np.zeros(64, np.uint32)
     emu.emu_plane_verify(keys.ctypes.data, n, plane, x_lo, x_hi, first, last, c.ctypes.data)
     assert c[31] == 0
     emu.emu_plane_verify(keys.ctypes.data, n, plane, x_lo, x_hi, first + 1, last, c.ctypes.data)
-    assert c[31] == 1      # a wrong prediction raises the sticky error word
+    assert c[31] == 1      # a wrong prediction raises the sticky error word (bit 0)
 
 
 def test_fuzz_against_the_cpu_port(emu):

@@ -80,6 +80,8 @@ struct SlabState {
     cudaStream_t commStream = nullptr;     // set-up / re-balancing collectives and the NCCL fallback's traffic
     cudaStream_t bndStream = nullptr;      // boundary-plane sweeps run here, concurrently with the interior sweeps
     bool useBndStream = false;
+    bool bndForked = false;                // the boundary stream carries work of the current step (see slabJoin)
+    int bndPriority = 0;                   // the boundary stream's (highest) priority, also set explicitly on its launches
     static constexpr int kEvents = 256;
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
@@ -174,6 +176,7 @@ struct akua_pbf_solver {
     int graphMissStreak = 0;     // consecutive steps whose parameters matched no cached graph
     int graphCooldown = 0;       // steps to run eagerly after a burst of misses (callers that change dt / box every step)
     float accumulator = 0.0f;  // fixed-timestep driver (akua_pbf_advance)
+    int launchPriority = 0;    // explicit priority of the launches issued through launchK (0 = none; see launchK)
 };
 
 namespace {
@@ -201,16 +204,28 @@ namespace {
 // stream serialization attribute: the kernel may be scheduled while its predecessor drains (pdl_wait() in every kernel keeps
 // the data dependencies those of plain stream order); captured into the step's CUDA graph as programmatic edges.
 inline bool usePdl(const akua_pbf_solver* s) { return s->opt.use_pdl != 0; }
+// Boundary-plane launches of the x-slab step additionally carry an explicit launch PRIORITY (s->launchPriority, set by BndScope):
+// the stream's own priority is not inherited by the kernel nodes of a captured graph, and a boundary kernel that queues behind
+// the 60 000 CTAs of the interior sweep would put every halo exchange on the critical path.
 template <typename... KArgs, typename... Args>
 inline void launchK(const akua_pbf_solver* s, void (*kernel)(KArgs...), uint32_t grid, uint32_t block, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = s->stream;
-    cudaLaunchAttribute at{};
+    cudaLaunchAttribute at[2]{};
+    unsigned na = 0;
     if (usePdl(s)) {
-        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &at; cfg.numAttrs = 1;
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
     }
+#ifndef AKUA_HOST_EMU
+    if (s->launchPriority != 0) {
+        at[na].id = cudaLaunchAttributePriority;
+        at[na].val.priority = s->launchPriority;
+        na++;
+    }
+#endif
+    if (na) { cfg.attrs = at; cfg.numAttrs = na; }
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -302,8 +317,9 @@ int launchBuildNeighbours(akua_pbf_solver* s) {
             (uint32_t)s->cfg.maxNeighbours, s->nbrList, s->nbrCount, s->grid, s->cfg.smoothRadius, dimWord(s, D_NOWN))
     const bool st = slabOn(s);
     if (s->opt.key_mode == AKUA_KEY_REFERENCE_HASH) AK_BUILD((k_build_neighbours<KEY_HASH, false>));
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) { if (st) AK_BUILD((k_build_neighbours_mask<4, 5, true>)); else AK_BUILD((k_build_neighbours_mask<4, 5, false>)); }
-    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) { if (st) AK_BUILD((k_build_neighbours_mask<8, 4, true>)); else AK_BUILD((k_build_neighbours_mask<8, 4, false>)); }
+    // (the mask kernels are always the looping instantiation: it allocates registers better than the single-trip one)
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK4) AK_BUILD((k_build_neighbours_mask<4, 5, true>));
+    else if (s->opt.list_build == AKUA_LIST_BUILD_MASK8) AK_BUILD((k_build_neighbours_mask<8, 4, true>));
     else { if (st) AK_BUILD((k_build_neighbours<KEY_LINEAR, true>)); else AK_BUILD((k_build_neighbours<KEY_LINEAR, false>)); }
 #undef AK_BUILD
     AK_LAUNCH_CHECK(s, "k_build_neighbours");
@@ -329,7 +345,7 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
         if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
     }
     s->ctr.kernel_launches += launches;
-    s->ctr.sort_passes_last = launches / 3;
+    s->ctr.sort_passes_last = rsort::passes_for_bits(s->keyBits);
     mark(s, PH_REORDER);
     if (hash)
         launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, nullptr, s->pos, s->vel, s->xs, s->id,
@@ -462,16 +478,35 @@ int launchXsph(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, c
 cudaEvent_t slabNextEvent(akua_pbf_solver* s);
 struct BndScope {
     akua_pbf_solver* s; cudaStream_t saved;
-    explicit BndScope(akua_pbf_solver* s_) : s(s_), saved(s_->stream) { if (s->slab.useBndStream) s->stream = s->slab.bndStream; }
-    ~BndScope() { s->stream = saved; }
+    explicit BndScope(akua_pbf_solver* s_) : s(s_), saved(s_->stream) {
+        if (s->slab.useBndStream) { s->stream = s->slab.bndStream; s->launchPriority = s->slab.bndPriority; }
+    }
+    ~BndScope() { s->stream = saved; s->launchPriority = 0; }
 };
+// The first join of a step is a FORK (the boundary stream waits for the main stream only): the boundary stream has no work of
+// this step yet, and under stream capture waiting for its un-captured past would be an error. slabJoinEnd closes the step:
+// the main stream waits for the boundary stream, which thereby leaves the capture.
 int slabJoin(akua_pbf_solver* s) {
-    if (!s->slab.enabled || !s->slab.useBndStream) return AKUA_OK;
-    cudaEvent_t a = slabNextEvent(s), b = slabNextEvent(s);
+    SlabState& sl = s->slab;
+    if (!sl.enabled || !sl.useBndStream) return AKUA_OK;
+    cudaEvent_t a = slabNextEvent(s);
     AK_CUDA(s, cudaEventRecord(a, s->stream));
-    AK_CUDA(s, cudaEventRecord(b, s->slab.bndStream));
+    if (sl.bndForked) {
+        cudaEvent_t b = slabNextEvent(s);
+        AK_CUDA(s, cudaEventRecord(b, sl.bndStream));
+        AK_CUDA(s, cudaStreamWaitEvent(s->stream, b, 0));
+    }
+    AK_CUDA(s, cudaStreamWaitEvent(sl.bndStream, a, 0));
+    sl.bndForked = true;
+    return AKUA_OK;
+}
+int slabJoinEnd(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.enabled || !sl.useBndStream || !sl.bndForked) return AKUA_OK;
+    cudaEvent_t b = slabNextEvent(s);
+    AK_CUDA(s, cudaEventRecord(b, sl.bndStream));
     AK_CUDA(s, cudaStreamWaitEvent(s->stream, b, 0));
-    AK_CUDA(s, cudaStreamWaitEvent(s->slab.bndStream, a, 0));
+    sl.bndForked = false;
     return AKUA_OK;
 }
 
@@ -596,7 +631,7 @@ int phasePost(akua_pbf_solver* s, float dt, int iterations) {
         const HaloSync hs = p2p ? slabHalo(s, pb + 1, -1) : HaloSync{};
         if ((rc = launchXsph(s, sp.boundary, sp.gridBoundary, P, hs))) return rc;
     }
-    if ((rc = slabJoin(s))) return rc;   // the step ends on the main stream
+    if ((rc = slabJoinEnd(s))) return rc;   // the step ends on the main stream
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
@@ -637,7 +672,10 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         rc = layoutGrid(s, bmin, bmax);  // may (re)allocate the cell table: stays outside any capture
         if (rc) return rc;
     }
-    auto body = [&]() { return slabMode ? stepSlabBody(s, dt, iterations, bmin, bmax) : stepEager(s, dt, iterations, bmin, bmax); };
+    auto body = [&]() {
+        s->slab.bndForked = false;
+        return slabMode ? stepSlabBody(s, dt, iterations, bmin, bmax) : stepEager(s, dt, iterations, bmin, bmax);
+    };
     const bool graphable = s->opt.use_graph && !s->timing && (slabMode ? (s->slab.p2p && !s->slab.graphBroken) : s->n != 0);
     if (!graphable) return body();
     uint64_t key[20];
@@ -788,6 +826,7 @@ void akua_pbf_default_options(akua_pbf_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->key_mode = AKUA_KEY_LINEAR_CELL; o->device = 0; o->use_graph = 1; o->fast_math = 1; o->capacity_factor = 1.0f;
     o->use_pdl = 1;
+    o->list_build = AKUA_LIST_BUILD_MASK4;
 }
 
 int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_config* cfg, const akua_corr_params* corr,
@@ -853,8 +892,10 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     AK_CUDA(s, dalloc(&s->nbrList, (size_t)s->nbrStride * (size_t)((cfg->maxNeighbours + 3) / 4 * 4)));
     AK_CUDA(s, dalloc(&s->nbrCount, cap));
     s->sortWs.maxTiles = rsort::max_tiles_for_capacity(cap);
-    AK_CUDA(s, dalloc(&s->sortWs.tileHist, (size_t)256 * s->sortWs.maxTiles));
-    AK_CUDA(s, dalloc(&s->sortWs.binTotal, 256));
+    AK_CUDA(s, dalloc(&s->sortWs.tileHist, rsort::tile_hist_words(s->sortWs.maxTiles)));
+    AK_CUDA(s, dalloc(&s->sortWs.binTotal, rsort::kCtrlWords));
+    if (const char* e = std::getenv("AKUA_SORT_MODE")) s->sortWs.mode = std::atoi(e);     // tuning experiments: 0 = three kernels per pass
+    if (const char* e = std::getenv("AKUA_SORT_ITEMS")) s->sortWs.items = std::atoi(e);   // tuning experiments: keys per thread (4 / 8 / 16)
     AK_CUDA(s, dalloc(&s->partSum, 1024)); AK_CUDA(s, dalloc(&s->partMax, 1024));
     for (float4* p : {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->omega, s->dpos, s->color})
         AK_CUDA(s, cudaMemsetAsync(p, 0, cap * sizeof(float4), s->stream));
@@ -1268,6 +1309,8 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         AK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.bndStream, cudaStreamNonBlocking, hi));
+        sl.bndPriority = hi;
+        if (const char* ep = std::getenv("AKUA_SLAB_BND_PRIORITY")) { if (ep[0] == '0') sl.bndPriority = 0; }   // tuning experiments
         for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
     }
     AK_CUDA(s, dalloc(&sl.dims, D_WORDS));

@@ -88,9 +88,12 @@ typedef enum akua_gather_layout {
 
 /* How the neighbour lists are built in LINEAR_CELL mode (REFERENCE_HASH always scans its buckets). Lists are bit-identical
  * in every variant (tests/test_list_build_host.py on the CPU, test_list_build_variants_identical on the GPU).
- *   scan  : one candidate at a time, test and append in the same loop (k_build_neighbours) — the measured default.
+ *   scan  : one candidate at a time, test and append in the same loop (k_build_neighbours): the plain statement of the
+ *           reference's traversal, kept as the cross-check of the other two.
  *   mask4 / mask8 : two phases per row chunk of <= 32 candidates — a hit bitmask from 4 / 8 independent loads in flight, then
- *           the set bits are appended (akuaengine_b200/csrc/list_build.cuh). Opt-in until timed on a B200. */
+ *           the set bits are appended — plus reachability culling: a neighbouring cell whose nearest point is at least h away
+ *           from the particle is never loaded (akuaengine_b200/csrc/list_build.cuh). mask4 is the default since round 2
+ *           (measured on a B200: profiles/r02_*). A zero-initialised options struct still selects scan. */
 typedef enum akua_list_build {
     AKUA_LIST_BUILD_SCAN = 0,
     AKUA_LIST_BUILD_MASK4 = 1,
@@ -107,8 +110,8 @@ typedef struct akua_pbf_options {
     int32_t gather_layout;   /* akua_gather_layout; default AKUA_GATHER_AUTO. Results are bit-identical in every layout. */
     int32_t use_pdl;         /* 1 (default) = the step's kernels are launched with programmatic dependent launch: each is
                                 scheduled while its predecessor drains (also between the eagerly launched kernels of the x-slab path); 0 = plain stream order */
-    int32_t list_build;      /* akua_list_build; default AKUA_LIST_BUILD_SCAN (takes the first of the formerly reserved words:
-                                a zero-initialised struct from an older caller selects the default) */
+    int32_t list_build;      /* akua_list_build; akua_pbf_default_options selects AKUA_LIST_BUILD_MASK4 (the field took the first of
+                                the formerly reserved words: a zero-initialised struct from an older caller selects scan) */
     int32_t reserved[5];
 } akua_pbf_options;
 

@@ -32,11 +32,13 @@ int bitsFor(uint64_t maxKey) { int b = 1; while (b < 32 && (maxKey >> b) != 0) b
 extern "C" {
 
 // Stable LSD radix sort of (key, index) pairs: the three kernels of radix_sort.cuh driven by rsort::sort_pairs itself.
-int emu_sort_pairs(const uint32_t* keysIn, uint32_t n, int keyBits, uint32_t* keysOut, uint32_t* valsOut) {
+// mode: 0 = three kernels per pass, 1 = one-sweep (decoupled look-back); items: keys per thread of the one-sweep tiles (0 = auto)
+int emu_sort_pairs(const uint32_t* keysIn, uint32_t n, int keyBits, uint32_t* keysOut, uint32_t* valsOut, int mode, int items) {
     std::vector<uint32_t> keyA(n), keyB(n), valA(n), valB(n);
     rsort::Workspace ws;
+    ws.mode = mode; ws.items = items;
     ws.maxTiles = rsort::max_tiles_for_capacity(n);
-    std::vector<uint32_t> tileHist((size_t)256 * ws.maxTiles), binTotal(256);
+    std::vector<uint32_t> tileHist(rsort::tile_hist_words(ws.maxTiles), 0xdeadbeefu), binTotal(rsort::kCtrlWords, 0xdeadbeefu);
     ws.tileHist = tileHist.data();
     ws.binTotal = binTotal.data();
     uint32_t *ko = nullptr, *vo = nullptr;
@@ -85,7 +87,7 @@ void* emu_create(uint32_t n, const akua_pbf_config* cfg, const akua_corr_params*
     s->nbrStride = (uint32_t)((cap + 31) / 32 * 32);
     s->nbrList.assign((size_t)s->nbrStride * (size_t)((cfg->maxNeighbours + 3) / 4 * 4), 0u);
     s->ws.maxTiles = rsort::max_tiles_for_capacity(cap);
-    s->tileHist.assign((size_t)256 * s->ws.maxTiles, 0u); s->binTotal.assign(256, 0u);
+    s->tileHist.assign(rsort::tile_hist_words(s->ws.maxTiles), 0u); s->binTotal.assign(rsort::kCtrlWords, 0u);
     s->ws.tileHist = s->tileHist.data(); s->ws.binTotal = s->binTotal.data();
     s->grid.cellSize = cfg->smoothRadius;
     s->grid.lookupCellSize = cfg->spatialHashCellSize;
@@ -160,8 +162,8 @@ int emu_step(void* h, float dt, int iterations, const float* bmin, const float* 
                          (const uint2*)s->cellRange.data(), n, s->nbrStride, (uint32_t)s->cfg.maxNeighbours, s->nbrList.data(), s->nbrCount.data(), \
                          s->grid, s->cfg.smoothRadius, (const uint32_t*)nullptr)
     if (hash) EMU_BUILD((k_build_neighbours<KEY_HASH, false>));
-    else if (s->listBuild == 1) EMU_BUILD((k_build_neighbours_mask<4, 5, false>));
-    else if (s->listBuild == 2) EMU_BUILD((k_build_neighbours_mask<8, 4, false>));
+    else if (s->listBuild == 1) EMU_BUILD((k_build_neighbours_mask<4, 5, true>));
+    else if (s->listBuild == 2) EMU_BUILD((k_build_neighbours_mask<8, 4, true>));
     else EMU_BUILD((k_build_neighbours<KEY_LINEAR, false>));
 #undef EMU_BUILD
     // phaseSolve (single GPU: one span over all particles; the last pass B commits)

@@ -88,6 +88,44 @@ def test_graphics_resource_export_rejects_a_null_handle(akua_lib):
     s.close()
 
 
+@pytest.mark.gpu
+def test_device_export_honours_the_renderer_layout(akua_lib):
+    """the GL consumer binds position @0, color @88, size @104 at stride 108
+    (src/Rendering/Renderer.cpp:201-213). akua_pbf_export_to_graphics_resource maps a registered VBO and runs exactly
+    akua_pbf_export_aos108_device on the mapped pointer; without a GL / EGL context on the box the mapped pointer is stood in
+    for by a plain device allocation (the export cannot tell the difference: it only sees a device pointer). The exported
+    buffer must equal the host download byte for byte and carry the payload at the offsets the renderer reads."""
+    import torch
+    from akuaengine_b200 import PARTICLE_DTYPE, PBFSolver, scenes
+    p, bmin, bmax = scenes.dam_break(20)
+    n = len(p)
+    rng = np.random.default_rng(3)
+    p["color"] = rng.random((n, 4), dtype=np.float32)
+    p["size"] = rng.uniform(10, 90, n).astype(np.float32)
+    s = PBFSolver(n)
+    s.upload_particles(p)
+    for _ in range(3):
+        s.step(0.0083, bmin, bmax)
+    vbo = torch.zeros(n * 108, dtype=torch.uint8, device="cuda")       # the "mapped VBO"
+    assert akua_lib.akua_pbf_export_aos108_device(s._h, vbo.data_ptr(), n) == 0
+    s.sync()
+    host = s.download_particles()
+    raw = vbo.cpu().numpy()
+    assert raw.tobytes() == host.tobytes()
+    got = raw.view(PARTICLE_DTYPE)
+    rec = raw.reshape(n, 108)
+    assert np.array_equal(rec[:, 0:12].copy().view(np.float32).reshape(n, 3), got["position"])      # attribute 0
+    assert np.array_equal(rec[:, 88:104].copy().view(np.float32).reshape(n, 4), got["color"])       # attribute 1
+    assert np.array_equal(rec[:, 104:108].copy().view(np.float32).reshape(n), got["size"])          # attribute 2
+    # the payload followed its particle through three sorts: match by the upload index carried in a colour channel
+    pos4, _, pid = s.download()
+    assert np.array_equal(got["color"], p["color"][pid]) and np.array_equal(got["size"], p["size"][pid])
+    assert np.array_equal(got["position"], pos4[:, :3])
+    # a buffer that is too small or a wrong count is refused, not overrun
+    assert akua_lib.akua_pbf_export_aos108_device(s._h, vbo.data_ptr(), n - 1) == 1
+    s.close()
+
+
 def test_ctypes_structs_match_the_c_header(tmp_path):
     """The Python binding re-declares the header's structs by hand; a C program compiled against include/akua_pbf.h prints
     sizeof / offsetof of every field and the ctypes mirrors must agree (catches drift when an option is added)."""

@@ -38,7 +38,7 @@ def emu():
         assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(str(OUT))
     vp = C.c_void_p
-    lib.emu_sort_pairs.argtypes = [vp, C.c_uint32, C.c_int, vp, vp]
+    lib.emu_sort_pairs.argtypes = [vp, C.c_uint32, C.c_int, vp, vp, C.c_int, C.c_int]
     lib.emu_create.restype = vp
     lib.emu_create.argtypes = [C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_destroy.argtypes = [vp]
@@ -91,14 +91,21 @@ class EmuSolver:
             self.h = None
 
 
-@pytest.mark.parametrize("n,bits", [(1, 8), (31, 5), (1024, 21), (1025, 21), (4097, 13), (20000, 32)])
-def test_radix_sort_kernels_are_a_stable_sort(emu, n, bits):
-    """k_count / k_scan / k_scatter driven by rsort::sort_pairs itself: keys sorted, equal keys in input order."""
+@pytest.mark.parametrize("mode,items", [(0, 0), (1, 0), (1, 4), (1, 8), (1, 16)], ids=["three-kernel", "onesweep", "onesweep4", "onesweep8", "onesweep16"])
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 5), (1024, 21), (1025, 21), (4097, 13), (20000, 32), (70001, 22)])
+def test_radix_sort_kernels_are_a_stable_sort(emu, n, bits, mode, items):
+    """Both sort variants driven by rsort::sort_pairs itself (three kernels per pass: k_count / k_scan / k_scatter; one-sweep:
+    k_hist + one k_onesweep per pass with decoupled look-back): keys sorted, equal keys in input order."""
     rng = np.random.default_rng(n)
     keys = rng.integers(0, 2 ** bits, n, dtype=np.uint64).astype(np.uint32)
+    if n == 70001:   # nearly sorted input with long runs of equal keys, like the cell keys of consecutive steps
+        keys = np.sort(keys) // 64 * 64
+        swap = rng.integers(0, n - 1, n // 20)
+        keys[swap], keys[swap + 1] = keys[swap + 1].copy(), keys[swap].copy()
     ko, vo = np.empty(n, np.uint32), np.empty(n, np.uint32)
-    launches = emu.emu_sort_pairs(keys.ctypes.data, n, bits, ko.ctypes.data, vo.ctypes.data)
-    assert launches == 3 * ((bits + 7) // 8)
+    launches = emu.emu_sort_pairs(keys.ctypes.data, n, bits, ko.ctypes.data, vo.ctypes.data, mode, items)
+    passes = (bits + 7) // 8
+    assert launches == (3 * passes if mode == 0 else 1 + passes)
     want = np.argsort(keys, kind="stable").astype(np.uint32)
     assert np.array_equal(vo, want) and np.array_equal(ko, keys[want])
 

@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "akua_pbf_velocities_device", "akua_pbf_host_alloc", "akua_pbf_host_free", "akua_pbf_phase_predict",
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
-    "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_stream",
+    "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_trace_next_step", "akua_pbf_stream",
     "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance",
 ]
 
@@ -180,6 +180,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.akua_pbf_enable_timing.argtypes = [vp, C.c_int32]
     lib.akua_pbf_last_step_timing.argtypes = [vp, f3]
+    lib.akua_pbf_trace_next_step.argtypes = [vp, C.c_char_p]
     lib.akua_pbf_stream.argtypes = [vp]
     lib.akua_pbf_stream.restype = vp
     lib.akua_pbf_comm_unique_id.argtypes = [vp, C.c_int64]
@@ -446,6 +447,10 @@ class PBFSolver:
 
     def enable_timing(self, on=True):
         self._ck(self._lib.akua_pbf_enable_timing(self._h, int(on)), "enable_timing")
+
+    def trace_next_step(self, path: str):
+        """The next step runs eagerly with an event after every launch; the timeline is appended to `path` (JSON lines)."""
+        self._ck(self._lib.akua_pbf_trace_next_step(self._h, str(path).encode()), "trace_next_step")
 
     def last_step_timing(self) -> dict:
         ms = (C.c_float * 10)()

@@ -373,6 +373,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
         if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
         s->ctr.kernel_launches += launches;
         s->ctr.sort_passes_last = rsort::passes_for_bits(sl.sortBits);
+        if (s->tracing) traceMark(s, "radix sort");
     }
     mark(s, PH_REORDER);
     launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(sl.estN), kBlock, s->keysSorted, s->perm, sl.estN, dims + D_NOWN, s->pos, s->vel, s->xs,

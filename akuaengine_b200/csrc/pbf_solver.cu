@@ -177,6 +177,11 @@ struct akua_pbf_solver {
     int graphCooldown = 0;       // steps to run eagerly after a burst of misses (callers that change dt / box every step)
     float accumulator = 0.0f;  // fixed-timestep driver (akua_pbf_advance)
     int launchPriority = 0;    // explicit priority of the launches issued through launchK (0 = none; see launchK)
+    // launch timeline of one step (akua_pbf_trace_next_step): an event after every launch, on the stream it went to
+    struct TraceRec { const char* name; int lane; cudaEvent_t ev; };
+    std::vector<TraceRec> trace;
+    bool traceArmed = false, tracing = false;
+    std::string tracePath;
 };
 
 namespace {
@@ -198,7 +203,16 @@ namespace {
             return AKUA_ERR_CUDA;                                                                      \
         }                                                                                              \
         (s)->ctr.kernel_launches++;                                                                    \
+        if ((s)->tracing) traceMark((s), name);                                                        \
     } while (0)
+
+// One event after a launch, on the stream the launch went to (lane 0 = solver stream, 1 = boundary stream of the x-slab step).
+inline void traceMark(akua_pbf_solver* s, const char* name) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s->stream);
+    s->trace.push_back({name, (s->slab.bndStream && s->stream == s->slab.bndStream) ? 1 : 0, e});
+}
 
 // Kernel launch on the solver's current stream. With options.use_pdl the launch carries the programmatic
 // stream serialization attribute: the kernel may be scheduled while its predecessor drains (pdl_wait() in every kernel keeps
@@ -346,6 +360,7 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     }
     s->ctr.kernel_launches += launches;
     s->ctr.sort_passes_last = rsort::passes_for_bits(s->keyBits);
+    if (s->tracing) traceMark(s, "radix sort");
     mark(s, PH_REORDER);
     if (hash)
         launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, nullptr, s->pos, s->vel, s->xs, s->id,
@@ -657,6 +672,37 @@ void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* b
     key[19] = slabOn(s) ? (uint64_t)sl.slot : (uint64_t)s->bucketsN;
 }
 
+// akua_pbf_trace_next_step: runs one step eagerly with an event after every launch and appends the timeline (completion time
+// of each launch relative to the start of the step, per stream) to the armed file, one JSON object per line.
+template <typename Body>
+int tracedStep(akua_pbf_solver* s, Body& body) {
+    s->traceArmed = false;
+    s->trace.clear();
+    s->tracing = true;
+    traceMark(s, "step begin");
+    const int rc = body();
+    s->tracing = false;
+    cudaStreamSynchronize(s->stream);
+    if (s->slab.bndStream) cudaStreamSynchronize(s->slab.bndStream);
+    FILE* f = std::fopen(s->tracePath.c_str(), "a");
+    if (f && !s->trace.empty()) {
+        float prev[2] = {0.0f, 0.0f};
+        for (size_t k = 1; k < s->trace.size(); k++) {
+            float t = 0.0f;
+            cudaEventElapsedTime(&t, s->trace[0].ev, s->trace[k].ev);
+            const int lane = s->trace[k].lane;
+            std::fprintf(f, "{\"rank\": %d, \"step\": %lld, \"seq\": %zu, \"lane\": %d, \"name\": \"%s\", \"end_ms\": %.4f, \"since_prev_on_lane_ms\": %.4f}\n",
+                         s->slab.rank, (long long)s->ctr.steps, k, lane, s->trace[k].name, t, t - prev[lane]);
+            prev[lane] = t;
+        }
+    }
+    if (f) std::fclose(f);
+    for (auto& r : s->trace) cudaEventDestroy(r.ev);
+    s->trace.clear();
+    cudaGetLastError();
+    return rc;
+}
+
 int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, const float* bmax) {
     if (!s || !bmin || !bmax) return AKUA_ERR_INVALID;
     if (iterations < 0) { s->err = "solverIterations must be >= 0"; return AKUA_ERR_INVALID; }
@@ -676,6 +722,7 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         s->slab.bndForked = false;
         return slabMode ? stepSlabBody(s, dt, iterations, bmin, bmax) : stepEager(s, dt, iterations, bmin, bmax);
     };
+    if (s->traceArmed) return tracedStep(s, body);
     const bool graphable = s->opt.use_graph && !s->timing && (slabMode ? (s->slab.p2p && !s->slab.graphBroken) : s->n != 0);
     if (!graphable) return body();
     uint64_t key[20];
@@ -1626,6 +1673,12 @@ int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on) {
     return AKUA_OK;
 }
 void* akua_pbf_stream(akua_pbf_solver* s) { return s ? (void*)s->stream : nullptr; }
+int akua_pbf_trace_next_step(akua_pbf_solver* s, const char* path) {
+    if (!s || !path || !*path) return AKUA_ERR_INVALID;
+    s->tracePath = path;
+    s->traceArmed = true;
+    return AKUA_OK;
+}
 int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[10]) {
     if (!s || !ms) return AKUA_ERR_INVALID;
     if (!s->timingValid) { s->err = "no timed step recorded (call akua_pbf_enable_timing first)"; return AKUA_ERR_INVALID; }

@@ -272,7 +272,7 @@ def id_checksums(ids: np.ndarray):
                          int(np.bitwise_xor.reduce(a)) if len(a) else 0], dtype=np.uint64)
 
 
-def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=False):
+def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=False, owned_log=None):
     """`rebalance`: multi-GPU runs re-balance the slab boundaries once per window, INSIDE the timed region (a flowing scene
     moves several per cent of the particles across a slab boundary within a hundred steps; a production run re-balances at
     this rate and pays for it)."""
@@ -289,6 +289,8 @@ def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance
             solver.step(DT, bmin, bmax)
         e1.record(stream)
         barrier()
+        if owned_log is not None:
+            owned_log.append(int(solver.n))
         # events on the solver's stream; the host clock only matters when a host-side wait (the re-balancing collective) was not
         # covered by them
         out.append(max(e0.elapsed_time(e1), 0.0))
@@ -343,12 +345,21 @@ def run_ours(args):
     c0 = solver.counters()
     sampler = ClockSampler(local)
     sampler.start()
+    owned_log = []
     win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows,
-                           rebalance=world > 1 and args.rebalance_every > 0)
+                           rebalance=world > 1 and args.rebalance_every > 0, owned_log=owned_log)
     clocks = sampler.stop()
     c1 = solver.counters()
     launches = (c1["kernel_launches"] - c0["kernel_launches"]) // args.windows
     graph_replays = (c1["graph_replays"] - c0["graph_replays"]) // args.windows
+
+    # ---- optional launch timeline of the step right after the timed region (one file per rank) ----
+    if args.trace:
+        barrier()
+        for _ in range(2):
+            solver.trace_next_step(f"{args.trace}.rank{rank}.jsonl")
+            solver.step(DT, bmin, bmax)
+        barrier()
 
     # ---- dominant-kernel timing, live, CUDA events around every pass-A / pass-B launch on the solver's stream ----
     solver.enable_timing(True)
@@ -433,6 +444,10 @@ def run_ours(args):
         fin = torch.tensor([1 if finite else 0], device="cuda")
         dist.all_reduce(fin, op=dist.ReduceOp.MIN)
         finite = bool(int(fin))
+        ol = torch.tensor(owned_log, device="cuda", dtype=torch.int64)
+        allol = [torch.zeros_like(ol) for _ in range(world)]
+        dist.all_gather(allol, ol)
+        owned_log = np.stack([t.cpu().numpy() for t in allol], axis=1).tolist()   # [window][rank]
     ms_step = float(np.median(win))
     slab_stats = solver.slab_stats() if world > 1 else None
     value = n_total * ITERS / (ms_step * 1e-3)
@@ -448,6 +463,7 @@ def run_ours(args):
         "config": config,
         "protocol": {"settle_steps": args.settle, "settle_wall_s": round(t_settle, 2), "windows": args.windows,
                      "window_ms_per_step": [round(float(x), 5) for x in win], "value_is": "median window",
+                     "owned_per_rank_after_each_window": owned_log if world > 1 else None,
                      "simulated_time_at_start_s": round((args.settle + args.warmup) * DT, 3),
                      "rebalance": (f"akua_pbf_rebalance every {args.rebalance_every} settle steps and once per timed window (inside it)"
                                    if world > 1 and args.rebalance_every > 0 else "none")},
@@ -638,6 +654,7 @@ def main():
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps each; the median is reported")
     ap.add_argument("--rebalance-every", type=int, default=25, help="multi-GPU: akua_pbf_rebalance every k settle steps")
     ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
+    ap.add_argument("--trace", default="", help="write a launch timeline of two steps after the timed region to PATH.rank<r>.jsonl")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs 2 / 3 extra block")
     ap.add_argument("--no-selfcheck", action="store_true", help="multi-GPU: skip the small-scene check against one GPU")

@@ -284,6 +284,12 @@ int akua_pbf_get_counters(const akua_pbf_solver* s, akua_pbf_counters* out);
  * 7 sum of the density+lambda launches (pass A), 8 sum of the delta-p+apply launches (pass B), 9 launches per pass. */
 int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on);
 int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[10]);
+/* Launch timeline of ONE step (a diagnostic, no reference counterpart): the NEXT akua_pbf_step runs eagerly (no graph replay)
+ * with a CUDA event after every launch on the stream it went to, synchronises, and appends one JSON object per launch to
+ * `path` (rank, step, seq, lane: 0 = solver stream / 1 = boundary stream of the x-slab step, name, end_ms since the start of
+ * the step, since_prev_on_lane_ms). In x-slab mode the time a rank spends waiting for a neighbour shows up in the launch
+ * that waits (k_slab_plan: the count message; the boundary sweeps: the ghost planes). */
+int akua_pbf_trace_next_step(akua_pbf_solver* s, const char* path);
 /* The CUDA stream (cudaStream_t) all of this solver's work is issued on, so callers can record their own events on it
  * or order other work after it. */
 void* akua_pbf_stream(akua_pbf_solver* s);

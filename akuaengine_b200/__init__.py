@@ -83,7 +83,8 @@ class PBFConfig(C.Structure):
 
 class PBFOptions(C.Structure):
     _fields_ = [("key_mode", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("fast_math", C.c_int32),
-                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("list_build", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("list_build", C.c_int32), ("canonical_order", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class Counters(C.Structure):
@@ -109,7 +110,7 @@ ABI_SYMBOLS = [
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
     "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_trace_next_step", "akua_pbf_stream",
-    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance",
+    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance", "akua_slab_partition", "akua_slab_rebalance_bounds", "akua_slab_rebalance_bounds_weighted",
 ]
 
 _lib = None
@@ -237,7 +238,7 @@ class PBFSolver:
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
                  capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None,
-                 list_build: int | None = None, lib=None):
+                 list_build: int | None = None, canonical_order: bool = False, lib=None):
         # `lib`: an alternative build of the same C ABI (load_library(path)), e.g. the host-emulated build of tests/emu
         self._lib = lib if lib is not None else load_library()
         self.config = config or PBFConfig()
@@ -252,6 +253,7 @@ class PBFSolver:
             opt.use_pdl = int(use_pdl)
         if list_build is not None:
             opt.list_build = int(list_build)
+        opt.canonical_order = int(bool(canonical_order))
         self.options = opt
         self._h = C.c_void_p()
         rc = self._lib.akua_pbf_create(C.byref(self._h), self.numParticles, C.byref(self.config),

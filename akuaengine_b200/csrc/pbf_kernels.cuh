@@ -18,9 +18,10 @@
 #ifndef AKUA_SWEEP_MINBLOCKS
 #define AKUA_SWEEP_MINBLOCKS 8
 #endif
-// SLAB instantiations (x-slab mode: grid-stride loop, halo wait / signal, peer pushes) carry a few more live values: one
-// resident CTA fewer per SM keeps them spill-free
-#define AKUA_SWEEP_BOUNDS __launch_bounds__(AKUA_SWEEP_BLOCK, SLAB ? AKUA_SWEEP_MINBLOCKS - 1 : AKUA_SWEEP_MINBLOCKS)
+// The SLAB instantiations (x-slab mode: device-resolved span, halo wait / signal, peer pushes) get the same residency as the
+// single-GPU ones: the sweeps are latency-bound gathers, one resident CTA fewer per SM costs ~10 % (measured, profiles/r02_c5_*);
+// the default instantiations (fast math, packed gathers, n = 4) fit 64 registers without spills either way.
+#define AKUA_SWEEP_BOUNDS __launch_bounds__(AKUA_SWEEP_BLOCK, AKUA_SWEEP_MINBLOCKS)
 
 namespace akua {
 
@@ -155,7 +156,10 @@ enum : uint32_t {   // bits of dims[D_ERROR]
 // the whole owned range (single GPU), the interior of a slab, or its two boundary planes (multi-GPU overlap).
 // mode 0: the host filled count/base/split/skip. Slab mode: resolved on the device from `dims` —
 // mode 1 = all owned particles, 2 = slab interior (needs no ghost data), 3 = the two boundary planes.
-enum : int { SPAN_FIXED = 0, SPAN_OWNED = 1, SPAN_INTERIOR = 2, SPAN_BOUNDARY = 3 };
+// mode 4 (SPAN_FUSED, CUDA-IPC transport) = interior AND boundary planes in ONE launch: the first CTAs of the grid take the
+// boundary planes (they wait for the ghosts, push their results to the neighbours and publish the epoch), the others the
+// interior — see sweep_cta().
+enum : int { SPAN_FIXED = 0, SPAN_OWNED = 1, SPAN_INTERIOR = 2, SPAN_BOUNDARY = 3, SPAN_FUSED = 4 };
 struct Span { uint32_t count, base, split, skip; const uint32_t* dims; int mode; };
 __device__ __forceinline__ Span resolve_span(Span sp) {
     if (sp.mode == SPAN_FIXED) return sp;
@@ -169,6 +173,38 @@ __device__ __forceinline__ Span resolve_span(Span sp) {
     return sp;
 }
 __device__ __forceinline__ uint32_t span_particle(const Span& sp, uint32_t t) { return sp.base + t + (t >= sp.split ? sp.skip : 0u); }
+// What one CTA of a slab-mode sweep does: its first thread index, stride and count within the (resolved) span, whether it runs
+// the halo protocol, and how many CTAs of the launch do (the last of them to finish publishes the epoch).
+// SPAN_FUSED: boundary CTAs come FIRST in the grid (CTAs are dispatched in index order, so the boundary planes are computed and
+// on their way over NVLink while the interior is still being swept: compute, halo push and synchronisation in one launch, no
+// second stream, no launch priorities). At least one CTA takes the boundary role even when the planes are empty (the neighbours
+// still wait for the epoch), and the interior keeps at least half of the grid whatever the host's size estimate was.
+struct SweepCta { uint32_t t0, tstep, haloCtas; bool halo; };
+__device__ __forceinline__ SweepCta sweep_cta(Span& sp) {
+    SweepCta c;
+    if (sp.mode != SPAN_FUSED) {
+        sp = resolve_span(sp);
+        c.t0 = blockIdx.x * blockDim.x + threadIdx.x; c.tstep = gridDim.x * blockDim.x; c.haloCtas = gridDim.x; c.halo = true;
+        return c;
+    }
+    const uint32_t n = sp.dims[D_NOWN], pl = sp.dims[D_PLANE_L], pr = sp.dims[D_PLANE_R];
+    const bool allBoundary = (uint64_t)pl + pr >= n;
+    const uint32_t bcount = allBoundary ? n : pl + pr;
+    const uint32_t want = (bcount + blockDim.x - 1) / blockDim.x;
+    const uint32_t nb = max(1u, min(want, max(1u, gridDim.x >> 1)));
+    c.haloCtas = nb;
+    c.halo = blockIdx.x < nb;
+    sp.split = 0xffffffffu; sp.skip = 0u; sp.base = 0u;
+    if (c.halo) {
+        sp.count = bcount;
+        if (!allBoundary) { sp.split = pl; sp.skip = n - pr - pl; }
+        c.t0 = blockIdx.x * blockDim.x + threadIdx.x; c.tstep = nb * blockDim.x;
+    } else {
+        sp.count = n - bcount; sp.base = pl;
+        c.t0 = (blockIdx.x - nb) * blockDim.x + threadIdx.x; c.tstep = (gridDim.x - nb) * blockDim.x;
+    }
+    return c;
+}
 
 // Fused compute + halo push (multi-GPU, CUDA-IPC transport): a boundary particle's result is also stored straight into the
 // neighbouring rank's ghost region through the peer-mapped pointer (NVLink P2P store), so no separate copy or
@@ -231,13 +267,13 @@ __device__ __forceinline__ void halo_wait(const HaloSync& hs) {
     __syncthreads();
 }
 // Call with ALL threads of the CTA (no early returns before it) once the CTA's pushes are issued.
-__device__ __forceinline__ void halo_signal(const HaloSync& hs) {
+__device__ __forceinline__ void halo_signal(const HaloSync& hs, uint32_t ctas) {
     if (!hs.doneCounter || hs.signalIdx < 0) return;
     __syncthreads();   // every thread's pushes happen-before thread 0's fence below (fences are cumulative)
     if (threadIdx.x == 0) {
         __threadfence_system();
         const uint32_t done = atomicAdd(hs.doneCounter, 1u);
-        if (done == gridDim.x - 1) {
+        if (done == ctas - 1) {
             __threadfence_system();
             const uint32_t epoch = hs.dims[D_EPOCH] + (uint32_t)hs.signalIdx + 1u;
             if (hs.signalL) *(volatile uint32_t*)hs.signalL = epoch;
@@ -365,6 +401,19 @@ __global__ void __launch_bounds__(256) k_reorder_ranges(const uint32_t* __restri
         }
     }
 }
+// options.canonical_order: after the particles were sorted by id (byId = that permutation), their cell keys are gathered in id
+// order and travel with the permutation into the stable sort by key — so particles of one cell end up ordered by id.
+__global__ void __launch_bounds__(256) k_gather_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ byId, uint32_t n,
+                                                     const uint32_t* __restrict__ nPtr, uint32_t* __restrict__ keysOut,
+                                                     uint32_t* __restrict__ valsOut) {
+    pdl_wait();
+    n = live_count(n, nPtr);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t src = byId[i];
+        keysOut[i] = keys[src];
+        valsOut[i] = src;
+    }
+}
 // Undo last step's bucket-start writes instead of refilling the 128*N-entry table (the reference allocates and fills
 // it with UINT32_MAX every step: NeighbourSearchCUDA.cu:157 — 512 B per particle per step).
 __global__ void __launch_bounds__(256) k_clear_buckets(const uint32_t* __restrict__ keysSorted, uint32_t n,
@@ -467,9 +516,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
                                                         float4* __restrict__ xl, SphParams P, PeerPush pushLambda,
                                                         HaloSync hs) {
     pdl_wait();
-    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushLambda); }
-    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    SweepCta cta{};
+    if (SLAB) { cta = sweep_cta(sp); if (cta.halo) halo_wait(hs); resolve_push(pushLambda); }
+    const uint32_t tstep = SLAB ? cta.tstep : 0u;
+    for (uint32_t t = SLAB ? cta.t0 : blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
     const uint32_t i = span_particle(sp, t);
     const float4 xi = xs[i];
     const uint32_t c = cnt[i];
@@ -509,7 +559,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_density_lambda(const float4* __restrict__ xs
     }
     if (!SLAB) break;
     }
-    if (SLAB) { pdl_trigger(); halo_signal(hs); }
+    if (SLAB) { pdl_trigger(); if (cta.halo) halo_signal(hs, cta.haloCtas); }
 }
 
 // ------------------------------------------------------------------------------------------------ K8 / K9 / K10 pieces
@@ -566,9 +616,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
                                                      const float* __restrict__ density, PosVel* __restrict__ pvOut,
                                                      float dt, PeerPush pushX, PeerPush pushV, HaloSync hs) {
     pdl_wait();
-    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushX); resolve_push(pushV); }
-    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    SweepCta cta{};
+    if (SLAB) { cta = sweep_cta(sp); if (cta.halo) halo_wait(hs); resolve_push(pushX); resolve_push(pushV); }
+    const uint32_t tstep = SLAB ? cta.tstep : 0u;
+    for (uint32_t t = SLAB ? cta.t0 : blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
     const uint32_t i = span_particle(sp, t);
     float4 xi;
     float li;
@@ -616,7 +667,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_delta_apply(const float4* __restrict__ xsIn,
     }
     if (!SLAB) break;
     }
-    if (SLAB) { pdl_trigger(); halo_signal(hs); }
+    if (SLAB) { pdl_trigger(); if (cta.halo) halo_signal(hs, cta.haloCtas); }
 }
 
 // (position, velocity) -> post-solve gather records, for callers that commit outside the fused final pass B (phase-level
@@ -665,9 +716,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
                                                    float* __restrict__ omegaLen, float4* __restrict__ xw, SphParams P,
                                                    PeerPush pushLen, HaloSync hs) {
     pdl_wait();
-    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushLen); }
-    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    SweepCta cta{};
+    if (SLAB) { cta = sweep_cta(sp); if (cta.halo) halo_wait(hs); resolve_push(pushLen); }
+    const uint32_t tstep = SLAB ? cta.tstep : 0u;
+    for (uint32_t t = SLAB ? cta.t0 : blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
     const uint32_t i = span_particle(sp, t);
     float4 xi, vi;
     if (REC) { const PosVel r = pv[i]; xi = r.x; vi = r.v; }
@@ -701,7 +753,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_vorticity(const float4* __restrict__ xs, con
     }
     if (!SLAB) break;
     }
-    if (SLAB) { pdl_trigger(); halo_signal(hs); }
+    if (SLAB) { pdl_trigger(); if (cta.halo) halo_signal(hs, cta.haloCtas); }
 }
 
 // ------------------------------------------------------------------------------------------------ K12
@@ -717,9 +769,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
                                                      PosVel* __restrict__ pvOut, SphParams P,
                                                      float dt, float eps, PeerPush pushV, HaloSync hs) {
     pdl_wait();
-    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); resolve_push(pushV); }
-    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    SweepCta cta{};
+    if (SLAB) { cta = sweep_cta(sp); if (cta.halo) halo_wait(hs); resolve_push(pushV); }
+    const uint32_t tstep = SLAB ? cta.tstep : 0u;
+    for (uint32_t t = SLAB ? cta.t0 : blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
     const uint32_t i = span_particle(sp, t);
     const float4 xi = PACK ? xw[i] : xs[i];
     const float4 oi = omega[i];
@@ -754,7 +807,7 @@ __global__ void AKUA_SWEEP_BOUNDS k_confinement(const float4* __restrict__ xs, c
     }
     if (!SLAB) break;
     }
-    if (SLAB) { pdl_trigger(); halo_signal(hs); }
+    if (SLAB) { pdl_trigger(); if (cta.halo) halo_signal(hs, cta.haloCtas); }
 }
 
 // ------------------------------------------------------------------------------------------------ K13
@@ -768,9 +821,10 @@ __global__ void AKUA_SWEEP_BOUNDS k_xsph(const float4* __restrict__ xs, const fl
                                               uint32_t stride, Span sp, float4* __restrict__ velOut, SphParams P,
                                               float cvisc, HaloSync hs) {
     pdl_wait();
-    if (SLAB) { halo_wait(hs); sp = resolve_span(sp); }
-    const uint32_t tstep = SLAB ? gridDim.x * blockDim.x : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
+    SweepCta cta{};
+    if (SLAB) { cta = sweep_cta(sp); if (cta.halo) halo_wait(hs); }
+    const uint32_t tstep = SLAB ? cta.tstep : 0u;
+    for (uint32_t t = SLAB ? cta.t0 : blockIdx.x * blockDim.x + threadIdx.x; t < sp.count; t += tstep) {
     const uint32_t i = span_particle(sp, t);
     float4 xi, vi;
     if (REC) { const PosVel r = pv[i]; xi = r.x; vi = r.v; }

@@ -367,13 +367,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
     {
         const uint32_t nSort = std::min<uint32_t>(sl.estN + sl.estIn, (uint32_t)s->capacity);
-        int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, nSort, sl.sortBits, s->sortWs, s->stream,
-                                         &s->keysSorted, &s->perm, usePdl(s), dims + D_NPRE);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
-        s->ctr.kernel_launches += launches;
-        s->ctr.sort_passes_last = rsort::passes_for_bits(sl.sortBits);
-        if (s->tracing) traceMark(s, "radix sort");
+        if ((rc = sortParticles(s, nSort, dims + D_NPRE, sl.sortBits))) return rc;
     }
     mark(s, PH_REORDER);
     launchK(s, k_reorder_ranges<KEY_LINEAR>, gridFor(sl.estN), kBlock, s->keysSorted, s->perm, sl.estN, dims + D_NOWN, s->pos, s->vel, s->xs,
@@ -439,7 +433,8 @@ int slabRebalance(akua_pbf_solver* s) {
     const GridParams& G = s->grid;   // slab-local grid of the last step; plane p of it is global plane planeOffset + p
     const int gx = sl.gxGlobal, R = sl.nranks;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
-    const size_t words = (size_t)gx + R;  // [0,gx): plane counts; [gx, gx+R): current lower bounds (grid-relative)
+    // [0, gx): plane counts; [gx, 2 gx): plane work (particles weighted by their neighbour count); then the R current lower bounds
+    const size_t words = (size_t)2 * gx + R;
     if (words > sl.histCap) {
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
@@ -450,24 +445,29 @@ int slabRebalance(akua_pbf_solver* s) {
     }
     AK_CUDA(s, cudaMemsetAsync(sl.dHist, 0, words * sizeof(unsigned long long), s->stream));
     const uint32_t n = (uint32_t)s->n;
-    launchPlain(s->stream, slab::k_plane_hist, (G.gridDim.x + 255) / 256, 256, s->keysSorted, n, planeCells, G.gridDim.x, sl.planeOffset, sl.dHist);
+    launchPlain(s->stream, slab::k_plane_hist, (uint32_t)G.gridDim.x, 256, s->keysSorted, s->nbrCount, n, planeCells, G.gridDim.x, sl.planeOffset,
+                sl.dHist, sl.dHist + gx);
     AK_LAUNCH_CHECK(s, "k_plane_hist");
     const int curLo = sl.rank == 0 ? 0 : sl.planeOffset + sl.xLoL;
     unsigned long long lo64 = (unsigned long long)curLo;
-    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 2 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.AllReduce(sl.dHist, sl.dHist, words, ncclUint64, ncclSum, (ncclComm_t)sl.comm, sl.commStream));
     AK_CUDA(s, cudaMemcpyAsync(sl.hHist, sl.dHist, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.commStream));
     AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
-    std::vector<int64_t> hist(gx);
-    for (int x = 0; x < gx; x++) hist[x] = (int64_t)sl.hHist[x];
+    std::vector<int64_t> hist(gx), work(gx);
+    for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[gx + x]; }
     std::vector<int32_t> bounds(R + 1), old(R + 1);
-    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[gx + r];
+    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[2 * (size_t)gx + r];
     old[0] = 0; old[R] = gx;
-    if (akua_slab_rebalance_bounds(hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, bounds.data()) != AKUA_OK) {
+    // boundaries follow the WORK (12 + neighbour count per particle); a partition within 2 % of balance is left alone
+    if (akua_slab_rebalance_bounds_weighted(work.data(), hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, sl.keepBelow, bounds.data()) != AKUA_OK) {
         s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
+    bool movedAny = false;
+    for (int r = 0; r <= R; r++) movedAny = movedAny || bounds[r] != old[r];
+    if (!movedAny) return AKUA_OK;
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
     const int gminGlobalX = G.gridMin.x - sl.planeOffset;
     sl.xLoAbs = gminGlobalX + bounds[sl.rank];

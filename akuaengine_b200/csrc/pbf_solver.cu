@@ -78,10 +78,6 @@ struct SlabState {
     int sortBits = 1;
     int64_t exchanges = 0;
     cudaStream_t commStream = nullptr;     // set-up / re-balancing collectives and the NCCL fallback's traffic
-    cudaStream_t bndStream = nullptr;      // boundary-plane sweeps run here, concurrently with the interior sweeps
-    bool useBndStream = false;
-    bool bndForked = false;                // the boundary stream carries work of the current step (see slabJoin)
-    int bndPriority = 0;                   // the boundary stream's (highest) priority, also set explicitly on its launches
     static constexpr int kEvents = 256;
     cudaEvent_t evPool[kEvents] = {};
     int evNext = 0;
@@ -98,7 +94,8 @@ struct SlabState {
                                            // completion counter, [4]/[5] epoch of the left / right rank's count message
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
-    int64_t rebalances = 0;
+    int64_t rebalances = 0;            // calls that moved a boundary
+    double keepBelow = 1.02;           // akua_pbf_rebalance leaves a partition alone whose heaviest slab is within this of the mean
 };
 
 struct akua_pbf_solver {
@@ -144,6 +141,7 @@ struct akua_pbf_solver {
     uint32_t *nbrList = nullptr, *nbrCount = nullptr;
     uint32_t nbrStride = 0;
     rsort::Workspace sortWs;
+    uint32_t *canonKeys = nullptr, *canonVals = nullptr;   // options.canonical_order: (cell key, index) pairs in id order
     // interchange staging
     void* aosStage = nullptr;
     float *partSum = nullptr, *partMax = nullptr;
@@ -176,7 +174,6 @@ struct akua_pbf_solver {
     int graphMissStreak = 0;     // consecutive steps whose parameters matched no cached graph
     int graphCooldown = 0;       // steps to run eagerly after a burst of misses (callers that change dt / box every step)
     float accumulator = 0.0f;  // fixed-timestep driver (akua_pbf_advance)
-    int launchPriority = 0;    // explicit priority of the launches issued through launchK (0 = none; see launchK)
     // launch timeline of one step (akua_pbf_trace_next_step): an event after every launch, on the stream it went to
     struct TraceRec { const char* name; int lane; cudaEvent_t ev; };
     std::vector<TraceRec> trace;
@@ -206,40 +203,28 @@ namespace {
         if ((s)->tracing) traceMark((s), name);                                                        \
     } while (0)
 
-// One event after a launch, on the stream the launch went to (lane 0 = solver stream, 1 = boundary stream of the x-slab step).
+// One event after a launch, on the solver's stream (every launch of a step goes there; `lane` is kept for tools that read it).
 inline void traceMark(akua_pbf_solver* s, const char* name) {
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, s->stream);
-    s->trace.push_back({name, (s->slab.bndStream && s->stream == s->slab.bndStream) ? 1 : 0, e});
+    s->trace.push_back({name, 0, e});
 }
 
 // Kernel launch on the solver's current stream. With options.use_pdl the launch carries the programmatic
 // stream serialization attribute: the kernel may be scheduled while its predecessor drains (pdl_wait() in every kernel keeps
 // the data dependencies those of plain stream order); captured into the step's CUDA graph as programmatic edges.
 inline bool usePdl(const akua_pbf_solver* s) { return s->opt.use_pdl != 0; }
-// Boundary-plane launches of the x-slab step additionally carry an explicit launch PRIORITY (s->launchPriority, set by BndScope):
-// the stream's own priority is not inherited by the kernel nodes of a captured graph, and a boundary kernel that queues behind
-// the 60 000 CTAs of the interior sweep would put every halo exchange on the critical path.
 template <typename... KArgs, typename... Args>
 inline void launchK(const akua_pbf_solver* s, void (*kernel)(KArgs...), uint32_t grid, uint32_t block, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = s->stream;
-    cudaLaunchAttribute at[2]{};
-    unsigned na = 0;
+    cudaLaunchAttribute at{};
     if (usePdl(s)) {
-        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[na].val.programmaticStreamSerializationAllowed = 1;
-        na++;
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
     }
-#ifndef AKUA_HOST_EMU
-    if (s->launchPriority != 0) {
-        at[na].id = cudaLaunchAttributePriority;
-        at[na].val.priority = s->launchPriority;
-        na++;
-    }
-#endif
-    if (na) { cfg.attrs = at; cfg.numAttrs = na; }
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -340,6 +325,31 @@ int launchBuildNeighbours(akua_pbf_solver* s) {
     return AKUA_OK;
 }
 
+// The step's sort: (cell key, index) pairs, stable. options.canonical_order first sorts the particles by id, so that ties inside
+// a cell are broken by id instead of by last step's order: the result no longer depends on how the particles were distributed
+// over GPUs or in which order migrants arrived (bit-identical trajectories at any GPU count; costs four more digit passes).
+// `n` sizes the grids; `nPtr` (x-slab mode) is the device-side count.
+int sortParticles(akua_pbf_solver* s, uint32_t n, const uint32_t* nPtr, int keyBits) {
+    int launches;
+    if (!s->opt.canonical_order) {
+        launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, n, keyBits, s->sortWs, s->stream,
+                                     &s->keysSorted, &s->perm, usePdl(s), nPtr);
+    } else {
+        uint32_t *idSorted = nullptr, *byId = nullptr;
+        launches = rsort::sort_pairs(s->id, s->keyA, s->valA, s->keyB, s->valB, n, 32, s->sortWs, s->stream, &idSorted, &byId,
+                                     usePdl(s), nPtr);
+        launchK(s, k_gather_keys, std::max(1u, gridFor(n)), kBlock, s->keysUnsorted, byId, n, nPtr, s->canonKeys, s->canonVals);
+        launches += 1 + rsort::sort_pairs(s->canonKeys, s->keyA, s->valA, s->keyB, s->valB, n, keyBits, s->sortWs, s->stream,
+                                          &s->keysSorted, &s->perm, usePdl(s), nPtr, s->canonVals);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
+    s->ctr.kernel_launches += launches;
+    s->ctr.sort_passes_last = rsort::passes_for_bits(keyBits) + (s->opt.canonical_order ? 4 : 0);
+    if (s->tracing) traceMark(s, "radix sort");
+    return AKUA_OK;
+}
+
 int phaseSortReorderLists(akua_pbf_solver* s) {
     const uint32_t n = (uint32_t)s->n;
     if (n == 0) return AKUA_OK;
@@ -352,15 +362,7 @@ int phaseSortReorderLists(akua_pbf_solver* s) {
     } else {
         AK_CUDA(s, cudaMemsetAsync(s->cellRange, 0, (size_t)s->ctr.num_cells * sizeof(uint2), s->stream));
     }
-    int launches = rsort::sort_pairs(s->keysUnsorted, s->keyA, s->valA, s->keyB, s->valB, n, s->keyBits, s->sortWs,
-                                     s->stream, &s->keysSorted, &s->perm, usePdl(s));
-    {
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { s->err = std::string("radix sort: ") + cudaGetErrorString(e); return AKUA_ERR_CUDA; }
-    }
-    s->ctr.kernel_launches += launches;
-    s->ctr.sort_passes_last = rsort::passes_for_bits(s->keyBits);
-    if (s->tracing) traceMark(s, "radix sort");
+    if (int rcs = sortParticles(s, n, nullptr, s->keyBits)) return rcs;
     mark(s, PH_REORDER);
     if (hash)
         launchK(s, k_reorder_ranges<KEY_HASH>, gridFor(n), kBlock, s->keysSorted, s->perm, n, nullptr, s->pos, s->vel, s->xs, s->id,
@@ -386,7 +388,7 @@ template <typename T> PeerPush slabPush(const akua_pbf_solver* s, T* arr);      
 // In-kernel wait (exchange index waitIdx, -1 none) / signal (signalIdx, -1 none) block of a boundary launch (p2p transport).
 HaloSync slabHalo(const akua_pbf_solver* s, int waitIdx, int signalIdx);
 template <typename T> int slabNcclPlanes(akua_pbf_solver* s, T* arr);             // NCCL fallback: blocking plane exchange
-struct SweepSpans { Span interior, boundary; uint32_t gridInterior, gridBoundary; };
+struct SweepSpans { Span interior, boundary, fused; uint32_t gridInterior, gridBoundary, gridFused; };
 
 // ---- sweep launchers over an index span ----
 // Gather layouts (akua_pbf_options::gather_layout). The 32-byte records are single-GPU only.
@@ -406,10 +408,14 @@ SweepSpans sweepSpans(const akua_pbf_solver* s) {
         sp.interior = fullSpan((uint32_t)s->n);
         sp.boundary = Span{0, 0, 0, 0, nullptr, SPAN_FIXED};
         sp.gridInterior = sweepGrid((uint64_t)s->n); sp.gridBoundary = 0;
+        sp.fused = sp.boundary; sp.gridFused = 0;
     } else {
         sp.interior = Span{0, 0, 0, 0, s->slab.dims, SPAN_INTERIOR};
         sp.boundary = Span{0, 0, 0, 0, s->slab.dims, SPAN_BOUNDARY};
         sp.gridInterior = sweepGrid(s->slab.estN); sp.gridBoundary = sweepGrid(s->slab.estBnd);
+        // CUDA-IPC transport: ONE launch per sweep, boundary CTAs first (sweep_cta in pbf_kernels.cuh)
+        sp.fused = Span{0, 0, 0, 0, s->slab.dims, SPAN_FUSED};
+        sp.gridFused = std::max(2u, sp.gridInterior + sp.gridBoundary);
     }
     return sp;
 }
@@ -486,45 +492,6 @@ int launchXsph(akua_pbf_solver* s, Span sp, uint32_t grid, const SphParams& P, c
     return AKUA_OK;
 }
 
-// Slab mode runs the small boundary-plane launches on a second stream so that they execute concurrently with the big
-// interior launches instead of adding their latency to the critical path. BndScope redirects s->stream for the duration of
-// a boundary section; slabJoin makes each of the two streams wait for the other (needed wherever a sweep reads what the
-// previous sweep wrote across the interior / boundary split).
-cudaEvent_t slabNextEvent(akua_pbf_solver* s);
-struct BndScope {
-    akua_pbf_solver* s; cudaStream_t saved;
-    explicit BndScope(akua_pbf_solver* s_) : s(s_), saved(s_->stream) {
-        if (s->slab.useBndStream) { s->stream = s->slab.bndStream; s->launchPriority = s->slab.bndPriority; }
-    }
-    ~BndScope() { s->stream = saved; s->launchPriority = 0; }
-};
-// The first join of a step is a FORK (the boundary stream waits for the main stream only): the boundary stream has no work of
-// this step yet, and under stream capture waiting for its un-captured past would be an error. slabJoinEnd closes the step:
-// the main stream waits for the boundary stream, which thereby leaves the capture.
-int slabJoin(akua_pbf_solver* s) {
-    SlabState& sl = s->slab;
-    if (!sl.enabled || !sl.useBndStream) return AKUA_OK;
-    cudaEvent_t a = slabNextEvent(s);
-    AK_CUDA(s, cudaEventRecord(a, s->stream));
-    if (sl.bndForked) {
-        cudaEvent_t b = slabNextEvent(s);
-        AK_CUDA(s, cudaEventRecord(b, sl.bndStream));
-        AK_CUDA(s, cudaStreamWaitEvent(s->stream, b, 0));
-    }
-    AK_CUDA(s, cudaStreamWaitEvent(sl.bndStream, a, 0));
-    sl.bndForked = true;
-    return AKUA_OK;
-}
-int slabJoinEnd(akua_pbf_solver* s) {
-    SlabState& sl = s->slab;
-    if (!sl.enabled || !sl.useBndStream || !sl.bndForked) return AKUA_OK;
-    cudaEvent_t b = slabNextEvent(s);
-    AK_CUDA(s, cudaEventRecord(b, sl.bndStream));
-    AK_CUDA(s, cudaStreamWaitEvent(s->stream, b, 0));
-    sl.bndForked = false;
-    return AKUA_OK;
-}
-
 // Exchange indices of a slab step (the epoch of exchange e is dims[D_EPOCH] + e + 1; all ranks run the same sequence):
 //   0 count message + migration records      1 x* after the reorder (for the list build)
 //   2 + 2 it : (x*, lambda) after pass A of iteration it         3 + 2 it : x* (last iteration: + v, rho) after pass B
@@ -535,10 +502,12 @@ inline int slabPostBaseIdx(int iterations) { return iterations > 0 ? 2 + 2 * ite
 inline int slabExchangesPerStep(int iterations) { return slabPostBaseIdx(iterations) + 2; }
 
 // `commit`: fold K9+K10 into the last iteration's pass B (whole-step path). dt is only read when commit is set.
-// Slab mode: every sweep is split into the slab interior (needs no ghost data) and its two boundary planes. The boundary
-// launch waits IN-KERNEL for the ghosts it reads, stores its own results straight into the neighbours' ghost regions
-// (P2P stores over NVLink) and its last CTA publishes the epoch; it runs on the boundary stream concurrently with the
-// interior launch, so no exchange sits on the critical path. (NCCL fallback: blocking send/recv after each boundary launch.)
+// Slab mode: a sweep covers the slab interior (needs no ghost data) and its two boundary planes. With the CUDA-IPC transport
+// both are ONE launch whose first CTAs take the boundary planes: they wait IN-KERNEL for the ghosts they read, store their
+// results straight into the neighbours' ghost regions (P2P stores over NVLink) and the last of them publishes the epoch,
+// while the other CTAs sweep the interior — no exchange sits on the critical path, and the step is a linear chain of
+// launches on one stream (CUDA-graph replay, programmatic dependent launch between all of them).
+// (NCCL fallback: interior launch, boundary launch, blocking send/recv.)
 int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const float* bmax, bool commit, float dt,
                bool* committed) {
     *committed = false;
@@ -554,29 +523,26 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
         const bool fin = commit && it == iterations - 1;
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
-        if (it == 0 && (rc = slabJoin(s))) return rc;   // boundary stream catches up with the list build
-        if ((rc = launchPassA(s, sp.interior, sp.gridInterior, P))) return rc;
-        if (slabMode) {
-            {   // ---- pass A on the boundary planes (boundary stream): needs the ghosts' x*, (x*, lambda) goes out
-                BndScope scope(s);
-                const HaloSync hs = p2p ? slabHalo(s, 1 + 2 * it, 2 + 2 * it) : HaloSync{};
-                if ((rc = launchPassA(s, sp.boundary, sp.gridBoundary, P, p2p, hs))) return rc;
-                if (!p2p && (rc = usePack(s) ? slabNcclPlanes(s, s->xl) : slabNcclPlanes(s, s->lambda))) return rc;
-            }
-            if ((rc = slabJoin(s))) return rc;   // pass B reads lambda across the interior / boundary split
+        if (slabMode && p2p) {
+            // ---- CUDA-IPC transport: one launch per sweep. Its first CTAs take the boundary planes: they wait in-kernel for the
+            // ghosts this sweep reads, store their results straight into the neighbours' ghost regions (P2P stores over NVLink)
+            // and the last of them publishes the epoch; the remaining CTAs sweep the interior meanwhile. Pass A needs the
+            // ghosts' x* and sends (x*, lambda); pass B needs those and sends the corrected x* (after the commit also v, rho).
+            if ((rc = launchPassA(s, sp.fused, sp.gridFused, P, true, slabHalo(s, 1 + 2 * it, 2 + 2 * it)))) return rc;
+            if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
+            if ((rc = launchPassB(s, sp.fused, sp.gridFused, P, B, fin, dt, true, slabHalo(s, 2 + 2 * it, 3 + 2 * it)))) return rc;
+        } else if (slabMode) {
+            // ---- NCCL fallback: interior launch, boundary launch, then a blocking send/recv of the planes, all in stream order
+            if ((rc = launchPassA(s, sp.interior, sp.gridInterior, P))) return rc;
+            if ((rc = launchPassA(s, sp.boundary, sp.gridBoundary, P))) return rc;
+            if ((rc = usePack(s) ? slabNcclPlanes(s, s->xl) : slabNcclPlanes(s, s->lambda))) return rc;
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
             if ((rc = launchPassB(s, sp.interior, sp.gridInterior, P, B, fin, dt))) return rc;
-            {   // ---- pass B on the boundary planes, corrected x* (and after the commit v + rho) go out
-                BndScope scope(s);
-                const HaloSync hs = p2p ? slabHalo(s, 2 + 2 * it, 3 + 2 * it) : HaloSync{};
-                if ((rc = launchPassB(s, sp.boundary, sp.gridBoundary, P, B, fin, dt, p2p, hs))) return rc;
-                if (!p2p) {
-                    if ((rc = slabNcclPlanes(s, s->xsAlt))) return rc;
-                    if (fin && (rc = slabNcclPlanes(s, s->vel))) return rc;
-                }
-            }
-            if ((rc = slabJoin(s))) return rc;   // the next sweep reads x* across the split
+            if ((rc = launchPassB(s, sp.boundary, sp.gridBoundary, P, B, fin, dt))) return rc;
+            if ((rc = slabNcclPlanes(s, s->xsAlt))) return rc;
+            if (fin && (rc = slabNcclPlanes(s, s->vel))) return rc;
         } else {
+            if ((rc = launchPassA(s, sp.interior, sp.gridInterior, P))) return rc;
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
             if ((rc = launchPassB(s, sp.interior, sp.gridInterior, P, B, fin, dt))) return rc;
         }
@@ -623,30 +589,22 @@ int phasePost(akua_pbf_solver* s, float dt, int iterations) {
     }
     const bool p2p = s->slab.p2p;
     const int lastX = slabLastXIdx(iterations), pb = slabPostBaseIdx(iterations);
-    if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchVorticity(s, sp.interior, sp.gridInterior, P))) return rc;
-    {   // K11 on the boundary planes: needs the ghosts' final x*, v; (x, |omega|) goes out for K12
-        BndScope scope(s);
-        const HaloSync hs = p2p ? slabHalo(s, lastX, pb) : HaloSync{};
-        if ((rc = launchVorticity(s, sp.boundary, sp.gridBoundary, P, p2p, hs))) return rc;
-        if (!p2p && (rc = usePack(s) ? slabNcclPlanes(s, s->xw) : slabNcclPlanes(s, s->omegaLen))) return rc;
+    if (p2p) {
+        // one fused launch per sweep (boundary CTAs first): K11 needs the ghosts' final x*, v and sends (x, |omega|); K12 needs
+        // those and sends the post-confinement v; K13 needs that
+        if ((rc = launchVorticity(s, sp.fused, sp.gridFused, P, true, slabHalo(s, lastX, pb)))) return rc;
+        if ((rc = launchConfinement(s, sp.fused, sp.gridFused, P, dt, true, slabHalo(s, pb, pb + 1)))) return rc;
+        if ((rc = launchXsph(s, sp.fused, sp.gridFused, P, slabHalo(s, pb + 1, -1)))) return rc;
+    } else {
+        if ((rc = launchVorticity(s, sp.interior, sp.gridInterior, P))) return rc;
+        if ((rc = launchVorticity(s, sp.boundary, sp.gridBoundary, P))) return rc;
+        if ((rc = usePack(s) ? slabNcclPlanes(s, s->xw) : slabNcclPlanes(s, s->omegaLen))) return rc;
+        if ((rc = launchConfinement(s, sp.interior, sp.gridInterior, P, dt))) return rc;
+        if ((rc = launchConfinement(s, sp.boundary, sp.gridBoundary, P, dt))) return rc;
+        if ((rc = slabNcclPlanes(s, s->vel))) return rc;
+        if ((rc = launchXsph(s, sp.interior, sp.gridInterior, P))) return rc;
+        if ((rc = launchXsph(s, sp.boundary, sp.gridBoundary, P))) return rc;
     }
-    if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchConfinement(s, sp.interior, sp.gridInterior, P, dt))) return rc;
-    {   // K12 on the boundary planes; the post-confinement v goes out for K13
-        BndScope scope(s);
-        const HaloSync hs = p2p ? slabHalo(s, pb, pb + 1) : HaloSync{};
-        if ((rc = launchConfinement(s, sp.boundary, sp.gridBoundary, P, dt, p2p, hs))) return rc;
-        if (!p2p && (rc = slabNcclPlanes(s, s->vel))) return rc;
-    }
-    if ((rc = slabJoin(s))) return rc;
-    if ((rc = launchXsph(s, sp.interior, sp.gridInterior, P))) return rc;
-    {
-        BndScope scope(s);
-        const HaloSync hs = p2p ? slabHalo(s, pb + 1, -1) : HaloSync{};
-        if ((rc = launchXsph(s, sp.boundary, sp.gridBoundary, P, hs))) return rc;
-    }
-    if ((rc = slabJoinEnd(s))) return rc;   // the step ends on the main stream
     std::swap(s->vel, s->velAlt);
     return AKUA_OK;
 }
@@ -683,7 +641,6 @@ int tracedStep(akua_pbf_solver* s, Body& body) {
     const int rc = body();
     s->tracing = false;
     cudaStreamSynchronize(s->stream);
-    if (s->slab.bndStream) cudaStreamSynchronize(s->slab.bndStream);
     FILE* f = std::fopen(s->tracePath.c_str(), "a");
     if (f && !s->trace.empty()) {
         float prev[2] = {0.0f, 0.0f};
@@ -719,7 +676,6 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         if (rc) return rc;
     }
     auto body = [&]() {
-        s->slab.bndForked = false;
         return slabMode ? stepSlabBody(s, dt, iterations, bmin, bmax) : stepEager(s, dt, iterations, bmin, bmax);
     };
     if (s->traceArmed) return tracedStep(s, body);
@@ -943,6 +899,8 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     AK_CUDA(s, dalloc(&s->sortWs.binTotal, rsort::kCtrlWords));
     if (const char* e = std::getenv("AKUA_SORT_MODE")) s->sortWs.mode = std::atoi(e);     // tuning experiments: 0 = three kernels per pass
     if (const char* e = std::getenv("AKUA_SORT_ITEMS")) s->sortWs.items = std::atoi(e);   // tuning experiments: keys per thread (4 / 8 / 16)
+    if (const char* e = std::getenv("AKUA_CANONICAL_ORDER")) s->opt.canonical_order = std::atoi(e) != 0;   // tests / experiments
+    if (s->opt.canonical_order) { AK_CUDA(s, dalloc(&s->canonKeys, cap)); AK_CUDA(s, dalloc(&s->canonVals, cap)); }
     AK_CUDA(s, dalloc(&s->partSum, 1024)); AK_CUDA(s, dalloc(&s->partMax, 1024));
     for (float4* p : {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->omega, s->dpos, s->color})
         AK_CUDA(s, cudaMemsetAsync(p, 0, cap * sizeof(float4), s->stream));
@@ -979,7 +937,7 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
     void* ptrs[] = {s->pos, s->posAlt, s->vel, s->velAlt, s->xs, s->xsAlt, s->id, s->idAlt, s->density, s->lambda,
                     s->omegaLen, s->omega, s->dpos, s->color, s->size, s->keysUnsorted, s->keyA, s->keyB, s->valA, s->valB,
                     s->bucketStart, s->cellRange, s->nbrList, s->nbrCount, s->sortWs.tileHist, s->sortWs.binTotal,
-                    s->aosStage, s->partSum, s->partMax, s->xl, s->xw, s->pv, s->dMassRange};
+                    s->aosStage, s->partSum, s->partMax, s->xl, s->xw, s->pv, s->dMassRange, s->canonKeys, s->canonVals};
     if (s->hMassRange) cudaFreeHost(s->hMassRange);
     for (auto& g : s->graphs) if (g.used && g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -996,7 +954,6 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
         if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
-        if (sl.bndStream) { cudaStreamSynchronize(sl.bndStream); cudaStreamDestroy(sl.bndStream); }
         for (int e = 0; e < SlabState::kEvents; e++) if (sl.evPool[e]) cudaEventDestroy(sl.evPool[e]);
         if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
     }
@@ -1355,9 +1312,6 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         int lo = 0, hi = 0;
         AK_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
         AK_CUDA(s, cudaStreamCreateWithPriority(&sl.commStream, cudaStreamNonBlocking, hi));
-        AK_CUDA(s, cudaStreamCreateWithPriority(&sl.bndStream, cudaStreamNonBlocking, hi));
-        sl.bndPriority = hi;
-        if (const char* ep = std::getenv("AKUA_SLAB_BND_PRIORITY")) { if (ep[0] == '0') sl.bndPriority = 0; }   // tuning experiments
         for (int e = 0; e < SlabState::kEvents; e++) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evPool[e], cudaEventDisableTiming));
     }
     AK_CUDA(s, dalloc(&sl.dims, D_WORDS));
@@ -1436,14 +1390,8 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
         cudaFree(dflag);
         sl.p2p = v != 0;
     }
-    {
-        // boundary-plane launches get their own stream (overlap with the interior launches) under the p2p transport; the NCCL
-        // fallback issues everything in order on the main stream
-        const char* eb = std::getenv("AKUA_SLAB_BND_STREAM");
-        sl.useBndStream = sl.p2p && !(eb && eb[0] == '0');
-        const char* eg = std::getenv("AKUA_SLAB_GRAPH");
-        if (eg && eg[0] == '0') sl.graphBroken = true;
-    }
+    if (const char* eg = std::getenv("AKUA_SLAB_GRAPH")) { if (eg[0] == '0') sl.graphBroken = true; }   // tuning experiments
+    if (const char* ek = std::getenv("AKUA_SLAB_KEEP_BELOW")) { const double v = std::atof(ek); if (v >= 1.0) sl.keepBelow = v; }
     AK_CUDA(s, cudaStreamSynchronize(s->stream));
     return AKUA_OK;
 }
@@ -1504,22 +1452,40 @@ int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int3
 // transfer: it stays strictly inside the two old slabs it separates (particles only ever move to an adjacent rank, and
 // arrivals never reach a slab's far boundary plane), every slab stays at least two planes wide, and at most maxMove
 // particles cross it.
-int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
-                               int32_t* bounds) {
-    if (!hist || !oldBounds || !bounds) return AKUA_ERR_INVALID;
+int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* count, int32_t ncols, int32_t nranks,
+                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int32_t* bounds) {
+    if (!work || !count || !oldBounds || !bounds || nranks < 1) return AKUA_ERR_INVALID;
     const int R = nranks;
     const int32_t* old = oldBounds;
-    if (akua_slab_partition(hist, ncols, nranks, bounds) != AKUA_OK) return AKUA_ERR_INVALID;
+    if (keepBelow > 1.0) {
+        // hysteresis: a partition whose heaviest slab is within keepBelow of the mean is left alone (moving a boundary costs a
+        // migration burst and a re-capture of the step's CUDA graph)
+        int64_t total = 0, heaviest = 0;
+        for (int r = 0; r < R; r++) {
+            int64_t w = 0;
+            for (int x = std::max(old[r], 0); x < std::min(old[r + 1], ncols); x++) w += work[x];
+            total += w; heaviest = std::max(heaviest, w);
+        }
+        if (total > 0 && (double)heaviest * R <= keepBelow * (double)total) {
+            for (int r = 0; r <= R; r++) bounds[r] = old[r];
+            return AKUA_OK;
+        }
+    }
+    if (akua_slab_partition(work, ncols, nranks, bounds) != AKUA_OK) return AKUA_ERR_INVALID;
     for (int r = 1; r < R; r++) {
         // stay inside the two old slabs and keep every slab at least two planes wide
         int b = std::min(std::max(bounds[r], std::max(old[r - 1] + 1, bounds[r - 1] + 2)), old[r + 1] - 2);
         int64_t moved = 0;
-        if (b > old[r]) { int x = old[r]; while (x < b && moved + hist[x] <= maxMove) { moved += hist[x]; x++; } b = x; }
-        else if (b < old[r]) { int x = old[r]; while (x > b && moved + hist[x - 1] <= maxMove) { moved += hist[x - 1]; x--; } b = x; }
+        if (b > old[r]) { int x = old[r]; while (x < b && moved + count[x] <= maxMove) { moved += count[x]; x++; } b = x; }
+        else if (b < old[r]) { int x = old[r]; while (x > b && moved + count[x - 1] <= maxMove) { moved += count[x - 1]; x--; } b = x; }
         if (b < bounds[r - 1] + 2) b = std::min(bounds[r - 1] + 2, old[r + 1] - 2);
         bounds[r] = b;
     }
     return AKUA_OK;
+}
+int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
+                               int32_t* bounds) {
+    return akua_slab_rebalance_bounds_weighted(hist, hist, ncols, nranks, oldBounds, maxMove, 0.0, bounds);
 }
 
 // ---- phase-level operators ----

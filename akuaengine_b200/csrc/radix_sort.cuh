@@ -396,16 +396,17 @@ inline void launch(bool pdl, void (*kernel)(KArgs...), uint32_t grid, cudaStream
 }
 
 // `nPtr` (optional): the actual number of pairs lives on the device; `n` is then the host's estimate (grid sizing only).
+// `valsIn0` (optional): the values that travel with keysIn (default: the indices 0..n-1). Must not alias bufA / bufB.
 inline int sort_pairs_three_kernel(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
-                      uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr) {
+                      uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr, const uint32_t* valsIn0 = nullptr) {
     const uint32_t numTiles = std::max(1u, tiles_for(n));
     const bool small = items_for(n) == kItemsSmall;
     const uint32_t tileSize = (uint32_t)kThreads * (small ? kItemsSmall : kItemsLarge);
     const uint32_t tileStride = ws.maxTiles;
     const int passes = passes_for_bits(keyBits);
     const uint32_t* kin = keysIn;
-    const uint32_t* vin = nullptr;
+    const uint32_t* vin = valsIn0;
     uint32_t* kout = keyA;
     uint32_t* vout = valA;
     int launches = 0;
@@ -415,7 +416,7 @@ inline int sort_pairs_three_kernel(const uint32_t* keysIn, uint32_t* keyA, uint3
         else       launch(pdl, k_count<kItemsLarge>, numTiles, st, kin, n, nPtr, shift, ws.tileHist, tileStride);
         launch(pdl, k_scan, 256u, st, ws.tileHist, n, nPtr, tileSize, tileStride, ws.binTotal);
 #define AK_SCATTER(F, I) launch(pdl, k_scatter<F, I>, numTiles, st, kin, vin, kout, vout, n, nPtr, shift, ws.tileHist, tileStride, ws.binTotal)
-        if (p == 0) { if (small) AK_SCATTER(true, kItemsSmall); else AK_SCATTER(true, kItemsLarge); }
+        if (p == 0 && !valsIn0) { if (small) AK_SCATTER(true, kItemsSmall); else AK_SCATTER(true, kItemsLarge); }
         else        { if (small) AK_SCATTER(false, kItemsSmall); else AK_SCATTER(false, kItemsLarge); }
 #undef AK_SCATTER
         launches += 3;
@@ -434,7 +435,7 @@ inline int onesweep_items_for(uint64_t n, int forced) {
 }
 inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
-                      uint32_t** valsOut, bool pdl, const uint32_t* nPtr) {
+                      uint32_t** valsOut, bool pdl, const uint32_t* nPtr, const uint32_t* valsIn0 = nullptr) {
     const int passes = std::min(passes_for_bits(keyBits), kMaxPasses);
     const int items = onesweep_items_for(n, ws.items);
     const uint32_t tileSize = (uint32_t)kThreads * items;
@@ -451,7 +452,7 @@ inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t*
     else if (items == 8) launch(pdl, k_hist<8>, histGrid, st, keysIn, n, nPtr, passes, gHist);
     else launch(pdl, k_hist<16>, histGrid, st, keysIn, n, nPtr, passes, gHist);
     const uint32_t* kin = keysIn;
-    const uint32_t* vin = nullptr;
+    const uint32_t* vin = valsIn0;
     uint32_t* kout = keyA;
     uint32_t* vout = valA;
     int launches = 1;
@@ -460,7 +461,7 @@ inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t*
         uint32_t* lb = ws.tileHist + (size_t)p * ws.maxTiles * 256;
 #define AK_SWEEP(F, I) launch(pdl, k_onesweep<F, I>, numTiles, st, kin, vin, kout, vout, n, nPtr, shift, (const uint32_t*)(gHist + p * 256), tickets + p, lb)
 #define AK_SWEEP_I(F) do { if (items == 4) AK_SWEEP(F, 4); else if (items == 8) AK_SWEEP(F, 8); else AK_SWEEP(F, 16); } while (0)
-        if (p == 0) AK_SWEEP_I(true); else AK_SWEEP_I(false);
+        if (p == 0 && !valsIn0) AK_SWEEP_I(true); else AK_SWEEP_I(false);
 #undef AK_SWEEP_I
 #undef AK_SWEEP
         launches++;
@@ -475,10 +476,10 @@ inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t*
 
 inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
-                      uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr) {
+                      uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr, const uint32_t* valsIn0 = nullptr) {
     if (ws.mode == 1 && passes_for_bits(keyBits) <= kMaxPasses)
-        return sort_pairs_onesweep(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr);
-    return sort_pairs_three_kernel(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr);
+        return sort_pairs_onesweep(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr, valsIn0);
+    return sort_pairs_three_kernel(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr, valsIn0);
 }
 
 }  // namespace rsort

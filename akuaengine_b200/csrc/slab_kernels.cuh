@@ -277,21 +277,38 @@ __global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t
     if (t == 0 && hasL && actual != dims[D_PLANE_L]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
     if (t == 1 && hasR && actual != dims[D_PLANE_R]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
 }
-// Per-x-plane population of the owned (key-sorted) particles: hist[planeOffset + x] = #{ i : key_i / planeCells == x }, by two
-// binary searches per plane (one thread per plane). Used to re-balance the slab boundaries.
-__global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, uint32_t nOwn, uint32_t planeCells,
-                                                    int gx, int planeOffset, unsigned long long* __restrict__ hist) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
+// Per-x-plane population and WORK of the owned (key-sorted) particles, one CTA per plane: two binary searches give the plane's
+// index range, count[planeOffset + x] = its size, work[planeOffset + x] = sum over it of (kWorkBase + neighbour count) — what a
+// particle costs the sweeps. Used to re-balance the slab boundaries (a sloshing tank is denser, hence dearer, on one side).
+constexpr uint32_t kWorkBase = 12;
+__global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, const uint32_t* __restrict__ nbrCount,
+                                                    uint32_t nOwn, uint32_t planeCells, int gx, int planeOffset,
+                                                    unsigned long long* __restrict__ count, unsigned long long* __restrict__ work) {
+    __shared__ uint32_t range[2];
+    __shared__ unsigned long long part[8];
+    const int x = blockIdx.x;
     if (x >= gx) return;
-    auto lower = [&](uint64_t bound) {
+    if (threadIdx.x < 2) {
+        const uint64_t bound = (uint64_t)(x + threadIdx.x) * planeCells;
         uint32_t lo = 0, hi = nOwn;
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
             if ((uint64_t)keysSorted[mid] < bound) lo = mid + 1; else hi = mid;
         }
-        return lo;
-    };
-    hist[planeOffset + x] = (unsigned long long)(lower((uint64_t)(x + 1) * planeCells) - lower((uint64_t)x * planeCells));
+        range[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const uint32_t a = range[0], b = range[1];
+    unsigned long long w = 0;
+    for (uint32_t i = a + threadIdx.x; i < b; i += blockDim.x) w += kWorkBase + nbrCount[i];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) w += part[k];
+        count[planeOffset + x] = (unsigned long long)(b - a);
+        work[planeOffset + x] = w;
+    }
 }
 
 // ---- fused halo push (CUDA IPC path) ----
@@ -308,7 +325,7 @@ __global__ void __launch_bounds__(256) k_push_planes(const T* __restrict__ src, 
         if (t < nL) static_cast<T*>(pp.dstL)[t] = src[t];
         else static_cast<T*>(pp.dstR)[t - nL] = src[pp.startR + (t - nL)];
     }
-    halo_signal(hs);
+    halo_signal(hs, gridDim.x);
 }
 // Ghost planes received from the neighbours (already key-sorted: one x plane each, ordered like this rank's cells): keys from
 // the received x*, and the (start, end) range of every ghost cell. Waits in-kernel for the x* exchange (CUDA IPC path).

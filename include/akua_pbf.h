@@ -112,7 +112,12 @@ typedef struct akua_pbf_options {
                                 scheduled while its predecessor drains (also between the eagerly launched kernels of the x-slab path); 0 = plain stream order */
     int32_t list_build;      /* akua_list_build; akua_pbf_default_options selects AKUA_LIST_BUILD_MASK4 (the field took the first of
                                 the formerly reserved words: a zero-initialised struct from an older caller selects scan) */
-    int32_t reserved[5];
+    int32_t canonical_order; /* 0 (default) = particles of one cell keep last step's relative order (stable sort by cell key, like the
+                                reference's sort); 1 = they are ordered by particle id (an id sort ahead of the key sort: four more
+                                digit passes). With 1 the neighbour order, hence every float sum, no longer depends on history: an
+                                x-slab run on any number of GPUs, with migration and re-balancing, is then BIT-IDENTICAL to the
+                                single-GPU run (tests/mgpu_worker.py --canonical). Ids must be unique. */
+    int32_t reserved[4];
 } akua_pbf_options;
 
 void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */
@@ -192,10 +197,13 @@ int akua_pbf_checkpoint_load(akua_pbf_solver* s, const char* path);
  *                                                        contiguous across ranks; the end ranks own everything beyond;
  *           upload the owned particles (upload_* sets the live count; akua_pbf_upload_ids gives them global ids);
  *           akua_pbf_step(...) with the SAME box on every rank. It migrates particles whose predicted position left the
- *           slab, exchanges ghost planes over NCCL/NVLink (x*, lambda per iteration; v, |omega| post-solve) and steps
- *           the owned particles. Downloads return the owned particles; akua_pbf_num_particles is the owned count.
- *           The render payload (color, size) is not migrated between ranks: AoS downloads in slab mode carry the
- *           reference scene's defaults (blue, 50 — Application.cpp:186-187); ids are what identifies a particle. */
+ *           slab, exchanges ghost planes over NVLink (x*, lambda per iteration; v, |omega| post-solve) and steps the owned
+ *           particles. Nothing of a step's sizes is known to the host: migration counts, plane sizes and the exchange
+ *           epochs live on the device, every sweep is ONE launch whose first CTAs compute the boundary planes, store them
+ *           into the neighbours' arrays (CUDA-IPC peer pointers) and publish an epoch the neighbours' CTAs wait for — the
+ *           step is a single CUDA graph (NCCL send/recv with one host synchronisation per step is the fallback transport).
+ *           Downloads return the owned particles; akua_pbf_num_particles is the owned count. The render payload (color,
+ *           size) migrates with its particle, like the reference's struct follows its sort (NeighbourSearchCUDA.cu:167-170). */
 int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
 /* COLLECTIVE CALLS in slab mode: akua_pbf_set_slab, akua_pbf_rebalance and — once akua_pbf_set_slab has been called — every
  * upload (akua_pbf_upload_aos108 / _soa, akua_pbf_checkpoint_load): each contains one small all-reduce in which the ranks
@@ -204,9 +212,10 @@ int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
-/* Collective (every rank, same step): moves the slab boundaries towards equal particle counts using the current
- * per-x-plane populations (one small ncclAllReduce); the following step's migration transfers the particles. Call every
- * few dozen steps for scenes whose fluid moves along x (dam break). */
+/* Collective (every rank, same step): moves the slab boundaries towards equal WORK (a particle weighs 12 + its neighbour
+ * count) using the current per-x-plane sums (one small ncclAllReduce); the following step's migration transfers the particles.
+ * A partition whose heaviest slab is within 2 % of the mean is left alone (environment AKUA_SLAB_KEEP_BELOW, default 1.02).
+ * Call every few dozen steps for scenes whose fluid moves along x (dam break, sloshing tank). */
 int akua_pbf_rebalance(akua_pbf_solver* s);
 /* out: 0 owned, 1 ghosts from left, 2 ghosts from right, 3 first-plane size, 4 last-plane size, 5 exchanges so far,
  * 6 bytes sent so far (NEGATIVE when the CUDA-IPC peer-to-peer transport is in use, positive for NCCL send/recv),
@@ -221,6 +230,12 @@ int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int3
  * and at most maxMove particles cross a boundary. oldBounds / bounds hold nranks + 1 entries (first 0, last ncols). */
 int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
                                int32_t* bounds);
+/* The same with a WORK histogram deciding where the boundaries go (akua_pbf_rebalance weighs a particle by 12 + its neighbour
+ * count: the sweeps' cost follows the neighbour count, and a sloshing tank is denser on one side) while `count` (particles per
+ * column) still bounds what may cross a boundary. keepBelow > 1: if the heaviest slab of the CURRENT partition carries at most
+ * keepBelow x the mean work, the boundaries are left where they are. */
+int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* count, int32_t ncols, int32_t nranks,
+                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int32_t* bounds);
 
 /* Page-locked host memory for the interchange buffers (so uploads/downloads run at full PCIe rate). */
 void* akua_pbf_host_alloc(int64_t bytes);
@@ -286,9 +301,9 @@ int akua_pbf_enable_timing(akua_pbf_solver* s, int32_t on);
 int akua_pbf_last_step_timing(akua_pbf_solver* s, float ms[10]);
 /* Launch timeline of ONE step (a diagnostic, no reference counterpart): the NEXT akua_pbf_step runs eagerly (no graph replay)
  * with a CUDA event after every launch on the stream it went to, synchronises, and appends one JSON object per launch to
- * `path` (rank, step, seq, lane: 0 = solver stream / 1 = boundary stream of the x-slab step, name, end_ms since the start of
- * the step, since_prev_on_lane_ms). In x-slab mode the time a rank spends waiting for a neighbour shows up in the launch
- * that waits (k_slab_plan: the count message; the boundary sweeps: the ghost planes). */
+ * `path` (rank, step, seq, lane (always 0: every launch goes to the solver's stream), name, end_ms since the start of the step,
+ * since_prev_on_lane_ms). In x-slab mode the time a rank spends waiting for a neighbour shows up in the launch that waits
+ * (k_slab_plan: the count message; a sweep: the ghost planes its boundary CTAs read). */
 int akua_pbf_trace_next_step(akua_pbf_solver* s, const char* path);
 /* The CUDA stream (cudaStream_t) all of this solver's work is issued on, so callers can record their own events on it
  * or order other work after it. */

@@ -12,7 +12,7 @@ REPO = Path(__file__).resolve().parents[1]
 
 def test_library_exports_every_declared_symbol(akua_lib):
     header = (REPO / "include" / "akua_pbf.h").read_text()
-    declared = set(re.findall(r"\b(akua_pbf_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(akua_(?:pbf|slab)_[a-z0-9_]+)\s*\(", header))
     assert len(declared) >= 30
     for name in sorted(declared):
         assert hasattr(akua_lib, name), f"libakua_pbf.so does not export {name}"

@@ -52,8 +52,8 @@ def _scene(nx=24, ny=8, nz=10, vx=0.0):
     return p, bmin, bmax
 
 
-def _run_single(lib, p, bmin, bmax, steps, g):
-    s = PBFSolver(len(p), lib=lib, use_graph=False)
+def _run_single(lib, p, bmin, bmax, steps, g, canonical=False):
+    s = PBFSolver(len(p), lib=lib, use_graph=False, canonical_order=canonical)
     s.upload_particles(p)
     s.setGravity(g)
     for _ in range(steps):
@@ -64,7 +64,7 @@ def _run_single(lib, p, bmin, bmax, steps, g):
     return pos, vel, pid, err
 
 
-def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, capacity_factor=4.0):
+def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, capacity_factor=4.0, canonical=False):
     """One thread per rank. Returns per-rank (pos4, vel4, ids, aos, stats) and raises the first exception of any rank."""
     n = len(p)
     ids = np.arange(n, dtype=np.uint32)
@@ -83,7 +83,8 @@ def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, 
             lo, hi = col_min + int(bounds[rank]), col_min + int(bounds[rank + 1])
             mine = (cols >= lo) & (cols < hi)
             own = np.ascontiguousarray(p[mine])
-            s = PBFSolver(n if skew else max(n // world, len(own)), lib=lib, use_graph=False, capacity_factor=capacity_factor, device=rank)
+            s = PBFSolver(n if skew else max(n // world, len(own)), lib=lib, use_graph=False, capacity_factor=capacity_factor, device=rank,
+                          canonical_order=canonical)
             s.comm_init(rank, world, uid)
             s.set_slab(lo, hi)
             s.upload_particles(own)
@@ -154,6 +155,24 @@ def test_slab_with_migration_matches_one_rank(emulib):
     # global density-constraint error agrees with the single-rank run
     tot = sum(o[5][0] * len(o[2]) for o in slab) / len(p)
     assert abs(tot - single[3][0]) < 1e-3 * max(single[3][0], 1e-3) + 1e-5
+
+
+@pytest.mark.parametrize("world,skew,rebalance_every", [(3, 0.0, 0), (2, 0.5, 2)])
+def test_canonical_order_makes_the_slab_run_bit_identical_with_migration(emulib, world, skew, rebalance_every):
+    """options.canonical_order: a cell's particles are ordered by id on every rank, so neighbour order — and every float sum —
+    is that of the single-rank run, whatever migrated and however the slabs were re-balanced."""
+    p, bmin, bmax = _scene(nx=32 if skew else 24, vx=2.0)
+    g = scenes.tank_gravity(15.0)
+    steps = 10
+    single = _run_single(emulib, p, bmin, bmax, steps, g, canonical=True)
+    slab = _run_slab(emulib, p, bmin, bmax, steps, g, world, skew=skew, rebalance_every=rebalance_every,
+                     capacity_factor=2.5 if skew else 4.0, canonical=True)
+    assert sum(o[4]["migrated_in"] for o in slab) > 0, "the scene was meant to migrate particles"
+    dp, dv = _compare(p, single, slab, 1e-6)
+    assert dp == 0.0 and dv == 0.0
+    # and it is a different order from the default one (otherwise the option would be vacuous)
+    plain = _run_single(emulib, p, bmin, bmax, steps, g, canonical=False)
+    assert np.array_equal(np.sort(plain[2]), np.sort(single[2]))
 
 
 def test_slab_rebalances_from_a_skewed_start(emulib):

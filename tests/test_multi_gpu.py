@@ -120,7 +120,9 @@ def _gpu_count():
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("scene,vx,steps,extra", [("dam", 0.0, 8, []), ("tank", 0.0, 8, []), ("tank", 1.5, 20, []),
-                                                  ("tank", 0.0, 30, ["--rebalance-every", "5", "--skew", "0.5"])])
+                                                  ("tank", 0.0, 30, ["--rebalance-every", "5", "--skew", "0.5"]),
+                                                  ("tank", 1.5, 24, ["--canonical"]),
+                                                  ("tank", 1.0, 30, ["--canonical", "--rebalance-every", "5", "--skew", "0.4"])])
 def test_multi_gpu_slab_matches_single_gpu(world, scene, vx, steps, extra):
     """N x-slab ranks against ONE GPU running the same library on the same scene: ids conserved, payload follows, positions and
     velocities within the free-running tolerance (bit-identical when nothing migrates). On a box with fewer GPUs than `world`

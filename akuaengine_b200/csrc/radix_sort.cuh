@@ -362,7 +362,7 @@ struct Workspace {
     uint32_t* tileHist = nullptr;  // three-kernel variant: [256][maxTiles]; one-sweep variant: look-back words [passes][maxTiles][256]
     uint32_t* binTotal = nullptr;  // three-kernel variant: [256]; one-sweep variant: [kMaxPasses][256] histograms + kMaxPasses tickets
     uint32_t maxTiles = 0;
-    int mode = 1;                  // 0 = three kernels per pass (count / scan / scatter), 1 = one-sweep
+    int mode = 2;                  // 0 = three kernels per pass (count / scan / scatter), 1 = one-sweep, 2 = by size (default)
     int items = 0;                 // keys per thread of the one-sweep tiles (0 = by size)
 };
 constexpr size_t kCtrlWords = (size_t)kMaxPasses * 256 + 8;   // binTotal allocation
@@ -431,8 +431,12 @@ inline int sort_pairs_three_kernel(const uint32_t* keysIn, uint32_t* keyA, uint3
 
 inline int onesweep_items_for(uint64_t n, int forced) {
     if (forced == 4 || forced == 8 || forced == 16) return forced;
-    return n < (2u << 20) ? 4 : 8;
+    return n < (2u << 20) ? 4 : 16;   // measured on a B200 at 8 M keys: 16 keys per thread 249 us, 8: 275 us, 4: 380 us
 }
+// Below this many keys the three-kernel passes win (1 M keys: 56 us against 80 us — the one-sweep variant pays a histogram
+// kernel, its look-back memsets and tile-serial look-back latency that small inputs cannot amortise); above it one-sweep does
+// (8 M keys: 249 us against 283 us). profiles/r02_c5_sort_variants.txt
+constexpr uint64_t kOnesweepMin = 4u << 20;
 inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
                       uint32_t** valsOut, bool pdl, const uint32_t* nPtr, const uint32_t* valsIn0 = nullptr) {
@@ -477,7 +481,7 @@ inline int sort_pairs_onesweep(const uint32_t* keysIn, uint32_t* keyA, uint32_t*
 inline int sort_pairs(const uint32_t* keysIn, uint32_t* keyA, uint32_t* valA, uint32_t* keyB, uint32_t* valB,
                       uint32_t n, int keyBits, const Workspace& ws, cudaStream_t st, uint32_t** keysOut,
                       uint32_t** valsOut, bool pdl = false, const uint32_t* nPtr = nullptr, const uint32_t* valsIn0 = nullptr) {
-    if (ws.mode == 1 && passes_for_bits(keyBits) <= kMaxPasses)
+    if ((ws.mode == 1 || (ws.mode == 2 && n >= kOnesweepMin)) && passes_for_bits(keyBits) <= kMaxPasses)
         return sort_pairs_onesweep(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr, valsIn0);
     return sort_pairs_three_kernel(keysIn, keyA, valA, keyB, valB, n, keyBits, ws, st, keysOut, valsOut, pdl, nPtr, valsIn0);
 }

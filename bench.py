@@ -83,8 +83,10 @@ def kernel_source_hash() -> str:
 
 
 def ncu_traffic(n_rank: int):
-    """DRAM bytes per pass-B launch from the committed `ncu --set full` capture (profiles/r02_ncu_traffic.json), looked up
-    by the per-rank particle count; only trusted while the kernel source it was captured from is unchanged."""
+    """DRAM bytes per pass-B launch and its DRAM throughput from the committed `ncu --set full` captures
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic_json.py): the capture nearest in size, its bytes PER PARTICLE
+    scaled to this rank's particle count (beyond the L2 the sweeps' traffic per particle does not depend on n). Only trusted
+    while the kernel sources it was captured from are unchanged."""
     f = REPO / "profiles" / "r02_ncu_traffic.json"
     if not f.exists():
         return None, None, "no committed ncu capture"
@@ -95,13 +97,18 @@ def ncu_traffic(n_rank: int):
     if d.get("kernel_source_sha") != kernel_source_hash():
         return None, None, "kernel source changed since the committed ncu capture (profiles/r02_ncu_traffic.json)"
     best = None
-    for key, row in d.get("pass_b", {}).items():
-        if abs(int(key) - n_rank) <= 0.02 * n_rank and (best is None or abs(int(key) - n_rank) < abs(int(best[0]) - n_rank)):
-            best = (key, row)
-    if best is None:
-        return None, None, f"no capture at ~{n_rank} particles per GPU"
-    row = best[1]
-    return int(row["dram_bytes"]), row.get("dram_pct_of_peak"), f"ncu --set full at {best[0]} particles ({d.get('source', '')})"
+    for label, cap in d.get("captures", {}).items():
+        row = cap.get("kernels", {}).get("k_delta_apply")
+        if not row or not row.get("dram_bytes_per_particle"):
+            continue
+        dist = abs(np.log(max(cap["particles"], 1) / max(n_rank, 1)))
+        if best is None or dist < best[0]:
+            best = (dist, label, cap["particles"], row)
+    if best is None or best[0] > np.log(2.5):
+        return None, None, f"no capture within 2.5x of {n_rank} particles per GPU"
+    _, label, n_cap, row = best
+    return (int(row["dram_bytes_per_particle"] * n_rank), row.get("dram_pct_of_peak"),
+            f"ncu --set full, {label} ({n_cap} particles): {row['dram_bytes_per_particle']:.1f} B per particle x {n_rank} particles")
 
 
 class ClockSampler:
@@ -189,6 +196,29 @@ def bind_to_gpu_numa_node(local: int):
         return {"numa_node": node, "cpus": 0}
     except Exception as e:  # no sysfs, no permission: run unbound
         return {"numa_node": None, "why": str(e)[:80]}
+
+
+def nvlink_counters(local: int):
+    """Cumulative NVLink payload counters of this rank's GPU, all links summed: (tx_bytes, rx_bytes), from NVML's
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX fields (KiB units). None where NVML does not expose them."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xffffffff),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xffffffff)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            t = v.valueType
+            raw = {0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(t, v.value.ullVal)
+            out.append(int(raw) * 1024)
+        return tuple(out)
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------------------------- workload
@@ -346,9 +376,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     owned_log = []
+    nv0 = nvlink_counters(local) if world > 1 else None
+    st0 = solver.slab_stats() if world > 1 else None
     win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows,
                            rebalance=world > 1 and args.rebalance_every > 0, owned_log=owned_log)
     clocks = sampler.stop()
+    nv1 = nvlink_counters(local) if world > 1 else None
+    st1 = solver.slab_stats() if world > 1 else None
     c1 = solver.counters()
     launches = (c1["kernel_launches"] - c0["kernel_launches"]) // args.windows
     graph_replays = (c1["graph_replays"] - c0["graph_replays"]) // args.windows
@@ -494,6 +528,20 @@ def run_ours(args):
         "finite": finite,
     }
     if world > 1:
+        # NVLink halo traffic against link bandwidth (north-star): what the solver counts per step (boundary-plane pushes +
+        # migration records, device-side counter) beside the NVML link counters of rank 0's GPU over the same timed windows
+        nsteps = args.steps * args.windows
+        halo_bytes_step = (st1["bytes_sent"] - st0["bytes_sent"]) / max(nsteps, 1)
+        link_peak = 900.0   # GB/s per direction per GPU (NVLink 5, 18 links x 50 GB/s)
+        out["nvlink"] = {
+            "rank": 0, "halo_bytes_sent_per_step_counted": halo_bytes_step,
+            "exchanges_per_step": (st1["exchanges"] - st0["exchanges"]) / max(nsteps, 1),
+            "nvml_tx_bytes_per_step": ((nv1[0] - nv0[0]) / max(nsteps, 1)) if nv0 and nv1 else None,
+            "nvml_rx_bytes_per_step": ((nv1[1] - nv0[1]) / max(nsteps, 1)) if nv0 and nv1 else None,
+            "link_peak_gbs_per_direction": link_peak,
+            "link_utilisation_over_step": halo_bytes_step / (ms_step * 1e-3) / 1e9 / link_peak,
+            "note": "end ranks have one neighbour, interior ranks two (twice the bytes); the pushes are P2P stores issued by the "
+                    "boundary CTAs of each sweep while the interior CTAs of the same launch compute"}
         out["slab_rank0"] = {"owned_start": n, "owned_end": int(n_rank), **slab_stats}
         out["mgpu_check"] = {"small_scene_vs_single_gpu": mgpu_check, "conservation": conservation}
     solver.close()

@@ -91,9 +91,9 @@ typedef enum akua_gather_layout {
  *   scan  : one candidate at a time, test and append in the same loop (k_build_neighbours): the plain statement of the
  *           reference's traversal, kept as the cross-check of the other two.
  *   mask4 / mask8 : two phases per row chunk of <= 32 candidates — a hit bitmask from 4 / 8 independent loads in flight, then
- *           the set bits are appended — plus reachability culling: a neighbouring cell whose nearest point is at least h away
- *           from the particle is never loaded (akuaengine_b200/csrc/list_build.cuh). mask4 is the default since round 2
- *           (measured on a B200: profiles/r02_*). A zero-initialised options struct still selects scan. */
+ *           the set bits are appended (akuaengine_b200/csrc/list_build.cuh). mask4 is the default since round 2 (measured on a
+ *           B200: -14 % at 1 M, -7 % at 4 M particles against scan; reachability culling on top of it was measured and
+ *           rejected, profiles/r02_c3_list_build_culling_rejected.txt). A zero-initialised options struct still selects scan. */
 typedef enum akua_list_build {
     AKUA_LIST_BUILD_SCAN = 0,
     AKUA_LIST_BUILD_MASK4 = 1,

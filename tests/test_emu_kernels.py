@@ -48,7 +48,7 @@ def emu():
     lib.emu_debug_get.argtypes = [vp, C.c_int, vp]
     lib.emu_migration.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
     lib.emu_span_push_check.argtypes = [vp, C.c_uint32, C.c_uint32]
-    lib.emu_plane_hist.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, vp]
+    lib.emu_plane_hist.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp]
     lib.emu_plane_verify.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]
     return lib
 
@@ -219,9 +219,12 @@ def test_plane_histogram_and_plane_verify(emu):
     rng = np.random.default_rng(4)
     plane, gx, n = 35, 20, 5000
     keys = np.sort((rng.integers(2, 17, n) * plane + rng.integers(0, plane, n)).astype(np.uint32))
-    hist = np.zeros(gx, np.uint64)
-    emu.emu_plane_hist(keys.ctypes.data, n, plane, gx, hist.ctypes.data)
+    hist, work = np.zeros(gx, np.uint64), np.zeros(gx, np.uint64)
+    nbr = rng.integers(0, 60, n).astype(np.uint32)
+    emu.emu_plane_hist(keys.ctypes.data, nbr.ctypes.data, n, plane, gx, hist.ctypes.data, work.ctypes.data)
     assert np.array_equal(hist, np.bincount(keys // plane, minlength=gx).astype(np.uint64))
+    # the work histogram weighs a particle by 12 + its neighbour count (what akua_pbf_rebalance balances)
+    assert np.array_equal(work, np.bincount(keys // plane, weights=12.0 + nbr, minlength=gx).astype(np.uint64))
     x_lo, x_hi = 2, 17
     first, last = int((keys // plane == x_lo).sum()), int((keys // plane == x_hi - 1).sum())
     c = np.zeros(64, np.uint32)

@@ -175,8 +175,11 @@ def test_origin_corner_hash_quirk():
 
 @pytest.mark.parametrize("n", [0, 1, 2, 33, 1023, 1024, 1025, 4095, 4096, 4097, 70001])
 @pytest.mark.parametrize("mode", MODES)
-def test_sort_and_ranges_on_ragged_sizes(n, mode):
-    """Radix sort + range detection at sizes around the sort tile (4096) and warp boundaries, incl. empty input."""
+@pytest.mark.parametrize("sort_mode", ["0", "1"], ids=["three-kernel", "onesweep"])
+def test_sort_and_ranges_on_ragged_sizes(n, mode, sort_mode, monkeypatch):
+    """Radix sort + range detection at sizes around the sort tile (4096) and warp boundaries, incl. empty input, with both sort
+    variants forced (by default the size picks: three kernels per pass below 4 M keys, one-sweep above)."""
+    monkeypatch.setenv("AKUA_SORT_MODE", sort_mode)
     p, bmin, bmax = scenes.uniform_cloud(max(n, 1), seed=11)
     p = p[:n].copy()
     p["new_position"] = p["position"]

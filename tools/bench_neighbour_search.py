@@ -1,5 +1,5 @@
 """Neighbour-search microbench (BASELINE config 5): cell keys + radix sort + cell ranges + reorder, and separately the
-27-cell list build, at 1 M - 64 M particles, uniform vs clustered density. CUDA-event phase timings from the library.
+27-cell list build, at 1 M - 128 M particles, uniform vs clustered density. CUDA-event phase timings from the library.
     python tools/bench_neighbour_search.py [--sizes 1,4,16,64] > profiles/r01_neighbour_search_microbench.jsonl"""
 import argparse
 import json
@@ -25,13 +25,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="1,4,16,64", help="millions of particles")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--linear-only", action="store_true")
     a = ap.parse_args()
     for m in [int(x) for x in a.sizes.split(",")]:
         n = m * 1_000_000
         for kind in ("uniform", "clustered"):
             pos, bmin, bmax = positions(kind, n)
             for mode, mname in ((KEY_LINEAR_CELL, "linear"), (KEY_REFERENCE_HASH, "hash")):
-                if mode == KEY_REFERENCE_HASH and n * 128 >= 2 ** 31:
+                if mode == KEY_REFERENCE_HASH and (n * 128 >= 2 ** 31 or a.linear_only):
                     continue  # the reference's int tableSize overflows (PBFSolver.cpp:15)
                 s = PBFSolver(n, key_mode=mode)
                 s.upload(pos)

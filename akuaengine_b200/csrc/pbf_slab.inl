@@ -195,12 +195,12 @@ int slabNcclPlanes(akua_pbf_solver* s, T* arr) {
 }
 // p2p: pushes the boundary planes of `arr` with a small copy kernel (no sweep produces them) and publishes exchange `idx`.
 template <typename T>
-int slabPushPlanes(akua_pbf_solver* s, T* arr, int idx) {
+int slabPushPlanes(akua_pbf_solver* s, T* arr, int idx, const slab::PlaneVerify& pv = slab::PlaneVerify{}) {
     SlabState& sl = s->slab;
     if (!sl.p2p) return slabNcclPlanes(s, arr);
     const PeerPush pp = slabPush(s, arr);
     const HaloSync hs = slabHalo(s, -1, idx);
-    launchK(s, slab::k_push_planes<T>, std::max(1u, gridFor(sl.estBnd)), kBlock, (const T*)arr, pp, hs);
+    launchK(s, slab::k_push_planes<T>, std::max(1u, gridFor(sl.estBnd)), kBlock, (const T*)arr, pp, hs, pv);
     AK_LAUNCH_CHECK(s, "k_push_planes");
     return AKUA_OK;
 }
@@ -301,7 +301,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
 
     // ---- 2. migration: leavers out (sentinel key), arrivals appended ----
     mark(s, PH_SORT);
-    const uint32_t migGrid = std::max(1u, std::min(gridFor(sl.estN), sl.migBlocksCap));
+    const uint32_t migGrid = std::max(1u, std::min((sl.estN + slab::kMigTile - 1) / slab::kMigTile, sl.migBlocksCap));
     AK_CUDA(s, cudaMemsetAsync(dims + D_STAY_FIRST, 0, 4 * sizeof(uint32_t), s->stream));   // the four plane populations
     launchPlain(s->stream, slab::k_mig_count, migGrid, kBlock, s->keysUnsorted, dims + D_N, planeCells, xLo, xHi, sl.blockCnt,
                                                          sl.migBlocksCap, dims + D_STAY_FIRST);
@@ -325,11 +325,12 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     caps.planeCapR = hasR ? (p2p ? std::min(sl.ghostCap, sl.peerR.ghostCap) : sl.ghostCap) : 0;
     caps.slotCap = (uint32_t)s->capacity;
     if (p2p) {
-        // the count message and the records travel by P2P stores; the plan kernel waits for the neighbours' message in-kernel
-        launchPlain(s->stream, slab::k_publish_counts, 1, 32, dims, hasL ? sl.peerL.dims : nullptr, hasR ? sl.peerR.dims : nullptr,
-                                                        hasL ? sl.peerL.flags + 5 : nullptr, hasR ? sl.peerR.flags + 4 : nullptr);
-        AK_LAUNCH_CHECK(s, "k_publish_counts");
-        launchPlain(s->stream, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 1, caps, kFlagWaitCycles);
+        // the count message and the records travel by P2P stores: the plan kernel publishes this rank's message, then waits
+        // in-kernel for the neighbours'
+        slab::PlanPublish pub;
+        if (hasL) { pub.peerDimsL = sl.peerL.dims; pub.peerFlagL = sl.peerL.flags + 5; }
+        if (hasR) { pub.peerDimsR = sl.peerR.dims; pub.peerFlagR = sl.peerR.flags + 4; }
+        launchPlain(s->stream, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 1, caps, kFlagWaitCycles, pub);
         AK_LAUNCH_CHECK(s, "k_slab_plan");
     } else {
         // NCCL fallback: count messages, then ONE host synchronisation (the record sizes are needed on the host), then records
@@ -341,7 +342,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
         if (hasL) AK_NCCL(s, g_nccl.Recv(dims + D_MSG_FROM_L, 12, ncclUint8, sl.rank - 1, comm, st));
         if (hasR) AK_NCCL(s, g_nccl.Recv(dims + D_MSG_FROM_R, 12, ncclUint8, sl.rank + 1, comm, st));
         AK_NCCL(s, g_nccl.GroupEnd());
-        launchPlain(st, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 0, caps, kFlagWaitCycles);
+        launchPlain(st, slab::k_slab_plan, 1, 32, dims, sl.flags + 4, hasL ? 1 : 0, hasR ? 1 : 0, 0, caps, kFlagWaitCycles, slab::PlanPublish{});
         AK_LAUNCH_CHECK(s, "k_slab_plan");
         AK_CUDA(s, cudaMemcpyAsync((void*)sl.hDims, dims, D_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         AK_CUDA(s, cudaStreamSynchronize(st));
@@ -377,9 +378,15 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     std::swap(sl.slot, sl.slotAlt);
 
     // ---- 4. ghost planes: x* of the neighbours' boundary planes (exchange 1), keyed and ranged in place ----
-    launchPlain(s->stream, slab::k_plane_verify, 1, 32, s->keysSorted, planeCells, xLo, xHi, hasL ? 1 : 0, hasR ? 1 : 0, dims);
-    AK_LAUNCH_CHECK(s, "k_plane_verify");
-    if ((rc = slabPushPlanes(s, s->xs, 1))) return rc;
+    if (p2p) {   // the plane-size check rides on the push kernel
+        slab::PlaneVerify pv;
+        pv.keysSorted = s->keysSorted; pv.planeCells = planeCells; pv.xLo = xLo; pv.xHi = xHi; pv.hasL = hasL; pv.hasR = hasR; pv.dims = dims;
+        if ((rc = slabPushPlanes(s, s->xs, 1, pv))) return rc;
+    } else {
+        launchPlain(s->stream, slab::k_plane_verify, 1, 32, s->keysSorted, planeCells, xLo, xHi, hasL ? 1 : 0, hasR ? 1 : 0, dims);
+        AK_LAUNCH_CHECK(s, "k_plane_verify");
+        if ((rc = slabPushPlanes(s, s->xs, 1))) return rc;
+    }
     {
         const HaloSync hs = p2p ? slabHalo(s, 1, -1) : HaloSync{};
         launchK(s, slab::k_ghost_ranges, std::max(1u, gridFor(sl.estGhost)), kBlock, (const float4*)s->xs, s->keysSorted, (const uint32_t*)dims,

@@ -20,7 +20,11 @@ namespace slab {
 // reference, which sorts whole structs: src/CUDA/NeighbourSearchCUDA.cu:167-170). meta = (global id, size bits, 0, 0).
 struct MigRecord { float4 pos, vel, xs, color; uint4 meta; };
 
-constexpr int kMigTile = 256;
+// A migration tile is 2048 consecutive particles: thread t of the CTA handles the 8 particles [8 t, 8 t + 8) of its tile (two
+// 16-byte key loads), so leavers are compacted in index order — deterministic, no atomics on the compaction path — while the
+// per-tile bookkeeping (one count per tile and direction, scanned by a single CTA) is 8 x smaller than with one particle per thread.
+constexpr int kMigItems = 8;
+constexpr int kMigTile = 256 * kMigItems;
 enum : int { D_FREE_TOP = 49, D_FREE_POP = 50 };   // payload-slot free stack: entries in use; pop base of this step's arrivals
 
 // Destination of a particle from its (slab-local, clamped) x cell: 0 = left neighbour, 1 = stays, 2 = right neighbour.
@@ -28,47 +32,62 @@ __device__ __forceinline__ int dest_of(uint32_t key, uint32_t planeCells, int xL
     int cx = (int)(key / planeCells);
     return cx < xLo ? 0 : (cx >= xHi ? 2 : 1);
 }
+// The (up to) 8 keys of thread `threadIdx.x` in tile `tile`; slots past n read as a stayer of an interior plane.
+__device__ __forceinline__ void mig_load_keys(const uint32_t* __restrict__ keys, uint32_t n, uint32_t base, uint32_t stayKey,
+                                              uint32_t (&k)[kMigItems]) {
+    if (base + kMigItems <= n) {
+        const uint4 a = *reinterpret_cast<const uint4*>(keys + base), b = *reinterpret_cast<const uint4*>(keys + base + 4);
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    } else {
+#pragma unroll
+        for (int r = 0; r < kMigItems; r++) k[r] = base + r < n ? keys[base + r] : stayKey;
+    }
+}
 
-// Pass 1: per-tile counts of leavers in each direction (deterministic compaction, no atomics on the compaction path),
-// plus the four plane populations that let every rank PREDICT its post-migration boundary-plane and ghost-plane sizes
-// from one count exchange (extra[0] stayers in my first plane, [1] stayers in my last plane, [2] leavers to the left that
-// land in the left rank's last plane, [3] leavers to the right that land in the right rank's first plane).
+// Pass 1: per-tile counts of leavers in each direction, plus the four plane populations that let every rank PREDICT its
+// post-migration boundary-plane and ghost-plane sizes from one count exchange (extra[0] stayers in my first plane, [1]
+// stayers in my last plane, [2] leavers to the left that land in the left rank's last plane, [3] leavers to the right that
+// land in the right rank's first plane).
 __global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nPtr,
                                                    uint32_t planeCells, int xLo, int xHi,
                                                    uint32_t* __restrict__ blockCnt /*[2][tileStride]*/, uint32_t tileStride,
                                                    uint32_t* __restrict__ extra /*[4], zeroed*/) {
-    __shared__ uint32_t sL[8], sR[8], sE[4];
+    __shared__ uint32_t sAcc[6];
     const uint32_t n = *nPtr;
     const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stayKey = (uint32_t)(xLo + 1) * planeCells;   // an interior plane when the slab has one; never a leaver
+    uint32_t tot[4] = {0, 0, 0, 0};                              // this thread's share of the four plane populations
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const uint32_t i = tile * kMigTile + threadIdx.x;
-        if (threadIdx.x < 4) sE[threadIdx.x] = 0;
+        if (threadIdx.x < 2) sAcc[threadIdx.x] = 0;
         __syncthreads();
-        int cx = i < n ? (int)(keys[i] / planeCells) : xLo + 1;
-        int d = i < n ? (cx < xLo ? 0 : (cx >= xHi ? 2 : 1)) : 1;
-        uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
-        uint32_t b0 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xLo);
-        uint32_t b1 = __ballot_sync(0xffffffffu, i < n && d == 1 && cx == xHi - 1);
-        uint32_t b2 = __ballot_sync(0xffffffffu, d == 0 && cx == xLo - 1);
-        uint32_t b3 = __ballot_sync(0xffffffffu, d == 2 && cx == xHi);
-        if (lane == 0) {
-            sL[warp] = __popc(bl); sR[warp] = __popc(br);
-            if (b0) atomicAdd(&sE[0], (uint32_t)__popc(b0));
-            if (b1) atomicAdd(&sE[1], (uint32_t)__popc(b1));
-            if (b2) atomicAdd(&sE[2], (uint32_t)__popc(b2));
-            if (b3) atomicAdd(&sE[3], (uint32_t)__popc(b3));
+        uint32_t k[kMigItems];
+        const uint32_t base = tile * kMigTile + threadIdx.x * kMigItems;
+        mig_load_keys(keys, n, base, stayKey, k);
+        uint32_t cl = 0, cr = 0;
+#pragma unroll
+        for (int r = 0; r < kMigItems; r++) {
+            const bool live = base + r < n;
+            const int cx = (int)(k[r] / planeCells);
+            const int d = cx < xLo ? 0 : (cx >= xHi ? 2 : 1);
+            cl += live && d == 0; cr += live && d == 2;
+            tot[0] += live && d == 1 && cx == xLo; tot[1] += live && d == 1 && cx == xHi - 1;
+            tot[2] += live && d == 0 && cx == xLo - 1; tot[3] += live && d == 2 && cx == xHi;
         }
+        cl = __reduce_add_sync(0xffffffffu, cl); cr = __reduce_add_sync(0xffffffffu, cr);
+        if ((threadIdx.x & 31) == 0) { if (cl) atomicAdd(&sAcc[0], cl); if (cr) atomicAdd(&sAcc[1], cr); }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t a = 0, b = 0;
-            for (int w = 0; w < 8; w++) { a += sL[w]; b += sR[w]; }
-            blockCnt[tile] = a;
-            blockCnt[tileStride + tile] = b;
-        }
-        if (threadIdx.x < 4 && sE[threadIdx.x]) atomicAdd(&extra[threadIdx.x], sE[threadIdx.x]);
+        if (threadIdx.x == 0) { blockCnt[tile] = sAcc[0]; blockCnt[tileStride + tile] = sAcc[1]; }
         __syncthreads();
     }
+    if (threadIdx.x < 4) sAcc[2 + threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t v = __reduce_add_sync(0xffffffffu, tot[q]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sAcc[2 + q], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && sAcc[2 + threadIdx.x]) atomicAdd(&extra[threadIdx.x], sAcc[2 + threadIdx.x]);
 }
 // Pass 2 (one CTA of 1024 threads): exclusive scan of the per-tile counts in place, both directions at once; totals ->
 // dims[D_OUT_L], dims[D_OUT_R]; also assembles the two count messages.
@@ -133,48 +152,51 @@ __global__ void __launch_bounds__(256) k_mig_pack(uint32_t* __restrict__ keys, c
     const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
     const uint32_t outL = min(dims[D_OUT_L], cap), freeTop = dims[D_FREE_TOP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stayKey = (uint32_t)(xLo + 1) * planeCells;
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const uint32_t i = tile * kMigTile + threadIdx.x;
-        int d = i < n ? dest_of(keys[i], planeCells, xLo, xHi) : 1;
-        uint32_t bl = __ballot_sync(0xffffffffu, d == 0), br = __ballot_sync(0xffffffffu, d == 2);
-        if (lane == 0) { sL[warp] = __popc(bl); sR[warp] = __popc(br); }
+        uint32_t k[kMigItems];
+        const uint32_t base = tile * kMigTile + threadIdx.x * kMigItems;
+        mig_load_keys(keys, n, base, stayKey, k);
+        uint32_t cl = 0, cr = 0;
+#pragma unroll
+        for (int r = 0; r < kMigItems; r++) {
+            const int d = base + r < n ? dest_of(k[r], planeCells, xLo, xHi) : 1;
+            cl += d == 0; cr += d == 2;
+        }
+        // exclusive prefix of (cl, cr) over the threads of the tile: index order = (thread, item) order
+        uint32_t il = cl, ir = cr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tl = __shfl_up_sync(0xffffffffu, il, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
+            if (lane >= o) { il += tl; ir += tr; }
+        }
+        if (lane == 31) { sL[warp] = il; sR[warp] = ir; }
         __syncthreads();
-        if (d != 1) {
-            uint32_t lt = (1u << lane) - 1;
-            uint32_t off = 0;
-            for (int w = 0; w < warp; w++) off += (d == 0 ? sL[w] : sR[w]);
-            off += __popc((d == 0 ? bl : br) & lt);
-            uint32_t dst = (d == 0 ? blockOff[tile] : blockOff[tileStride + tile]) + off;
-            if (dst < cap) {
-                const uint32_t ps = slot[i];
-                MigRecord r;
-                r.pos = pos[i]; r.vel = vel[i]; r.xs = xs[i]; r.color = color[ps];
-                r.meta = make_uint4(id[i], __float_as_uint(size[ps]), 0, 0);
-                (d == 0 ? sendL : sendR)[dst] = r;
-                freeSlots[freeTop + (d == 0 ? dst : outL + dst)] = ps;
+        if (sL[0] + sL[1] + sL[2] + sL[3] + sL[4] + sL[5] + sL[6] + sL[7] + sR[0] + sR[1] + sR[2] + sR[3] + sR[4] + sR[5] + sR[6] + sR[7]) {
+            uint32_t offL = il - cl, offR = ir - cr;
+            for (int w = 0; w < warp; w++) { offL += sL[w]; offR += sR[w]; }
+            offL += blockOff[tile]; offR += blockOff[tileStride + tile];
+            if (cl | cr) {
+#pragma unroll 1
+                for (int r = 0; r < kMigItems; r++) {
+                    const uint32_t i = base + r;
+                    const int d = i < n ? dest_of(k[r], planeCells, xLo, xHi) : 1;
+                    if (d == 1) continue;
+                    const uint32_t dst = d == 0 ? offL++ : offR++;
+                    if (dst < cap) {
+                        const uint32_t ps = slot[i];
+                        MigRecord rec;
+                        rec.pos = pos[i]; rec.vel = vel[i]; rec.xs = xs[i]; rec.color = color[ps];
+                        rec.meta = make_uint4(id[i], __float_as_uint(size[ps]), 0, 0);
+                        (d == 0 ? sendL : sendR)[dst] = rec;
+                        freeSlots[freeTop + (d == 0 ? dst : outL + dst)] = ps;
+                    }
+                    keys[i] = sentinel;
+                }
             }
-            keys[i] = sentinel;
         }
         __syncthreads();
     }
-}
-
-// CUDA-IPC transport of the per-step count message: the three counters for each neighbour (assembled by k_mig_scan) are
-// stored straight into the neighbour's dims block (the slots it reads them from: D_MSG_FROM_R of the left rank, D_MSG_FROM_L
-// of the right rank), then the message epoch is published in the neighbour's flag word. The migration records were stored
-// into the neighbour's inbox by k_mig_pack earlier in the same stream, so one flag covers both. One thread.
-__global__ void k_publish_counts(const uint32_t* __restrict__ dims, uint32_t* __restrict__ peerDimsL,
-                                 uint32_t* __restrict__ peerDimsR, uint32_t* __restrict__ peerFlagL,
-                                 uint32_t* __restrict__ peerFlagR) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint32_t epoch = dims[D_EPOCH] + 1u;
-    __threadfence_system();
-    if (peerDimsL) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerDimsL)[D_MSG_FROM_R + k] = dims[D_MSG_TO_L + k];
-    if (peerDimsR) for (int k = 0; k < 3; k++) ((volatile uint32_t*)peerDimsR)[D_MSG_FROM_L + k] = dims[D_MSG_TO_R + k];
-    __threadfence_system();
-    if (peerFlagL) *(volatile uint32_t*)peerFlagL = epoch;
-    if (peerFlagR) *(volatile uint32_t*)peerFlagR = epoch;
-    __threadfence_system();
 }
 
 // The step's plan, computed on the device by one thread once both neighbours' count messages are in (CUDA-IPC transport:
@@ -189,10 +211,26 @@ struct PlanCaps {
     uint32_t ghostCap;       // ghost particles per side that fit this rank's ghost regions
     uint32_t slotCap;        // payload slots
 };
+// `pub` (CUDA-IPC transport): the kernel first publishes this rank's own count message — the three counters for each
+// neighbour (assembled by k_mig_scan) are stored straight into the neighbour's dims block (D_MSG_FROM_R of the left rank,
+// D_MSG_FROM_L of the right rank), then the message epoch goes into the neighbour's flag word; the migration records were
+// stored into the neighbour's inbox by k_mig_pack earlier in the same stream, so one flag covers both — and then waits for
+// the neighbours' messages.
+struct PlanPublish { uint32_t *peerDimsL = nullptr, *peerDimsR = nullptr, *peerFlagL = nullptr, *peerFlagR = nullptr; };
 __global__ void k_slab_plan(uint32_t* __restrict__ dims, const uint32_t* __restrict__ countFlags /* [0] left, [1] right */,
-                            int hasL, int hasR, int waitFlags, PlanCaps caps, long long timeoutCycles) {
+                            int hasL, int hasR, int waitFlags, PlanCaps caps, long long timeoutCycles, PlanPublish pub) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t err = 0;
+    if (pub.peerFlagL || pub.peerFlagR) {
+        const uint32_t epoch = dims[D_EPOCH] + 1u;
+        __threadfence_system();   // the migration records k_mig_pack stored into the neighbours' inboxes come first
+        if (pub.peerDimsL) for (int k = 0; k < 3; k++) ((volatile uint32_t*)pub.peerDimsL)[D_MSG_FROM_R + k] = dims[D_MSG_TO_L + k];
+        if (pub.peerDimsR) for (int k = 0; k < 3; k++) ((volatile uint32_t*)pub.peerDimsR)[D_MSG_FROM_L + k] = dims[D_MSG_TO_R + k];
+        __threadfence_system();
+        if (pub.peerFlagL) *(volatile uint32_t*)pub.peerFlagL = epoch;
+        if (pub.peerFlagR) *(volatile uint32_t*)pub.peerFlagR = epoch;
+        __threadfence_system();
+    }
     if (waitFlags) {
         const uint32_t epoch = dims[D_EPOCH] + 1u;
         if (hasL && !spin_until(countFlags + 0, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
@@ -262,8 +300,9 @@ __global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict_
 }
 // Verifies the predicted boundary-plane sizes against the sorted keys (binary searches; two threads): a mismatch raises the
 // sticky error word.
-__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
-                               int hasL, int hasR, uint32_t* __restrict__ dims) {
+struct PlaneVerify { const uint32_t* keysSorted = nullptr; uint32_t planeCells = 0; int xLo = 0, xHi = 0, hasL = 0, hasR = 0; uint32_t* dims = nullptr; };
+__device__ __forceinline__ void plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
+                                             int hasL, int hasR, uint32_t* __restrict__ dims) {
     int t = threadIdx.x;
     if (t > 1) return;
     const uint32_t nOwn = dims[D_NOWN];
@@ -276,6 +315,10 @@ __global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t
     uint32_t actual = t == 0 ? lo : nOwn - lo;
     if (t == 0 && hasL && actual != dims[D_PLANE_L]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
     if (t == 1 && hasR && actual != dims[D_PLANE_R]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
+}
+__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
+                               int hasL, int hasR, uint32_t* __restrict__ dims) {
+    plane_verify(keysSorted, planeCells, xLo, xHi, hasL, hasR, dims);
 }
 // Per-x-plane population and WORK of the owned (key-sorted) particles, one CTA per plane: two binary searches give the plane's
 // index range, count[planeOffset + x] = its size, work[planeOffset + x] = sum over it of (kWorkBase + neighbour count) — what a
@@ -315,9 +358,12 @@ __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__
 // Copies this rank's first / last boundary plane of `src` straight into the neighbours' ghost regions with P2P stores over
 // NVLink; the last CTA publishes the exchange's epoch (halo_signal). Used where no sweep produces the planes (x* after the
 // reorder; v when solverIterations == 0) — the sweeps push their own results (PeerPush in pbf_kernels.cuh).
+// `pv` (optional): CTA 0 also checks the predicted plane sizes against the sorted keys (plane_verify) — the stand-alone
+// k_plane_verify launch of the NCCL path folded into this one.
 template <typename T>
-__global__ void __launch_bounds__(256) k_push_planes(const T* __restrict__ src, PeerPush pp, HaloSync hs) {
+__global__ void __launch_bounds__(256) k_push_planes(const T* __restrict__ src, PeerPush pp, HaloSync hs, PlaneVerify pv) {
     pdl_wait();
+    if (pv.keysSorted && blockIdx.x == 0) plane_verify(pv.keysSorted, pv.planeCells, pv.xLo, pv.xHi, pv.hasL, pv.hasR, pv.dims);
     resolve_push(pp);
     const uint32_t n = pp.dims[D_NOWN];
     const uint32_t nL = pp.dstL ? pp.nL : 0u, nR = (pp.dstR && pp.startR <= n) ? n - pp.startR : 0u;

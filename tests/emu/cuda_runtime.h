@@ -160,6 +160,12 @@ inline uint32_t __reduce_min_sync(uint32_t mask, uint32_t v) {
     for (int l = 0; l < 32; l++) if ((p >> l) & 1u) r = (uint32_t)o[l] < r ? (uint32_t)o[l] : r;
     return r;
 }
+inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) {
+    uint64_t o[32]; uint32_t p; emu::warp_exchange(mask, v, o, &p);
+    uint32_t r = 0;
+    for (int l = 0; l < 32; l++) if ((p >> l) & 1u) r += (uint32_t)o[l];
+    return r;
+}
 inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
     uint64_t o[32]; uint32_t p; emu::warp_exchange(mask, v, o, &p);
     uint32_t r = v;

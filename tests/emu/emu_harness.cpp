@@ -298,7 +298,7 @@ int emu_span_push_check(void* h, uint32_t planeL, uint32_t planeR) {
 // counts[64] = the device dims block; idsL / idsR receive the ids of the records packed for the left / right rank in order.
 int emu_migration(uint32_t* keys, uint32_t n, uint32_t planeCells, int xLo, int xHi, uint32_t sentinel, const uint32_t* ids,
                   uint32_t cap, uint32_t* counts, uint32_t* idsL, uint32_t* idsR) {
-    const uint32_t blocks = std::max(1u, gridFor(n));
+    const uint32_t blocks = std::max(1u, (n + slab::kMigTile - 1) / slab::kMigTile);
     const uint32_t tileStride = blocks + 1;
     std::vector<uint32_t> blockCnt((size_t)2 * tileStride, 0u);
     std::vector<float4> pos(n ? n : 1, make_float4(1, 2, 3, 4)), vel(pos), xs(pos), color(pos);

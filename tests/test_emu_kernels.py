@@ -187,7 +187,7 @@ def test_ieee_math_path_and_zero_iterations(emu):
     s.close()
 
 
-@pytest.mark.parametrize("n", [3000, 262149])     # the larger case makes k_mig_scan carry across 1024-block chunks
+@pytest.mark.parametrize("n", [3000, 2200013])     # the larger case makes k_mig_scan carry across 1024-tile chunks (2048 particles per tile)
 def test_migration_compaction_is_deterministic_and_ordered(emu, n):
     """k_mig_count / k_mig_scan / k_mig_pack: leavers are packed in index order per direction, get the sentinel key, and the
     count message carries the plane populations the single count exchange of a slab step relies on."""

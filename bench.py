@@ -94,8 +94,7 @@ def ncu_traffic(n_rank: int):
         d = json.loads(f.read_text())
     except Exception:
         return None, None, "unreadable profiles/r02_ncu_traffic.json"
-    if d.get("kernel_source_sha") != kernel_source_hash():
-        return None, None, "kernel source changed since the committed ncu capture (profiles/r02_ncu_traffic.json)"
+    stale = d.get("kernel_source_sha") != kernel_source_hash()
     best = None
     for label, cap in d.get("captures", {}).items():
         row = cap.get("kernels", {}).get("k_delta_apply")
@@ -108,7 +107,8 @@ def ncu_traffic(n_rank: int):
         return None, None, f"no capture within 2.5x of {n_rank} particles per GPU"
     _, label, n_cap, row = best
     return (int(row["dram_bytes_per_particle"] * n_rank), row.get("dram_pct_of_peak"),
-            f"ncu --set full, {label} ({n_cap} particles): {row['dram_bytes_per_particle']:.1f} B per particle x {n_rank} particles")
+            f"ncu --set full, {label} ({n_cap} particles): {row['dram_bytes_per_particle']:.1f} B per particle x {n_rank} particles"
+            + ("; STALE: pbf_kernels.cuh changed since this capture" if stale else "; kernel source unchanged since the capture"))
 
 
 class ClockSampler:
@@ -212,11 +212,21 @@ def nvlink_counters(local: int):
         out = []
         for v in vals:
             if v.nvmlReturn != 0:
-                return None
+                raise RuntimeError("field not supported")
             t = v.valueType
             raw = {0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(t, v.value.ullVal)
             out.append(int(raw) * 1024)
         return tuple(out)
+    except Exception:
+        pass
+    try:   # the same counters through nvidia-smi (per link, KiB): "Link 0: Data Tx: 123 KiB"
+        import re
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(local)], capture_output=True, text=True, timeout=20).stdout
+        tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+        rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+        if "Data Tx" not in txt:
+            return None
+        return tx * 1024, rx * 1024
     except Exception:
         return None
 
@@ -302,7 +312,7 @@ def id_checksums(ids: np.ndarray):
                          int(np.bitwise_xor.reduce(a)) if len(a) else 0], dtype=np.uint64)
 
 
-def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=False, owned_log=None):
+def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=False, owned_log=None, step_log=None):
     """`rebalance`: multi-GPU runs re-balance the slab boundaries once per window, INSIDE the timed region (a flowing scene
     moves several per cent of the particles across a slab boundary within a hundred steps; a production run re-balances at
     this rate and pays for it)."""
@@ -315,10 +325,21 @@ def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance
         e0.record(stream)
         if rebalance:
             solver.rebalance()
+        marks = []
         for _ in range(steps):
             solver.step(DT, bmin, bmax)
+            if step_log is not None:   # one event per step: shows a one-off cost (graph re-capture after a re-balance) as what it is
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks.append(ev)
         e1.record(stream)
         barrier()
+        if step_log is not None:
+            prev, row = e0, []
+            for ev in marks:
+                row.append(round(prev.elapsed_time(ev), 4))
+                prev = ev
+            step_log.append(row)
         if owned_log is not None:
             owned_log.append(int(solver.n))
         # events on the solver's stream; the host clock only matters when a host-side wait (the re-balancing collective) was not
@@ -378,8 +399,9 @@ def run_ours(args):
     owned_log = []
     nv0 = nvlink_counters(local) if world > 1 else None
     st0 = solver.slab_stats() if world > 1 else None
+    step_log = []
     win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows,
-                           rebalance=world > 1 and args.rebalance_every > 0, owned_log=owned_log)
+                           rebalance=world > 1 and args.rebalance_every > 0, owned_log=owned_log, step_log=step_log)
     clocks = sampler.stop()
     nv1 = nvlink_counters(local) if world > 1 else None
     st1 = solver.slab_stats() if world > 1 else None
@@ -498,6 +520,7 @@ def run_ours(args):
         "protocol": {"settle_steps": args.settle, "settle_wall_s": round(t_settle, 2), "windows": args.windows,
                      "window_ms_per_step": [round(float(x), 5) for x in win], "value_is": "median window",
                      "owned_per_rank_after_each_window": owned_log if world > 1 else None,
+                     "rank0_step_ms_in_each_window": step_log,
                      "simulated_time_at_start_s": round((args.settle + args.warmup) * DT, 3),
                      "rebalance": (f"akua_pbf_rebalance every {args.rebalance_every} settle steps and once per timed window (inside it)"
                                    if world > 1 and args.rebalance_every > 0 else "none")},

@@ -2,6 +2,7 @@
 DRAM / L1 / issue percentages. bench.py reads it (roofline.traffic, roofline.dram_frac_ncu) as long as the kernel sources are
 unchanged.   python tools/ncu_traffic_json.py N_PARTICLES label=raw.csv [label=raw.csv ...] > profiles/r02_ncu_traffic.json"""
 import csv
+import os
 import json
 import sys
 from pathlib import Path
@@ -52,4 +53,4 @@ for arg in sys.argv[1:]:
             "registers": f(r, "launch__registers_per_thread"),
         }
     out["captures"][label] = cap
-print(json.dumps(out, indent=1))
+os.write(bench._REAL_STDOUT, (json.dumps(out, indent=1) + "\n").encode())

@@ -69,6 +69,17 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// Nanosecond wall clock of the GPU (x-slab mode: per-rank busy time for the re-balancing). 0 under the host emulation.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+#ifdef AKUA_HOST_EMU
+    return 0ull;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ device math
 // dist2 / cell_of / clampi / linear_key are __host__ __device__ so that tests/cpp/list_build_host.cu can run the per-particle
 // list-build functions of list_build.cuh on the CPU (same source, IEEE-identical float expressions); the device code is unchanged.
@@ -145,6 +156,14 @@ enum : int {
     D_EPOCH = 41,                                                   // epoch base of this step: exchange e carries D_EPOCH + e + 1
     D_STAT_MIG_IN = 42, D_STAT_MIG_OUT = 44, D_STAT_BYTES = 46,     // u64 accumulators (two words each)
     D_STEPS = 48,                                                   // steps completed on the device
+    // 49, 50: payload-slot free stack (slab_kernels.cuh)
+    D_PLAN_WAIT_NS = 51,                                            // this step: time k_slab_plan spent waiting for the neighbours' count messages
+    D_T_LAST = 52, D_BUSY_NS = 54,                                  // u64: globaltimer at the end of the last step; busy time (step time minus
+                                                                    // that wait) accumulated since the last re-balancing — what it balances
+    D_BUSY_STEPS = 56,                                              // steps accumulated in D_BUSY_NS
+    D_XLO = 57, D_XHI = 58,                                         // owned x planes [lo, hi) in slab-local grid coordinates: written by the
+                                                                    // host when the slab interval changes (akua_pbf_set_slab / _rebalance), read
+                                                                    // by the migration kernels — moving a boundary does not touch the step's graph
     D_WORDS = 64
 };
 enum : uint32_t {   // bits of dims[D_ERROR]

@@ -250,10 +250,15 @@ void slabUpdateEstimates(akua_pbf_solver* s) {
     sl.estN = std::min(sl.estN, cap);
 }
 
-// Slab-local cell grid: the global grid of the box (shared by all ranks: same y / z extent and origin) restricted in x to this
-// rank's planes plus, towards each neighbour, the ghost plane and one "far" plane into which everything beyond is clamped (a
-// leaver that lands deeper than the neighbour's boundary plane must not be counted into that plane). Keys are therefore
-// slab-relative: a 64 M-particle scene on 8 GPUs sorts 22-bit keys (3 digit passes) and clears an 8th of the cell table.
+// Slab-local cell grid: the global grid of the box (shared by all ranks: same y / z extent and origin) restricted in x to a
+// WINDOW of planes around this rank's slab: its owned planes, towards each neighbour the ghost plane and one "far" plane into
+// which everything beyond is clamped (a leaver that lands deeper than the neighbour's boundary plane must not be counted into
+// that plane), plus kWindowMargin spare planes on each inner side. Keys are window-relative: a 64 M-particle scene on 8 GPUs
+// sorts 23-bit keys (3 digit passes) and clears an 8th of the cell table. The window — and with it every kernel argument of
+// the step: grid, sentinel key, sort passes, cell-table size — only changes when a re-balancing pushes a boundary out of the
+// margin; the owned interval itself lives in dims[D_XLO / D_XHI], so an ordinary re-balancing costs two words written to the
+// device and NO re-capture of the step's CUDA graph.
+constexpr int kWindowMargin = 6;
 int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     SlabState& sl = s->slab;
     if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
@@ -266,19 +271,37 @@ int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     const int xHiG = !hasR ? gdim.x : std::min(std::max(sl.xHiAbs - gmin.x, 0), gdim.x);
     if (xHiG <= xLoG) { s->err = "slab is empty in the current grid (box does not cover this rank's x range)"; return AKUA_ERR_INVALID; }
     if (xHiG - xLoG < 2 && sl.nranks > 1) { s->err = "slab must be at least two x planes wide"; return AKUA_ERR_INVALID; }
-    const int x0 = hasL ? std::max(xLoG - 2, 0) : 0, x1 = hasR ? std::min(xHiG + 2, gdim.x) : gdim.x;
+    const int needLo = hasL ? std::max(xLoG - 2, 0) : 0, needHi = hasR ? std::min(xHiG + 2, gdim.x) : gdim.x;
+    const bool sameGrid = sl.winValid && sl.winGmin.x == gmin.x && sl.winGmin.y == gmin.y && sl.winGmin.z == gmin.z &&
+                          sl.winGdim.x == gdim.x && sl.winGdim.y == gdim.y && sl.winGdim.z == gdim.z;
+    if (!sameGrid || needLo < sl.winX0 || needHi > sl.winX1) {
+        sl.winX0 = hasL ? std::max(needLo - kWindowMargin, 0) : 0;
+        sl.winX1 = hasR ? std::min(needHi + kWindowMargin, gdim.x) : gdim.x;
+        sl.winGmin = gmin; sl.winGdim = gdim; sl.winValid = true;
+        sl.windowChanges++;
+    }
+    const int x0 = sl.winX0, x1 = sl.winX1;
     const int64_t cells = (int64_t)(x1 - x0) * gdim.y * gdim.z;
     if (cells + 1 >= (int64_t)1 << 31) { s->err = "LINEAR_CELL grid too large (>= 2^31 cells)"; return AKUA_ERR_INVALID; }
     if (cells > s->cellCapacity) {
+        const double t0 = hostMs();
         if (s->cellRange) { AK_CUDA(s, cudaStreamSynchronize(s->stream)); AK_CUDA(s, cudaFree(s->cellRange)); }
         s->cellRange = nullptr;
         AK_CUDA(s, dalloc(&s->cellRange, (size_t)cells));
         s->cellCapacity = cells;
+        if (slabVerbose()) std::fprintf(stderr, "[akua rank %d] cell table grown to %lld cells in %.2f ms (host)\n", sl.rank, (long long)cells, hostMs() - t0);
     }
     s->grid.gridMin = make_int3(gmin.x + x0, gmin.y, gmin.z);
     s->grid.gridDim = make_int3(x1 - x0, gdim.y, gdim.z);
     s->ctr.num_cells = cells;
-    sl.xLoL = xLoG - x0; sl.xHiL = xHiG - x0; sl.planeOffset = x0; sl.gxGlobal = gdim.x;
+    const int xLoL = xLoG - x0, xHiL = xHiG - x0;
+    if (xLoL != sl.xLoL || xHiL != sl.xHiL || !sl.intervalOnDevice) {
+        // stream-ordered ahead of the step that uses it (and outside any capture: slabLayout runs before the step is replayed)
+        sl.hInterval[0] = (uint32_t)xLoL; sl.hInterval[1] = (uint32_t)xHiL;
+        AK_CUDA(s, cudaMemcpyAsync(sl.dims + D_XLO, (const void*)sl.hInterval, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        sl.intervalOnDevice = true;
+    }
+    sl.xLoL = xLoL; sl.xHiL = xHiL; sl.planeOffset = x0; sl.gxGlobal = gdim.x;
     sl.sentinel = (uint32_t)cells;                 // one past the last valid key: leavers sort behind the owned range
     sl.sortBits = bitsFor((uint64_t)cells);
     s->keyBits = sl.sortBits;
@@ -290,7 +313,6 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     int rc;
     const GridParams& G = s->grid;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
-    const int xLo = sl.xLoL, xHi = sl.xHiL;
     const bool hasL = sl.rank > 0, hasR = sl.rank + 1 < sl.nranks;
     const bool p2p = sl.p2p;
     uint32_t* dims = sl.dims;
@@ -303,7 +325,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     mark(s, PH_SORT);
     const uint32_t migGrid = std::max(1u, std::min((sl.estN + slab::kMigTile - 1) / slab::kMigTile, sl.migBlocksCap));
     AK_CUDA(s, cudaMemsetAsync(dims + D_STAY_FIRST, 0, 4 * sizeof(uint32_t), s->stream));   // the four plane populations
-    launchPlain(s->stream, slab::k_mig_count, migGrid, kBlock, s->keysUnsorted, dims + D_N, planeCells, xLo, xHi, sl.blockCnt,
+    launchPlain(s->stream, slab::k_mig_count, migGrid, kBlock, s->keysUnsorted, (const uint32_t*)dims, planeCells, sl.blockCnt,
                                                          sl.migBlocksCap, dims + D_STAY_FIRST);
     AK_LAUNCH_CHECK(s, "k_mig_count");
     launchPlain(s->stream, slab::k_mig_scan, 1, 1024, sl.blockCnt, dims + D_N, sl.migBlocksCap, dims);
@@ -315,7 +337,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     uint32_t packCap = sl.migCap;
     if (p2p && hasL) packCap = std::min(packCap, sl.peerL.migCap);
     if (p2p && hasR) packCap = std::min(packCap, sl.peerR.migCap);
-    launchPlain(s->stream, slab::k_mig_pack, migGrid, kBlock, s->keysUnsorted, dims, planeCells, xLo, xHi, sl.blockCnt, sl.migBlocksCap,
+    launchPlain(s->stream, slab::k_mig_pack, migGrid, kBlock, s->keysUnsorted, dims, planeCells, sl.blockCnt, sl.migBlocksCap,
                                                         sl.sentinel, s->pos, s->vel, s->xs, s->id, sl.slot, s->color, s->size,
                                                         sl.freeSlots, outBufL, outBufR, packCap);
     AK_LAUNCH_CHECK(s, "k_mig_pack");
@@ -361,7 +383,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
         sl.estN = std::max<uint32_t>(sl.estN, (uint32_t)sl.hDims[D_NPRE]);
     }
     launchPlain(s->stream, slab::k_mig_unpack, std::max(1u, gridFor(sl.estIn)), kBlock, sl.recvL, sl.recvR, dims, s->pos, s->vel, s->xs, s->id,
-        sl.slot, s->color, s->size, sl.freeSlots, s->keysUnsorted, G, xLo, xHi);
+        sl.slot, s->color, s->size, sl.freeSlots, s->keysUnsorted, G);
     AK_LAUNCH_CHECK(s, "k_mig_unpack");
 
     // ---- 3. sort everything resident (leavers end up past nOwn), reorder the owned range, owned cell ranges ----
@@ -380,10 +402,10 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     // ---- 4. ghost planes: x* of the neighbours' boundary planes (exchange 1), keyed and ranged in place ----
     if (p2p) {   // the plane-size check rides on the push kernel
         slab::PlaneVerify pv;
-        pv.keysSorted = s->keysSorted; pv.planeCells = planeCells; pv.xLo = xLo; pv.xHi = xHi; pv.hasL = hasL; pv.hasR = hasR; pv.dims = dims;
+        pv.keysSorted = s->keysSorted; pv.planeCells = planeCells; pv.hasL = hasL; pv.hasR = hasR; pv.dims = dims;
         if ((rc = slabPushPlanes(s, s->xs, 1, pv))) return rc;
     } else {
-        launchPlain(s->stream, slab::k_plane_verify, 1, 32, s->keysSorted, planeCells, xLo, xHi, hasL ? 1 : 0, hasR ? 1 : 0, dims);
+        launchPlain(s->stream, slab::k_plane_verify, 1, 32, s->keysSorted, planeCells, hasL ? 1 : 0, hasR ? 1 : 0, dims);
         AK_LAUNCH_CHECK(s, "k_plane_verify");
         if ((rc = slabPushPlanes(s, s->xs, 1))) return rc;
     }
@@ -433,6 +455,7 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
 int slabRebalance(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     if (!sl.enabled || !s->haveBox) { s->err = "rebalance: slab mode with at least one completed step required"; return AKUA_ERR_INVALID; }
+    const double tReb0 = hostMs();
     {
         int rcr = slabRefresh(s);   // exact owned count; reports any pending device-side error
         if (rcr) return rcr;
@@ -440,8 +463,10 @@ int slabRebalance(akua_pbf_solver* s) {
     const GridParams& G = s->grid;   // slab-local grid of the last step; plane p of it is global plane planeOffset + p
     const int gx = sl.gxGlobal, R = sl.nranks;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
-    // [0, gx): plane counts; [gx, 2 gx): plane work (particles weighted by their neighbour count); then the R current lower bounds
-    const size_t words = (size_t)2 * gx + R;
+    // [0, gx): plane counts; [gx, 2 gx): plane work (particles weighted by their neighbour count); [2 gx, 3 gx): plane TIME (the
+    // work scaled by the owner's measured busy time per unit of work); then the R current lower bounds and the number of ranks
+    // that had a busy-time measurement
+    const size_t words = (size_t)3 * gx + R + 1;
     if (words > sl.histCap) {
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
@@ -455,25 +480,38 @@ int slabRebalance(akua_pbf_solver* s) {
     launchPlain(s->stream, slab::k_plane_hist, (uint32_t)G.gridDim.x, 256, s->keysSorted, s->nbrCount, n, planeCells, G.gridDim.x, sl.planeOffset,
                 sl.dHist, sl.dHist + gx);
     AK_LAUNCH_CHECK(s, "k_plane_hist");
+    launchPlain(s->stream, slab::k_plane_time, 1, 256, (const unsigned long long*)(sl.dHist + gx), sl.dHist + 2 * (size_t)gx, gx, sl.dims,
+                sl.dHist + 3 * (size_t)gx + R);
+    AK_LAUNCH_CHECK(s, "k_plane_time");
     const int curLo = sl.rank == 0 ? 0 : sl.planeOffset + sl.xLoL;
     unsigned long long lo64 = (unsigned long long)curLo;
-    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 2 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 3 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.AllReduce(sl.dHist, sl.dHist, words, ncclUint64, ncclSum, (ncclComm_t)sl.comm, sl.commStream));
     AK_CUDA(s, cudaMemcpyAsync(sl.hHist, sl.dHist, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.commStream));
     AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
     std::vector<int64_t> hist(gx), work(gx);
-    for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[gx + x]; }
+    // Boundaries follow the planes' estimated TIME when every rank had a busy-time measurement since the last call (feedback:
+    // the heaviest rank by the clock gives planes away, whatever makes its particles dear), else the raw work (12 + neighbour
+    // count per particle: first call, host emulation). A partition within 2 % of balance is left alone.
+    const bool measured = sl.hHist[3 * (size_t)gx + R] == (unsigned long long)R;
+    for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[(measured ? 2 : 1) * (size_t)gx + x]; }
+    sl.lastRebalanceMeasured = measured;
     std::vector<int32_t> bounds(R + 1), old(R + 1);
-    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[2 * (size_t)gx + r];
+    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[3 * (size_t)gx + r];
     old[0] = 0; old[R] = gx;
-    // boundaries follow the WORK (12 + neighbour count per particle); a partition within 2 % of balance is left alone
     if (akua_slab_rebalance_bounds_weighted(work.data(), hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, sl.keepBelow, bounds.data()) != AKUA_OK) {
         s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
     bool movedAny = false;
     for (int r = 0; r <= R; r++) movedAny = movedAny || bounds[r] != old[r];
+    if (slabVerbose() && sl.rank == 0) {
+        std::fprintf(stderr, "[akua] rebalance after step %lld: %s, %s, %.2f ms (host); bounds", (long long)s->ctr.steps,
+                     measured ? "measured busy time" : "work estimate", movedAny ? "moved" : "kept", hostMs() - tReb0);
+        for (int r = 0; r <= R; r++) std::fprintf(stderr, " %d", bounds[r]);
+        std::fprintf(stderr, "\n");
+    }
     if (!movedAny) return AKUA_OK;
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
     const int gminGlobalX = G.gridMin.x - sl.planeOffset;

@@ -16,6 +16,7 @@
 #include <nccl.h>  // types only: the library itself is dlopen'ed by akua_pbf_comm_init (pbf_slab.inl)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -71,7 +72,14 @@ struct SlabState {
     uint32_t nPlaneL = 0, nPlaneR = 0, nGhostL = 0, nGhostR = 0;
     // launch-size estimates (bucketed; kernels loop, so any estimate is correct) and the step's layout in the local grid
     uint32_t estN = 1, estBnd = 1, estGhost = 1, estIn = 1;
-    int xLoL = 0, xHiL = 0;                // owned planes in slab-local grid coordinates
+    int xLoL = -1, xHiL = -1;              // owned planes in slab-local (window) grid coordinates; mirrored in dims[D_XLO / D_XHI]
+    bool intervalOnDevice = false;
+    uint32_t hInterval[2] = {0, 0};
+    // the window of global grid planes the local grid covers (slabLayout): fixed while the slab stays inside it
+    bool winValid = false;
+    int winX0 = 0, winX1 = 0;
+    int3 winGmin = {0, 0, 0}, winGdim = {0, 0, 0};
+    int64_t windowChanges = 0;
     int planeOffset = 0;                   // local plane 0 in global grid planes
     int gxGlobal = 0;
     uint32_t sentinel = 0;
@@ -95,6 +103,7 @@ struct SlabState {
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
     int64_t rebalances = 0;            // calls that moved a boundary
+    bool lastRebalanceMeasured = false;   // the last akua_pbf_rebalance balanced measured busy time (else the raw work estimate)
     double keepBelow = 1.02;           // akua_pbf_rebalance leaves a partition alone whose heaviest slab is within this of the mean
 };
 
@@ -250,6 +259,10 @@ SphParams makeSph(const akua_pbf_solver* s) { return make_sph_params(s->cfg, s->
 BoxParams makeBox(const float* bmin, const float* bmax) { return make_box_params(bmin, bmax); }
 
 int bitsFor(uint64_t maxKey) { return bits_for_key(maxKey); }
+
+// AKUA_SLAB_VERBOSE=1: host-side cost of the rare events of a slab run (re-balancing, graph re-capture, cell-table growth) on stderr
+inline bool slabVerbose() { static const bool v = [] { const char* e = std::getenv("AKUA_SLAB_VERBOSE"); return e && e[0] == '1'; }(); return v; }
+inline double hostMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void rememberBox(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     for (int a = 0; a < 3; a++) { s->lastBoxMin[a] = bmin[a]; s->lastBoxMax[a] = bmax[a]; }
@@ -624,7 +637,7 @@ void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* b
     key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u) | (slabOn(s) ? 8u : 0u);
     // x-slab mode: the slab interval fixes the local grid, the (bucketed) size estimates fix the launch grids
     const SlabState& sl = s->slab;
-    key[16] = slabOn(s) ? (((uint64_t)(uint32_t)sl.xLoAbs << 32) | (uint32_t)sl.xHiAbs) : 0;
+    key[16] = slabOn(s) ? (((uint64_t)(uint32_t)sl.winX0 << 32) | (uint32_t)sl.winX1) : 0;   // the window, not the interval inside it
     key[17] = slabOn(s) ? (((uint64_t)sl.estN << 32) | sl.estBnd) : 0;
     key[18] = slabOn(s) ? (((uint64_t)sl.estGhost << 32) | sl.estIn) : 0;
     key[19] = slabOn(s) ? (uint64_t)sl.slot : (uint64_t)s->bucketsN;
@@ -711,6 +724,7 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
             s->slab.slot = sl0; s->slab.slotAlt = sl1; s->bucketsN = bucketsN0; s->hashFromUpload = hfu0;
             s->ctr.kernel_launches = launches0; s->ctr.steps = steps0; s->slab.exchanges = exch0;
         };
+        const double tCap0 = hostMs();
         if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             s->opt.use_graph = 0;     // a stream that cannot be captured (or a runtime without graphs): step eagerly from now on
@@ -745,6 +759,8 @@ int stepImpl(akua_pbf_solver* s, float dt, int iterations, const float* bmin, co
         g.used = true;
         restore();
         hit = &g;
+        if (slabVerbose()) std::fprintf(stderr, "[akua rank %d] step %lld: graph captured + instantiated in %.2f ms (host)\n", s->slab.rank,
+                                        (long long)s->ctr.steps, hostMs() - tCap0);
     }
     AK_CUDA(s, cudaGraphLaunch(hit->exec, s->stream));
     s->pos = hit->pos; s->posAlt = hit->posAlt; s->vel = hit->vel; s->velAlt = hit->velAlt; s->xs = hit->xs; s->xsAlt = hit->xsAlt;

@@ -48,12 +48,13 @@ __device__ __forceinline__ void mig_load_keys(const uint32_t* __restrict__ keys,
 // post-migration boundary-plane and ghost-plane sizes from one count exchange (extra[0] stayers in my first plane, [1]
 // stayers in my last plane, [2] leavers to the left that land in the left rank's last plane, [3] leavers to the right that
 // land in the right rank's first plane).
-__global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nPtr,
-                                                   uint32_t planeCells, int xLo, int xHi,
+__global__ void __launch_bounds__(256) k_mig_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ dims,
+                                                   uint32_t planeCells,
                                                    uint32_t* __restrict__ blockCnt /*[2][tileStride]*/, uint32_t tileStride,
                                                    uint32_t* __restrict__ extra /*[4], zeroed*/) {
     __shared__ uint32_t sAcc[6];
-    const uint32_t n = *nPtr;
+    const uint32_t n = dims[D_N];
+    const int xLo = (int)dims[D_XLO], xHi = (int)dims[D_XHI];
     const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
     const uint32_t stayKey = (uint32_t)(xLo + 1) * planeCells;   // an interior plane when the slab has one; never a leaver
     uint32_t tot[4] = {0, 0, 0, 0};                              // this thread's share of the four plane populations
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(1024) k_mig_scan(uint32_t* __restrict__ blockC
 // neighbour's inbox over NVLink — and get the sentinel key, which sorts them past the owned range so the reorder drops
 // them. Their payload slots go back on the free stack (in send-buffer order: deterministic).
 __global__ void __launch_bounds__(256) k_mig_pack(uint32_t* __restrict__ keys, const uint32_t* __restrict__ dims,
-                                                  uint32_t planeCells, int xLo, int xHi, const uint32_t* __restrict__ blockOff,
+                                                  uint32_t planeCells, const uint32_t* __restrict__ blockOff,
                                                   uint32_t tileStride, uint32_t sentinel,
                                                   const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                   const float4* __restrict__ xs, const uint32_t* __restrict__ id,
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256) k_mig_pack(uint32_t* __restrict__ keys, c
                                                   uint32_t cap) {
     __shared__ uint32_t sL[8], sR[8];
     const uint32_t n = dims[D_N];
+    const int xLo = (int)dims[D_XLO], xHi = (int)dims[D_XHI];
     const uint32_t numTiles = (n + kMigTile - 1) / kMigTile;
     const uint32_t outL = min(dims[D_OUT_L], cap), freeTop = dims[D_FREE_TOP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,11 +233,17 @@ __global__ void k_slab_plan(uint32_t* __restrict__ dims, const uint32_t* __restr
         if (pub.peerFlagR) *(volatile uint32_t*)pub.peerFlagR = epoch;
         __threadfence_system();
     }
+    dims[D_PLAN_WAIT_NS] = 0u;
     if (waitFlags) {
         const uint32_t epoch = dims[D_EPOCH] + 1u;
+        const unsigned long long t0 = global_timer_ns();
         if (hasL && !spin_until(countFlags + 0, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
         if (hasR && !spin_until(countFlags + 1, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
         __threadfence_system();
+        // a rank that is ahead of its neighbours idles HERE once per step: the measured idle time is what the re-balancing
+        // feeds back on (akua_pbf_rebalance)
+        const unsigned long long waited = global_timer_ns() - t0;
+        dims[D_PLAN_WAIT_NS] = waited > 0xffffffffull ? 0xffffffffu : (uint32_t)waited;
     }
     const volatile uint32_t* d = dims;
     uint32_t outL = d[D_OUT_L], outR = d[D_OUT_R];
@@ -283,7 +291,8 @@ __global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict_
                                                     float4* __restrict__ xs, uint32_t* __restrict__ id,
                                                     uint32_t* __restrict__ slot, float4* __restrict__ color,
                                                     float* __restrict__ size, const uint32_t* __restrict__ freeSlots,
-                                                    uint32_t* __restrict__ keys, GridParams G, int xLo, int xHi) {
+                                                    uint32_t* __restrict__ keys, GridParams G) {
+    const int xLo = (int)dims[D_XLO], xHi = (int)dims[D_XHI];
     const uint32_t inL = dims[D_IN_L], count = inL + dims[D_IN_R], base = dims[D_N], popBase = dims[D_FREE_POP];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
         const MigRecord r = t < inL ? recvL[t] : recvR[t - inL];
@@ -300,11 +309,12 @@ __global__ void __launch_bounds__(256) k_mig_unpack(const MigRecord* __restrict_
 }
 // Verifies the predicted boundary-plane sizes against the sorted keys (binary searches; two threads): a mismatch raises the
 // sticky error word.
-struct PlaneVerify { const uint32_t* keysSorted = nullptr; uint32_t planeCells = 0; int xLo = 0, xHi = 0, hasL = 0, hasR = 0; uint32_t* dims = nullptr; };
-__device__ __forceinline__ void plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
+struct PlaneVerify { const uint32_t* keysSorted = nullptr; uint32_t planeCells = 0; int hasL = 0, hasR = 0; uint32_t* dims = nullptr; };
+__device__ __forceinline__ void plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells,
                                              int hasL, int hasR, uint32_t* __restrict__ dims) {
     int t = threadIdx.x;
     if (t > 1) return;
+    const int xLo = (int)dims[D_XLO], xHi = (int)dims[D_XHI];
     const uint32_t nOwn = dims[D_NOWN];
     uint64_t bound = (uint64_t)(t == 0 ? (xLo + 1) : (xHi - 1)) * planeCells;
     uint32_t lo = 0, hi = nOwn;
@@ -316,9 +326,9 @@ __device__ __forceinline__ void plane_verify(const uint32_t* __restrict__ keysSo
     if (t == 0 && hasL && actual != dims[D_PLANE_L]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
     if (t == 1 && hasR && actual != dims[D_PLANE_R]) atomicOr(dims + D_ERROR, (uint32_t)SLAB_ERR_PLANE_PREDICTION);
 }
-__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells, int xLo, int xHi,
+__global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t planeCells,
                                int hasL, int hasR, uint32_t* __restrict__ dims) {
-    plane_verify(keysSorted, planeCells, xLo, xHi, hasL, hasR, dims);
+    plane_verify(keysSorted, planeCells, hasL, hasR, dims);
 }
 // Per-x-plane population and WORK of the owned (key-sorted) particles, one CTA per plane: two binary searches give the plane's
 // index range, count[planeOffset + x] = its size, work[planeOffset + x] = sum over it of (kWorkBase + neighbour count) — what a
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) k_push_planes(const T* __restrict__ src, PeerPush pp, HaloSync hs, PlaneVerify pv) {
     pdl_wait();
-    if (pv.keysSorted && blockIdx.x == 0) plane_verify(pv.keysSorted, pv.planeCells, pv.xLo, pv.xHi, pv.hasL, pv.hasR, pv.dims);
+    if (pv.keysSorted && blockIdx.x == 0) plane_verify(pv.keysSorted, pv.planeCells, pv.hasL, pv.hasR, pv.dims);
     resolve_push(pp);
     const uint32_t n = pp.dims[D_NOWN];
     const uint32_t nL = pp.dstL ? pp.nL : 0u, nR = (pp.dstR && pp.startR <= n) ? n - pp.startR : 0u;
@@ -408,6 +418,42 @@ __global__ void k_step_end(uint32_t* __restrict__ dims, uint32_t exchanges, uint
     st[2] += (unsigned long long)(dims[D_PLANE_L] + dims[D_PLANE_R]) * planeBytes
            + (unsigned long long)(dims[D_OUT_L] + dims[D_OUT_R]) * sizeof(MigRecord);
     dims[D_STEPS] += 1;
+    // busy time of this rank: step to step on the GPU's clock, minus the idle wait for the neighbours' count messages
+    unsigned long long* tl = reinterpret_cast<unsigned long long*>(dims + D_T_LAST);
+    unsigned long long* busy = reinterpret_cast<unsigned long long*>(dims + D_BUSY_NS);
+    const unsigned long long now = global_timer_ns();
+    if (*tl != 0ull && now > *tl) {
+        const unsigned long long dt = now - *tl, w = dims[D_PLAN_WAIT_NS];
+        if (dt < 2000000000ull) { *busy += dt > w ? dt - w : 0ull; dims[D_BUSY_STEPS] += 1; }   // (a gap of seconds is the host, not a step)
+    }
+    *tl = now;
+}
+// Re-balancing: turns this rank's per-plane WORK into estimated TIME, work[x] * busyNs / sum(work) (so that the planes of a
+// rank add up to its measured busy time), and restarts the busy-time accumulation. One CTA. valid[0] += 1 when this rank
+// had a measurement (all ranks must, or the caller falls back to the raw work).
+__global__ void __launch_bounds__(256) k_plane_time(const unsigned long long* __restrict__ work, unsigned long long* __restrict__ timeOut,
+                                                    int gx, uint32_t* __restrict__ dims, unsigned long long* __restrict__ valid) {
+    __shared__ unsigned long long part[8];
+    __shared__ unsigned long long total;
+    unsigned long long w = 0;
+    for (int x = threadIdx.x; x < gx; x += blockDim.x) w += work[x];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int k = 1; k < 8; k++) w += part[k]; total = w; }
+    __syncthreads();
+    const unsigned long long busy = *reinterpret_cast<const unsigned long long*>(dims + D_BUSY_NS);
+    const uint32_t steps = dims[D_BUSY_STEPS];
+    const bool ok = busy > 0ull && steps > 0u && total > 0ull;
+    const double scale = ok ? (double)busy / (double)steps / (double)total : 0.0;   // ns per step per unit of work
+    for (int x = threadIdx.x; x < gx; x += blockDim.x) timeOut[x] = (unsigned long long)((double)work[x] * scale * 1024.0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (ok || total == 0ull) *valid += 1ull;   // a rank without particles has nothing to measure and nothing to contribute
+        *reinterpret_cast<unsigned long long*>(dims + D_BUSY_NS) = 0ull;
+        *reinterpret_cast<unsigned long long*>(dims + D_T_LAST) = 0ull;   // the host-side part of this call is not a step
+        dims[D_BUSY_STEPS] = 0u;
+    }
 }
 // (Re)initialises the device-side bookkeeping after an upload: owned count, identity payload slots, full free stack.
 __global__ void __launch_bounds__(256) k_slab_reset(uint32_t* __restrict__ dims, uint32_t n, uint32_t cap,
@@ -417,7 +463,11 @@ __global__ void __launch_bounds__(256) k_slab_reset(uint32_t* __restrict__ dims,
         if (t < n) slot[t] = t;
         if (t < cap - n) freeSlots[t] = cap - 1u - t;   // popping yields n, n + 1, ...
     }
-    if (t0 == 0) { dims[D_N] = n; dims[D_NOWN] = n; dims[D_NPRE] = n; dims[D_FREE_TOP] = cap - n; dims[D_FREE_POP] = cap - n; }
+    if (t0 == 0) {
+        dims[D_N] = n; dims[D_NOWN] = n; dims[D_NPRE] = n; dims[D_FREE_TOP] = cap - n; dims[D_FREE_POP] = cap - n;
+        // an upload interrupts the step-to-step clock of the busy-time measurement
+        dims[D_T_LAST] = 0u; dims[D_T_LAST + 1] = 0u; dims[D_BUSY_NS] = 0u; dims[D_BUSY_NS + 1] = 0u; dims[D_BUSY_STEPS] = 0u;
+    }
 }
 
 }  // namespace slab

@@ -312,10 +312,10 @@ def id_checksums(ids: np.ndarray):
                          int(np.bitwise_xor.reduce(a)) if len(a) else 0], dtype=np.uint64)
 
 
-def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=False, owned_log=None, step_log=None):
-    """`rebalance`: multi-GPU runs re-balance the slab boundaries once per window, INSIDE the timed region (a flowing scene
-    moves several per cent of the particles across a slab boundary within a hundred steps; a production run re-balances at
-    this rate and pays for it)."""
+def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance=0, owned_log=None, step_log=None):
+    """`rebalance` = k > 0: multi-GPU runs call akua_pbf_rebalance every k steps, INSIDE the timed region (a sloshing scene shifts
+    the load between slabs by several per cent within twenty steps; a production run re-balances at this rate and pays for
+    it: one stream synchronisation and a small all-reduce per call, a graph re-capture only when a slab leaves its window)."""
     import torch
     out = []
     for _ in range(windows):
@@ -323,10 +323,10 @@ def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
-        if rebalance:
-            solver.rebalance()
         marks = []
-        for _ in range(steps):
+        for k in range(steps):
+            if rebalance and k % rebalance == 0:
+                solver.rebalance()
             solver.step(DT, bmin, bmax)
             if step_log is not None:   # one event per step: shows a one-off cost (graph re-capture after a re-balance) as what it is
                 ev = torch.cuda.Event(enable_timing=True)
@@ -401,7 +401,7 @@ def run_ours(args):
     st0 = solver.slab_stats() if world > 1 else None
     step_log = []
     win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows,
-                           rebalance=world > 1 and args.rebalance_every > 0, owned_log=owned_log, step_log=step_log)
+                           rebalance=args.rebalance_every if world > 1 else 0, owned_log=owned_log, step_log=step_log)
     clocks = sampler.stop()
     nv1 = nvlink_counters(local) if world > 1 else None
     st1 = solver.slab_stats() if world > 1 else None
@@ -522,7 +522,7 @@ def run_ours(args):
                      "owned_per_rank_after_each_window": owned_log if world > 1 else None,
                      "rank0_step_ms_in_each_window": step_log,
                      "simulated_time_at_start_s": round((args.settle + args.warmup) * DT, 3),
-                     "rebalance": (f"akua_pbf_rebalance every {args.rebalance_every} settle steps and once per timed window (inside it)"
+                     "rebalance": (f"akua_pbf_rebalance every {args.rebalance_every} steps, in the settle phase and inside the timed windows"
                                    if world > 1 and args.rebalance_every > 0 else "none")},
         "impl_config": {"key_mode": args.key_mode, "fast_math": bool(args.fast_math), "particles_rank0": int(n_rank),
                         "list_build": os.environ.get("AKUA_LIST_BUILD", "default"),
@@ -723,7 +723,7 @@ def main():
     ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
     ap.add_argument("--settle", type=int, default=300, help="untimed steps before the warm-up, so that the fluid is disordered")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps each; the median is reported")
-    ap.add_argument("--rebalance-every", type=int, default=25, help="multi-GPU: akua_pbf_rebalance every k settle steps")
+    ap.add_argument("--rebalance-every", type=int, default=10, help="multi-GPU: akua_pbf_rebalance every k steps (settle phase and timed windows)")
     ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
     ap.add_argument("--trace", default="", help="write a launch timeline of two steps after the timed region to PATH.rank<r>.jsonl")
     ap.add_argument("--no-cpu-baseline", action="store_true")

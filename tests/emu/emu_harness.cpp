@@ -307,12 +307,12 @@ int emu_migration(uint32_t* keys, uint32_t n, uint32_t planeCells, int xLo, int 
     for (uint32_t i = 0; i < n; i++) slot[i] = i;
     std::vector<slab::MigRecord> sendL(cap), sendR(cap);
     std::fill(counts, counts + D_WORDS, 0u);
-    counts[D_N] = n;
+    counts[D_N] = n; counts[D_XLO] = (uint32_t)xLo; counts[D_XHI] = (uint32_t)xHi;
     const uint32_t grid = std::max(1u, blocks / 3);   // fewer CTAs than tiles: the tile loops run
-    run(slab::k_mig_count, grid, 256u, (const uint32_t*)keys, (const uint32_t*)(counts + D_N), planeCells, xLo, xHi, blockCnt.data(), tileStride,
+    run(slab::k_mig_count, grid, 256u, (const uint32_t*)keys, (const uint32_t*)counts, planeCells, blockCnt.data(), tileStride,
         counts + D_STAY_FIRST);
     run(slab::k_mig_scan, 1u, 1024u, blockCnt.data(), (const uint32_t*)(counts + D_N), tileStride, counts);
-    run(slab::k_mig_pack, grid, 256u, keys, (const uint32_t*)counts, planeCells, xLo, xHi, (const uint32_t*)blockCnt.data(), tileStride, sentinel,
+    run(slab::k_mig_pack, grid, 256u, keys, (const uint32_t*)counts, planeCells, (const uint32_t*)blockCnt.data(), tileStride, sentinel,
         (const float4*)pos.data(), (const float4*)vel.data(), (const float4*)xs.data(), ids, (const uint32_t*)slot.data(),
         (const float4*)color.data(), (const float*)size.data(), freeSlots.data(), sendL.data(), sendR.data(), cap);
     for (uint32_t k = 0; k < std::min(counts[0], cap); k++) idsL[k] = sendL[k].meta.x;
@@ -329,7 +329,8 @@ int emu_plane_hist(const uint32_t* keysSorted, const uint32_t* nbrCount, uint32_
 int emu_plane_verify(const uint32_t* keysSorted, uint32_t n, uint32_t planeCells, int xLo, int xHi, uint32_t predictFirst,
                      uint32_t predictLast, uint32_t* counts64) {
     counts64[D_NOWN] = n; counts64[D_PLANE_L] = predictFirst; counts64[D_PLANE_R] = predictLast;
-    run(slab::k_plane_verify, 1u, 32u, keysSorted, planeCells, xLo, xHi, 1, 1, counts64);
+    counts64[D_XLO] = (uint32_t)xLo; counts64[D_XHI] = (uint32_t)xHi;
+    run(slab::k_plane_verify, 1u, 32u, keysSorted, planeCells, 1, 1, counts64);
     return 0;
 }
 

@@ -233,20 +233,27 @@ int slabAgreeMass(akua_pbf_solver* s) {
 }
 
 // ---- the slab step ------------------------------------------------------------------------------------------------------
-// Launch-size estimates from the (asynchronously refreshed, possibly a step or two old) pinned mirror of dims. Bucketed with
-// hysteresis so that the CUDA graph of the step, whose grids they fix, is re-captured rarely.
+// Launch-size estimates from the (asynchronously refreshed, possibly a step or two old) pinned mirror of dims. They only size
+// grids (every kernel loops over the device-side counts, so any estimate is correct) but they are arguments of the step's CUDA
+// graph: an estimate that changes re-captures it. So: the owned count is bucketed with hysteresis; the plane, ghost and arrival
+// sizes — small launches whose grids cost nothing when oversized, and which jump after every re-balancing — only ever GROW,
+// with 50 % head-room (reset by an upload).
 void slabEstimate(uint32_t actual, uint32_t bucket, uint32_t* est) {
     if (actual > *est || (uint64_t)actual + 2ull * bucket < *est || *est == 0)
         *est = (uint32_t)(((uint64_t)actual + bucket / 2 + bucket) / bucket * bucket);
 }
+void slabEstimateGrowOnly(uint32_t actual, uint32_t bucket, uint32_t* est) {
+    if (actual > *est || *est == 0)
+        *est = (uint32_t)(((uint64_t)actual + actual / 2 + bucket) / bucket * bucket);
+}
 void slabUpdateEstimates(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     const uint32_t cap = (uint32_t)s->capacity;
-    const uint32_t bN = std::max(8192u, cap / 128), bS = std::max(2048u, cap / 1024);
+    const uint32_t bN = std::max(8192u, cap / 64), bS = std::max(2048u, cap / 1024);
     slabEstimate(sl.hDims[D_N], bN, &sl.estN);
-    slabEstimate(sl.hDims[D_PLANE_L] + sl.hDims[D_PLANE_R], bS, &sl.estBnd);
-    slabEstimate(sl.hDims[D_GHOST_L] + sl.hDims[D_GHOST_R], bS, &sl.estGhost);
-    slabEstimate(sl.hDims[D_IN_L] + sl.hDims[D_IN_R], bS, &sl.estIn);
+    slabEstimateGrowOnly(sl.hDims[D_PLANE_L] + sl.hDims[D_PLANE_R], bS, &sl.estBnd);
+    slabEstimateGrowOnly(sl.hDims[D_GHOST_L] + sl.hDims[D_GHOST_R], bS, &sl.estGhost);
+    slabEstimateGrowOnly(sl.hDims[D_IN_L] + sl.hDims[D_IN_R], bS, &sl.estIn);
     sl.estN = std::min(sl.estN, cap);
 }
 
@@ -463,10 +470,9 @@ int slabRebalance(akua_pbf_solver* s) {
     const GridParams& G = s->grid;   // slab-local grid of the last step; plane p of it is global plane planeOffset + p
     const int gx = sl.gxGlobal, R = sl.nranks;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
-    // [0, gx): plane counts; [gx, 2 gx): plane work (particles weighted by their neighbour count); [2 gx, 3 gx): plane TIME (the
-    // work scaled by the owner's measured busy time per unit of work); then the R current lower bounds and the number of ranks
-    // that had a busy-time measurement
-    const size_t words = (size_t)3 * gx + R + 1;
+    // [0, gx): plane counts; [gx, 2 gx): plane work (particles weighted by their neighbour count); then per rank: its current
+    // lower bound, its measured busy time per step (ns) and the sum of its work
+    const size_t words = (size_t)2 * gx + 3 * (size_t)R;
     if (words > sl.histCap) {
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
@@ -480,27 +486,43 @@ int slabRebalance(akua_pbf_solver* s) {
     launchPlain(s->stream, slab::k_plane_hist, (uint32_t)G.gridDim.x, 256, s->keysSorted, s->nbrCount, n, planeCells, G.gridDim.x, sl.planeOffset,
                 sl.dHist, sl.dHist + gx);
     AK_LAUNCH_CHECK(s, "k_plane_hist");
-    launchPlain(s->stream, slab::k_plane_time, 1, 256, (const unsigned long long*)(sl.dHist + gx), sl.dHist + 2 * (size_t)gx, gx, sl.dims,
-                sl.dHist + 3 * (size_t)gx + R);
-    AK_LAUNCH_CHECK(s, "k_plane_time");
+    launchPlain(s->stream, slab::k_rank_busy, 1, 256, (const unsigned long long*)(sl.dHist + gx), gx, sl.dims,
+                sl.dHist + 2 * (size_t)gx + R + sl.rank, sl.dHist + 2 * (size_t)gx + 2 * (size_t)R + sl.rank);
+    AK_LAUNCH_CHECK(s, "k_rank_busy");
     const int curLo = sl.rank == 0 ? 0 : sl.planeOffset + sl.xLoL;
     unsigned long long lo64 = (unsigned long long)curLo;
-    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 3 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
+    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 2 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
     int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.AllReduce(sl.dHist, sl.dHist, words, ncclUint64, ncclSum, (ncclComm_t)sl.comm, sl.commStream));
     AK_CUDA(s, cudaMemcpyAsync(sl.hHist, sl.dHist, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.commStream));
     AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
     std::vector<int64_t> hist(gx), work(gx);
-    // Boundaries follow the planes' estimated TIME when every rank had a busy-time measurement since the last call (feedback:
-    // the heaviest rank by the clock gives planes away, whatever makes its particles dear), else the raw work (12 + neighbour
-    // count per particle: first call, host emulation). A partition within 2 % of balance is left alone.
-    const bool measured = sl.hHist[3 * (size_t)gx + R] == (unsigned long long)R;
-    for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[(measured ? 2 : 1) * (size_t)gx + x]; }
-    sl.lastRebalanceMeasured = measured;
+    for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[gx + x]; }
     std::vector<int32_t> bounds(R + 1), old(R + 1);
-    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[3 * (size_t)gx + r];
+    for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[2 * (size_t)gx + r];
     old[0] = 0; old[R] = gx;
+    // Feedback from the clock: a rank whose measured busy time per unit of work is above (below) the mean has its planes made
+    // dearer (cheaper) by that ratio, clamped to [0.8, 1.25] — the work estimate (12 + neighbour count per particle) decides the
+    // bulk, the measurement corrects what it cannot know (how well a rank's gathers cache, a free surface, a wall). The clamp
+    // keeps small, latency-bound scenes (where time does not follow the particle count at all) balanced by work. Applied only
+    // when every rank with particles had a measurement since the last call.
+    bool measured = true;
+    double busyAll = 0.0, workAll = 0.0;
+    for (int r = 0; r < R; r++) {
+        const double b = (double)sl.hHist[2 * (size_t)gx + R + r], w = (double)sl.hHist[2 * (size_t)gx + 2 * (size_t)R + r];
+        if (w > 0.0 && b <= 0.0) measured = false;
+        busyAll += b; workAll += w;
+    }
+    if (measured && busyAll > 0.0 && workAll > 0.0) {
+        for (int r = 0; r < R; r++) {
+            const double b = (double)sl.hHist[2 * (size_t)gx + R + r], w = (double)sl.hHist[2 * (size_t)gx + 2 * (size_t)R + r];
+            if (w <= 0.0) continue;
+            const double c = std::min(1.25, std::max(0.8, (b / w) / (busyAll / workAll)));
+            for (int x = std::max(old[r], 0); x < std::min(old[r + 1], gx); x++) work[x] = (int64_t)((double)work[x] * c);
+        }
+    } else measured = false;
+    sl.lastRebalanceMeasured = measured;
     if (akua_slab_rebalance_bounds_weighted(work.data(), hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, sl.keepBelow, bounds.data()) != AKUA_OK) {
         s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
@@ -508,7 +530,7 @@ int slabRebalance(akua_pbf_solver* s) {
     for (int r = 0; r <= R; r++) movedAny = movedAny || bounds[r] != old[r];
     if (slabVerbose() && sl.rank == 0) {
         std::fprintf(stderr, "[akua] rebalance after step %lld: %s, %s, %.2f ms (host); bounds", (long long)s->ctr.steps,
-                     measured ? "measured busy time" : "work estimate", movedAny ? "moved" : "kept", hostMs() - tReb0);
+                     measured ? "work estimate x measured busy-time correction" : "work estimate", movedAny ? "moved" : "kept", hostMs() - tReb0);
         for (int r = 0; r <= R; r++) std::fprintf(stderr, " %d", bounds[r]);
         std::fprintf(stderr, "\n");
     }

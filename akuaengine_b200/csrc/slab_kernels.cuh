@@ -428,28 +428,22 @@ __global__ void k_step_end(uint32_t* __restrict__ dims, uint32_t exchanges, uint
     }
     *tl = now;
 }
-// Re-balancing: turns this rank's per-plane WORK into estimated TIME, work[x] * busyNs / sum(work) (so that the planes of a
-// rank add up to its measured busy time), and restarts the busy-time accumulation. One CTA. valid[0] += 1 when this rank
-// had a measurement (all ranks must, or the caller falls back to the raw work).
-__global__ void __launch_bounds__(256) k_plane_time(const unsigned long long* __restrict__ work, unsigned long long* __restrict__ timeOut,
-                                                    int gx, uint32_t* __restrict__ dims, unsigned long long* __restrict__ valid) {
+// Re-balancing: exports this rank's measured busy time per step (ns) and the sum of its per-plane work, and restarts the
+// busy-time accumulation. One CTA.
+__global__ void __launch_bounds__(256) k_rank_busy(const unsigned long long* __restrict__ work, int gx, uint32_t* __restrict__ dims,
+                                                   unsigned long long* __restrict__ busyOut, unsigned long long* __restrict__ workOut) {
     __shared__ unsigned long long part[8];
-    __shared__ unsigned long long total;
     unsigned long long w = 0;
     for (int x = threadIdx.x; x < gx; x += blockDim.x) w += work[x];
     for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
     __syncthreads();
-    if (threadIdx.x == 0) { for (int k = 1; k < 8; k++) w += part[k]; total = w; }
-    __syncthreads();
-    const unsigned long long busy = *reinterpret_cast<const unsigned long long*>(dims + D_BUSY_NS);
-    const uint32_t steps = dims[D_BUSY_STEPS];
-    const bool ok = busy > 0ull && steps > 0u && total > 0ull;
-    const double scale = ok ? (double)busy / (double)steps / (double)total : 0.0;   // ns per step per unit of work
-    for (int x = threadIdx.x; x < gx; x += blockDim.x) timeOut[x] = (unsigned long long)((double)work[x] * scale * 1024.0);
-    __syncthreads();
     if (threadIdx.x == 0) {
-        if (ok || total == 0ull) *valid += 1ull;   // a rank without particles has nothing to measure and nothing to contribute
+        for (int k = 1; k < 8; k++) w += part[k];
+        const unsigned long long busy = *reinterpret_cast<const unsigned long long*>(dims + D_BUSY_NS);
+        const uint32_t steps = dims[D_BUSY_STEPS];
+        *busyOut = steps ? busy / steps : 0ull;
+        *workOut = w;
         *reinterpret_cast<unsigned long long*>(dims + D_BUSY_NS) = 0ull;
         *reinterpret_cast<unsigned long long*>(dims + D_T_LAST) = 0ull;   // the host-side part of this call is not a step
         dims[D_BUSY_STEPS] = 0u;

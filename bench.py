@@ -318,6 +318,7 @@ def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance
     it: one stream synchronisation and a small all-reduce per call, a graph re-capture only when a slab leaves its window)."""
     import torch
     out = []
+    done = 0   # steps since the start of the timed region: the re-balancing cadence runs through the windows
     for _ in range(windows):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -325,9 +326,10 @@ def timed_windows(solver, stream, barrier, bmin, bmax, steps, windows, rebalance
         e0.record(stream)
         marks = []
         for k in range(steps):
-            if rebalance and k % rebalance == 0:
-                solver.rebalance()
             solver.step(DT, bmin, bmax)
+            done += 1
+            if rebalance and done % rebalance == 0:
+                solver.rebalance()
             if step_log is not None:   # one event per step: shows a one-off cost (graph re-capture after a re-balance) as what it is
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(stream)

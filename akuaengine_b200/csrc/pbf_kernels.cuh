@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(256) k_unpack_aos(const uint32_t* __restrict__
                                                     float4* __restrict__ dpos, float* __restrict__ density,
                                                     float* __restrict__ lambda, uint32_t* __restrict__ keys,
                                                     float4* __restrict__ color, float* __restrict__ size,
-                                                    uint32_t* __restrict__ id) {
+                                                    uint32_t* __restrict__ id, uint32_t idBase) {
     __shared__ uint32_t sm[256 * kAosWords];
     const uint32_t base = blockIdx.x * 256u;
     const uint32_t count = min(256u, n - base);
@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(256) k_unpack_aos(const uint32_t* __restrict__
     keys[i] = sm[threadIdx.x * kAosWords + 21];
     color[i] = make_float4(f[22], f[23], f[24], f[25]);
     size[i] = f[26];
-    id[i] = i;
+    id[i] = idBase + i;   // (a chunked upload passes arrays offset to the chunk: the id is the index in the whole upload)
 }
 __global__ void __launch_bounds__(256) k_pack_aos(uint32_t* __restrict__ aos, uint32_t n, const float4* __restrict__ pos,
                                                   const float4* __restrict__ vel, const float4* __restrict__ xs,

@@ -151,8 +151,11 @@ struct akua_pbf_solver {
     uint32_t nbrStride = 0;
     rsort::Workspace sortWs;
     uint32_t *canonKeys = nullptr, *canonVals = nullptr;   // options.canonical_order: (cell key, index) pairs in id order
-    // interchange staging
+    // interchange staging; the AoS transfers are chunked: copy engine on copyStream, (un)pack kernels on the solver's stream
     void* aosStage = nullptr;
+    cudaStream_t copyStream = nullptr;
+    static constexpr int kXferChunks = 8;
+    cudaEvent_t xferEv[kXferChunks + 1] = {};
     float *partSum = nullptr, *partMax = nullptr;
     // bookkeeping
     akua_pbf_counters ctr{};
@@ -293,7 +296,19 @@ int layoutGrid(akua_pbf_solver* s, const float* bmin, const float* bmax) {
 
 int ensureStage(akua_pbf_solver* s) {
     if (!s->aosStage) AK_CUDA(s, cudaMalloc(&s->aosStage, (size_t)s->capacity * 108));
+    if (!s->copyStream) {
+        AK_CUDA(s, cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+        for (auto& e : s->xferEv) AK_CUDA(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return AKUA_OK;
+}
+// Chunk c of an n-particle AoS transfer: [first, first + count), chunk boundaries on multiples of the 256-particle tiles of
+// k_pack_aos / k_unpack_aos; small transfers are one chunk.
+inline int xferChunks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(akua_pbf_solver::kXferChunks, n / 131072)); }
+inline void xferChunk(int64_t n, int chunks, int c, int64_t* first, int64_t* count) {
+    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;
+    *first = std::min<int64_t>(n, per * c);
+    *count = std::min<int64_t>(n, per * (c + 1)) - *first;
 }
 
 void mark(akua_pbf_solver* s, Phase p) {
@@ -976,6 +991,8 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
     for (int p = 0; p < PH_COUNT; p++) if (s->ev[p]) cudaEventDestroy(s->ev[p]);
     for (int i = 0; i < akua_pbf_solver::kMaxTimedIters; i++)
         for (int k = 0; k < 3; k++) if (s->evPass[i][k]) cudaEventDestroy(s->evPass[i][k]);
+    if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
+    for (auto& e : s->xferEv) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1041,13 +1058,28 @@ int akua_pbf_upload_aos108(akua_pbf_solver* s, const void* src, int64_t n) {
     if (rc) return rc;
     if (n == 0) { s->massUniform = false; return slabAgreeMass(s); }   // still takes part in the slab-mode verdict
     if ((rc = ensureStage(s))) return rc;
-    AK_CUDA(s, cudaMemcpyAsync(s->aosStage, src, (size_t)n * 108, cudaMemcpyHostToDevice, s->stream));
-    s->ctr.h2d_bytes += n * 108;
+    // Chunked: the copy engine moves chunk c + 1 from the host while k_unpack_aos scatters chunk c into the SoA arrays.
     // Particle::hash goes to the debug copy of the unsorted keys, NOT to keysSorted: in REFERENCE_HASH mode keysSorted must keep
     // describing the bucket table's current entries (they are un-written from it at the next step)
-    launchPlain(s->stream, k_unpack_aos, gridFor(n), kBlock, (const uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega,
-        s->omegaLen, s->dpos, s->density, s->lambda, s->keysUnsorted, s->color, s->size, s->id);
-    AK_LAUNCH_CHECK(s, "k_unpack_aos");
+    {
+        const int chunks = xferChunks(n);
+        AK_CUDA(s, cudaEventRecord(s->xferEv[akua_pbf_solver::kXferChunks], s->stream));       // the staging buffer's last user
+        AK_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->xferEv[akua_pbf_solver::kXferChunks], 0));
+        for (int c = 0; c < chunks; c++) {
+            int64_t a, m;
+            xferChunk(n, chunks, c, &a, &m);
+            if (m <= 0) continue;
+            char* stage = (char*)s->aosStage + (size_t)a * 108;
+            AK_CUDA(s, cudaMemcpyAsync(stage, (const char*)src + (size_t)a * 108, (size_t)m * 108, cudaMemcpyHostToDevice, s->copyStream));
+            AK_CUDA(s, cudaEventRecord(s->xferEv[c], s->copyStream));
+            AK_CUDA(s, cudaStreamWaitEvent(s->stream, s->xferEv[c], 0));
+            launchPlain(s->stream, k_unpack_aos, gridFor(m), kBlock, (const uint32_t*)stage, (uint32_t)m, s->pos + a, s->vel + a, s->xs + a,
+                s->omega + a, s->omegaLen + a, s->dpos + a, s->density + a, s->lambda + a, s->keysUnsorted + a, s->color + a, s->size + a,
+                s->id + a, (uint32_t)a);
+            AK_LAUNCH_CHECK(s, "k_unpack_aos");
+        }
+        s->ctr.h2d_bytes += n * 108;
+    }
     int rcm = massRangeAsync(s);
     if (rcm) return rcm;
     AK_CUDA(s, cudaStreamSynchronize(s->stream));  // `src` may be reused by the caller as soon as we return
@@ -1062,12 +1094,26 @@ int akua_pbf_download_aos108(akua_pbf_solver* s, void* dst, int64_t n) {
     if (n != s->n) { s->err = "download_aos108: n must equal numParticles"; return AKUA_ERR_INVALID; }
     if (n == 0) return AKUA_OK;
     if ((rc = ensureStage(s))) return rc;
-    launchPlain(s->stream, k_pack_aos, gridFor(n), kBlock, (uint32_t*)s->aosStage, (uint32_t)n, s->pos, s->vel, s->xs, s->omega, s->dpos,
-        s->density, s->lambda, hashField(s), s->color, s->size, s->id, s->slab.enabled ? s->slab.slot : nullptr);
-    AK_LAUNCH_CHECK(s, "k_pack_aos");
-    AK_CUDA(s, cudaMemcpyAsync(dst, s->aosStage, (size_t)n * 108, cudaMemcpyDeviceToHost, s->stream));
-    AK_CUDA(s, cudaStreamSynchronize(s->stream));
-    s->ctr.d2h_bytes += n * 108;
+    // Chunked: k_pack_aos gathers chunk c + 1 into the staging buffer while the copy engine moves chunk c to the host.
+    {
+        const int chunks = xferChunks(n);
+        const uint32_t* slot = s->slab.enabled ? s->slab.slot : nullptr;
+        for (int c = 0; c < chunks; c++) {
+            int64_t a, m;
+            xferChunk(n, chunks, c, &a, &m);
+            if (m <= 0) continue;
+            char* stage = (char*)s->aosStage + (size_t)a * 108;
+            launchPlain(s->stream, k_pack_aos, gridFor(m), kBlock, (uint32_t*)stage, (uint32_t)m, s->pos + a, s->vel + a, s->xs + a, s->omega + a,
+                s->dpos + a, s->density + a, s->lambda + a, hashField(s) + a, s->color, s->size, s->id + a, slot ? slot + a : nullptr);
+            AK_LAUNCH_CHECK(s, "k_pack_aos");
+            AK_CUDA(s, cudaEventRecord(s->xferEv[c], s->stream));
+            AK_CUDA(s, cudaStreamWaitEvent(s->copyStream, s->xferEv[c], 0));
+            AK_CUDA(s, cudaMemcpyAsync((char*)dst + (size_t)a * 108, stage, (size_t)m * 108, cudaMemcpyDeviceToHost, s->copyStream));
+        }
+        AK_CUDA(s, cudaStreamSynchronize(s->copyStream));
+        AK_CUDA(s, cudaStreamSynchronize(s->stream));
+        s->ctr.d2h_bytes += n * 108;
+    }
     return AKUA_OK;
 }
 

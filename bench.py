@@ -610,6 +610,36 @@ def extra_configs(args, local):
             s.close()
         except Exception as e:  # never lose the headline line to an extra
             res[name] = {"error": str(e)[:200]}
+    # BASELINE.json config 5: neighbour-search microbench (key + sort + ranges + reorder, and the list build apart) at 1 M and
+    # 16 M particles, uniform vs clustered (the full 1 M - 128 M table: profiles/r02_neighbour_search_microbench.jsonl)
+    try:
+        from akuaengine_b200 import DBG
+        rows = []
+        for m in (1, 16):
+            n = m * 1_000_000
+            for kind in ("uniform", "clustered"):
+                p, bmin, bmax = scenes.uniform_cloud(n, seed=42) if kind == "uniform" else scenes.clustered_cloud(n)
+                pos = p["position"].copy()
+                del p
+                s = PBFSolver(n, device=local)
+                s.upload(pos)
+                s.enable_timing(True)
+                t = []
+                for _ in range(4):
+                    s.findParticleNeighbours(bmin, bmax)
+                    t.append(s.last_step_timing())
+                med = {k: float(np.median([r[k] for r in t[1:]])) for k in ("predict_key", "sort", "reorder_ranges", "neighbour_lists")}
+                search = med["predict_key"] + med["sort"] + med["reorder_ranges"]
+                passes = s.counters()["sort_passes_last"]
+                cnt = s.debug(DBG.NBR_COUNT)
+                rows.append({"n": n, "density": kind, "search_ms": search, "list_build_ms": med["neighbour_lists"], "ms": med,
+                             "search_particles_per_s": n / (search * 1e-3), "sort_passes": passes,
+                             "search_algorithmic_GBps": (24 + 16 * passes + 104) * n / (search * 1e-3) / 1e9,
+                             "neighbours_mean": float(cnt.mean()), "particles_at_the_128_cap": int((cnt >= 128).sum())})
+                s.close()
+        res["config5_neighbour_search"] = rows
+    except Exception as e:
+        res["config5_neighbour_search"] = {"error": str(e)[:200]}
     return res
 
 

@@ -106,7 +106,7 @@ int emu_upload_aos108(void* h, const void* src) {
     const uint32_t n = s->n;
     if (!n) return 0;
     run(k_unpack_aos, gridFor(n), 256u, (const uint32_t*)src, n, s->pPos, s->pVel, s->pXs, s->omega.data(), s->omegaLen.data(),
-        s->dpos.data(), s->density.data(), s->lambda.data(), s->keysSorted, s->color.data(), s->size.data(), s->pId);
+        s->dpos.data(), s->density.data(), s->lambda.data(), s->keysSorted, s->color.data(), s->size.data(), s->pId, 0u);
     uint32_t range[2] = {0xffffffffu, 0u};   // massRangeAsync / massRangeFinish
     run(k_mass_range, std::min<uint32_t>(gridFor(n), 148 * 8), 256u, (const float4*)s->pPos, n, range);
     s->massUniform = range[0] == range[1];

@@ -408,6 +408,23 @@ def test_aos108_roundtrip_and_payload_follow_particles():
     s.close()
 
 
+def test_chunked_aos_transfer_roundtrip_at_a_ragged_size():
+    """Above 256 K particles the AoS upload / download run in up to 8 chunks (copy engine and (un)pack kernels overlapped): a
+    ragged size that is no multiple of the 256-particle tile must come back byte for byte, ids = upload index."""
+    n = 1_100_003
+    rng = np.random.default_rng(7)
+    init = np.zeros(n, PARTICLE_DTYPE)
+    raw = init.view(np.uint32).reshape(n, 27)
+    raw[:] = rng.integers(0, 1 << 30, (n, 27), dtype=np.uint32)      # arbitrary (finite) bit patterns in every field
+    init["new_velocity"] = init["velocity"]                             # documented: new_velocity := velocity on export
+    s = PBFSolver(n)
+    s.upload_particles(init)
+    back = s.download_particles()
+    assert np.array_equal(back.view(np.uint32), init.view(np.uint32))
+    assert np.array_equal(s.debug(DBG.ID), np.arange(n, dtype=np.uint32))
+    s.close()
+
+
 def test_set_gravity_and_step_iters_and_errors():
     from akuaengine_b200 import AkuaError
     init, bmin, bmax = scenes.dam_break(8)

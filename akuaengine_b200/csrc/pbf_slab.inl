@@ -125,7 +125,7 @@ int slabResetCounts(akua_pbf_solver* s) {
     sl.hDims[D_N] = n; sl.hDims[D_NOWN] = n;
     sl.hDims[D_PLANE_L] = sl.hDims[D_PLANE_R] = sl.hDims[D_GHOST_L] = sl.hDims[D_GHOST_R] = 0;
     sl.hDims[D_IN_L] = sl.hDims[D_IN_R] = 0;
-    sl.estN = sl.estBnd = sl.estGhost = sl.estIn = 0;   // re-derived at the next step
+    // (the launch-size estimates stay: they only size grids, and keeping them keeps the step's CUDA graph across uploads)
     return AKUA_OK;
 }
 
@@ -260,12 +260,14 @@ void slabUpdateEstimates(akua_pbf_solver* s) {
 // Slab-local cell grid: the global grid of the box (shared by all ranks: same y / z extent and origin) restricted in x to a
 // WINDOW of planes around this rank's slab: its owned planes, towards each neighbour the ghost plane and one "far" plane into
 // which everything beyond is clamped (a leaver that lands deeper than the neighbour's boundary plane must not be counted into
-// that plane), plus kWindowMargin spare planes on each inner side. Keys are window-relative: a 64 M-particle scene on 8 GPUs
+// that plane), plus windowMargin() spare planes on each inner side. Keys are window-relative: a 64 M-particle scene on 8 GPUs
 // sorts 23-bit keys (3 digit passes) and clears an 8th of the cell table. The window — and with it every kernel argument of
 // the step: grid, sentinel key, sort passes, cell-table size — only changes when a re-balancing pushes a boundary out of the
 // margin; the owned interval itself lives in dims[D_XLO / D_XHI], so an ordinary re-balancing costs two words written to the
 // device and NO re-capture of the step's CUDA graph.
-constexpr int kWindowMargin = 6;
+// Spare planes per inner side: a quarter of the slab's width, between 6 and 32 (a sloshing tank on 8 GPUs moves a boundary by up
+// to eight planes between two re-balancing calls ten steps apart: profiles/r02_c14_*).
+inline int windowMargin(int width) { return std::max(6, std::min(32, width / 4)); }
 int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     SlabState& sl = s->slab;
     if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
@@ -282,8 +284,9 @@ int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
     const bool sameGrid = sl.winValid && sl.winGmin.x == gmin.x && sl.winGmin.y == gmin.y && sl.winGmin.z == gmin.z &&
                           sl.winGdim.x == gdim.x && sl.winGdim.y == gdim.y && sl.winGdim.z == gdim.z;
     if (!sameGrid || needLo < sl.winX0 || needHi > sl.winX1) {
-        sl.winX0 = hasL ? std::max(needLo - kWindowMargin, 0) : 0;
-        sl.winX1 = hasR ? std::min(needHi + kWindowMargin, gdim.x) : gdim.x;
+        const int margin = windowMargin(xHiG - xLoG);
+        sl.winX0 = hasL ? std::max(needLo - margin, 0) : 0;
+        sl.winX1 = hasR ? std::min(needHi + margin, gdim.x) : gdim.x;
         sl.winGmin = gmin; sl.winGdim = gdim; sl.winValid = true;
         sl.windowChanges++;
     }
@@ -294,9 +297,10 @@ int slabLayout(akua_pbf_solver* s, const float* bmin, const float* bmax) {
         const double t0 = hostMs();
         if (s->cellRange) { AK_CUDA(s, cudaStreamSynchronize(s->stream)); AK_CUDA(s, cudaFree(s->cellRange)); }
         s->cellRange = nullptr;
-        AK_CUDA(s, dalloc(&s->cellRange, (size_t)cells));
-        s->cellCapacity = cells;
-        if (slabVerbose()) std::fprintf(stderr, "[akua rank %d] cell table grown to %lld cells in %.2f ms (host)\n", sl.rank, (long long)cells, hostMs() - t0);
+        const int64_t want = cells + cells / 4;   // head-room: the next, slightly wider window does not reallocate
+        AK_CUDA(s, dalloc(&s->cellRange, (size_t)want));
+        s->cellCapacity = want;
+        if (slabVerbose()) std::fprintf(stderr, "[akua rank %d] cell table grown to %lld cells in %.2f ms (host)\n", sl.rank, (long long)want, hostMs() - t0);
     }
     s->grid.gridMin = make_int3(gmin.x + x0, gmin.y, gmin.z);
     s->grid.gridDim = make_int3(x1 - x0, gdim.y, gdim.z);

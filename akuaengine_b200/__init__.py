@@ -110,7 +110,7 @@ ABI_SYMBOLS = [
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
     "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_trace_next_step", "akua_pbf_stream",
-    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance", "akua_slab_partition", "akua_slab_rebalance_bounds", "akua_slab_rebalance_bounds_weighted",
+    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance", "akua_pbf_rebalance_async", "akua_slab_partition", "akua_slab_rebalance_bounds", "akua_slab_rebalance_bounds_weighted",
 ]
 
 _lib = None
@@ -190,6 +190,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_upload_ids.argtypes = [vp, vp, C.c_int64]
     lib.akua_pbf_slab_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.akua_pbf_rebalance.argtypes = [vp]
+    lib.akua_pbf_rebalance_async.argtypes = [vp]
     lib.akua_slab_partition.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.akua_slab_rebalance_bounds.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64,
                                                C.POINTER(C.c_int32)]
@@ -429,6 +430,10 @@ class PBFSolver:
     def upload_ids(self, ids: np.ndarray):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._ck(self._lib.akua_pbf_upload_ids(self._h, ids.ctypes.data, len(ids)), "upload_ids")
+
+    def rebalance_async(self):
+        """akua_pbf_rebalance without the host synchronisation: applies the previous call's measurement, enqueues the next."""
+        self._ck(self._lib.akua_pbf_rebalance_async(self._h), "rebalance_async")
 
     def rebalance(self):
         """Collective: re-balance the slab boundaries from the current particle distribution (all ranks, same step)."""

@@ -458,19 +458,20 @@ int stepSlabBody(akua_pbf_solver* s, float dt, int iterations, const float* bmin
     return AKUA_OK;
 }
 
-// Re-balances the slab boundaries from the current per-x-plane particle counts of all ranks (collective: every rank
-// calls it at the same step). The owned particles are sorted by x plane after a step, so each rank histograms its own
-// planes with binary searches, the histograms are summed with one ncclAllReduce, and every rank computes the same new
-// boundaries (akua_slab_partition). A boundary may only move inside the two slabs it separates, and by no more
-// particles than the migration buffers hold, so the ordinary per-step migration of the NEXT step performs the transfer.
-int slabRebalance(akua_pbf_solver* s) {
+// Re-balances the slab boundaries from the current per-x-plane particle counts and work of all ranks (collective: every rank
+// calls it at the same step). The owned particles are sorted by x plane after a step, so each rank histograms its own planes
+// (binary searches + a sum of neighbour counts), the histograms are summed with one ncclAllReduce, and every rank computes the
+// same new boundaries. A boundary may only move inside the two slabs it separates, and by no more particles than the
+// migration buffers hold, so the ordinary per-step migration of the NEXT step performs the transfer.
+// Two halves: slabRebalanceMeasure enqueues the histogram kernels, the all-reduce and the copy to pinned memory WITHOUT any
+// host synchronisation; slabRebalanceApply waits for that copy and moves the boundaries. akua_pbf_rebalance = measure + apply
+// (one pipeline drain per call); akua_pbf_rebalance_async = apply the PREVIOUS call's measurement, then measure again: the
+// host never waits and the GPU never idles, at the price of boundaries that lag one call behind the fluid.
+int slabRebalanceMeasure(akua_pbf_solver* s) {
     SlabState& sl = s->slab;
     if (!sl.enabled || !s->haveBox) { s->err = "rebalance: slab mode with at least one completed step required"; return AKUA_ERR_INVALID; }
-    const double tReb0 = hostMs();
-    {
-        int rcr = slabRefresh(s);   // exact owned count; reports any pending device-side error
-        if (rcr) return rcr;
-    }
+    int rc;
+    if ((rc = slabCheckError(s))) return rc;
     const GridParams& G = s->grid;   // slab-local grid of the last step; plane p of it is global plane planeOffset + p
     const int gx = sl.gxGlobal, R = sl.nranks;
     const uint32_t planeCells = (uint32_t)G.gridDim.y * (uint32_t)G.gridDim.z;
@@ -478,6 +479,7 @@ int slabRebalance(akua_pbf_solver* s) {
     // lower bound, its measured busy time per step (ns) and the sum of its work
     const size_t words = (size_t)2 * gx + 3 * (size_t)R;
     if (words > sl.histCap) {
+        AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
         sl.dHist = nullptr; sl.hHist = nullptr;
@@ -485,22 +487,32 @@ int slabRebalance(akua_pbf_solver* s) {
         AK_CUDA(s, cudaMallocHost((void**)&sl.hHist, words * sizeof(unsigned long long)));
         sl.histCap = words;
     }
+    if (!sl.evRebalance) AK_CUDA(s, cudaEventCreateWithFlags(&sl.evRebalance, cudaEventDisableTiming));
     AK_CUDA(s, cudaMemsetAsync(sl.dHist, 0, words * sizeof(unsigned long long), s->stream));
-    const uint32_t n = (uint32_t)s->n;
-    launchPlain(s->stream, slab::k_plane_hist, (uint32_t)G.gridDim.x, 256, s->keysSorted, s->nbrCount, n, planeCells, G.gridDim.x, sl.planeOffset,
-                sl.dHist, sl.dHist + gx);
+    launchPlain(s->stream, slab::k_plane_hist, (uint32_t)G.gridDim.x, 256, s->keysSorted, s->nbrCount, (const uint32_t*)(sl.dims + D_N), planeCells,
+                G.gridDim.x, sl.planeOffset, sl.dHist, sl.dHist + gx);
     AK_LAUNCH_CHECK(s, "k_plane_hist");
     launchPlain(s->stream, slab::k_rank_busy, 1, 256, (const unsigned long long*)(sl.dHist + gx), gx, sl.dims,
-                sl.dHist + 2 * (size_t)gx + R + sl.rank, sl.dHist + 2 * (size_t)gx + 2 * (size_t)R + sl.rank);
+                sl.dHist + 2 * (size_t)gx + R + sl.rank, sl.dHist + 2 * (size_t)gx + 2 * (size_t)R + sl.rank, sl.planeOffset + sl.xLoL,
+                sl.rank == 0 ? 1 : 0, sl.dHist + 2 * (size_t)gx + sl.rank);
     AK_LAUNCH_CHECK(s, "k_rank_busy");
-    const int curLo = sl.rank == 0 ? 0 : sl.planeOffset + sl.xLoL;
-    unsigned long long lo64 = (unsigned long long)curLo;
-    AK_CUDA(s, cudaMemcpyAsync(sl.dHist + 2 * (size_t)gx + sl.rank, &lo64, sizeof(lo64), cudaMemcpyHostToDevice, s->stream));
-    int rc;
     if ((rc = slabCommAfterMain(s))) return rc;
     AK_NCCL(s, g_nccl.AllReduce(sl.dHist, sl.dHist, words, ncclUint64, ncclSum, (ncclComm_t)sl.comm, sl.commStream));
     AK_CUDA(s, cudaMemcpyAsync(sl.hHist, sl.dHist, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.commStream));
-    AK_CUDA(s, cudaStreamSynchronize(sl.commStream));
+    AK_CUDA(s, cudaEventRecord(sl.evRebalance, sl.commStream));
+    // the next step's memset of dHist must not overtake the all-reduce: the main stream waits for the comm stream's copy only
+    // when the next measurement is enqueued (slabCommAfterMain orders comm after main; the reverse edge is the event below)
+    sl.pendValid = true; sl.pendGx = gx; sl.pendGminGlobalX = G.gridMin.x - sl.planeOffset; sl.pendStep = s->ctr.steps;
+    return AKUA_OK;
+}
+int slabRebalanceApply(akua_pbf_solver* s) {
+    SlabState& sl = s->slab;
+    if (!sl.pendValid) return AKUA_OK;
+    const double tReb0 = hostMs();
+    AK_CUDA(s, cudaEventSynchronize(sl.evRebalance));
+    AK_CUDA(s, cudaStreamWaitEvent(s->stream, sl.evRebalance, 0));   // dHist is free for the next measurement's memset
+    sl.pendValid = false;
+    const int gx = sl.pendGx, R = sl.nranks;
     std::vector<int64_t> hist(gx), work(gx);
     for (int x = 0; x < gx; x++) { hist[x] = (int64_t)sl.hHist[x]; work[x] = (int64_t)sl.hHist[gx + x]; }
     std::vector<int32_t> bounds(R + 1), old(R + 1);
@@ -534,14 +546,15 @@ int slabRebalance(akua_pbf_solver* s) {
     bool movedAny = false;
     for (int r = 0; r <= R; r++) movedAny = movedAny || bounds[r] != old[r];
     if (slabVerbose() && sl.rank == 0) {
-        std::fprintf(stderr, "[akua] rebalance after step %lld: %s, %s, %.2f ms (host); bounds", (long long)s->ctr.steps,
+        std::fprintf(stderr, "[akua] rebalance measured after step %lld, applied after step %lld: %s, %s, %.2f ms (host); bounds", (long long)sl.pendStep,
+                     (long long)s->ctr.steps,
                      measured ? "work estimate x measured busy-time correction" : "work estimate", movedAny ? "moved" : "kept", hostMs() - tReb0);
         for (int r = 0; r <= R; r++) std::fprintf(stderr, " %d", bounds[r]);
         std::fprintf(stderr, "\n");
     }
     if (!movedAny) return AKUA_OK;
     // monotonic by construction (each stays within its old neighbours' interval); take this rank's new interval
-    const int gminGlobalX = G.gridMin.x - sl.planeOffset;
+    const int gminGlobalX = sl.pendGminGlobalX;
     sl.xLoAbs = gminGlobalX + bounds[sl.rank];
     sl.xHiAbs = gminGlobalX + bounds[sl.rank + 1];
     sl.rebalances++;

@@ -103,6 +103,11 @@ struct SlabState {
     unsigned long long *dHist = nullptr, *hHist = nullptr;  // re-balancing histogram (+ current bounds)
     size_t histCap = 0;
     int64_t rebalances = 0;            // calls that moved a boundary
+    // a measurement in flight (akua_pbf_rebalance_async): enqueued, not yet applied
+    cudaEvent_t evRebalance = nullptr;
+    bool pendValid = false;
+    int pendGx = 0, pendGminGlobalX = 0;
+    int64_t pendStep = 0;
     bool lastRebalanceMeasured = false;   // the last akua_pbf_rebalance balanced measured busy time (else the raw work estimate)
     double keepBelow = 1.02;           // akua_pbf_rebalance leaves a partition alone whose heaviest slab is within this of the mean
 };
@@ -984,6 +989,7 @@ void akua_pbf_destroy(akua_pbf_solver* s) {
         if (sl.hDims) cudaFreeHost((void*)sl.hDims);
         if (sl.dHist) cudaFree(sl.dHist);
         if (sl.hHist) cudaFreeHost(sl.hHist);
+        if (sl.evRebalance) cudaEventDestroy(sl.evRebalance);
         if (sl.commStream) { cudaStreamSynchronize(sl.commStream); cudaStreamDestroy(sl.commStream); }
         for (int e = 0; e < SlabState::kEvents; e++) if (sl.evPool[e]) cudaEventDestroy(sl.evPool[e]);
         if (sl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)sl.comm);
@@ -1471,7 +1477,17 @@ int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi) {
 int akua_pbf_rebalance(akua_pbf_solver* s) {
     if (!s) return AKUA_ERR_INVALID;
     AK_CUDA(s, cudaSetDevice(s->device));
-    return slabRebalance(s);
+    int rc = slabRebalanceApply(s);          // a measurement left in flight by akua_pbf_rebalance_async comes first
+    if (rc) return rc;
+    if ((rc = slabRebalanceMeasure(s))) return rc;
+    return slabRebalanceApply(s);
+}
+int akua_pbf_rebalance_async(akua_pbf_solver* s) {
+    if (!s) return AKUA_ERR_INVALID;
+    AK_CUDA(s, cudaSetDevice(s->device));
+    int rc = slabRebalanceApply(s);
+    if (rc) return rc;
+    return slabRebalanceMeasure(s);
 }
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
     if (!s || !out) return AKUA_ERR_INVALID;

@@ -335,10 +335,11 @@ __global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t
 // particle costs the sweeps. Used to re-balance the slab boundaries (a sloshing tank is denser, hence dearer, on one side).
 constexpr uint32_t kWorkBase = 12;
 __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, const uint32_t* __restrict__ nbrCount,
-                                                    uint32_t nOwn, uint32_t planeCells, int gx, int planeOffset,
+                                                    const uint32_t* __restrict__ nOwnPtr, uint32_t planeCells, int gx, int planeOffset,
                                                     unsigned long long* __restrict__ count, unsigned long long* __restrict__ work) {
     __shared__ uint32_t range[2];
     __shared__ unsigned long long part[8];
+    const uint32_t nOwn = *nOwnPtr;
     const int x = blockIdx.x;
     if (x >= gx) return;
     if (threadIdx.x < 2) {
@@ -428,10 +429,11 @@ __global__ void k_step_end(uint32_t* __restrict__ dims, uint32_t exchanges, uint
     }
     *tl = now;
 }
-// Re-balancing: exports this rank's measured busy time per step (ns) and the sum of its per-plane work, and restarts the
-// busy-time accumulation. One CTA.
+// Re-balancing: exports this rank's measured busy time per step (ns), the sum of its per-plane work and its current lower
+// bound (global plane; 0 for the first rank), and restarts the busy-time accumulation. One CTA.
 __global__ void __launch_bounds__(256) k_rank_busy(const unsigned long long* __restrict__ work, int gx, uint32_t* __restrict__ dims,
-                                                   unsigned long long* __restrict__ busyOut, unsigned long long* __restrict__ workOut) {
+                                                   unsigned long long* __restrict__ busyOut, unsigned long long* __restrict__ workOut,
+                                                   int lowerBound, int firstRank, unsigned long long* __restrict__ boundOut) {
     __shared__ unsigned long long part[8];
     unsigned long long w = 0;
     for (int x = threadIdx.x; x < gx; x += blockDim.x) w += work[x];
@@ -444,6 +446,7 @@ __global__ void __launch_bounds__(256) k_rank_busy(const unsigned long long* __r
         const uint32_t steps = dims[D_BUSY_STEPS];
         *busyOut = steps ? busy / steps : 0ull;
         *workOut = w;
+        *boundOut = firstRank ? 0ull : (unsigned long long)lowerBound;
         *reinterpret_cast<unsigned long long*>(dims + D_BUSY_NS) = 0ull;
         *reinterpret_cast<unsigned long long*>(dims + D_T_LAST) = 0ull;   // the host-side part of this call is not a step
         dims[D_BUSY_STEPS] = 0u;

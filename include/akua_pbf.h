@@ -217,6 +217,10 @@ int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
  * A partition whose heaviest slab is within 2 % of the mean is left alone (environment AKUA_SLAB_KEEP_BELOW, default 1.02).
  * Call every few dozen steps for scenes whose fluid moves along x (dam break, sloshing tank). */
 int akua_pbf_rebalance(akua_pbf_solver* s);
+/* The same without a host synchronisation: applies the measurement the PREVIOUS call enqueued (histogram kernels, all-reduce,
+ * copy to pinned memory — long finished by then), then enqueues the next one behind the last step. The host never waits and
+ * the GPU never idles; the boundaries lag one call behind the fluid. Collective like akua_pbf_rebalance; the two may be mixed. */
+int akua_pbf_rebalance_async(akua_pbf_solver* s);
 /* out: 0 owned, 1 ghosts from left, 2 ghosts from right, 3 first-plane size, 4 last-plane size, 5 exchanges so far,
  * 6 bytes sent so far (NEGATIVE when the CUDA-IPC peer-to-peer transport is in use, positive for NCCL send/recv),
  * 7 particles migrated in so far. Transport: ghost planes are copied straight into the neighbour's arrays through

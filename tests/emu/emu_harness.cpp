@@ -323,7 +323,8 @@ int emu_migration(uint32_t* keys, uint32_t n, uint32_t planeCells, int xLo, int 
 // Per-x-plane histogram of sorted keys (k_plane_hist, used by akua_pbf_rebalance) and the plane-size check (k_plane_verify).
 int emu_plane_hist(const uint32_t* keysSorted, const uint32_t* nbrCount, uint32_t n, uint32_t planeCells, int gx, unsigned long long* hist,
                    unsigned long long* work) {
-    run(slab::k_plane_hist, (uint32_t)gx, 256u, keysSorted, nbrCount, n, planeCells, gx, 0, hist, work);
+    const uint32_t nOwn = n;
+    run(slab::k_plane_hist, (uint32_t)gx, 256u, keysSorted, nbrCount, (const uint32_t*)&nOwn, planeCells, gx, 0, hist, work);
     return 0;
 }
 int emu_plane_verify(const uint32_t* keysSorted, uint32_t n, uint32_t planeCells, int xLo, int xHi, uint32_t predictFirst,

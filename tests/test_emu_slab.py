@@ -64,7 +64,8 @@ def _run_single(lib, p, bmin, bmax, steps, g, canonical=False):
     return pos, vel, pid, err
 
 
-def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, capacity_factor=4.0, canonical=False):
+def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, capacity_factor=4.0, canonical=False,
+              rebalance_async=False):
     """One thread per rank. Returns per-rank (pos4, vel4, ids, aos, stats) and raises the first exception of any rank."""
     n = len(p)
     ids = np.arange(n, dtype=np.uint32)
@@ -93,7 +94,7 @@ def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, 
             for k in range(steps):
                 s.step(DT, bmin, bmax)
                 if rebalance_every and (k + 1) % rebalance_every == 0:
-                    s.rebalance()
+                    s.rebalance_async() if rebalance_async else s.rebalance()
             pos, vel, pid = s.download()
             aos = s.download_particles()
             st = s.slab_stats()
@@ -182,6 +183,21 @@ def test_slab_rebalances_from_a_skewed_start(emulib):
     single = _run_single(emulib, p, bmin, bmax, steps, g)
     slab = _run_slab(emulib, p, bmin, bmax, steps, g, 2, skew=0.5, rebalance_every=2, capacity_factor=2.5)
     _compare(p, single, slab, 1e-3)
+    owned = [len(o[2]) for o in slab]
+    assert max(owned) / (sum(owned) / 2) < 1.2, owned
+
+
+def test_async_rebalance_lags_one_call_and_stays_bit_identical(emulib):
+    """akua_pbf_rebalance_async applies the previous call's measurement (no host synchronisation): from a skewed start the slabs
+    still balance, one call later, and in canonical order the run stays bit-identical to one rank."""
+    p, bmin, bmax = _scene(nx=32)
+    g = np.array([0.0, -9.8, 0.0], np.float32)
+    steps = 14
+    single = _run_single(emulib, p, bmin, bmax, steps, g, canonical=True)
+    slab = _run_slab(emulib, p, bmin, bmax, steps, g, 2, skew=0.5, rebalance_every=2, capacity_factor=2.5, canonical=True,
+                     rebalance_async=True)
+    dp, dv = _compare(p, single, slab, 1e-6)
+    assert dp == 0.0 and dv == 0.0
     owned = [len(o[2]) for o in slab]
     assert max(owned) / (sum(owned) / 2) < 1.2, owned
 

@@ -194,6 +194,8 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_slab_partition.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.akua_slab_rebalance_bounds.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64,
                                                C.POINTER(C.c_int32)]
+    lib.akua_slab_rebalance_bounds_weighted.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                                        C.c_int64, C.c_double, C.c_int64, C.POINTER(C.c_int32)]
     if path is None:
         _lib = lib
     return lib

@@ -262,11 +262,16 @@ struct HaloSync {
     uint32_t* dims = nullptr;              // D_EPOCH, D_ERROR
     long long timeoutCycles = 0;
 };
-// Bounded spin of ONE thread on a flag word until it reaches `epoch` (wrap-safe); false on time-out.
-__device__ __forceinline__ bool spin_until(const volatile uint32_t* f, uint32_t epoch, long long timeoutCycles) {
+// Bounded spin of ONE thread on a flag word until it reaches `epoch` (wrap-safe); false on time-out. `err` (the sticky error
+// word of dims): once ANY wait of this rank has timed out, the neighbour is gone and every later wait gives up at once — a rank
+// whose neighbour died pays the time-out once, not once per queued kernel (its queue drains in milliseconds and the host's
+// next look at the error word reports AKUA_ERR_COMM).
+__device__ __forceinline__ bool spin_until(const volatile uint32_t* f, uint32_t epoch, long long timeoutCycles,
+                                           const volatile uint32_t* err = nullptr) {
     const long long t0 = clock64();
     unsigned ns = 32;
     while ((int32_t)(*f - epoch) < 0) {
+        if (err && (*err & SLAB_ERR_TIMEOUT)) return false;
         if (clock64() - t0 > timeoutCycles) return false;
         __nanosleep(ns);
         if (ns < 1024) ns <<= 1;
@@ -279,7 +284,7 @@ __device__ __forceinline__ void halo_wait(const HaloSync& hs) {
         const uint32_t epoch = hs.dims[D_EPOCH] + (uint32_t)hs.waitIdx + 1u;
         for (int side = 0; side < 2; side++) {
             if (!(side == 0 ? hs.waitL : hs.waitR)) continue;
-            if (!spin_until(hs.waitFlags + side, epoch, hs.timeoutCycles)) { atomicOr(hs.dims + D_ERROR, (uint32_t)SLAB_ERR_TIMEOUT); break; }
+            if (!spin_until(hs.waitFlags + side, epoch, hs.timeoutCycles, hs.dims + D_ERROR)) { atomicOr(hs.dims + D_ERROR, (uint32_t)SLAB_ERR_TIMEOUT); break; }
         }
         __threadfence_system();
     }

@@ -57,10 +57,11 @@ const char* loadNccl() {
         }                                                                                         \
     } while (0)
 
-// Bound of the in-kernel flag waits in SM clock cycles (~20 s at 1.97 GHz): long enough for any host-side skew between the
+// Bound of the in-kernel flag waits in SM clock cycles (~10 s at 1.97 GHz): long enough for any host-side skew between the
 // ranks' launch loops (the count exchange at the top of a step is where a late rank is waited for), short enough that a
-// lost neighbour ends in an error instead of a hung GPU. One bound for every wait (count message and ghost planes).
-constexpr long long kFlagWaitCyclesDefault = 40000000000LL;
+// lost neighbour ends in an error instead of a hung GPU. One bound for every wait (count message and ghost planes); after the
+// first time-out of a rank every later wait returns at once (spin_until), so a dead neighbour costs this once.
+constexpr long long kFlagWaitCyclesDefault = 20000000000LL;
 long long flagWaitCycles() {   // AKUA_SLAB_WAIT_CYCLES: override for tests (a time-out must be reachable in a unit test)
     static const long long v = [] { const char* e = std::getenv("AKUA_SLAB_WAIT_CYCLES"); return e ? std::atoll(e) : kFlagWaitCyclesDefault; }();
     return v > 0 ? v : kFlagWaitCyclesDefault;
@@ -519,10 +520,8 @@ int slabRebalanceApply(akua_pbf_solver* s) {
     for (int r = 0; r < R; r++) old[r] = (int32_t)sl.hHist[2 * (size_t)gx + r];
     old[0] = 0; old[R] = gx;
     // Feedback from the clock: a rank whose measured busy time per unit of work is above (below) the mean has its planes made
-    // dearer (cheaper) by that ratio, clamped to [0.9, 1.1] — the work estimate (12 + neighbour count per particle) decides the
-    // bulk, the measurement corrects what it cannot know (how well a rank's gathers cache, a free surface, a wall). The clamp
-    // keeps small, latency-bound scenes (where time does not follow the particle count at all: a 64 K-particle test scene takes
-    // the same time per step on every rank whatever it owns) balanced by work. Applied only when every rank with particles had
+    // dearer (cheaper) by that ratio, clamped to [0.8, 1.25] — the work estimate decides the bulk, the measurement corrects what
+    // it cannot know (how well a rank's gathers cache, a free surface, a wall). Applied only when every rank with particles had
     // a measurement since the last call.
     bool measured = true;
     double busyAll = 0.0, workAll = 0.0;
@@ -531,16 +530,23 @@ int slabRebalanceApply(akua_pbf_solver* s) {
         if (w > 0.0 && b <= 0.0) measured = false;
         busyAll += b; workAll += w;
     }
+    // (the clock only means something when a step is long enough to be bound by the particles rather than by launch latency:
+    // every rank's busy time must reach 2 ms per step)
+    double busyMin = 1e30;
+    for (int r = 0; r < R; r++) if ((double)sl.hHist[2 * (size_t)gx + 2 * (size_t)R + r] > 0.0) busyMin = std::min(busyMin, (double)sl.hHist[2 * (size_t)gx + R + r]);
+    if (busyMin < 2.0e6) measured = false;
     if (measured && busyAll > 0.0 && workAll > 0.0) {
         for (int r = 0; r < R; r++) {
             const double b = (double)sl.hHist[2 * (size_t)gx + R + r], w = (double)sl.hHist[2 * (size_t)gx + 2 * (size_t)R + r];
             if (w <= 0.0) continue;
-            const double c = std::min(1.1, std::max(0.9, (b / w) / (busyAll / workAll)));
+            const double c = std::min(1.25, std::max(0.8, (b / w) / (busyAll / workAll)));
             for (int x = std::max(old[r], 0); x < std::min(old[r + 1], gx); x++) work[x] = (int64_t)((double)work[x] * c);
         }
     } else measured = false;
     sl.lastRebalanceMeasured = measured;
-    if (akua_slab_rebalance_bounds_weighted(work.data(), hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, sl.keepBelow, bounds.data()) != AKUA_OK) {
+    // no slab gets more particles than 80 % of the room below its ghost regions (the fluid keeps flowing between two calls)
+    const int64_t maxCount = (int64_t)sl.ghostBaseL * 4 / 5;
+    if (akua_slab_rebalance_bounds_weighted(work.data(), hist.data(), gx, R, old.data(), (int64_t)sl.migCap / 2, sl.keepBelow, maxCount, bounds.data()) != AKUA_OK) {
         s->err = "rebalance: grid has fewer x planes than ranks"; return AKUA_ERR_INVALID;
     }
     bool movedAny = false;

@@ -1392,8 +1392,10 @@ int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const v
     AK_CUDA(s, dalloc(&sl.blockCnt, (size_t)2 * sl.migBlocksCap));
     AK_CUDA(s, dalloc(&sl.sendL, sl.migCap)); AK_CUDA(s, dalloc(&sl.sendR, sl.migCap));
     AK_CUDA(s, dalloc(&sl.recvL, sl.migCap)); AK_CUDA(s, dalloc(&sl.recvR, sl.migCap));
-    // fixed ghost regions: the top two eighths of every per-particle array
-    sl.ghostCap = (uint32_t)(s->capacity / 8);
+    // fixed ghost regions at the top of every per-particle array: an eighth of the capacity each for small solvers (a plane of
+    // a test scene can be a tenth of the slab), a sixteenth each from a million particles on (a plane of an 8 M-particle slab is
+    // 1 - 2 % of it; the space goes to the owned region instead)
+    sl.ghostCap = (uint32_t)(s->capacity < (1 << 20) ? s->capacity / 8 : s->capacity / 16);
     sl.ghostBaseL = (uint32_t)s->capacity - 2 * sl.ghostCap;
     sl.ghostBaseR = (uint32_t)s->capacity - sl.ghostCap;
     if (s->n > (int64_t)sl.ghostBaseL) { s->err = "comm_init: capacity_factor too small for the ghost regions (use >= 1.4)"; return AKUA_ERR_INVALID; }
@@ -1531,11 +1533,16 @@ int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int3
 // arrivals never reach a slab's far boundary plane), every slab stays at least two planes wide, and at most maxMove
 // particles cross it.
 int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* count, int32_t ncols, int32_t nranks,
-                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int32_t* bounds) {
+                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int64_t maxCount, int32_t* bounds) {
     if (!work || !count || !oldBounds || !bounds || nranks < 1) return AKUA_ERR_INVALID;
     const int R = nranks;
     const int32_t* old = oldBounds;
-    if (keepBelow > 1.0) {
+    std::vector<int64_t> pre((size_t)ncols + 1, 0);
+    for (int x = 0; x < ncols; x++) pre[x + 1] = pre[x] + count[x];
+    auto cnt = [&](int a, int b) { a = std::min(std::max(a, 0), ncols); b = std::min(std::max(b, 0), ncols); return b > a ? pre[b] - pre[a] : (int64_t)0; };
+    bool oldFits = true;
+    if (maxCount > 0) for (int r = 0; r < R; r++) oldFits = oldFits && cnt(old[r], old[r + 1]) <= maxCount;
+    if (keepBelow > 1.0 && oldFits) {
         // hysteresis: a partition whose heaviest slab is within keepBelow of the mean is left alone (moving a boundary costs a
         // migration burst and a re-capture of the step's CUDA graph)
         int64_t total = 0, heaviest = 0;
@@ -1550,6 +1557,14 @@ int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* coun
         }
     }
     if (akua_slab_partition(work, ncols, nranks, bounds) != AKUA_OK) return AKUA_ERR_INVALID;
+    if (maxCount > 0) {
+        // no slab may hold more particles than its arrays have room for, whatever the work says: pull the upper boundary of an
+        // over-full slab down (left to right), then push the lower boundary of one that is still over-full up (right to left)
+        for (int r = 0; r + 1 < R; r++)
+            while (cnt(bounds[r], bounds[r + 1]) > maxCount && bounds[r + 1] > bounds[r] + 2) bounds[r + 1]--;
+        for (int r = R - 1; r >= 1; r--)
+            while (cnt(bounds[r], bounds[r + 1]) > maxCount && bounds[r] < bounds[r + 1] - 2) bounds[r]++;
+    }
     for (int r = 1; r < R; r++) {
         // stay inside the two old slabs and keep every slab at least two planes wide
         int b = std::min(std::max(bounds[r], std::max(old[r - 1] + 1, bounds[r - 1] + 2)), old[r + 1] - 2);
@@ -1563,7 +1578,7 @@ int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* coun
 }
 int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nranks, const int32_t* oldBounds, int64_t maxMove,
                                int32_t* bounds) {
-    return akua_slab_rebalance_bounds_weighted(hist, hist, ncols, nranks, oldBounds, maxMove, 0.0, bounds);
+    return akua_slab_rebalance_bounds_weighted(hist, hist, ncols, nranks, oldBounds, maxMove, 0.0, 0, bounds);
 }
 
 // ---- phase-level operators ----

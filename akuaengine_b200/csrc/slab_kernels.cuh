@@ -237,8 +237,8 @@ __global__ void k_slab_plan(uint32_t* __restrict__ dims, const uint32_t* __restr
     if (waitFlags) {
         const uint32_t epoch = dims[D_EPOCH] + 1u;
         const unsigned long long t0 = global_timer_ns();
-        if (hasL && !spin_until(countFlags + 0, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
-        if (hasR && !spin_until(countFlags + 1, epoch, timeoutCycles)) err |= SLAB_ERR_TIMEOUT;
+        if (hasL && !spin_until(countFlags + 0, epoch, timeoutCycles, dims + D_ERROR)) err |= SLAB_ERR_TIMEOUT;
+        if (hasR && !(err & SLAB_ERR_TIMEOUT) && !spin_until(countFlags + 1, epoch, timeoutCycles, dims + D_ERROR)) err |= SLAB_ERR_TIMEOUT;
         __threadfence_system();
         // a rank that is ahead of its neighbours idles HERE once per step: the measured idle time is what the re-balancing
         // feeds back on (akua_pbf_rebalance)
@@ -331,8 +331,10 @@ __global__ void k_plane_verify(const uint32_t* __restrict__ keysSorted, uint32_t
     plane_verify(keysSorted, planeCells, hasL, hasR, dims);
 }
 // Per-x-plane population and WORK of the owned (key-sorted) particles, one CTA per plane: two binary searches give the plane's
-// index range, count[planeOffset + x] = its size, work[planeOffset + x] = sum over it of (kWorkBase + neighbour count) — what a
-// particle costs the sweeps. Used to re-balance the slab boundaries (a sloshing tank is denser, hence dearer, on one side).
+// index range, count[planeOffset + x] = its size, work[planeOffset + x] = sum over it of (kWorkBase + the LARGEST neighbour count
+// among the 32 consecutive particles it shares a warp with) — what a particle costs the sweeps, whose warps run as long as their
+// busiest lane (a free surface or spray has few neighbours on average but ragged counts: it is dearer than its mean suggests).
+// Used to re-balance the slab boundaries (a sloshing tank is denser, hence dearer, on one side).
 constexpr uint32_t kWorkBase = 12;
 __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__ keysSorted, const uint32_t* __restrict__ nbrCount,
                                                     const uint32_t* __restrict__ nOwnPtr, uint32_t planeCells, int gx, int planeOffset,
@@ -354,7 +356,12 @@ __global__ void __launch_bounds__(256) k_plane_hist(const uint32_t* __restrict__
     __syncthreads();
     const uint32_t a = range[0], b = range[1];
     unsigned long long w = 0;
-    for (uint32_t i = a + threadIdx.x; i < b; i += blockDim.x) w += kWorkBase + nbrCount[i];
+    for (uint32_t i0 = a; i0 < b; i0 += blockDim.x) {        // uniform trip count: the warp-wide maximum needs every lane
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t c = i < b ? nbrCount[i] : 0u;
+        const uint32_t m = __reduce_max_sync(0xffffffffu, c);
+        if (i < b) w += kWorkBase + m;
+    }
     for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
     __syncthreads();

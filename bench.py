@@ -266,7 +266,7 @@ def workload(args, world: int):
     return (nx, ny, nz), origin, bmin, bmax, gravity, scaling, config
 
 
-def make_solver(args, world, rank, local, dist, dims, origin, gravity, capacity_factor=1.6):
+def make_solver(args, world, rank, local, dist, dims, origin, gravity, capacity_factor=2.0):
     """Creates the solver with this rank's share of the lattice uploaded. Returns (solver, n_local)."""
     from akuaengine_b200 import KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PBFSolver, scenes
     nx, ny, nz = dims
@@ -755,7 +755,7 @@ def main():
     ap.add_argument("--key-mode", default="linear", choices=["linear", "hash"])
     ap.add_argument("--settle", type=int, default=300, help="untimed steps before the warm-up, so that the fluid is disordered")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps each; the median is reported")
-    ap.add_argument("--rebalance-every", type=int, default=10, help="multi-GPU: akua_pbf_rebalance every k steps (settle phase and timed windows)")
+    ap.add_argument("--rebalance-every", type=int, default=5, help="multi-GPU: akua_pbf_rebalance every k steps (settle phase and timed windows)")
     ap.add_argument("--fast-math", type=int, default=1, help="1: rsqrt-based spiky gradient (default); 0: IEEE sqrt/div")
     ap.add_argument("--trace", default="", help="write a launch timeline of two steps after the timed region to PATH.rank<r>.jsonl")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -766,8 +766,19 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    else:
+        return
+    try:
         run_ours(args)
+    except BaseException:
+        # A rank that fails must not linger: its peers are waiting for it inside kernels and collectives, and the interpreter's
+        # orderly shutdown (destructors synchronising streams whose kernels wait for those peers) can take minutes. Report and
+        # leave at once, so that the launcher sees the failure and ends the other ranks.
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            os._exit(1)
+        raise
 
 
 if __name__ == "__main__":

@@ -212,8 +212,10 @@ int akua_pbf_comm_unique_id(void* out, int64_t out_bytes);
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id);
 int akua_pbf_set_slab(akua_pbf_solver* s, int32_t xCellLo, int32_t xCellHi);
 int akua_pbf_upload_ids(akua_pbf_solver* s, const uint32_t* ids, int64_t n);
-/* Collective (every rank, same step): moves the slab boundaries towards equal WORK (a particle weighs 12 + its neighbour
- * count) using the current per-x-plane sums (one small ncclAllReduce); the following step's migration transfers the particles.
+/* Collective (every rank, same step): moves the slab boundaries towards equal WORK (a particle weighs 12 + the largest
+ * neighbour count in its warp, corrected per rank by its measured busy time when steps are long enough for the clock to
+ * mean something) using the current per-x-plane sums (one small ncclAllReduce); no slab is given more particles than 80 % of
+ * what its arrays hold; the following step's migration transfers the particles.
  * A partition whose heaviest slab is within 2 % of the mean is left alone (environment AKUA_SLAB_KEEP_BELOW, default 1.02).
  * Call every few dozen steps for scenes whose fluid moves along x (dam break, sloshing tank). */
 int akua_pbf_rebalance(akua_pbf_solver* s);
@@ -237,9 +239,10 @@ int akua_slab_rebalance_bounds(const int64_t* hist, int32_t ncols, int32_t nrank
 /* The same with a WORK histogram deciding where the boundaries go (akua_pbf_rebalance weighs a particle by 12 + its neighbour
  * count: the sweeps' cost follows the neighbour count, and a sloshing tank is denser on one side) while `count` (particles per
  * column) still bounds what may cross a boundary. keepBelow > 1: if the heaviest slab of the CURRENT partition carries at most
- * keepBelow x the mean work, the boundaries are left where they are. */
+ * keepBelow x the mean work, the boundaries are left where they are. maxCount > 0: no slab of the target partition holds more
+ * particles than that (the room of a rank's arrays), whatever the work says. */
 int akua_slab_rebalance_bounds_weighted(const int64_t* work, const int64_t* count, int32_t ncols, int32_t nranks,
-                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int32_t* bounds);
+                                        const int32_t* oldBounds, int64_t maxMove, double keepBelow, int64_t maxCount, int32_t* bounds);
 
 /* Page-locked host memory for the interchange buffers (so uploads/downloads run at full PCIe rate). */
 void* akua_pbf_host_alloc(int64_t bytes);

@@ -202,6 +202,69 @@ def test_async_rebalance_lags_one_call_and_stays_bit_identical(emulib):
     assert max(owned) / (sum(owned) / 2) < 1.2, owned
 
 
+def test_a_dead_neighbour_costs_one_timeout_not_one_per_kernel(emulib):
+    """Rank 1 stops stepping. Rank 0's next step waits for its count message, times out ONCE (bounded in-kernel spin), raises the
+    sticky error word, and every later wait of that rank gives up at once: the queue drains, the next host call reports
+    AKUA_ERR_COMM, and closing the solver does not hang. (On a GPU the same logic turns a lost peer into an error within ~10 s
+    instead of one time-out per queued kernel.)"""
+    import time
+    from akuaengine_b200 import AkuaError
+    p, bmin, bmax = _scene()
+    g = np.array([0.0, -9.8, 0.0], np.float32)
+    n, world = len(p), 2
+    ids = np.arange(n, dtype=np.uint32)
+    cols = x_columns(p["position"][:, 0], H)
+    col_min = int(cols.min())
+    bounds = partition_columns(np.bincount(cols - col_min).astype(np.int64), world)
+    uid = PBFSolver.comm_unique_id(emulib)
+    res, errs = {}, []
+    gate = threading.Event()
+
+    def work(rank):
+        try:
+            lo, hi = col_min + int(bounds[rank]), col_min + int(bounds[rank + 1])
+            mine = (cols >= lo) & (cols < hi)
+            s = PBFSolver(n // world, lib=emulib, use_graph=False, capacity_factor=4.0)
+            s.comm_init(rank, world, uid)
+            s.set_slab(lo, hi)
+            s.upload_particles(np.ascontiguousarray(p[mine]))
+            s.upload_ids(ids[mine])
+            s.setGravity(g)
+            for _ in range(2):
+                s.step(DT, bmin, bmax)
+            s.sync()
+            if rank == 1:
+                gate.wait(timeout=600)       # the "dead" rank: alive (its memory stays mapped) but silent
+                s.close()
+                return
+            t0 = time.perf_counter()
+            failed = None
+            try:
+                for _ in range(3):
+                    s.step(DT, bmin, bmax)
+                s.sync()
+            except AkuaError as e:
+                failed = str(e)
+            res["elapsed"] = time.perf_counter() - t0
+            res["error"] = failed
+            t1 = time.perf_counter()
+            s.close()
+            res["close"] = time.perf_counter() - t1
+        except Exception as e:  # noqa: BLE001
+            errs.append((rank, e))
+        finally:
+            if rank == 0:
+                gate.set()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=600) for t in ts]
+    assert not any(t.is_alive() for t in ts) and not errs, errs
+    assert res["error"] and "timed out" in res["error"], res
+    # three steps = dozens of waits: with one time-out per wait this would take tens of times longer than the first one did
+    assert res["close"] < max(2.0, res["elapsed"]), res
+
+
 def test_slab_nccl_fallback_transport(emulib, monkeypatch):
     monkeypatch.setenv("AKUA_SLAB_P2P", "0")
     p, bmin, bmax = _scene(vx=1.5)

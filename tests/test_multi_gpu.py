@@ -72,6 +72,35 @@ def test_rebalance_bounds_keep_the_migration_contract(akua_lib):
                 assert blocked_by_size or blocked_by_width, (r, cur, target, hist[plane], max_move)
 
 
+def test_weighted_rebalance_respects_the_particle_capacity(akua_lib):
+    """akua_slab_rebalance_bounds_weighted: the WORK histogram decides where the boundaries go, but no slab of the target
+    partition may hold more particles than maxCount (a region of cheap particles must not overflow a rank's arrays), and a
+    partition that is balanced within keepBelow is left alone only if it also fits."""
+    import ctypes as C
+    ncols, R = 64, 4
+    count = np.full(ncols, 1000, np.int64)
+    work = count.copy()
+    work[48:] = 200                       # the last quarter of the box is five times cheaper per particle
+    old = np.array([0, 16, 32, 48, 64], np.int32)
+
+    def run(keep, max_count, max_move=10 ** 9):
+        out = np.zeros(R + 1, np.int32)
+        rc = akua_lib.akua_slab_rebalance_bounds_weighted(work.ctypes.data_as(C.POINTER(C.c_int64)), count.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                          ncols, R, old.ctypes.data_as(C.POINTER(C.c_int32)), max_move, keep, max_count,
+                                                          out.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert rc == 0
+        return out
+    free = run(0.0, 0)
+    owned = np.diff(np.concatenate([[0], np.cumsum(count)])[free])
+    assert owned[-1] > 20000                                   # by work alone the last slab takes most of the cheap quarter and more
+    capped = run(0.0, 18000)
+    owned = np.diff(np.concatenate([[0], np.cumsum(count)])[capped])
+    assert owned.max() <= 18000 and capped[0] == 0 and capped[-1] == ncols and np.all(np.diff(capped) >= 2)
+    # hysteresis: the equal-count partition is balanced in count, not in work; a generous keepBelow keeps it, unless it does not fit
+    assert np.array_equal(run(2.0, 0), old)
+    assert not np.array_equal(run(2.0, 15000), old)
+
+
 def _gloo_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch

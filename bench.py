@@ -266,7 +266,7 @@ def workload(args, world: int):
     return (nx, ny, nz), origin, bmin, bmax, gravity, scaling, config
 
 
-def make_solver(args, world, rank, local, dist, dims, origin, gravity, capacity_factor=2.0):
+def make_solver(args, world, rank, local, dist, dims, origin, gravity, capacity_factor=2.5):
     """Creates the solver with this rank's share of the lattice uploaded. Returns (solver, n_local)."""
     from akuaengine_b200 import KEY_LINEAR_CELL, KEY_REFERENCE_HASH, PBFSolver, scenes
     nx, ny, nz = dims
@@ -459,7 +459,7 @@ def run_ours(args):
                         "check": "count, sum, sum of squares and xor of all ranks' particle ids equal those of 0..n-1"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------------
-    cap = int(max(n, n_rank) * 1.6) + 1024
+    cap = int(max(n, n_rank) * 2.0) + 1024
     pin = PinnedBuffer((cap,), PARTICLE_DTYPE)
     pin_ids = np.empty(cap, np.uint32)
 

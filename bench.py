@@ -75,11 +75,38 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# The kernels the committed ncu captures describe (roofline.traffic / dram_frac_ncu): pass B and pass A of the default single-GPU step.
+PROFILED_KERNELS = ["k_delta_applyILb1ELb0ELb1ELb1ELb0EE", "k_density_lambdaILb1ELb0EE"]
+
+
 def kernel_source_hash() -> str:
+    """Identity of the profiled kernels: a hash of their SASS (opcodes and operands of every instruction, addresses and encodings
+    dropped) read from the built library with cuobjdump — an ncu capture stays valid exactly as long as the machine code of the
+    kernels it describes is unchanged, whatever else in the source file moved. Falls back to a hash of the source file."""
+    try:
+        import re
+        lib = REPO / "akuaengine_b200" / "libakua_pbf.so"
+        txt = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, timeout=120, check=True).stdout
+        h = hashlib.sha256()
+        found = 0
+        for blk in re.split(r"\n\s*Function : ", txt)[1:]:
+            name = blk.split("\n", 1)[0].strip()
+            if not any(k in name for k in PROFILED_KERNELS):
+                continue
+            found += 1
+            h.update(name.encode())
+            for line in blk.split("\n"):
+                m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+                if m:
+                    h.update(m.group(1).strip().encode())
+        if found == len(PROFILED_KERNELS):
+            return "sass:" + h.hexdigest()[:16]
+    except Exception:
+        pass
     h = hashlib.sha256()
     for rel in KERNEL_SOURCES:
         h.update((REPO / rel).read_bytes())
-    return h.hexdigest()[:16]
+    return "src:" + h.hexdigest()[:16]
 
 
 def ncu_traffic(n_rank: int):
@@ -108,7 +135,7 @@ def ncu_traffic(n_rank: int):
     _, label, n_cap, row = best
     return (int(row["dram_bytes_per_particle"] * n_rank), row.get("dram_pct_of_peak"),
             f"ncu --set full, {label} ({n_cap} particles): {row['dram_bytes_per_particle']:.1f} B per particle x {n_rank} particles"
-            + ("; STALE: pbf_kernels.cuh changed since this capture" if stale else "; kernel source unchanged since the capture"))
+            + ("; STALE: the profiled kernels changed since this capture" if stale else "; SASS of the profiled kernels unchanged since the capture"))
 
 
 class ClockSampler:

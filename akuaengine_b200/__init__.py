@@ -84,7 +84,7 @@ class PBFConfig(C.Structure):
 class PBFOptions(C.Structure):
     _fields_ = [("key_mode", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("fast_math", C.c_int32),
                 ("capacity_factor", C.c_float), ("gather_layout", C.c_int32), ("use_pdl", C.c_int32), ("list_build", C.c_int32), ("canonical_order", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("wall_model", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Counters(C.Structure):
@@ -241,7 +241,7 @@ class PBFSolver:
     def __init__(self, numParticles: int, config: PBFConfig | None = None, corrParams: LambdaCorrParams | None = None,
                  key_mode: int = KEY_LINEAR_CELL, device: int = 0, fast_math: bool = True, use_graph: bool = True,
                  capacity_factor: float = 1.0, gather_layout: int = GATHER_AUTO, use_pdl: bool | None = None,
-                 list_build: int | None = None, canonical_order: bool = False, lib=None):
+                 list_build: int | None = None, canonical_order: bool = False, wall_model: int = 0, lib=None):
         # `lib`: an alternative build of the same C ABI (load_library(path)), e.g. the host-emulated build of tests/emu
         self._lib = lib if lib is not None else load_library()
         self.config = config or PBFConfig()
@@ -257,6 +257,7 @@ class PBFSolver:
         if list_build is not None:
             opt.list_build = int(list_build)
         opt.canonical_order = int(bool(canonical_order))
+        opt.wall_model = int(wall_model)   # 0 = reference (soft clamp only), 1 = opt-in virtual-fluid walls (akua_wall_model)
         self.options = opt
         self._h = C.c_void_p()
         rc = self._lib.akua_pbf_create(C.byref(self._h), self.numParticles, C.byref(self.config),

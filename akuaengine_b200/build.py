@@ -15,7 +15,7 @@ REPO_DIR = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libakua_pbf.so"
 SOURCES = [CSRC / "pbf_solver.cu"]
-HEADERS = [CSRC / "pbf_kernels.cuh", CSRC / "list_build.cuh", CSRC / "pbf_params.h", CSRC / "radix_sort.cuh", CSRC / "slab_kernels.cuh", CSRC / "pbf_slab.inl",
+HEADERS = [CSRC / "pbf_kernels.cuh", CSRC / "list_build.cuh", CSRC / "pbf_params.h", CSRC / "radix_sort.cuh", CSRC / "slab_kernels.cuh", CSRC / "wall_model.cuh", CSRC / "pbf_slab.inl",
            REPO_DIR / "include" / "akua_pbf.h"]
 
 NVCC_FLAGS = [

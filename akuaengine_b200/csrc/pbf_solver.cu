@@ -11,6 +11,7 @@
 #include "list_build.cuh"
 #include "radix_sort.cuh"
 #include "slab_kernels.cuh"
+#include "wall_model.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library itself is dlopen'ed by akua_pbf_comm_init (pbf_slab.inl)
@@ -264,6 +265,17 @@ cudaError_t dalloc(T** p, size_t count) {
 }
 
 SphParams makeSph(const akua_pbf_solver* s) { return make_sph_params(s->cfg, s->corr, s->uniformMass); }
+inline bool wallOn(const akua_pbf_solver* s) { return s->opt.wall_model == AKUA_WALL_VIRTUAL_FLUID; }
+WallParams makeWall(const akua_pbf_solver* s, const SphParams& P, const float* bmin, const float* bmax) {
+    WallParams W{};
+    const float pi = 3.14159265358979f;
+    W.h = P.h; W.rhoW = s->cfg.restDensity;
+    W.fCoef = 0.25f * pi * P.poly6Coef;
+    W.pH = wall_P(P.h, P.h);
+    W.sCoef = std::fabs(P.spikyCoef) * (2.0f * pi / 3.0f);
+    W.bmin = make_float3(bmin[0], bmin[1], bmin[2]); W.bmax = make_float3(bmax[0], bmax[1], bmax[2]);
+    return W;
+}
 BoxParams makeBox(const float* bmin, const float* bmax) { return make_box_params(bmin, bmax); }
 
 int bitsFor(uint64_t maxKey) { return bits_for_key(maxKey); }
@@ -554,7 +566,7 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
     s->timedIters = 0;
     for (int it = 0; it < iterations; it++) {
         const bool timeIt = s->timing && it < akua_pbf_solver::kMaxTimedIters;
-        const bool fin = commit && it == iterations - 1;
+        const bool fin = commit && !wallOn(s) && it == iterations - 1;   // (the wall model inserts a kernel between pass B and the commit)
         if (timeIt) cudaEventRecord(s->evPass[it][0], s->stream);
         if (slabMode && p2p) {
             // ---- CUDA-IPC transport: one launch per sweep. Its first CTAs take the boundary planes: they wait in-kernel for the
@@ -576,8 +588,19 @@ int phaseSolve(akua_pbf_solver* s, int iterations, const float* bmin, const floa
             if (fin && (rc = slabNcclPlanes(s, s->vel))) return rc;
         } else {
             if ((rc = launchPassA(s, sp.interior, sp.gridInterior, P))) return rc;
+            if (wallOn(s)) {   // opt-in wall model: near-wall particles get rho, grad C and lambda with the virtual half-spaces
+                const WallParams W = makeWall(s, P, bmin, bmax);
+                launchK(s, k_wall_lambda, sweepGrid((uint64_t)s->n), kSweepBlock, s->xs, s->nbrList, s->nbrCount, s->nbrStride, (uint32_t)s->n,
+                        s->density, s->lambda, usePack(s) ? s->xl : nullptr, P, W);
+                AK_LAUNCH_CHECK(s, "k_wall_lambda");
+            }
             if (timeIt) cudaEventRecord(s->evPass[it][1], s->stream);
             if ((rc = launchPassB(s, sp.interior, sp.gridInterior, P, B, fin, dt))) return rc;
+            if (wallOn(s)) {   // ... and the wall's share of delta-p (pass B never commits in this mode: see stepEager)
+                const WallParams W = makeWall(s, P, bmin, bmax);
+                launchK(s, k_wall_dp, sweepGrid((uint64_t)s->n), kSweepBlock, s->xs, s->xsAlt, s->lambda, s->dpos, (uint32_t)s->n, P, B, W);
+                AK_LAUNCH_CHECK(s, "k_wall_dp");
+            }
         }
         if (timeIt) { cudaEventRecord(s->evPass[it][2], s->stream); s->timedIters = it + 1; }
         std::swap(s->xs, s->xsAlt);
@@ -654,7 +677,8 @@ void graphKey(const akua_pbf_solver* s, float dt, int iterations, const float* b
     key[9] = f2(bmin[0], bmin[1]); key[10] = f2(bmin[2], bmax[0]); key[11] = f2(bmax[1], bmax[2]);
     key[12] = (uint64_t)s->cellRange; key[13] = (uint64_t)s->perm; key[14] = (uint64_t)s->opt.fast_math;
     uint32_t mbits; std::memcpy(&mbits, &s->uniformMass, 4);
-    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u) | (slabOn(s) ? 8u : 0u);
+    key[15] = ((uint64_t)mbits << 8) | (usePack(s) ? 1u : 0u) | (useRec(s) ? 2u : 0u) | (usePdl(s) ? 4u : 0u) | (slabOn(s) ? 8u : 0u) |
+              (wallOn(s) ? 16u : 0u);
     // x-slab mode: the slab interval fixes the local grid, the (bucketed) size estimates fix the launch grids
     const SlabState& sl = s->slab;
     key[16] = slabOn(s) ? (((uint64_t)(uint32_t)sl.winX0 << 32) | (uint32_t)sl.winX1) : 0;   // the window, not the interval inside it
@@ -909,6 +933,8 @@ int akua_pbf_create(akua_pbf_solver** out, int64_t numParticles, const akua_pbf_
     if (s->opt.gather_layout < AKUA_GATHER_AUTO || s->opt.gather_layout > AKUA_GATHER_PACKED_RECORDS) { s->err = "unknown gather_layout"; return AKUA_ERR_INVALID; }
     if (const char* e = std::getenv("AKUA_LIST_BUILD")) s->opt.list_build = std::atoi(e);   // tuning experiments
     if (s->opt.list_build < AKUA_LIST_BUILD_SCAN || s->opt.list_build > AKUA_LIST_BUILD_MASK8) { s->err = "unknown list_build"; return AKUA_ERR_INVALID; }
+    if (const char* e = std::getenv("AKUA_WALL_MODEL")) s->opt.wall_model = std::atoi(e);   // experiments
+    if (s->opt.wall_model != AKUA_WALL_REFERENCE && s->opt.wall_model != AKUA_WALL_VIRTUAL_FLUID) { s->err = "unknown wall_model"; return AKUA_ERR_INVALID; }
     {
         const int g = s->opt.gather_layout;
         if (g != AKUA_GATHER_PLAIN && g != AKUA_GATHER_RECORDS) {
@@ -1366,6 +1392,7 @@ int akua_pbf_comm_unique_id(void* out, int64_t out_bytes) {
 int akua_pbf_comm_init(akua_pbf_solver* s, int32_t rank, int32_t nranks, const void* unique_id) {
     if (!s || !unique_id || nranks < 1 || rank < 0 || rank >= nranks) return AKUA_ERR_INVALID;
     if (s->opt.key_mode != AKUA_KEY_LINEAR_CELL) { s->err = "comm_init: slab mode needs LINEAR_CELL keys"; return AKUA_ERR_INVALID; }
+    if (wallOn(s)) { s->err = "comm_init: the opt-in wall model is single-GPU only"; return AKUA_ERR_INVALID; }
     if (const char* e = loadNccl()) { s->err = e; return AKUA_ERR_COMM; }
     AK_CUDA(s, cudaSetDevice(s->device));
     SlabState& sl = s->slab;

@@ -100,6 +100,16 @@ typedef enum akua_list_build {
     AKUA_LIST_BUILD_MASK8 = 2
 } akua_list_build;
 
+/* Boundary handling. 0 = the reference's: no boundary model, only the soft clamp of handle_particle_collision
+ * (src/CUDA/ConstraintSolverCUDA.cu:132-157, "Later we will use virtual particles") — the default, and the only mode inside the
+ * parity contract. 1 = OPT-IN upgrade: every box wall is backed by a half-space of virtual fluid at rest density in closed form
+ * (its poly6 density and spiky gradient enter a near-wall particle's density, lambda and delta-p; akuaengine_b200/csrc/wall_model.cuh),
+ * on top of the clamp. Changes results by design; single-GPU only; the measured kernels are not touched by it. */
+typedef enum akua_wall_model {
+    AKUA_WALL_REFERENCE = 0,
+    AKUA_WALL_VIRTUAL_FLUID = 1
+} akua_wall_model;
+
 typedef struct akua_pbf_options {
     int32_t key_mode;        /* akua_key_mode; default AKUA_KEY_LINEAR_CELL */
     int32_t device;          /* CUDA device ordinal; default 0 */
@@ -117,7 +127,8 @@ typedef struct akua_pbf_options {
                                 digit passes). With 1 the neighbour order, hence every float sum, no longer depends on history: an
                                 x-slab run on any number of GPUs, with migration and re-balancing, is then BIT-IDENTICAL to the
                                 single-GPU run (tests/mgpu_worker.py --canonical). Ids must be unique. */
-    int32_t reserved[4];
+    int32_t wall_model;      /* akua_wall_model; default AKUA_WALL_REFERENCE */
+    int32_t reserved[3];
 } akua_pbf_options;
 
 void akua_pbf_default_config(akua_pbf_config* cfg);   /* PBFConfig{} defaults */

@@ -772,8 +772,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50, help="steps per timed window (BASELINE.md §3: >= 50)")
+    ap.add_argument("--warmup", type=int, default=20, help="untimed steps right before the timed windows (BASELINE.md §3: >= 20)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tank", choices=["dam", "tank"])
     ap.add_argument("--tank-per-gpu", default="200,200,200", help="tank lattice per GPU (weak scaling): nx,ny,nz")

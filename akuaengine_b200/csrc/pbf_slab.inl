@@ -4,12 +4,15 @@
 // cell coordinates floor(x/h); the first / last rank own everything below / above). Layout of every per-particle array
 // during a step:   [ owned, key-sorted | ghost plane from the left rank | ghost plane from the right rank ].
 // Because keys are x-major, the planes a rank sends are the first and last contiguous stretch of its owned range, and
-// what it receives is already sorted: no pack/unpack kernels and no re-sort on the per-iteration path, only
-// ncclSend/ncclRecv of array slices on the solver's stream. Exchanges per step (1-cell halo): x* once for the neighbour
+// what it receives is already sorted: no pack/unpack kernels and no re-sort on the per-iteration path. With the CUDA-IPC
+// transport (default) the first CTAs of every sweep store those planes straight into the neighbours' ghost regions and
+// publish an epoch the neighbours' CTAs wait for (pbf_kernels.cuh: sweep_cta, peer_push, halo_wait / halo_signal); every size
+// of the step lives on the device (dims) and the step is one CUDA graph. The fallback is ncclSend/ncclRecv of array slices on
+// the solver's stream with one host synchronisation per step. Exchanges per step (1-cell halo): x* once for the neighbour
 // search; lambda after pass A and x* after pass B in every iteration; v after the commit; |omega| after K11; v after K12.
-// Migration happens once per step, right after the prediction: leavers are compacted deterministically into send
-// buffers and get a sentinel key that sorts them out of the owned range; arrivals are appended before the sort.
-// NCCL is loaded with dlopen so single-GPU users need no NCCL at all.
+// Migration happens once per step, right after the prediction: leavers are compacted deterministically into the
+// neighbours' inboxes and get a sentinel key that sorts them out of the owned range; arrivals are appended before the sort.
+// NCCL (set-up, re-balancing, fallback transport) is loaded with dlopen so single-GPU users need no NCCL at all.
 
 struct NcclApi {
     void* lib = nullptr;

@@ -146,12 +146,18 @@ def _gpu_count():
         return 0
 
 
+_CASES2 = [("dam", 0.0, 8, []), ("tank", 0.0, 8, []), ("tank", 1.5, 20, []),
+           ("tank", 0.0, 30, ["--rebalance-every", "5", "--skew", "0.5"]),
+           ("tank", 1.5, 24, ["--canonical"]),
+           ("tank", 1.0, 30, ["--canonical", "--rebalance-every", "5", "--skew", "0.4"])]
+# 4 and 8 ranks: the exact statement (canonical order, bit-identical with migration, re-balancing and a skewed start) and one
+# default-order run — the cases run on 4 / 8 B200s in round 2 (profiles/r02_c14_worker*.log, r02_c15_worker8_default_order.log)
+_CASES = ([(2, *c) for c in _CASES2] + [(4, "tank", 1.5, 24, ["--canonical"]), (4, "tank", 1.5, 20, []),
+          (8, "tank", 1.0, 30, ["--canonical", "--rebalance-every", "5", "--skew", "0.4"]), (8, "tank", 1.5, 20, [])])
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("scene,vx,steps,extra", [("dam", 0.0, 8, []), ("tank", 0.0, 8, []), ("tank", 1.5, 20, []),
-                                                  ("tank", 0.0, 30, ["--rebalance-every", "5", "--skew", "0.5"]),
-                                                  ("tank", 1.5, 24, ["--canonical"]),
-                                                  ("tank", 1.0, 30, ["--canonical", "--rebalance-every", "5", "--skew", "0.4"])])
+@pytest.mark.parametrize("world,scene,vx,steps,extra", _CASES)
 def test_multi_gpu_slab_matches_single_gpu(world, scene, vx, steps, extra):
     """N x-slab ranks against ONE GPU running the same library on the same scene: ids conserved, payload follows, positions and
     velocities within the free-running tolerance (bit-identical when nothing migrates). On a box with fewer GPUs than `world`

@@ -42,14 +42,16 @@ def main():
     lib.emu_create.argtypes = [C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_destroy.argtypes = [vp]; lib.emu_upload_aos108.argtypes = [vp, vp]; lib.emu_download_aos108.argtypes = [vp, vp]
     lib.emu_step.argtypes = [vp, C.c_float, C.c_int, vp, vp]; lib.emu_debug_get.argtypes = [vp, C.c_int, vp]
-    lib.emu_sort_pairs.argtypes = [vp, C.c_uint32, C.c_int, vp, vp]
+    lib.emu_sort_pairs.argtypes = [vp, C.c_uint32, C.c_int, vp, vp, C.c_int, C.c_int]
+    lib.emu_plane_hist.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp]
     lib.emu_migration.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
     rng = np.random.default_rng(0)
     for n, bits in [(1, 8), (1025, 21), (5000, 32)]:
         keys = rng.integers(0, 2 ** bits, n, dtype=np.uint64).astype(np.uint32)
         ko, vo = np.empty(n, np.uint32), np.empty(n, np.uint32)
-        lib.emu_sort_pairs(keys.ctypes.data, n, bits, ko.ctypes.data, vo.ctypes.data)
-        print("sort", n, "clean", flush=True)
+        for mode, items in ((0, 0), (1, 4), (1, 8), (1, 16)):
+            lib.emu_sort_pairs(keys.ctypes.data, n, bits, ko.ctypes.data, vo.ctypes.data, mode, items)
+        print("sort", n, "clean (three-kernel and one-sweep variants)", flush=True)
     for name in ["jittered block, cap 20", "dense blob (cap 128 bites, rows > 32 candidates)"]:
         init, bmin, bmax, cap = Z._scene(name)
         init = init[:1500]
@@ -62,12 +64,16 @@ def main():
                 s.step(0.0083, bmin, bmax, iters=0)
                 s.debug(7, (len(init), cap)); s.download(); s.close()
                 print(f"{name}: key_mode {mode} list_build {lb} pack {pack} clean", flush=True)
-    n = 3000
-    keys = (rng.integers(0, 12, n) * 35 + rng.integers(0, 35, n)).astype(np.uint32)
-    ids = np.arange(n, dtype=np.uint32)
-    counts, il, ir = np.zeros(32, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
-    lib.emu_migration(keys.ctypes.data, n, 35, 4, 9, 12 * 35, ids.ctypes.data, n, counts.ctypes.data, il.ctypes.data, ir.ctypes.data)
-    print("migration clean")
+    for n in (1, 3000, 2048 * 3 + 5):     # migration tiles are 2048 particles: one partial tile, two tiles, a ragged fourth
+        keys = (rng.integers(0, 12, n) * 35 + rng.integers(0, 35, n)).astype(np.uint32)
+        ids = np.arange(n, dtype=np.uint32)
+        counts, il, ir = np.zeros(64, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        lib.emu_migration(keys.ctypes.data, n, 35, 4, 9, 12 * 35, ids.ctypes.data, n, counts.ctypes.data, il.ctypes.data, ir.ctypes.data)
+        ks = np.sort(keys)
+        hist, work = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
+        nbr = rng.integers(0, 60, n).astype(np.uint32)
+        lib.emu_plane_hist(ks.ctypes.data, nbr.ctypes.data, n, 35, 12, hist.ctypes.data, work.ctypes.data)
+        print("migration + plane histogram", n, "clean", flush=True)
 
 
 if __name__ == "__main__":

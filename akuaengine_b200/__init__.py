@@ -110,7 +110,7 @@ ABI_SYMBOLS = [
     "akua_pbf_phase_neighbours", "akua_pbf_phase_solve", "akua_pbf_phase_update", "akua_pbf_phase_damping",
     "akua_pbf_phase_vorticity_viscosity", "akua_pbf_debug_get", "akua_pbf_debug_size", "akua_pbf_density_error",
     "akua_pbf_get_counters", "akua_pbf_enable_timing", "akua_pbf_last_step_timing", "akua_pbf_trace_next_step", "akua_pbf_stream",
-    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_rebalance", "akua_pbf_rebalance_async", "akua_slab_partition", "akua_slab_rebalance_bounds", "akua_slab_rebalance_bounds_weighted",
+    "akua_pbf_comm_unique_id", "akua_pbf_comm_init", "akua_pbf_set_slab", "akua_pbf_upload_ids", "akua_pbf_slab_stats", "akua_pbf_slab_wait_stats", "akua_pbf_rebalance", "akua_pbf_rebalance_async", "akua_slab_partition", "akua_slab_rebalance_bounds", "akua_slab_rebalance_bounds_weighted",
 ]
 
 _lib = None
@@ -189,6 +189,7 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     lib.akua_pbf_set_slab.argtypes = [vp, C.c_int32, C.c_int32]
     lib.akua_pbf_upload_ids.argtypes = [vp, vp, C.c_int64]
     lib.akua_pbf_slab_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.akua_pbf_slab_wait_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.akua_pbf_rebalance.argtypes = [vp]
     lib.akua_pbf_rebalance_async.argtypes = [vp]
     lib.akua_slab_partition.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
@@ -450,6 +451,11 @@ class PBFSolver:
         d["transport"] = "cuda-ipc p2p" if d["bytes_sent"] < 0 else "nccl"
         d["bytes_sent"] = abs(d["bytes_sent"])
         return d
+
+    def slab_wait_stats(self) -> dict:
+        out = (C.c_int64 * 4)()
+        self._ck(self._lib.akua_pbf_slab_wait_stats(self._h, out), "slab_wait_stats")
+        return {"plan_wait_ns": int(out[0]), "halo_wait_ns": int(out[1]), "device_steps": int(out[2]), "rebalances_moved": int(out[3])}
 
     def stream_ptr(self) -> int:
         """cudaStream_t of the solver, e.g. for torch.cuda.ExternalStream."""

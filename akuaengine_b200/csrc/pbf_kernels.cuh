@@ -164,6 +164,8 @@ enum : int {
     D_XLO = 57, D_XHI = 58,                                         // owned x planes [lo, hi) in slab-local grid coordinates: written by the
                                                                     // host when the slab interval changes (akua_pbf_set_slab / _rebalance), read
                                                                     // by the migration kernels — moving a boundary does not touch the step's graph
+    D_STAT_PLAN_WAIT_NS = 60, D_STAT_HALO_WAIT_NS = 62,            // u64 accumulators: idle time waiting for the neighbours' count message;
+                                                                    // time CTA 0 of the sweeps spent waiting for ghost planes (exposed halo latency)
     D_WORDS = 64
 };
 enum : uint32_t {   // bits of dims[D_ERROR]
@@ -282,11 +284,14 @@ __device__ __forceinline__ void halo_wait(const HaloSync& hs) {
     if (!hs.waitFlags || hs.waitIdx < 0) return;
     if (threadIdx.x == 0) {
         const uint32_t epoch = hs.dims[D_EPOCH] + (uint32_t)hs.waitIdx + 1u;
+        const unsigned long long t0 = blockIdx.x == 0 ? global_timer_ns() : 0ull;
         for (int side = 0; side < 2; side++) {
             if (!(side == 0 ? hs.waitL : hs.waitR)) continue;
             if (!spin_until(hs.waitFlags + side, epoch, hs.timeoutCycles, hs.dims + D_ERROR)) { atomicOr(hs.dims + D_ERROR, (uint32_t)SLAB_ERR_TIMEOUT); break; }
         }
         __threadfence_system();
+        // the first boundary CTA of every sweep records how long the ghosts kept it waiting: the halo latency that was NOT hidden
+        if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(hs.dims + D_STAT_HALO_WAIT_NS), global_timer_ns() - t0);
     }
     __syncthreads();
 }

@@ -1530,6 +1530,17 @@ int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]) {
     out[5] = sl.exchanges; out[6] = sl.p2p ? -(int64_t)st[2] : (int64_t)st[2]; out[7] = (int64_t)st[0];  // negative bytes: p2p transport
     return rc;
 }
+int akua_pbf_slab_wait_stats(const akua_pbf_solver* s, int64_t out[4]) {
+    if (!s || !out) return AKUA_ERR_INVALID;
+    akua_pbf_solver* m = const_cast<akua_pbf_solver*>(s);
+    cudaSetDevice(m->device);
+    const int rc = slabRefresh(m);
+    const SlabState& sl = s->slab;
+    unsigned long long w[2] = {0, 0};
+    if (sl.hDims) std::memcpy(w, (const void*)(sl.hDims + D_STAT_PLAN_WAIT_NS), sizeof(w));
+    out[0] = (int64_t)w[0]; out[1] = (int64_t)w[1]; out[2] = sl.hDims ? (int64_t)sl.hDims[D_STEPS] : 0; out[3] = sl.rebalances;
+    return rc;
+}
 // Balanced x-slab boundaries from a histogram of particles per absolute x cell column (pure host code, no CUDA):
 // bounds[r] .. bounds[r+1] is rank r's interval of columns (indices into hist); bounds[0] = 0, bounds[nranks] = ncols.
 int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds) {

@@ -244,6 +244,7 @@ __global__ void k_slab_plan(uint32_t* __restrict__ dims, const uint32_t* __restr
         // feeds back on (akua_pbf_rebalance)
         const unsigned long long waited = global_timer_ns() - t0;
         dims[D_PLAN_WAIT_NS] = waited > 0xffffffffull ? 0xffffffffu : (uint32_t)waited;
+        *reinterpret_cast<unsigned long long*>(dims + D_STAT_PLAN_WAIT_NS) += waited;
     }
     const volatile uint32_t* d = dims;
     uint32_t outL = d[D_OUT_L], outR = d[D_OUT_R];

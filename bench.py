@@ -428,12 +428,14 @@ def run_ours(args):
     owned_log = []
     nv0 = nvlink_counters(local) if world > 1 else None
     st0 = solver.slab_stats() if world > 1 else None
+    wt0 = solver.slab_wait_stats() if world > 1 else None
     step_log = []
     win_ms = timed_windows(solver, stream, barrier, bmin, bmax, args.steps, args.windows,
                            rebalance=args.rebalance_every if world > 1 else 0, owned_log=owned_log, step_log=step_log)
     clocks = sampler.stop()
     nv1 = nvlink_counters(local) if world > 1 else None
     st1 = solver.slab_stats() if world > 1 else None
+    wt1 = solver.slab_wait_stats() if world > 1 else None
     c1 = solver.counters()
     launches = (c1["kernel_launches"] - c0["kernel_launches"]) // args.windows
     graph_replays = (c1["graph_replays"] - c0["graph_replays"]) // args.windows
@@ -594,6 +596,20 @@ def run_ours(args):
             "link_utilisation_over_step": halo_bytes_step / (ms_step * 1e-3) / 1e9 / link_peak,
             "note": "end ranks have one neighbour, interior ranks two (twice the bytes); the pushes are P2P stores issued by the "
                     "boundary CTAs of each sweep while the interior CTAs of the same launch compute"}
+        # where the ranks waited for each other during the timed windows (device clock): idle in the count exchange = load
+        # imbalance; wait of the first boundary CTA for ghost planes = halo latency that was not hidden behind the interior
+        dsteps = max(wt1["device_steps"] - wt0["device_steps"], 1)
+        waits = torch.tensor([(wt1["plan_wait_ns"] - wt0["plan_wait_ns"]) / dsteps / 1e3, (wt1["halo_wait_ns"] - wt0["halo_wait_ns"]) / dsteps / 1e3],
+                             device="cuda", dtype=torch.float64)
+        allw = [torch.zeros_like(waits) for _ in range(world)]
+        dist.all_gather(allw, waits)
+        allw = np.stack([t.cpu().numpy() for t in allw])
+        out["sync_waits"] = {"count_exchange_idle_us_per_step_by_rank": [round(float(x), 1) for x in allw[:, 0]],
+                             "ghost_plane_wait_us_per_step_by_rank": [round(float(x), 1) for x in allw[:, 1]],
+                             "exchanges_per_step": 12, "rebalances_that_moved_a_boundary": int(wt1["rebalances_moved"] - wt0["rebalances_moved"]),
+                             "what": "device-clock time per step a rank idled for its neighbours' count message (k_slab_plan: a rank ahead of "
+                                     "its neighbours waits here) and that the first boundary CTA of its 11 sweeps + the ghost-key kernel "
+                                     "waited for ghost planes (halo_wait)"}
         out["slab_rank0"] = {"owned_start": n, "owned_end": int(n_rank), **slab_stats}
         out["mgpu_check"] = {"small_scene_vs_single_gpu": mgpu_check, "conservation": conservation}
     solver.close()

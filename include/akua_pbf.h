@@ -239,6 +239,11 @@ int akua_pbf_rebalance_async(akua_pbf_solver* s);
  * 7 particles migrated in so far. Transport: ghost planes are copied straight into the neighbour's arrays through
  * CUDA IPC when every rank could open its neighbours' allocations (environment AKUA_SLAB_P2P=0 forces NCCL). */
 int akua_pbf_slab_stats(const akua_pbf_solver* s, int64_t out[8]);
+/* Where a rank waited for its neighbours, cumulative, measured on the device clock: out[0] nanoseconds idle in the per-step
+ * count exchange (a rank that is ahead of its neighbours idles there: load imbalance), out[1] nanoseconds the first boundary
+ * CTA of the sweeps waited for ghost planes (halo latency that was not hidden behind the interior), out[2] steps completed
+ * on the device, out[3] re-balancing calls that moved a boundary. Synchronises. */
+int akua_pbf_slab_wait_stats(const akua_pbf_solver* s, int64_t out[4]);
 /* Balanced slab boundaries from a per-x-column particle histogram. Pure host code (callable without a GPU). */
 int akua_slab_partition(const int64_t* hist, int32_t ncols, int32_t nranks, int32_t* bounds /* nranks + 1 */);
 /* Boundaries for a re-balancing step from the global per-column histogram and the current boundaries (pure host code; what

@@ -98,6 +98,7 @@ def _run_slab(lib, p, bmin, bmax, steps, g, world, skew=0.0, rebalance_every=0, 
             pos, vel, pid = s.download()
             aos = s.download_particles()
             st = s.slab_stats()
+            st["waits"] = s.slab_wait_stats()
             err = s.density_error()
             out[rank] = (pos, vel, pid, aos, st, err)
             s.close()
@@ -142,6 +143,8 @@ def test_slab_without_migration_is_bit_identical_to_one_rank(emulib, world):
     if migrated == 0:
         assert dp == 0.0 and dv == 0.0      # same sort order, same list order: no float may differ
     assert all(o[4]["transport"] == "cuda-ipc p2p" and o[4]["exchanges"] > 0 for o in slab)
+    # the device-side wait statistics come through the ABI (the emulator's device clock stands still: zero nanoseconds, 3 steps)
+    assert all(o[4]["waits"]["device_steps"] == 3 and o[4]["waits"]["plan_wait_ns"] == 0 for o in slab)
     assert sum(o[4]["bytes_sent"] for o in slab) > 0
 
 

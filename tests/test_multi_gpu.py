@@ -72,6 +72,39 @@ def test_rebalance_bounds_keep_the_migration_contract(akua_lib):
                 assert blocked_by_size or blocked_by_width, (r, cur, target, hist[plane], max_move)
 
 
+def test_weighted_capped_rebalance_keeps_the_migration_contract(akua_lib):
+    """The same contract for akua_slab_rebalance_bounds_weighted with a work histogram that differs from the particle counts,
+    a particle cap and the hysteresis: whatever the target, every boundary stays strictly inside the two old slabs, slabs stay
+    two planes wide, and at most max_move PARTICLES (not work units) cross a boundary."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        R = int(rng.integers(2, 9))
+        gx = int(rng.integers(4 * R, 12 * R))
+        count = rng.integers(0, 2000, gx).astype(np.int64)
+        work = (count * rng.uniform(8.0, 70.0, gx)).astype(np.int64)          # 12 + neighbours per particle, varying along x
+        cuts = np.sort(rng.choice(np.arange(1, gx // 2), R - 1, replace=False)) * 2
+        cur = np.concatenate([[0], cuts, [gx]]).astype(np.int32)
+        max_move = int(rng.integers(500, 20000))
+        max_count = int(rng.choice([0, int(count.sum() / R * rng.uniform(1.05, 2.0))]))
+        keep = float(rng.choice([0.0, 1.02, 1.2]))
+        for it in range(60):
+            new = np.zeros(R + 1, np.int32)
+            rc = akua_lib.akua_slab_rebalance_bounds_weighted(work.ctypes.data_as(C.POINTER(C.c_int64)), count.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                              gx, R, cur.ctypes.data_as(C.POINTER(C.c_int32)), max_move, keep, max_count,
+                                                              new.ctypes.data_as(C.POINTER(C.c_int32)))
+            assert rc == 0
+            assert new[0] == 0 and new[-1] == gx and np.all(np.diff(new) >= 2), (cur, new)
+            for r in range(1, R):
+                assert cur[r - 1] < new[r] <= cur[r + 1] - 2, (r, cur, new)
+                lo, hi = sorted((int(cur[r]), int(new[r])))
+                forced = new[r] == new[r - 1] + 2 and new[r] > cur[r]
+                assert int(count[lo:hi].sum()) <= max_move or forced, (r, cur, new, max_move)
+            if np.array_equal(new, cur):
+                break
+            cur = new
+
+
 def test_weighted_rebalance_respects_the_particle_capacity(akua_lib):
     """akua_slab_rebalance_bounds_weighted: the WORK histogram decides where the boundaries go, but no slab of the target
     partition may hold more particles than maxCount (a region of cheap particles must not overflow a rank's arrays), and a

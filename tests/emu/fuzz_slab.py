@@ -6,7 +6,11 @@ import sys
 import time
 from pathlib import Path
 
+import os
+
 import numpy as np
+
+os.environ.setdefault("AKUA_SLAB_WAIT_CYCLES", "300000000")   # bounded waits in the emulated library (a failed rank must not hang the others)
 
 REPO = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(REPO / "tests")); sys.path.insert(0, str(REPO))

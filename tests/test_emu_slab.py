@@ -27,12 +27,15 @@ CSRC = REPO / "akuaengine_b200" / "csrc"
 DEPS = [EMU / "emu_core.cpp", EMU / "emu_nccl.cpp", EMU / "cuda_runtime.h", EMU / "cuda_host_shim.h", EMU / "nccl.h",
         *CSRC.glob("*.cuh"), *CSRC.glob("*.h"), *CSRC.glob("*.inl"), CSRC / "pbf_solver.cu", REPO / "include" / "akua_pbf.h"]
 H, DT = 0.1, 0.0083
-# a rank that stops (error) must not hang its neighbours for the emulator's lifetime: bounded waits, short for the tests
-os.environ.setdefault("AKUA_SLAB_WAIT_CYCLES", "30000000")
+# a rank that stops (error) must not hang its neighbours for the emulator's lifetime: bounded waits, short for the tests. Set by
+# the fixture (not at import: collecting this module on a GPU box must not shorten the real library's time-outs, which the
+# multi-GPU tests' worker processes would inherit) and read once by the emulated library at its first wait.
+EMU_WAIT_CYCLES = "30000000"
 
 
 @pytest.fixture(scope="module")
 def emulib():
+    os.environ.setdefault("AKUA_SLAB_WAIT_CYCLES", EMU_WAIT_CYCLES)
     if not OUT.exists() or any(p.stat().st_mtime > OUT.stat().st_mtime for p in DEPS):
         OUT.parent.mkdir(parents=True, exist_ok=True)
         cmd = ["g++", "-O1", "-std=c++17", "-DAKUA_HOST_EMU", "-U_FORTIFY_SOURCE", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",

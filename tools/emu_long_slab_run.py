@@ -2,7 +2,8 @@
 8 ranks as 8 threads, sloshing tank, asynchronous re-balancing every CAD steps: no rank may raise (capacity, ghost-plane or
 migration overflow, time-outs), particles must be conserved, and the owned counts are printed every 20 steps.
     python tools/emu_long_slab_run.py SIDE STEPS CAD        (e.g. 16 300 5 -> profiles/r02_emu_8rank_300steps_async_rebalance.txt)"""
-import sys, numpy as np, time, threading
+import os, sys, numpy as np, time, threading
+os.environ.setdefault("AKUA_SLAB_WAIT_CYCLES", "300000000")   # bounded waits in the emulated library
 from pathlib import Path
 REPO = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(REPO / 'tests')); sys.path.insert(0, str(REPO))
